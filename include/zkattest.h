@@ -1,0 +1,145 @@
+/* zkattest.h — C ABI of libzkattest, the B200-native ZKAttest prover/verifier.
+ *
+ * Drop-in boundary for the hot path of cloudflare/zkp-ecdsa v0.2.6.  The reference has no
+ * FFI of its own (pure TypeScript); these entry points are what a node-addon-api shim
+ * binds so that the three public functions keep their TypeScript signatures
+ * (INTEGRATION.md shows the shim):
+ *
+ *   zka_params_generate  <-> generateParamsList   /root/reference/src/zkpAttestList.ts:88-92
+ *   zka_prove_batch      <-> proveSignatureList   /root/reference/src/zkpAttestList.ts:104-145
+ *   zka_verify_batch     <-> verifySignatureList  /root/reference/src/zkpAttestList.ts:147-184
+ *   zka_key_to_int       <-> keyToInt             /root/reference/src/zkpAttestList.ts:94-102
+ *
+ * All integers and points cross the boundary in the reference's own encodings:
+ *   Group.Point.toBytes():  P-256 0x04||x||y = 65 B (weier.ts:244-255),
+ *                           tomEdwards256 0x04||x||y = 67 B (edwards.ts:195-203)
+ *   Group.Scalar.toBytes(): big-endian, 32 B (p256) / 33 B (tomEdwards256) (group.ts:196-199)
+ *   bigint ring entries:    32-byte big-endian (keyToInt output, < 2^256)
+ *
+ * Flat proof layout (the reference only has typedjson JSON, serde.ts:21-36; field order is
+ * that of the reference classes):
+ *   proof   := R(65) comS1(65) keyXcom(67) keyYcom(67) rep[SecLevel] GK     zkpAttestList.ts:30-35
+ *   rep     := tag(1) A(65) Tx(67) Ty(67) body                              exp.ts:27-40
+ *   body    := tag==1: alpha(32) beta1(32) beta2(33) beta3(33)
+ *              tag==0: z(32) z2(32) PointAddProof(3266) r1(33) r2(33)
+ *   PointAddProof := C_8 C_10 C_11 C_13 pi_8 pi_10 pi_11 pi_13 pi_x pi_y     pointAdd.ts:29-38
+ *   MultProof(633)     := C_4 A_x A_y A_z A_4_1 A_4_2 t_x t_y t_z t_rx t_ry t_rz t_r4   mult.ts:27-39
+ *   EqualityProof(233) := A_1 A_2 t_x t_r1 t_r2                              equality.ts:28-32
+ *   GK      := n(1) cl[n] ca[n] cb[n] cd[n] f[n] za[n] zb[n] zd              gk.ts:32-39
+ *
+ * Randomness.  The reference draws from crypto.getRandomValues inside rnd() (big.ts:171-181).
+ * Here the caller supplies the randomness as a TAPE of 32-byte big-endian draws per proof, in
+ * the reference's call order:
+ *   prove:  [0] comS1.r (mod p256.n)  [1],[2] keyXcom.r, keyYcom.r (mod tom.order)
+ *           [3+4i..6+4i] alpha_i, r_i (mod p256.n), Tx_i.r, Ty_i.r (mod tom.order), i < SecLevel
+ *           then 40 draws (mod tom.order) per 0-bit repetition in index order, then 5 per GK round.
+ *           Total 3 + 4*SecLevel + 40*Z + 5*n draws; zka_prove_tape_len() gives the worst case.
+ *   Every draw must already be below its modulus (rnd()'s rejection loop is done by the host:
+ *   the modulus of draw k depends only on k); otherwise status = ZKA_ERR_TAPE_RANGE.
+ *
+ * Pointers may be host or CUDA device pointers (detected per argument); host buffers are
+ * staged through the library's stream.  The caller owns every buffer.
+ * Return value: 0 on success, negative on a fatal (argument/CUDA) error — see zka_last_error.
+ * Per-item `status[i]` mirrors the reference's throw sites (0 = ok).
+ */
+#ifndef ZKATTEST_H
+#define ZKATTEST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zka_ctx zka_ctx;
+typedef struct zka_params zka_params;
+
+enum {
+  ZKA_OK = 0,
+  ZKA_ERR_INVALID_PK = 1,        /* 'invalid public key' / 'point not in group'  zkpAttestList.ts:117, weier.ts:83 */
+  ZKA_ERR_T_INFINITY = 2,        /* 'T[i] is at infinity'                        exp.ts:151 */
+  ZKA_ERR_T1_INFINITY = 3,       /* 'T1 is at infinity'                          exp.ts:193 */
+  ZKA_ERR_POINTS_DONT_ADD = 4,   /* "Points don't add up!"                       pointAdd.ts:105 */
+  ZKA_ERR_TAPE_RANGE = 5,        /* a draw >= its modulus or tape too short (host must pre-filter) */
+  ZKA_ERR_BAD_INDEX = 6,         /* `which` outside the ring */
+  ZKA_ERR_IDENTITY_ENC = 7,      /* a P-256 proof point is the identity (1-byte encoding, weier.ts:247) */
+  ZKA_ERR_R_INFINITY = 8,        /* 'R is at infinity'                           zkpAttestList.ts:159 */
+  ZKA_ERR_MALFORMED = 9,         /* proof bytes do not parse (deserializePoint / deserializeScalar throw) */
+  ZKA_ERR_PARAMS_NOT_FOUND = 10  /* exp.ts:270,302 */
+};
+
+enum {
+  ZKA_E_ARG = -1,     /* bad argument */
+  ZKA_E_CUDA = -2,    /* CUDA runtime failure (no CPU fallback exists) */
+  ZKA_E_NOMEM = -3
+};
+
+/* Create a context on CUDA device `device`.  Builds the fixed-base tables of the P-256 and
+ * tomEdwards256 generators (instances.ts:22-54).  Fails (ZKA_E_CUDA) if no GPU is present. */
+int zka_init(int device, zka_ctx** out);
+void zka_shutdown(zka_ctx* ctx);
+const char* zka_last_error(const zka_ctx* ctx);
+int zka_version(void);
+/* number of GPU kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t zka_launch_count(const zka_ctx* ctx);
+
+/* generateParamsList (zkpAttestList.ts:88-92, pedersen.ts:61-69): h_nist = G * rnd[0..32),
+ * h_proof = g * rnd[32..64).  Draws must be < p256.n and < tom.order respectively. */
+int zka_params_generate(zka_ctx* ctx, const uint8_t rnd[64], uint8_t h_nist[65], uint8_t h_proof[67]);
+/* SystemParametersList{NistGroup.h, ProofGroup.h, SecLevel} (zkpAttestList.ts:65-78) as a device
+ * handle holding the fixed-base tables of both h points.  g is the curve generator. */
+int zka_params_create(zka_ctx* ctx, const uint8_t h_nist[65], const uint8_t h_proof[67], uint32_t sec_level,
+                      zka_params** out);
+void zka_params_destroy(zka_params* params);
+
+/* keyToInt (zkpAttestList.ts:94-102): x-coordinate of a raw P-256 key, 32 bytes big-endian.
+ * status[i] = ZKA_ERR_INVALID_PK when pk[i] is not a point of the curve. */
+int zka_key_to_int(zka_ctx* ctx, uint32_t count, const uint8_t* pk /*count x 65*/, uint8_t* x_out /*count x 32*/,
+                   int32_t* status);
+
+size_t zka_proof_max_len(uint32_t ring_size, uint32_t sec_level);
+size_t zka_prove_tape_len(uint32_t ring_size, uint32_t sec_level);
+size_t zka_verify_tape_len(uint32_t ring_size, uint32_t sec_level);
+
+/* B independent proveSignatureList calls sharing one ring (zkpAttestList.ts:104-145). */
+int zka_prove_batch(zka_ctx* ctx, const zka_params* params, uint32_t B,
+                    const uint8_t* msg_hash /* B x 32 */, const uint8_t* sig /* B x 64, r||s */,
+                    const uint8_t* pk /* B x 65 */, const uint32_t* which /* B */,
+                    const uint8_t* ring /* N x 32 */, uint32_t N,
+                    const uint8_t* tape /* B x tape_stride */, size_t tape_stride,
+                    uint8_t* proofs /* B x proof_stride */, size_t proof_stride,
+                    uint32_t* proof_len /* B */, int32_t* status /* B */);
+
+/* B independent verifySignatureList calls sharing one ring (zkpAttestList.ts:147-184).
+ * ok[i] = 1 iff the reference would return true.  The verifier tape holds, per proof, the
+ * random relation scalars of Relation.drain (multimult.ts:168-173) and the 78 index draws of
+ * generateIndices (exp.ts:95-109); layout in zk_verify.cuh. */
+int zka_verify_batch(zka_ctx* ctx, const zka_params* params, uint32_t B,
+                     const uint8_t* msg_hash /* B x 32 */, const uint8_t* ring /* N x 32 */, uint32_t N,
+                     const uint8_t* proofs /* B x proof_stride */, size_t proof_stride,
+                     const uint32_t* proof_len /* B */,
+                     const uint8_t* tape /* B x tape_stride */, size_t tape_stride,
+                     uint8_t* ok /* B */, int32_t* status /* B */);
+
+/* ---- layer-wise entry points (parity tests of the arithmetic underneath) ---- */
+/* Pedersen commit in the proof group: out[i] = v[i]*g + r[i]*h  (pedersen.ts:53-58 with r given) */
+int zka_tom_commit_batch(zka_ctx* ctx, const zka_params* params, uint32_t count,
+                         const uint8_t* v /* count x 32 */, const uint8_t* r /* count x 32 */,
+                         uint8_t* out /* count x 67 */);
+/* P-256 scalar multiplication out[i] = k[i] * base[i] (Point.mul, group.ts:133-152);
+ * base == NULL means the generator.  Identity result is encoded as 65 zero bytes. */
+int zka_p256_mul_batch(zka_ctx* ctx, uint32_t count, const uint8_t* base /* count x 65 or NULL */,
+                       const uint8_t* k /* count x 32 */, uint8_t* out /* count x 65 */);
+/* field arithmetic: field 0 = p256.p (= tom.order), 1 = p256.n, 2 = tom.p (33-byte operands);
+ * op 0 = a*b, 1 = a+b, 2 = a-b, 3 = a^-1 (0 -> 0).  Operands/results big-endian, canonical. */
+int zka_field_op_batch(zka_ctx* ctx, int field, int op, uint32_t count, const uint8_t* a, const uint8_t* b,
+                       uint8_t* out);
+/* hashPoints (group.ts:221-233): 80-bit challenge (10 bytes) of `len[i]` message bytes each */
+int zka_hash80_batch(zka_ctx* ctx, uint32_t count, const uint8_t* msgs, size_t msg_stride, const uint32_t* len,
+                     uint8_t* out /* count x 10 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKATTEST_H */

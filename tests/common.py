@@ -1,0 +1,109 @@
+"""Shared parity checks: any library object with the capi.ZkaLib interface is compared with the oracle."""
+import hashlib
+import os
+
+import numpy as np
+
+from oracle import flat
+from oracle import zkattest as OZ
+from oracle.big import Tape
+from oracle.curves import p256, tomEdwards256 as tom
+from zkp_ecdsa_b200 import synth
+
+
+def be(vals, nb):
+    return np.array([list(int(v).to_bytes(nb, 'big')) for v in vals], dtype=np.uint8)
+
+
+def check_field_ops(L, seed=0, count=24):
+    d = synth.Drbg(seed, 'field')
+    for field, (mod, nb) in enumerate([(p256.p, 32), (p256.order, 32), (tom.p, 33)]):
+        va = [int.from_bytes(d.bytes(40), 'big') % mod for _ in range(count)] + [0, 1, mod - 1, mod - 1]
+        vb = [int.from_bytes(d.bytes(40), 'big') % mod for _ in range(count)] + [mod - 1, 0, mod - 1, 1]
+        a, b = be(va, nb), be(vb, nb)
+        fns = [lambda x, y: x * y % mod, lambda x, y: (x + y) % mod, lambda x, y: (x - y) % mod,
+               lambda x, y: pow(x, -1, mod) if x else 0]
+        for op, fn in enumerate(fns):
+            out = L.field_op_batch(field, op, a, b)
+            for i in range(len(va)):
+                assert int.from_bytes(out[i].tobytes(), 'big') == fn(va[i], vb[i]), (field, op, i)
+
+
+def check_hash(L, seed=0):
+    d = synth.Drbg(seed, 'hash')
+    lens = np.array([0, 1, 55, 56, 63, 64, 65, 268, 603, 1000], dtype=np.uint32)
+    msgs = np.frombuffer(d.bytes(len(lens) * 1000), np.uint8).reshape(len(lens), 1000).copy()
+    out = L.hash80_batch(msgs, lens)
+    for i, ln in enumerate(lens):
+        assert out[i].tobytes() == hashlib.sha256(msgs[i, :ln].tobytes()).digest()[:10], i
+
+
+def check_p256_mul(L, seed=0, count=6):
+    d = synth.Drbg(seed, 'p256mul')
+    ks = [d.below(p256.order) for _ in range(count)] + [0, 1, p256.order - 1, 16, 0xf0]
+    k = be(ks, 32)
+    G = p256.generator()
+
+    def enc(pt):
+        e = pt.to_bytes()
+        return bytes(65) if len(e) == 1 else e
+    out = L.p256_mul_batch(None, k)
+    for i, v in enumerate(ks):
+        assert out[i].tobytes() == enc(G.mul(p256.new_scalar(v))), i
+    bases = [G.mul(p256.new_scalar(d.below(p256.order))) for _ in ks]
+    out = L.p256_mul_batch(np.array([list(b.to_bytes()) for b in bases], dtype=np.uint8), k)
+    for i, v in enumerate(ks):
+        assert out[i].tobytes() == enc(bases[i].mul(p256.new_scalar(v))), i
+
+
+def make_params(L, seed=0, sec_level=80):
+    rnd = synth.params_rnd(seed)
+    hn, hp = L.params_generate(rnd)
+    po = OZ.generate_params_list(Tape(rnd), sec_level)
+    assert hn == po.NistGroup.h.to_bytes() and hp == po.ProofGroup.h.to_bytes()
+    return L.params_create(hn, hp, sec_level), po
+
+
+def check_tom_commit(L, P, po, seed=0, count=6):
+    d = synth.Drbg(seed, 'commit')
+    q = tom.order
+    vs = [d.below(q) for _ in range(count)] + [0, 1, q - 1, 0]
+    rs = [d.below(q) for _ in range(count)] + [0, q - 1, 1, 5]
+    out = L.tom_commit_batch(P, be(vs, 32), be(rs, 32))
+    for i in range(len(vs)):
+        e = po.ProofGroup.h.dblmul(tom.new_scalar(rs[i]), po.ProofGroup.g, tom.new_scalar(vs[i])).to_bytes()
+        assert out[i].tobytes() == e, i
+
+
+def run_prove(L, P, wl, tape, sec_level=80):
+    B, N = wl.B, wl.N
+    ps = L.proof_max_len(N, sec_level)
+    proofs = np.zeros((B, ps), np.uint8)
+    plen = np.zeros(B, np.uint32)
+    status = np.zeros(B, np.int32)
+    L.prove_batch(P, B, wl.msg_hash, wl.sig, wl.pk, wl.which, wl.ring, N, tape, tape.shape[1], proofs, ps, plen, status)
+    return proofs, plen, status
+
+
+def oracle_proof(po, wl, tape, b):
+    tp = Tape(tape[b].tobytes())
+    pr = OZ.prove_signature_list(po, wl.msg_hash[b].tobytes(), wl.sig[b].tobytes(), wl.pk[b].tobytes(),
+                                 int(wl.which[b]), wl.ring_ints(), tp)
+    return pr, tp
+
+
+def check_prove_parity(L, B=2, N=6, seed=3, sec_level=80):
+    P, po = make_params(L, seed, sec_level)
+    wl = synth.Workload(B=B, N=N, seed=seed)
+    tape = synth.random_tape(B, L.prove_tape_len(N, sec_level), seed=seed + 100)
+    proofs, plen, status = run_prove(L, P, wl, tape, sec_level)
+    assert (status == 0).all(), status
+    n = max(1, (N - 1).bit_length())
+    for b in range(B):
+        pr, tp = oracle_proof(po, wl, tape, b)
+        assert proofs[b, :plen[b]].tobytes() == flat.ser_proof(pr), f'proof {b} differs'
+        z = sum(1 for e in pr.expProof if e.alpha is None)
+        assert tp.calls == 3 + 4 * sec_level + 40 * z + 5 * n      # SURVEY.md 3.1 draw-count contract
+        assert plen[b] == flat.proof_len(z, n, sec_level)
+    L.params_destroy(P)
+    return proofs, plen

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def hostsim():
+    """Host-simulator build of the task bodies (tests only; never part of the product)."""
+    import __graft_entry__ as g
+    g.build_hostsim()
+    from zkp_ecdsa_b200.capi import ZkaLib
+    return ZkaLib(g.HOSTSIM)
+
+
+@pytest.fixture(scope='session')
+def gpu_engine():
+    """The product path: libzkattest.so on cuda:0.  Fails loudly without it."""
+    from zkp_ecdsa_b200 import api
+    return api.Engine(device=0)

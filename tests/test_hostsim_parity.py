@@ -1,0 +1,34 @@
+"""CPU-only parity of the kernel task bodies (host-simulator build) against the oracle.
+
+The simulator is a test aid: it executes the SAME task functors the CUDA kernels run, one
+work item at a time, so layout/arithmetic logic is checked in the GPU-less container.  The
+GPU tests (tests/test_gpu_parity.py) repeat these checks on the real sm_100a library.
+"""
+import common
+
+
+def test_field_ops(hostsim):
+    common.check_field_ops(hostsim)
+
+
+def test_hash80(hostsim):
+    common.check_hash(hostsim)
+
+
+def test_p256_mul(hostsim):
+    common.check_p256_mul(hostsim)
+
+
+def test_params_and_commit(hostsim):
+    P, po = common.make_params(hostsim, seed=5)
+    common.check_tom_commit(hostsim, P, po)
+    hostsim.params_destroy(P)
+
+
+def test_prove_bit_exact_small_ring(hostsim):
+    common.check_prove_parity(hostsim, B=2, N=6, seed=3)
+
+
+def test_prove_bit_exact_sec_level_16(hostsim):
+    # smaller SecLevel keeps the oracle fast while exercising every code path
+    common.check_prove_parity(hostsim, B=3, N=17, seed=4, sec_level=16)

@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference's public interface for the hot path.
+
+The reference exports (src/index.ts:17-19, src/zkpAttestList.ts):
+    generateParamsList(secLevel = 80)                                   :88
+    keyToInt(publicKey)                                                 :94
+    proveSignatureList(params, msgHash, sigBytes, publicKey, which, keys)  :104
+    verifySignatureList(params, msgHash, keys, proof)                   :147
+Node/TypeScript is not available in this image, so the host layer above the C ABI is
+Python with the same names (snake_case), argument meaning and error behaviour: malformed
+input raises `ZkaProofError(message)` with the reference's message, a failed verification
+returns False.  `bindings/node/` holds the TypeScript host + node-addon-api shim a
+maintainer would compile where node exists.
+
+All compute happens in libzkattest.so on the GPU; this module only marshals bytes.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import synth
+from .capi import STATUS_MESSAGES, ZkaError, ZkaLib
+
+P256_N = synth.P256_N
+TOM_ORDER = synth.P256_P
+
+
+class ZkaProofError(Exception):
+    """Mirrors the reference's `throw new Error(...)` sites (status codes in include/zkattest.h)."""
+
+    def __init__(self, status: int):
+        self.status = int(status)
+        super().__init__(STATUS_MESSAGES.get(int(status), f'status {status}'))
+
+
+@dataclass
+class SystemParametersList:
+    """zkpAttestList.ts:65-78: NistGroup = (p256, G, h_nist), ProofGroup = (tomEdwards256, g, h_proof)."""
+    h_nist: bytes     # 65 B
+    h_proof: bytes    # 67 B
+    sec_level: int
+    handle: object = None   # device tables (zka_params*)
+
+    def eq(self, o: 'SystemParametersList') -> bool:
+        return self.h_nist == o.h_nist and self.h_proof == o.h_proof and self.sec_level == o.sec_level
+
+
+@dataclass
+class SignatureProofList:
+    """zkpAttestList.ts:29-61 as its flat byte string (layout in include/zkattest.h)."""
+    data: bytes
+
+    def eq(self, o: 'SignatureProofList') -> bool:
+        return self.data == o.data
+
+
+@dataclass
+class ProveResult:
+    proofs: np.ndarray      # [B, stride] uint8
+    proof_len: np.ndarray   # [B] uint32
+    status: np.ndarray      # [B] int32
+
+    def proof_bytes(self, b: int) -> bytes:
+        return self.proofs[b, :int(self.proof_len[b])].tobytes()
+
+
+def _keys_to_ring(keys: Sequence[int]) -> np.ndarray:
+    out = np.zeros((len(keys), 32), np.uint8)
+    for i, k in enumerate(keys):
+        # pad() wraps every key in newScalar (gk.ts:77): reduce mod the proof-group order
+        out[i] = np.frombuffer((int(k) % TOM_ORDER).to_bytes(32, 'big'), np.uint8)
+    return out
+
+
+class Engine:
+    """One GPU context (zka_ctx).  Raises ZkaError when the CUDA library/device is missing."""
+
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None):
+        self.lib = ZkaLib(lib_path, device)
+
+    def close(self):
+        self.lib.close()
+
+    # ------------------------------------------------------------------ reference API
+    def generate_params_list(self, sec_level: int = 80, rnd: Optional[bytes] = None) -> SystemParametersList:
+        """generateParamsList (zkpAttestList.ts:88-92).  `rnd` = the two rnd() draws (64 B)."""
+        if rnd is None:
+            rnd = _rnd_below(P256_N) + _rnd_below(TOM_ORDER)
+        hn, hp = self.lib.params_generate(rnd)
+        return self.load_params(hn, hp, sec_level)
+
+    def load_params(self, h_nist: bytes, h_proof: bytes, sec_level: int = 80) -> SystemParametersList:
+        h = self.lib.params_create(h_nist, h_proof, sec_level)
+        return SystemParametersList(bytes(h_nist), bytes(h_proof), sec_level, h)
+
+    def key_to_int(self, public_key: bytes) -> int:
+        """keyToInt (zkpAttestList.ts:94-102) on the raw 65-byte key (WebCrypto exportKey('raw'))."""
+        x, st = self.lib.key_to_int(np.frombuffer(public_key, np.uint8).reshape(1, 65).copy())
+        if st[0]:
+            raise ZkaProofError(st[0])
+        return int.from_bytes(x[0].tobytes(), 'big')
+
+    def prove_signature_list(self, params: SystemParametersList, msg_hash: bytes, sig_bytes: bytes,
+                             public_key: bytes, which: int, keys: Sequence[int],
+                             tape: Optional[bytes] = None) -> SignatureProofList:
+        """proveSignatureList (zkpAttestList.ts:104-145); `tape` replaces crypto.getRandomValues."""
+        ring = _keys_to_ring(keys)
+        ts = self.lib.prove_tape_len(len(keys), params.sec_level)
+        if tape is None:
+            t = synth_os_tape(1, ts)
+        else:
+            t = np.zeros((1, ts), np.uint8)
+            t[0, :min(ts, len(tape))] = np.frombuffer(tape[:ts], np.uint8)
+        res = self.prove_batch(params, np.frombuffer(msg_hash, np.uint8).reshape(1, 32).copy(),
+                               np.frombuffer(sig_bytes, np.uint8).reshape(1, 64).copy(),
+                               np.frombuffer(public_key, np.uint8).reshape(1, 65).copy(),
+                               np.array([which], np.uint32), ring, t)
+        if res.status[0]:
+            raise ZkaProofError(res.status[0])
+        return SignatureProofList(res.proof_bytes(0))
+
+    def verify_signature_list(self, params: SystemParametersList, msg_hash: bytes, keys: Sequence[int],
+                              proof: SignatureProofList, tape: Optional[bytes] = None) -> bool:
+        """verifySignatureList (zkpAttestList.ts:147-184): True/False, raises on malformed input."""
+        ring = _keys_to_ring(keys)
+        ts = self.lib.verify_tape_len(len(keys), params.sec_level)
+        if tape is None:
+            t = synth_os_verify_tape(1, ts, len(keys))
+        else:
+            t = np.zeros((1, ts), np.uint8)
+            t[0, :min(ts, len(tape))] = np.frombuffer(tape[:ts], np.uint8)
+        stride = max(len(proof.data), 1)
+        pr = np.frombuffer(proof.data, np.uint8).reshape(1, stride).copy()
+        ok, st = self.verify_batch(params, np.frombuffer(msg_hash, np.uint8).reshape(1, 32).copy(), ring, pr,
+                                   np.array([len(proof.data)], np.uint32), t)
+        if st[0]:
+            raise ZkaProofError(st[0])
+        return bool(ok[0])
+
+    # ------------------------------------------------------------------ batch variants (additive)
+    def prove_batch(self, params, msg_hash, sig, pk, which, ring, tape, proofs=None) -> ProveResult:
+        B = msg_hash.shape[0]
+        N = ring.shape[0]
+        stride = self.lib.proof_max_len(N, params.sec_level)
+        if proofs is None:
+            proofs = np.zeros((B, stride), np.uint8)
+        plen = np.zeros(B, np.uint32)
+        status = np.zeros(B, np.int32)
+        self.lib.prove_batch(params.handle, B, msg_hash, sig, pk, which, ring, N, tape, tape.shape[1], proofs,
+                             proofs.shape[1], plen, status)
+        return ProveResult(proofs, plen, status)
+
+    def verify_batch(self, params, msg_hash, ring, proofs, proof_len, tape):
+        B = msg_hash.shape[0]
+        ok = np.zeros(B, np.uint8)
+        status = np.zeros(B, np.int32)
+        self.lib.verify_batch(params.handle, B, msg_hash, ring, ring.shape[0], proofs, proofs.shape[1], proof_len,
+                              tape, tape.shape[1], ok, status)
+        return ok, status
+
+
+def _rnd_below(m: int) -> bytes:
+    while True:
+        v = int.from_bytes(os.urandom(32), 'big')
+        if v < m:
+            return v.to_bytes(32, 'big')
+
+
+def synth_os_tape(rows: int, stride: int) -> np.ndarray:
+    """OS-random prover tape, every draw below min(p256.n, tom.order) (see synth.random_tape)."""
+    return synth.random_tape(rows, stride, int.from_bytes(os.urandom(8), 'big'))
+
+
+def synth_os_verify_tape(rows: int, stride: int, ring_size: int, sec_level: int = 80) -> np.ndarray:
+    from .verify_tape import random_verify_tape
+    return random_verify_tape(rows, stride, ring_size, sec_level, int.from_bytes(os.urandom(8), 'big'))

@@ -1,0 +1,184 @@
+"""ctypes binding of the C ABI in include/zkattest.h (libzkattest.so).
+
+This is the tested surface of the drop-in boundary: the node-addon-api shim of
+INTEGRATION.md binds exactly these symbols.  Buffers are numpy uint8 arrays (host) or raw
+CUDA device pointers given as ints (e.g. `torch.Tensor.data_ptr()`).
+
+The product library is `zkp_ecdsa_b200/libzkattest.so` (nvcc, sm_100a).  There is no CPU
+implementation: `ZkaLib()` raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, 'libzkattest.so')
+
+SYMBOLS = [
+    'zka_init', 'zka_shutdown', 'zka_last_error', 'zka_version', 'zka_launch_count',
+    'zka_params_generate', 'zka_params_create', 'zka_params_destroy', 'zka_key_to_int',
+    'zka_proof_max_len', 'zka_prove_tape_len', 'zka_verify_tape_len',
+    'zka_prove_batch', 'zka_verify_batch',
+    'zka_tom_commit_batch', 'zka_p256_mul_batch', 'zka_field_op_batch', 'zka_hash80_batch',
+]
+
+STATUS_MESSAGES = {
+    0: 'ok',
+    1: 'invalid public key',                 # zkpAttestList.ts:117 / weier.ts:83
+    2: 'T[i] is at infinity',                # exp.ts:151
+    3: 'T1 is at infinity',                  # exp.ts:193
+    4: "Points don't add up!",               # pointAdd.ts:105
+    5: 'randomness tape draw out of range',
+    6: 'index outside the ring',
+    7: 'identity point cannot be encoded in a fixed slot',
+    8: 'R is at infinity',                   # zkpAttestList.ts:159
+    9: 'malformed proof bytes',
+    10: 'params not found',                  # exp.ts:270,302
+}
+
+
+class ZkaError(RuntimeError):
+    pass
+
+
+def _ptr(x):
+    """numpy array / bytes / int device pointer / None -> c_void_p"""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        if not x.flags['C_CONTIGUOUS']:
+            raise ValueError('array must be C-contiguous')
+        return C.c_void_p(x.ctypes.data)
+    if isinstance(x, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(x)), C.c_void_p)
+    raise TypeError(type(x))
+
+
+class ZkaLib:
+    def __init__(self, path: Optional[str] = None, device: int = 0):
+        path = path or os.environ.get('ZKA_LIB', DEFAULT_LIB)
+        if not os.path.exists(path):
+            raise ZkaError(f'{path} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                           '(there is no CPU fallback)')
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.zka_init.restype = C.c_int
+        L.zka_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.zka_shutdown.argtypes = [C.c_void_p]
+        L.zka_last_error.restype = C.c_char_p
+        L.zka_last_error.argtypes = [C.c_void_p]
+        L.zka_launch_count.restype = C.c_uint64
+        L.zka_launch_count.argtypes = [C.c_void_p]
+        for f in ('zka_proof_max_len', 'zka_prove_tape_len', 'zka_verify_tape_len'):
+            getattr(L, f).restype = C.c_size_t
+            getattr(L, f).argtypes = [C.c_uint32, C.c_uint32]
+        L.zka_params_generate.argtypes = [C.c_void_p] * 4
+        L.zka_params_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.zka_params_destroy.argtypes = [C.c_void_p]
+        L.zka_key_to_int.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zka_prove_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_size_t, C.c_void_p, C.c_void_p]
+        L.zka_verify_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_void_p]
+        L.zka_tom_commit_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zka_p256_mul_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zka_field_op_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zka_hash80_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        ctx = C.c_void_p()
+        rc = L.zka_init(device, C.byref(ctx))
+        if rc != 0 or not ctx:
+            raise ZkaError(f'zka_init(device={device}) failed with {rc}: no usable CUDA device '
+                           '(libzkattest has no CPU fallback)')
+        self.ctx = ctx
+        self.device = device
+
+    # ------------------------------------------------------------------ helpers
+    def close(self):
+        if getattr(self, 'ctx', None):
+            self.lib.zka_shutdown(self.ctx)
+            self.ctx = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise ZkaError(f'{what} failed ({rc}): {self.lib.zka_last_error(self.ctx).decode()}')
+
+    def launch_count(self) -> int:
+        return int(self.lib.zka_launch_count(self.ctx))
+
+    def proof_max_len(self, ring_size, sec_level=80): return int(self.lib.zka_proof_max_len(ring_size, sec_level))
+    def prove_tape_len(self, ring_size, sec_level=80): return int(self.lib.zka_prove_tape_len(ring_size, sec_level))
+    def verify_tape_len(self, ring_size, sec_level=80): return int(self.lib.zka_verify_tape_len(ring_size, sec_level))
+
+    # ------------------------------------------------------------------ params
+    def params_generate(self, rnd: bytes):
+        assert len(rnd) == 64
+        hn = np.zeros(65, np.uint8)
+        hp = np.zeros(67, np.uint8)
+        self._check(self.lib.zka_params_generate(self.ctx, _ptr(rnd), _ptr(hn), _ptr(hp)), 'zka_params_generate')
+        return hn.tobytes(), hp.tobytes()
+
+    def params_create(self, h_nist: bytes, h_proof: bytes, sec_level: int = 80):
+        h = C.c_void_p()
+        self._check(self.lib.zka_params_create(self.ctx, _ptr(h_nist), _ptr(h_proof), sec_level, C.byref(h)),
+                    'zka_params_create')
+        return h
+
+    def params_destroy(self, h):
+        self.lib.zka_params_destroy(h)
+
+    def key_to_int(self, pk: np.ndarray):
+        count = pk.shape[0]
+        out = np.zeros((count, 32), np.uint8)
+        st = np.zeros(count, np.int32)
+        self._check(self.lib.zka_key_to_int(self.ctx, count, _ptr(pk), _ptr(out), _ptr(st)), 'zka_key_to_int')
+        return out, st
+
+    # ------------------------------------------------------------------ hot path
+    def prove_batch(self, params, B, msg_hash, sig, pk, which, ring, N, tape, tape_stride,
+                    proofs, proof_stride, proof_len, status):
+        self._check(self.lib.zka_prove_batch(self.ctx, params, B, _ptr(msg_hash), _ptr(sig), _ptr(pk), _ptr(which),
+                                             _ptr(ring), N, _ptr(tape), tape_stride, _ptr(proofs), proof_stride,
+                                             _ptr(proof_len), _ptr(status)), 'zka_prove_batch')
+
+    def verify_batch(self, params, B, msg_hash, ring, N, proofs, proof_stride, proof_len, tape, tape_stride,
+                     ok, status):
+        self._check(self.lib.zka_verify_batch(self.ctx, params, B, _ptr(msg_hash), _ptr(ring), N, _ptr(proofs),
+                                              proof_stride, _ptr(proof_len), _ptr(tape), tape_stride, _ptr(ok),
+                                              _ptr(status)), 'zka_verify_batch')
+
+    # ------------------------------------------------------------------ layer-wise ops
+    def tom_commit_batch(self, params, v: np.ndarray, r: np.ndarray) -> np.ndarray:
+        count = v.shape[0]
+        out = np.zeros((count, 67), np.uint8)
+        self._check(self.lib.zka_tom_commit_batch(self.ctx, params, count, _ptr(v), _ptr(r), _ptr(out)),
+                    'zka_tom_commit_batch')
+        return out
+
+    def p256_mul_batch(self, base: Optional[np.ndarray], k: np.ndarray) -> np.ndarray:
+        count = k.shape[0]
+        out = np.zeros((count, 65), np.uint8)
+        self._check(self.lib.zka_p256_mul_batch(self.ctx, count, _ptr(base), _ptr(k), _ptr(out)), 'zka_p256_mul_batch')
+        return out
+
+    def field_op_batch(self, field: int, op: int, a: np.ndarray, b: Optional[np.ndarray]) -> np.ndarray:
+        count, nb = a.shape
+        out = np.zeros((count, nb), np.uint8)
+        self._check(self.lib.zka_field_op_batch(self.ctx, field, op, count, _ptr(a), _ptr(b), _ptr(out)),
+                    'zka_field_op_batch')
+        return out
+
+    def hash80_batch(self, msgs: np.ndarray, lens: np.ndarray) -> np.ndarray:
+        count, stride = msgs.shape
+        out = np.zeros((count, 10), np.uint8)
+        self._check(self.lib.zka_hash80_batch(self.ctx, count, _ptr(msgs), stride, _ptr(lens), _ptr(out)),
+                    'zka_hash80_batch')
+        return out

@@ -1,0 +1,341 @@
+// zk_field.cuh — Montgomery arithmetic for the four moduli of the ZKAttest hot path.
+//
+// Replaces the reference's BigInt `(a*b) % p`, posMod, invMod, expMod
+// (/root/reference/src/bignum/big.ts:36-119) with fixed-width 32-bit-limb Montgomery
+// arithmetic that lives in registers:
+//   FpP256  p256.p  (8 limbs, strict  [0,p))   P-256 coordinates AND tomEdwards256 scalars
+//                                              (tom.order == p256.p, src/curves/instances.ts:48)
+//   FnP256  p256.n  (8 limbs, strict  [0,n))   P-256 scalars
+//   FpTom   tom.p   (9 limbs, LAZY    [0,2^12 p)) tomEdwards256 coordinates; 258-bit prime,
+//                                              R = 2^288 leaves 30 bits of headroom so
+//                                              add/sub never reduce and mul needs no final
+//                                              conditional subtraction.
+// All code is __host__ __device__ so the identical arithmetic can be exercised by the
+// host-side simulator used in CPU tests (tests/hostsim); the product library is the
+// nvcc/sm_100a build only.
+#pragma once
+#include <stdint.h>
+#include "zk_field_consts.inc"
+
+#if defined(__CUDACC__)
+#define ZK_HD __host__ __device__ __forceinline__
+#define ZK_HDN __host__ __device__ __noinline__
+#else
+#define ZK_HD inline __attribute__((always_inline))
+#define ZK_HDN __attribute__((noinline))
+#endif
+
+namespace zk {
+
+// ------------------------------------------------------------------------------------
+// Field descriptors.  Limbs little-endian (limb 0 = least significant 32 bits).
+// ------------------------------------------------------------------------------------
+#define ZK_FIELD_DESC(NAME, PFX, NL, LAZY)                                   \
+  struct NAME {                                                              \
+    static constexpr int N = NL;                                             \
+    static constexpr bool kLazy = LAZY;                                      \
+    static constexpr uint32_t kN0Inv = PFX##_N0INV;                          \
+    ZK_HD static constexpr uint32_t p(int i) {                               \
+      constexpr uint32_t t[NL] = PFX##_P;                                    \
+      return t[i];                                                           \
+    }                                                                        \
+    ZK_HD static constexpr uint32_t rr(int i) {                              \
+      constexpr uint32_t t[NL] = PFX##_RR;                                   \
+      return t[i];                                                           \
+    }                                                                        \
+    ZK_HD static constexpr uint32_t one(int i) {                             \
+      constexpr uint32_t t[NL] = PFX##_ONE;                                  \
+      return t[i];                                                           \
+    }                                                                        \
+  };
+ZK_FIELD_DESC(FpP256, ZK_P256P, 8, false)
+ZK_FIELD_DESC(FnP256, ZK_P256N, 8, false)
+ZK_FIELD_DESC(FpTom, ZK_TOMP, 9, true)
+#undef ZK_FIELD_DESC
+
+template <int N>
+struct Fe {
+  uint32_t v[N];
+};
+using Fe8 = Fe<8>;
+using Fe9 = Fe<9>;
+
+// ------------------------------------------------------------------------------------
+// Multi-word helpers (portable 64-bit carries; nvcc lowers them to IADD3/IADD3.X)
+// ------------------------------------------------------------------------------------
+template <int N>
+ZK_HD uint32_t add_n(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    c += (uint64_t)a[i] + b[i];
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  return (uint32_t)c;
+}
+template <int N>
+ZK_HD uint32_t sub_n(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  int64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    c += (int64_t)a[i] - (int64_t)b[i];
+    r[i] = (uint32_t)c;
+    c >>= 32;  // arithmetic shift: 0 or -1
+  }
+  return (uint32_t)(c & 1);  // borrow
+}
+template <class F>
+ZK_HD uint32_t sub_p(uint32_t* r, const uint32_t* a) {  // r = a - p, returns borrow
+  int64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) {
+    c += (int64_t)a[i] - (int64_t)F::p(i);
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  return (uint32_t)(c & 1);
+}
+template <class F>
+ZK_HD bool geq_p(const uint32_t* a) {
+#pragma unroll
+  for (int i = F::N - 1; i >= 0; i--) {
+    if (a[i] > F::p(i)) return true;
+    if (a[i] < F::p(i)) return false;
+  }
+  return true;
+}
+template <int N>
+ZK_HD bool is_zero_n(const uint32_t* a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) o |= a[i];
+  return o == 0;
+}
+template <int N>
+ZK_HD bool eq_n(const uint32_t* a, const uint32_t* b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) o |= a[i] ^ b[i];
+  return o == 0;
+}
+template <int N>
+ZK_HD void copy_n(uint32_t* r, const uint32_t* a) {
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = a[i];
+}
+template <int N>
+ZK_HD void zero_n(uint32_t* r) {
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = 0;
+}
+template <int N>
+ZK_HD void csel_n(uint32_t* r, bool c, const uint32_t* a, const uint32_t* b) {  // r = c ? a : b
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = c ? a[i] : b[i];
+}
+
+// ------------------------------------------------------------------------------------
+// Field operations
+// ------------------------------------------------------------------------------------
+template <class F>
+struct Field {
+  static constexpr int N = F::N;
+
+  // canonical reduce of a lazy value (< 2^12 p) or a strict value (< 2p) into [0,p)
+  ZK_HD static void reduce(uint32_t* a) {
+    if (F::kLazy) {
+      // value < 2^14 p: subtract 2^k p for k = 13..0 when possible (branch-free selects)
+#pragma unroll 1
+      for (int k = 13; k >= 0; k--) {
+        uint32_t pk[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          uint32_t lo = F::p(i) << k;
+          uint32_t hi = (i > 0 && k > 0) ? (F::p(i - 1) >> (32 - k)) : 0u;
+          pk[i] = lo | hi;
+        }
+        uint32_t t[N];
+        uint32_t br = sub_n<N>(t, a, pk);
+        csel_n<N>(a, br == 0, t, a);
+      }
+    } else {
+      uint32_t t[N];
+      uint32_t br = sub_p<F>(t, a);
+      csel_n<N>(a, br == 0, t, a);
+    }
+  }
+
+  ZK_HD static void add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    if (F::kLazy) {
+      add_n<N>(r, a, b);
+    } else {
+      uint32_t s[N], t[N];
+      uint32_t c = add_n<N>(s, a, b);
+      uint32_t br = sub_p<F>(t, s);
+      csel_n<N>(r, (c != 0) || (br == 0), t, s);
+    }
+  }
+  // lazy: r = a + 8p - b  (requires b < 8p)
+  ZK_HD static void sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    if (F::kLazy) {
+      uint32_t p8[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) p8[i] = (F::p(i) << 3) | (i > 0 ? (F::p(i - 1) >> 29) : 0u);
+      uint32_t t[N];
+      add_n<N>(t, a, p8);
+      sub_n<N>(r, t, b);
+    } else {
+      uint32_t s[N], t[N];
+      uint32_t br = sub_n<N>(s, a, b);
+      uint32_t pp[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) pp[i] = F::p(i);
+      add_n<N>(t, s, pp);
+      csel_n<N>(r, br != 0, t, s);
+    }
+  }
+  ZK_HD static void neg(uint32_t* r, const uint32_t* a) {
+    uint32_t z[N];
+    zero_n<N>(z);
+    sub(r, z, a);
+  }
+  ZK_HD static void dbl(uint32_t* r, const uint32_t* a) { add(r, a, a); }
+
+  // Montgomery product r = a*b/R mod p  (CIOS).  r may alias a or b.
+  ZK_HD static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t t[N + 2];
+#pragma unroll
+    for (int i = 0; i < N + 2; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      uint64_t c = 0;
+      const uint32_t bi = b[i];
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        uint64_t s = (uint64_t)a[j] * bi + t[j] + c;
+        t[j] = (uint32_t)s;
+        c = s >> 32;
+      }
+      uint64_t s = (uint64_t)t[N] + c;
+      t[N] = (uint32_t)s;
+      t[N + 1] = (uint32_t)(s >> 32);
+      const uint32_t m = t[0] * F::kN0Inv;
+      c = ((uint64_t)m * F::p(0) + t[0]) >> 32;
+#pragma unroll
+      for (int j = 1; j < N; j++) {
+        uint64_t s2 = (uint64_t)m * F::p(j) + t[j] + c;
+        t[j - 1] = (uint32_t)s2;
+        c = s2 >> 32;
+      }
+      s = (uint64_t)t[N] + c;
+      t[N - 1] = (uint32_t)s;
+      t[N] = t[N + 1] + (uint32_t)(s >> 32);
+    }
+    if (F::kLazy) {
+      copy_n<N>(r, t);  // < a*b/R + p < 2p for inputs < 2^13 p
+    } else {
+      uint32_t u[N];
+      uint32_t br = sub_p<F>(u, t);
+      csel_n<N>(r, (t[N] != 0) || (br == 0), u, t);
+    }
+  }
+  ZK_HD static void sqr(uint32_t* r, const uint32_t* a) { mul(r, a, a); }
+
+  ZK_HD static void set_one(uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = F::one(i);
+  }
+  ZK_HD static void to_mont(uint32_t* r, const uint32_t* a) {
+    uint32_t rr[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) rr[i] = F::rr(i);
+    mul(r, a, rr);
+  }
+  // out of Montgomery form AND canonical
+  ZK_HD static void from_mont(uint32_t* r, const uint32_t* a) {
+    uint32_t o[N];
+    zero_n<N>(o);
+    o[0] = 1;
+    mul(r, a, o);
+    reduce(r);
+  }
+  // canonical zero test of a (possibly lazy) Montgomery value
+  ZK_HD static bool is_zero(const uint32_t* a) {
+    uint32_t t[N];
+    copy_n<N>(t, a);
+    reduce(t);
+    return is_zero_n<N>(t);
+  }
+  ZK_HD static bool eq(const uint32_t* a, const uint32_t* b) {
+    uint32_t t[N], u[N];
+    copy_n<N>(t, a);
+    copy_n<N>(u, b);
+    reduce(t);
+    reduce(u);
+    return eq_n<N>(t, u);
+  }
+
+  // r = a^(p-2) (Fermat inverse), a in Montgomery form; returns 0 for a == 0.
+  // Not inlined: called once per batch-inversion chunk.
+  static ZK_HDN void inv(uint32_t* r, const uint32_t* a) {
+    uint32_t e[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) e[i] = F::p(i);
+    e[0] -= 2;  // p is odd and p(0) >= 2 for all our moduli
+    uint32_t acc[N], base[N];
+    set_one(acc);
+    copy_n<N>(base, a);
+    // left-to-right binary with 4-bit fixed window would be faster; the plain
+    // square-and-multiply ladder keeps code size small (one mul + one sqr site).
+    int top = N * 32 - 1;
+    while (top > 0 && !((e[top >> 5] >> (top & 31)) & 1)) top--;
+#pragma unroll 1
+    for (int bit = top; bit >= 0; bit--) {
+      sqr(acc, acc);
+      if ((e[bit >> 5] >> (bit & 31)) & 1) mul(acc, acc, base);
+    }
+    copy_n<N>(r, acc);
+  }
+};
+
+using P256p = Field<FpP256>;
+using P256n = Field<FnP256>;
+using Tomp = Field<FpTom>;
+using Tomq = Field<FpP256>;  // tomEdwards256 scalar field == P-256 base field
+
+// ------------------------------------------------------------------------------------
+// Big-endian byte <-> limb conversion (reference toBytes/fromBytes, big.ts:121-168)
+// ------------------------------------------------------------------------------------
+template <int N>
+ZK_HD void limbs_from_be(uint32_t* r, const uint8_t* b, int nbytes) {
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = 0;
+  for (int k = 0; k < nbytes; k++) {
+    int pos = nbytes - 1 - k;  // byte significance
+    if ((pos >> 2) < N) r[pos >> 2] |= (uint32_t)b[k] << (8 * (pos & 3));
+  }
+}
+template <int N>
+ZK_HD void limbs_to_be(uint8_t* b, const uint32_t* a, int nbytes) {
+  for (int k = 0; k < nbytes; k++) {
+    int pos = nbytes - 1 - k;
+    b[k] = ((pos >> 2) < N) ? (uint8_t)(a[pos >> 2] >> (8 * (pos & 3))) : 0;
+  }
+}
+// a < m (canonical compare of raw limbs)
+template <int N>
+ZK_HD bool lt_n(const uint32_t* a, const uint32_t* m) {
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    if (a[i] < m[i]) return true;
+    if (a[i] > m[i]) return false;
+  }
+  return false;
+}
+template <class F>
+ZK_HD bool lt_p(const uint32_t* a) {
+  return !geq_p<F>(a);
+}
+
+}  // namespace zk

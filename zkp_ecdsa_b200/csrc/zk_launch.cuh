@@ -1,0 +1,129 @@
+// zk_launch.cuh — task launcher and device-memory helpers.
+//
+// CUDA build (the product): every task runs as one thread of `zk_task_kernel<Task>` on the
+// library's stream; there is NO CPU execution path in that build.
+// ZKA_HOSTSIM build (tests only, compiled by tests/hostsim/build.sh with g++): the same task
+// bodies are executed by a plain loop so the arithmetic/layout logic can be unit-tested in
+// the GPU-less CI container.  It is never part of libzkattest.so.
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+
+#if !defined(ZKA_HOSTSIM)
+#include <cuda_runtime.h>
+#endif
+
+namespace zk {
+
+#if !defined(ZKA_HOSTSIM)
+
+#define ZK_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));                    \
+  } while (0)
+
+template <class Task>
+__global__ void __launch_bounds__(128) zk_task_kernel(int n, Task task) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) task(t);
+}
+
+struct Stream {
+  cudaStream_t s = nullptr;
+  uint64_t launches = 0;
+};
+
+template <class Task>
+inline void launch(Stream& st, long long n, const Task& task) {
+  if (n <= 0) return;
+  if (n > 0x7fffffffLL) throw std::runtime_error("launch too large");
+  const int threads = 128;
+  const int blocks = (int)((n + threads - 1) / threads);
+  zk_task_kernel<Task><<<blocks, threads, 0, st.s>>>((int)n, task);
+  ZK_CUDA_CHECK(cudaGetLastError());
+  st.launches++;
+}
+
+inline void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  ZK_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+  return p;
+}
+inline void dev_free(void* p) {
+  if (p) cudaFree(p);
+}
+inline void copy_h2d(Stream& st, void* d, const void* h, size_t n) {
+  if (n) ZK_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyDefault, st.s));
+}
+inline void copy_d2h(Stream& st, void* h, const void* d, size_t n) {
+  if (n) ZK_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDefault, st.s));
+}
+inline void copy_d2d(Stream& st, void* d, const void* s, size_t n) {
+  if (n) ZK_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s));
+}
+inline void dev_memset(Stream& st, void* d, int v, size_t n) {
+  if (n) ZK_CUDA_CHECK(cudaMemsetAsync(d, v, n, st.s));
+}
+inline void sync(Stream& st) { ZK_CUDA_CHECK(cudaStreamSynchronize(st.s)); }
+// is `p` a device-accessible pointer that kernels may dereference directly?
+inline bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+#else  // ------------------------------------------------------------------ host simulator
+
+struct Stream {
+  uint64_t launches = 0;
+};
+template <class Task>
+inline void launch(Stream& st, long long n, const Task& task) {
+  for (long long t = 0; t < n; t++) task((int)t);
+  st.launches++;
+}
+inline void* dev_alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+inline void dev_free(void* p) { free(p); }
+inline void copy_h2d(Stream&, void* d, const void* h, size_t n) { if (n) memcpy(d, h, n); }
+inline void copy_d2h(Stream&, void* h, const void* d, size_t n) { if (n) memcpy(h, d, n); }
+inline void copy_d2d(Stream&, void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
+inline void dev_memset(Stream&, void* d, int v, size_t n) { if (n) memset(d, v, n); }
+inline void sync(Stream&) {}
+inline bool is_device_ptr(const void*) { return false; }
+
+#endif
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T>
+  T* get(size_t count) {
+    size_t bytes = count * sizeof(T);
+    if (bytes > cap) {
+      dev_free(p);
+      size_t want = bytes + bytes / 8 + 256;
+      p = dev_alloc(want);
+      cap = want;
+    }
+    return reinterpret_cast<T*>(p);
+  }
+  void release() {
+    dev_free(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace zk

@@ -1,0 +1,392 @@
+// zk_ops.cuh — building-block tasks: precomputed tables, scalar multiplication, batched
+// affine normalisation + serialisation, SHA-256 over point encodings.
+//
+// A "task" is a functor `void operator()(int t) const` executed once per work item; the
+// CUDA build runs it as one thread of a grid (zk_launch.cuh).  All tables and staging
+// buffers live in HBM/L2: the path is integer-pipe bound, the staging
+// traffic is < 1 % of HBM bandwidth.
+//
+// Reference mapping:
+//   Point.mul / Point.dblmul (4-bit windows, /root/reference/src/curves/group.ts:97-152)
+//     -> positional fixed-window tables, NO doublings at evaluation time:
+//        k*P = sum_j T[j][digit_j(k)],  T[j][d] = d * 2^(w j) * P   (affine / precomputed)
+//   toAffine + toBytes (weier.ts:231-255, edwards.ts:184-203; one invEuclid each)
+//     -> Montgomery's trick over chunks of points, one Fermat inversion per chunk.
+#pragma once
+#include "zk_curves.cuh"
+#include "zk_layout.h"
+#include "zk_sha256.cuh"
+
+namespace zk {
+
+#if defined(__CUDA_ARCH__)
+#define ZK_SET_STATUS(ptr, code) atomicCAS((int*)(ptr), 0, (int)(code))
+#else
+#define ZK_SET_STATUS(ptr, code) \
+  do {                           \
+    if (*(ptr) == 0) *(ptr) = (code); \
+  } while (0)
+#endif
+
+// ----------------------------------------------------------------------------- loads/stores
+template <int N>
+ZK_HD void ld(uint32_t* r, const uint32_t* p) {
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = p[i];
+}
+template <int N>
+ZK_HD void st(uint32_t* p, const uint32_t* r) {
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = r[i];
+}
+
+enum : int {
+  P256_PROJ_WORDS = 24,
+  P256_AFF_WORDS = 16,
+  TOM_PROJ_WORDS = 27,   // X, Y, Z (T is not needed after the last addition)
+  TOM_AFF_WORDS = 18,    // x', y on the a'=1 image curve, Montgomery
+  TOM_PRE_WORDS = 32,    // x', y, k = d' x' y + 5 pad words: one 128-byte line per entry
+  NORM_CHUNK = 8,
+};
+
+ZK_HD void p256_ld_proj(P256Pt& p, const uint32_t* m) {
+  ld<8>(p.x, m); ld<8>(p.y, m + 8); ld<8>(p.z, m + 16);
+}
+ZK_HD void p256_st_proj(uint32_t* m, const P256Pt& p) {
+  st<8>(m, p.x); st<8>(m + 8, p.y); st<8>(m + 16, p.z);
+}
+ZK_HD void p256_ld_aff(P256Aff& a, const uint32_t* m) { ld<8>(a.x, m); ld<8>(a.y, m + 8); }
+ZK_HD void p256_st_aff(uint32_t* m, const P256Aff& a) { st<8>(m, a.x); st<8>(m + 8, a.y); }
+
+ZK_HD void tom_ld_pre(TomPre& q, const uint32_t* m) {
+#if defined(__CUDA_ARCH__)
+  // one 128-byte line, eight 16-byte loads (entries are 128-byte aligned)
+  const uint4* v = reinterpret_cast<const uint4*>(m);
+  uint32_t w[32];
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    uint4 u = __ldg(v + i);
+    w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) { q.x[i] = w[i]; q.y[i] = w[9 + i]; q.k[i] = w[18 + i]; }
+#else
+  ld<9>(q.x, m); ld<9>(q.y, m + 9); ld<9>(q.k, m + 18);
+#endif
+}
+
+// digit j of width w (w in {4, 8}) of a canonical 256-bit scalar
+ZK_HD uint32_t digit4(const uint32_t* k, int j) { return (k[j >> 3] >> (4 * (j & 7))) & 15u; }
+ZK_HD uint32_t digit8(const uint32_t* k, int j) { return (k[j >> 2] >> (8 * (j & 3))) & 255u; }
+// generic: bits [pos, pos+w) of a 256-bit scalar, w <= 16
+ZK_HD uint32_t digit_w(const uint32_t* k, int pos, int w) {
+  int wi = pos >> 5, sh = pos & 31;
+  uint64_t v = k[wi];
+  if (wi + 1 < 8) v |= (uint64_t)k[wi + 1] << 32;
+  return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+}
+
+// read a 32-byte big-endian tape draw into 8 limbs
+ZK_HD void tape_draw(uint32_t* r, const uint8_t* tape, int draw) {
+  const uint8_t* p = tape + 32 * (size_t)draw;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint8_t* q = p + 28 - 4 * i;
+    r[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+  }
+}
+
+// ============================================================================ P-256 tables
+// pows[j] = 2^(w j) * base  for j < nwin  (one thread per base; sequential doublings)
+struct P256PowsTask {
+  const uint32_t* base_aff;  // [nbase][16]
+  const uint8_t* base_inf;   // [nbase] or null
+  uint32_t* pows;            // [nbase][nwin][24]
+  int nbase, nwin, w;
+  ZK_HD void operator()(int t) const {
+    P256Aff a;
+    p256_ld_aff(a, base_aff + (size_t)t * P256_AFF_WORDS);
+    P256Pt p;
+    p256_from_affine(p, a);
+    if (base_inf && base_inf[t]) p256_set_identity(p);
+    for (int j = 0; j < nwin; j++) {
+      p256_st_proj(pows + ((size_t)t * nwin + j) * P256_PROJ_WORDS, p);
+      for (int k = 0; k < w; k++) p256_dbl(p, p);
+    }
+  }
+};
+// rows[(b*nwin + j)*(2^w) + d] = d * pows[b][j], d = 1..2^w-1  (entry 0 left untouched)
+struct P256RowsTask {
+  const uint32_t* pows;  // [nbase*nwin][24]
+  uint32_t* rows;        // [nbase*nwin][2^w][24]
+  int w;
+  ZK_HD void operator()(int t) const {
+    P256Pt p, acc;
+    p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
+    acc = p;
+    const int ne = 1 << w;
+    uint32_t* out = rows + (size_t)t * ne * P256_PROJ_WORDS;
+    // entry 0: store the base itself so the normaliser never sees garbage (it is never read)
+    p256_st_proj(out, p);
+    for (int d = 1; d < ne; d++) {
+      p256_st_proj(out + (size_t)d * P256_PROJ_WORDS, acc);
+      p256_add(acc, acc, p);
+    }
+  }
+};
+
+// Batched normalisation: proj[count] -> affine Montgomery (+ optional 65-byte encodings)
+struct P256NormTask {
+  const uint32_t* proj;  // [count][24]
+  uint32_t* aff;         // [count][16]
+  uint8_t* bytes;        // [count][BSTRIDE] or null
+  uint8_t* inf;          // [count] or null
+  int count;
+  ZK_HD void operator()(int t) const {
+    using F = P256p;
+    const int lo = t * NORM_CHUNK;
+    int n = count - lo;
+    if (n > NORM_CHUNK) n = NORM_CHUNK;
+    if (n <= 0) return;
+    uint32_t pre[NORM_CHUNK][8];
+    uint32_t acc[8], z[8], one[8];
+    F::set_one(one);
+    copy_n<8>(acc, one);
+    for (int k = 0; k < n; k++) {
+      ld<8>(z, proj + (size_t)(lo + k) * P256_PROJ_WORDS + 16);
+      if (is_zero_n<8>(z)) copy_n<8>(z, one);
+      F::mul(acc, acc, z);
+      copy_n<8>(pre[k], acc);
+    }
+    uint32_t inv[8];
+    F::inv(inv, acc);
+    for (int k = n - 1; k >= 0; k--) {
+      const uint32_t* src = proj + (size_t)(lo + k) * P256_PROJ_WORDS;
+      ld<8>(z, src + 16);
+      const bool isinf = is_zero_n<8>(z);
+      if (isinf) copy_n<8>(z, one);
+      uint32_t zi[8];
+      if (k > 0) F::mul(zi, inv, pre[k - 1]); else copy_n<8>(zi, inv);
+      F::mul(inv, inv, z);
+      P256Aff a;
+      uint32_t X[8], Y[8];
+      ld<8>(X, src);
+      ld<8>(Y, src + 8);
+      F::mul(a.x, X, zi);
+      F::mul(a.y, Y, zi);
+      p256_st_aff(aff + (size_t)(lo + k) * P256_AFF_WORDS, a);
+      if (inf) inf[lo + k] = isinf ? 1 : 0;
+      if (bytes) {
+        uint8_t* o = bytes + (size_t)(lo + k) * BSTRIDE;
+        if (isinf) {
+          for (int i = 0; i < NP; i++) o[i] = 0;
+        } else {
+          uint32_t c[8];
+          o[0] = 0x04;
+          F::from_mont(c, a.x);
+          limbs_to_be<8>(o + 1, c, 32);
+          F::from_mont(c, a.y);
+          limbs_to_be<8>(o + 33, c, 32);
+        }
+      }
+    }
+  }
+};
+
+// acc += sum_j T[j][digit_j(k)] for a w=8 fixed table [32][256] of affine entries
+ZK_HD void p256_accum_fixed8(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
+  for (int j = 0; j < 32; j++) {
+    uint32_t d = digit8(k, j);
+    if (d) {
+      P256Aff q;
+      p256_ld_aff(q, tab + ((size_t)j * 256 + d) * P256_AFF_WORDS);
+      p256_madd(acc, acc, q);
+    }
+  }
+}
+// acc += sum_j T[j][digit_j(k)] for a w=4 table [64][16] of affine entries
+ZK_HD void p256_accum_tab4(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
+  for (int j = 0; j < 64; j++) {
+    uint32_t d = digit4(k, j);
+    if (d) {
+      P256Aff q;
+      p256_ld_aff(q, tab + ((size_t)j * 16 + d) * P256_AFF_WORDS);
+      p256_madd(acc, acc, q);
+    }
+  }
+}
+// r = k * base, 4-bit fixed window, one-shot variable base (used once per proof for u2*pk)
+ZK_HD void p256_mul_var(P256Pt& r, const P256Aff& base, const uint32_t* k) {
+  P256Pt tb[16];
+  p256_set_identity(tb[0]);
+  p256_from_affine(tb[1], base);
+  for (int d = 2; d < 16; d++) p256_madd(tb[d], tb[d - 1], base);
+  p256_set_identity(r);
+  for (int j = 63; j >= 0; j--) {
+    p256_dbl(r, r); p256_dbl(r, r); p256_dbl(r, r); p256_dbl(r, r);
+    p256_add(r, r, tb[digit4(k, j)]);
+  }
+}
+
+// ===================================================================== tomEdwards256 tables
+struct TomPowsTask {
+  const uint32_t* base_aff;  // [nbase][18] image-curve affine (x', y), Montgomery
+  uint32_t* pows;            // [nbase][nwin][36] extended (X,Y,T,Z)
+  int nbase, nwin, w;
+  ZK_HD void operator()(int t) const {
+    uint32_t x[9], y[9];
+    ld<9>(x, base_aff + (size_t)t * TOM_AFF_WORDS);
+    ld<9>(y, base_aff + (size_t)t * TOM_AFF_WORDS + 9);
+    TomPt p;
+    tom_from_affine(p, x, y);
+    for (int j = 0; j < nwin; j++) {
+      uint32_t* o = pows + ((size_t)t * nwin + j) * 36;
+      st<9>(o, p.x); st<9>(o + 9, p.y); st<9>(o + 18, p.t); st<9>(o + 27, p.z);
+      for (int k = 0; k < w; k++) tom_dbl(p, p);
+    }
+  }
+};
+// rows: proj store [(base*nwin + j) * 2^w + d][27] = d * pows[base][j]  (d = 0 is the identity)
+struct TomRowsTask {
+  const uint32_t* pows;
+  uint32_t* rows;
+  int w;
+  ZK_HD void operator()(int t) const {
+    TomPt p, acc;
+    const uint32_t* s = pows + (size_t)t * 36;
+    ld<9>(p.x, s); ld<9>(p.y, s + 9); ld<9>(p.t, s + 18); ld<9>(p.z, s + 27);
+    tom_set_identity(acc);
+    const int ne = 1 << w;
+    uint32_t* out = rows + (size_t)t * ne * TOM_PROJ_WORDS;
+    for (int d = 0; d < ne; d++) {
+      uint32_t* o = out + (size_t)d * TOM_PROJ_WORDS;
+      st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.z);
+      tom_add(acc, acc, p);
+    }
+  }
+};
+// aff (x', y) -> table entry (x', y, d' x' y), canonical residues, 128-byte stride
+struct TomPreTask {
+  const uint32_t* aff;  // [count][18]
+  uint32_t* pre;        // [count][32]
+  ZK_HD void operator()(int t) const {
+    using F = Tomp;
+    uint32_t x[9], y[9], k[9], d1[9];
+    ld<9>(x, aff + (size_t)t * TOM_AFF_WORDS);
+    ld<9>(y, aff + (size_t)t * TOM_AFF_WORDS + 9);
+    tom_const(d1, TOM_D1);
+    F::mul(k, x, y);
+    F::mul(k, k, d1);
+    F::reduce(x); F::reduce(y); F::reduce(k);
+    uint32_t* o = pre + (size_t)t * TOM_PRE_WORDS;
+    st<9>(o, x); st<9>(o + 9, y); st<9>(o + 18, k);
+    for (int i = 27; i < 32; i++) o[i] = 0;
+  }
+};
+
+// Batched normalisation of tomEdwards256 points: proj (X,Y,Z) -> image-curve affine (x', y)
+// Montgomery (+ optional 67-byte reference encoding of (x = x'/sqrt(a), y)).
+struct TomNormTask {
+  const uint32_t* proj;  // [count][27]
+  uint32_t* aff;         // [count][18]
+  uint8_t* bytes;        // [count][BSTRIDE] or null
+  int count;
+  ZK_HD void operator()(int t) const {
+    using F = Tomp;
+    const int lo = t * NORM_CHUNK;
+    int n = count - lo;
+    if (n > NORM_CHUNK) n = NORM_CHUNK;
+    if (n <= 0) return;
+    uint32_t pre[NORM_CHUNK][9];
+    uint32_t acc[9], z[9];
+    F::set_one(acc);
+    for (int k = 0; k < n; k++) {
+      ld<9>(z, proj + (size_t)(lo + k) * TOM_PROJ_WORDS + 18);
+      F::mul(acc, acc, z);   // Z != 0 always on a complete Edwards curve
+      copy_n<9>(pre[k], acc);
+    }
+    uint32_t inv[9], isa[9];
+    F::inv(inv, acc);
+    tom_const(isa, TOM_INVSQRTA);
+    for (int k = n - 1; k >= 0; k--) {
+      const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
+      ld<9>(z, src + 18);
+      uint32_t zi[9];
+      if (k > 0) F::mul(zi, inv, pre[k - 1]); else copy_n<9>(zi, inv);
+      F::mul(inv, inv, z);
+      uint32_t X[9], Y[9], x[9], y[9];
+      ld<9>(X, src);
+      ld<9>(Y, src + 9);
+      F::mul(x, X, zi);
+      F::mul(y, Y, zi);
+      uint32_t* a = aff + (size_t)(lo + k) * TOM_AFF_WORDS;
+      st<9>(a, x);
+      st<9>(a + 9, y);
+      if (bytes) {
+        uint8_t* o = bytes + (size_t)(lo + k) * BSTRIDE;
+        uint32_t c[9];
+        o[0] = 0x04;
+        F::mul(c, x, isa);      // back to the reference curve: x = x' / sqrt(a)
+        F::from_mont(c, c);
+        limbs_to_be<9>(o + 1, c, 33);
+        F::from_mont(c, y);
+        limbs_to_be<9>(o + 34, c, 33);
+      }
+    }
+  }
+};
+
+// Pedersen commitment in the proof group:  C = v*g + r*h   (pedersen.ts:53-58, gk.ts:88-92),
+// both bases fixed => two positional tables, 2*nwin mixed additions, no doublings.
+struct TomCommitTask {
+  const uint32_t* jv;    // [count][8] canonical value scalars (mod tom.order)
+  const uint32_t* jr;    // [count][8] canonical blinders
+  const uint32_t* gtab;  // [nwin][2^w][32]
+  const uint32_t* htab;
+  uint32_t* proj;        // [count][27]
+  int w, nwin;
+  ZK_HD void operator()(int t) const {
+    uint32_t v[8], r[8];
+    ld<8>(v, jv + (size_t)t * 8);
+    ld<8>(r, jr + (size_t)t * 8);
+    TomPt acc;
+    tom_set_identity(acc);
+    const size_t ne = (size_t)1 << w;
+    for (int j = 0; j < nwin; j++) {
+      TomPre q;
+      int width = (256 - j * w) < w ? (256 - j * w) : w;
+      uint32_t dv = digit_w(v, j * w, width), dr = digit_w(r, j * w, width);
+      tom_ld_pre(q, gtab + ((size_t)j * ne + dv) * TOM_PRE_WORDS);
+      tom_madd<true>(acc, acc, q);
+      tom_ld_pre(q, htab + ((size_t)j * ne + dr) * TOM_PRE_WORDS);
+      tom_madd<true>(acc, acc, q);
+    }
+    uint32_t* o = proj + (size_t)t * TOM_PROJ_WORDS;
+    st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.z);
+  }
+};
+
+// ================================================================================== hashing
+// Streams `npts` encoded points (given as (pointer, length) by a functor) through SHA-256.
+template <class Src>
+ZK_HD void hash_points80(uint32_t* c3, const Src& src, int npts) {
+  Sha256 h;
+  h.init();
+  for (int i = 0; i < npts; i++) {
+    int len;
+    const uint8_t* p = src(i, len);
+    h.update(p, len);
+  }
+  h.final80(c3);
+}
+
+// challenge (80 bit, c3) as a canonical 8-limb scalar
+ZK_HD void challenge_to_limbs(uint32_t* r, const uint32_t* c3) {
+  zero_n<8>(r);
+  r[0] = c3[0]; r[1] = c3[1]; r[2] = c3[2];
+}
+
+// write a canonical 8-limb scalar as a big-endian field of `len` bytes (32 or 33)
+ZK_HD void put_scalar(uint8_t* o, const uint32_t* c, int len) { limbs_to_be<8>(o, c, len); }
+
+}  // namespace zk

@@ -1,0 +1,923 @@
+// zk_prove.cuh — stage tasks of the batched prover (proveSignatureList over B proofs).
+//
+// Reference call tree being replaced (per proof):
+//   /root/reference/src/zkpAttestList.ts:104-145  proveSignatureList
+//   /root/reference/src/exp/exp.ts:126-231        proveExp        (80 cut-and-choose reps)
+//   /root/reference/src/exp/pointAdd.ts:92-163    provePointAdd   (per 0-bit rep)
+//   /root/reference/src/commit/mult.ts:93-131     proveMult       (4 per pointAdd)
+//   /root/reference/src/commit/equality.ts:60-78  proveEquality   (2 per pointAdd)
+//   /root/reference/src/proofGK/gk.ts:94-195      proveMembership
+//
+// Key restructuring (results identical, only affine encodings are observable):
+//  * every tomEdwards256 point the prover emits is a commitment whose opening (v, r) the
+//    prover knows — including the reference's variable-base products C4 = Cy*x and
+//    A4_2 = Cy*k_x (mult.ts:103,114), since Cy = y*g + ry*h gives Cy*x = (xy)*g + (x ry)*h.
+//    All ~1 560 Tom scalar multiplications per proof therefore run on the two fixed-base
+//    tables of g and h (TomCommitTask) with scalars computed mod tom.order = p256.p.
+//  * derived commitments C7, C9, C12, Cint (pointAdd.ts:137-159) are single point additions.
+//  * all commitments of all repetitions of all proofs of a stage form ONE batch; the
+//    Fiat-Shamir hashes are the only sequencing points.
+#pragma once
+#include "zk_ops.cuh"
+
+namespace zk {
+
+struct ProveCtx {
+  // dimensions
+  int B;        // proofs in this chunk
+  int S;        // repetitions (SecLevel, <= 80)
+  int N;        // ring size
+  int n;        // ceil(log2 N)
+  int M;        // total 0-bit repetitions (items) in the chunk (valid after the scan)
+  int tom_w, tom_nwin;
+  // inputs (device copies)
+  const uint8_t* msg_hash;   // [B][32]
+  const uint8_t* sig;        // [B][64]
+  const uint8_t* pk;         // [B][65]
+  const uint32_t* which;     // [B]
+  const uint8_t* tape;       // [B][tape_stride]
+  size_t tape_stride;
+  uint32_t tape_draws;       // draws available per proof
+  const uint32_t* ring_m;    // [2^n] ring values mod tom.order, Montgomery, padded with ring[0]
+  // parameters / tables
+  const uint32_t* g_tab8;    // P-256 generator, w=8 affine table [32][256][16]
+  const uint32_t* h_tab8;    // NistGroup.h,     w=8 affine table
+  const uint32_t* tg_tab;    // ProofGroup.g table [nwin][2^w][32]
+  const uint32_t* th_tab;    // ProofGroup.h table
+  const uint8_t* tg_bytes;   // 67-byte encoding of ProofGroup.g (C_14, pointAdd.ts:144)
+  // per proof state
+  uint32_t* s1;        // [B][8]  s1 canonical mod n
+  uint32_t* pk_aff;    // [B][16] pk affine Montgomery
+  uint32_t* q_aff;     // [B][16] Q = z1*G
+  uint8_t* q_inf;      // [B]
+  uint32_t* r_aff;     // [B][16] R
+  uint8_t* r_bytes;    // [B][BSTRIDE]
+  uint32_t* rpows;     // [B][64][24]
+  uint32_t* rrows;     // [B][64][16][24]
+  uint32_t* rtab;      // [B][64][16][16] affine
+  // phase A (P-256): slot i in [0,S] per proof; slot S is comS1
+  uint32_t* pa_T;      // [B][S+1][24]
+  uint32_t* pa_A;      // [B][S+1][24]
+  uint32_t* pa_T_aff;  // [B][S+1][16]
+  uint8_t* pa_T_inf;   // [B][S+1]
+  uint32_t* pa_A_aff;  // [B][S+1][16] (unused values, bytes matter)
+  uint8_t* pa_A_bytes; // [B][S+1][BSTRIDE]
+  uint8_t* pa_A_inf;   // [B][S+1]
+  // Tom store 1 (pre-challenge): per proof 2 + 2S points: pkX, pkY, (Tx_i, Ty_i)
+  uint32_t *s1_jv, *s1_jr, *s1_proj, *s1_aff;
+  uint8_t* s1_bytes;
+  // challenge / items
+  uint32_t* chal;      // [B][3]  80-bit exp challenge
+  uint32_t* zcount;    // [B]     zero bits
+  uint32_t* item_base; // [B]     exclusive prefix of zcount
+  uint32_t* item_total;// [1]
+  uint32_t* rep_off;   // [B][S]  byte offset of each repetition inside the proof
+  uint32_t* gk_off;    // [B]     byte offset of the GK proof
+  uint32_t* item_b;    // [M]     proof of item
+  uint32_t* item_i;    // [M]     repetition of item
+  uint32_t* item_k;    // [M]     rank of the item among the proof's zero bits
+  // phase B (P-256)
+  uint32_t* pb_T1;     // [M][24]
+  uint32_t* pb_T1_aff; // [M][16]
+  uint8_t* pb_T1_inf;  // [M]
+  // Tom store 2 (post-challenge): [34 M jobs][5 M derived][4n B GK]
+  uint32_t *s2_jv, *s2_jr, *s2_proj, *s2_aff;
+  uint8_t* s2_bytes;
+  uint32_t* secrets;   // [M][34][8] Montgomery mod tom.order
+  uint32_t* item_chal; // [M][6][3]
+  // GK
+  uint32_t* gk_dv;     // [B][n][8]  d(omega_w), Montgomery
+  uint32_t* gk_lag;    // [n][n][8]  Lagrange matrix for nodes 0..n-1, Montgomery
+  uint32_t* gk_x;      // [B][3]
+  // outputs
+  uint8_t* proofs;     // [B][proof_stride]
+  size_t proof_stride;
+  uint32_t* proof_len; // [B]
+  int32_t* status;     // [B]
+
+  ZK_HD size_t s2_job(size_t item, int j) const { return item * JOBS_PER_ITEM + j; }
+  ZK_HD size_t s2_der(size_t item, int j) const { return (size_t)M * JOBS_PER_ITEM + item * DERS_PER_ITEM + j; }
+  ZK_HD size_t s2_gk(size_t b, int j) const { return (size_t)M * (JOBS_PER_ITEM + DERS_PER_ITEM) + b * 4 * n + j; }
+  ZK_HD size_t s2_count() const { return (size_t)M * (JOBS_PER_ITEM + DERS_PER_ITEM) + (size_t)B * 4 * n; }
+  ZK_HD size_t s1_pt(size_t b, int j) const { return b * (2 + 2 * S) + j; }  // 0 pkX, 1 pkY, 2+2i Tx_i, 3+2i Ty_i
+  ZK_HD const uint8_t* tape_of(int b) const { return tape + (size_t)b * tape_stride; }
+};
+
+// draw a scalar and check it is below the modulus (the host pre-filters, see include/zkattest.h)
+template <class F>
+ZK_HD bool draw_checked(uint32_t* r, const ProveCtx& c, int b, int draw) {
+  if ((uint32_t)draw >= c.tape_draws) {
+    zero_n<8>(r);
+    ZK_SET_STATUS(c.status + b, ZKA_ERR_TAPE_RANGE);
+    return false;
+  }
+  tape_draw(r, c.tape_of(b), draw);
+  if (!lt_p<F>(r)) {
+    ZK_SET_STATUS(c.status + b, ZKA_ERR_TAPE_RANGE);
+    sub_p<F>(r, r);  // keep arithmetic well defined; the proof is flagged anyway
+    return false;
+  }
+  return true;
+}
+
+// reduce a raw 256-bit integer mod the field prime (inputs < 2^256 < 2p for all our moduli)
+template <class F>
+ZK_HD void reduce_once(uint32_t* a) {
+  uint32_t t[8];
+  uint32_t br = sub_p<F>(t, a);
+  csel_n<8>(a, br == 0, t, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 0 — ECDSA statement (zkpAttestList.ts:112-136): one thread per proof.
+//   R = u1*G + u2*pk, Q = z1*G, s1 = s/r;   sinv, rinv by Fermat (invMod(0) = 0 as in big.ts).
+// ---------------------------------------------------------------------------------------------
+struct PreTask {
+  ProveCtx c;
+  ZK_HD void operator()(int b) const {
+    using Fp = P256p;
+    using Fn = P256n;
+    c.status[b] = ZKA_OK;
+    const uint8_t* pkb = c.pk + (size_t)b * 65;
+    uint32_t px[8], py[8];
+    limbs_from_be<8>(px, pkb + 1, 32);
+    limbs_from_be<8>(py, pkb + 33, 32);
+    P256Aff pk;
+    bool ok = (pkb[0] == 0x04);
+    // weier.ts:74-89 does not range-check x,y; isOnGroup works mod p.  Reduce then test.
+    reduce_once<FpP256>(px);
+    reduce_once<FpP256>(py);
+    Fp::to_mont(pk.x, px);
+    Fp::to_mont(pk.y, py);
+    ok = ok && p256_on_curve(pk.x, pk.y);
+    if (!ok) {
+      ZK_SET_STATUS(c.status + b, ZKA_ERR_INVALID_PK);
+      // keep going with the generator so later stages stay well defined
+      p256_set_generator(pk);
+    }
+    p256_st_aff(c.pk_aff + (size_t)b * 16, pk);
+
+    uint32_t z[8], r[8], s[8];
+    limbs_from_be<8>(z, c.msg_hash + (size_t)b * 32, 32);   // truncateToN is the identity for 32 bytes
+    limbs_from_be<8>(r, c.sig + (size_t)b * 64, 32);
+    limbs_from_be<8>(s, c.sig + (size_t)b * 64 + 32, 32);
+    reduce_once<FnP256>(z);
+    reduce_once<FnP256>(r);
+    reduce_once<FnP256>(s);
+    uint32_t zm[8], rm[8], sm[8], sinv[8], rinv[8], t[8];
+    Fn::to_mont(zm, z);
+    Fn::to_mont(rm, r);
+    Fn::to_mont(sm, s);
+    Fn::inv(sinv, sm);
+    Fn::inv(rinv, rm);
+    uint32_t u1[8], u2[8], s1[8], z1[8];
+    Fn::mul(t, sinv, zm); Fn::from_mont(u1, t);
+    Fn::mul(t, sinv, rm); Fn::from_mont(u2, t);
+    Fn::mul(t, rinv, sm); Fn::from_mont(s1, t);
+    Fn::mul(t, rinv, zm); Fn::from_mont(z1, t);
+    st<8>(c.s1 + (size_t)b * 8, s1);
+
+    // R = u1*G + u2*pk
+    P256Pt R, U;
+    p256_set_identity(R);
+    p256_accum_fixed8(R, c.g_tab8, u1);
+    p256_mul_var(U, pk, u2);
+    p256_add(R, R, U);
+    // Q = z1*G
+    P256Pt Q;
+    p256_set_identity(Q);
+    p256_accum_fixed8(Q, c.g_tab8, z1);
+
+    // affine R, Q (own Fermat inversions: once per proof)
+    uint32_t zi[8];
+    P256Aff Ra, Qa;
+    bool rinf = p256_is_identity(R);
+    if (rinf) {
+      ZK_SET_STATUS(c.status + b, ZKA_ERR_T_INFINITY);  // T_i = R*alpha is the identity (exp.ts:151)
+      p256_set_generator(Ra);
+    } else {
+      Fp::inv(zi, R.z);
+      Fp::mul(Ra.x, R.x, zi);
+      Fp::mul(Ra.y, R.y, zi);
+    }
+    if (is_zero_n<8>(r)) ZK_SET_STATUS(c.status + b, ZKA_ERR_POINTS_DONT_ADD);  // rinv = 0: T1 + pk != T (pointAdd.ts:105)
+    p256_st_aff(c.r_aff + (size_t)b * 16, Ra);
+    uint8_t* rb = c.r_bytes + (size_t)b * BSTRIDE;
+    uint32_t cv[8];
+    rb[0] = 0x04;
+    Fp::from_mont(cv, Ra.x); limbs_to_be<8>(rb + 1, cv, 32);
+    Fp::from_mont(cv, Ra.y); limbs_to_be<8>(rb + 33, cv, 32);
+    bool qinf = p256_is_identity(Q);
+    if (qinf) {
+      p256_set_generator(Qa);
+    } else {
+      Fp::inv(zi, Q.z);
+      Fp::mul(Qa.x, Q.x, zi);
+      Fp::mul(Qa.y, Q.y, zi);
+    }
+    p256_st_aff(c.q_aff + (size_t)b * 16, Qa);
+    c.q_inf[b] = qinf ? 1 : 0;
+    if (c.which[b] >= (uint32_t)c.N) ZK_SET_STATUS(c.status + b, ZKA_ERR_BAD_INDEX);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1 — exp.ts:144-148: T_i = alpha_i*R, A_i = T_i + r_i*h; slot S: comS1 = s1*R + r*h
+// (zkpAttestList.ts:137-138).  One thread per (proof, slot).
+// ---------------------------------------------------------------------------------------------
+struct PhaseAP256Task {
+  ProveCtx c;
+  ZK_HD void operator()(int t) const {
+    const int S1 = c.S + 1;
+    const int b = t / S1, i = t % S1;
+    uint32_t alpha[8], r[8];
+    if (i < c.S) {
+      draw_checked<FnP256>(alpha, c, b, DRAW_REP0 + DRAWS_PER_REP * i);
+      draw_checked<FnP256>(r, c, b, DRAW_REP0 + DRAWS_PER_REP * i + 1);
+    } else {
+      ld<8>(alpha, c.s1 + (size_t)b * 8);
+      draw_checked<FnP256>(r, c, b, DRAW_COMS1_R);
+    }
+    P256Pt T, A;
+    p256_set_identity(T);
+    p256_accum_tab4(T, c.rtab + (size_t)b * 64 * 16 * P256_AFF_WORDS, alpha);
+    A = T;
+    p256_accum_fixed8(A, c.h_tab8, r);
+    p256_st_proj(c.pa_T + (size_t)t * P256_PROJ_WORDS, T);
+    p256_st_proj(c.pa_A + (size_t)t * P256_PROJ_WORDS, A);
+  }
+};
+
+// Stage 2a — commitment jobs for pkX, pkY (zkpAttestList.ts:139-140) and Tx_i, Ty_i
+// (exp.ts:154-155).  One thread per (proof, j), j in [0, 2+2S).
+struct JobsATask {
+  ProveCtx c;
+  ZK_HD void operator()(int t) const {
+    using Fp = P256p;
+    const int per = 2 + 2 * c.S;
+    const int b = t / per, j = t % per;
+    uint32_t v[8], r[8], m[8];
+    if (j < 2) {
+      ld<8>(m, c.pk_aff + (size_t)b * 16 + 8 * j);
+      draw_checked<FpP256>(r, c, b, DRAW_PKX_R + j);
+    } else {
+      const int i = (j - 2) >> 1, xy = (j - 2) & 1;
+      const size_t slot = (size_t)b * (c.S + 1) + i;
+      if (c.pa_T_inf[slot]) ZK_SET_STATUS(c.status + b, ZKA_ERR_T_INFINITY);   // exp.ts:150-152
+      if (c.pa_A_inf[slot]) ZK_SET_STATUS(c.status + b, ZKA_ERR_IDENTITY_ENC);
+      ld<8>(m, c.pa_T_aff + slot * 16 + 8 * xy);
+      draw_checked<FpP256>(r, c, b, DRAW_REP0 + DRAWS_PER_REP * i + 2 + xy);
+    }
+    Fp::from_mont(v, m);  // coordinate as an integer: a scalar of the proof group
+    st<8>(c.s1_jv + (size_t)t * 8, v);
+    st<8>(c.s1_jr + (size_t)t * 8, r);
+  }
+};
+
+// Stage 3 — exp.ts:158-165 challenge = H(pkX, pkY, A_0, Tx_0, Ty_0, ...); per proof.
+// Also lays the proof out: repetition offsets, item ranks, header + tags.
+struct ExpChallengeTask {
+  ProveCtx c;
+  struct Src {
+    const ProveCtx* c;
+    int b;
+    ZK_HD const uint8_t* operator()(int k, int& len) const {
+      if (k < 2) { len = WP; return c->s1_bytes + c->s1_pt(b, k) * BSTRIDE; }
+      const int i = (k - 2) / 3, w = (k - 2) % 3;
+      if (w == 0) { len = NP; return c->pa_A_bytes + ((size_t)b * (c->S + 1) + i) * BSTRIDE; }
+      len = WP;
+      return c->s1_bytes + c->s1_pt(b, 2 + 2 * i + (w - 1)) * BSTRIDE;
+    }
+  };
+  ZK_HD void operator()(int b) const {
+    uint32_t c3[3];
+    Src src{&c, b};
+    hash_points80(c3, src, 2 + 3 * c.S);
+    st<3>(c.chal + (size_t)b * 3, c3);
+    uint32_t off = HEAD_LEN, z = 0;
+    for (int i = 0; i < c.S; i++) {
+      const uint32_t bit = (c3[i >> 5] >> (i & 31)) & 1u;   // LSB first (exp.ts:169,228)
+      c.rep_off[(size_t)b * c.S + i] = off;
+      off += bit ? REP1_LEN : REP0_LEN;
+      z += bit ? 0 : 1;
+    }
+    c.zcount[b] = z;
+    c.gk_off[b] = off;
+    c.proof_len[b] = off + gk_len(c.n);
+  }
+};
+// single-thread exclusive scan of zcount (B <= a few thousand per chunk)
+struct ScanTask {
+  ProveCtx c;
+  ZK_HD void operator()(int) const {
+    uint32_t acc = 0;
+    for (int b = 0; b < c.B; b++) {
+      c.item_base[b] = acc;
+      acc += c.zcount[b];
+    }
+    c.item_total[0] = acc;
+  }
+};
+struct ItemsTask {
+  ProveCtx c;
+  ZK_HD void operator()(int b) const {
+    uint32_t c3[3];
+    ld<3>(c3, c.chal + (size_t)b * 3);
+    uint32_t k = 0;
+    for (int i = 0; i < c.S; i++) {
+      const uint32_t bit = (c3[i >> 5] >> (i & 31)) & 1u;
+      if (!bit) {
+        const uint32_t it = c.item_base[b] + k;
+        c.item_b[it] = b;
+        c.item_i[it] = i;
+        c.item_k[it] = k;
+        k++;
+      }
+    }
+  }
+};
+
+// Stage 4 — exp.ts:186-190: z = alpha_i - s1, T1 = z*R (+ Q).  One thread per item.
+struct PhaseBP256Task {
+  ProveCtx c;
+  ZK_HD void operator()(int it) const {
+    const int b = c.item_b[it], i = c.item_i[it];
+    uint32_t alpha[8], s1[8], z[8];
+    draw_checked<FnP256>(alpha, c, b, DRAW_REP0 + DRAWS_PER_REP * i);
+    ld<8>(s1, c.s1 + (size_t)b * 8);
+    uint32_t br = sub_n<8>(z, alpha, s1);
+    if (br) {
+      uint32_t nn[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) nn[k] = FnP256::p(k);
+      add_n<8>(z, z, nn);
+    }
+    P256Pt T1;
+    p256_set_identity(T1);
+    p256_accum_tab4(T1, c.rtab + (size_t)b * 64 * 16 * P256_AFF_WORDS, z);
+    if (!c.q_inf[b]) {
+      P256Aff Q;
+      p256_ld_aff(Q, c.q_aff + (size_t)b * 16);
+      p256_madd(T1, T1, Q);
+    }
+    p256_st_proj(c.pb_T1 + (size_t)it * P256_PROJ_WORDS, T1);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Stage 5 — pointAdd.ts:125-160 witnesses + every commitment opening of one 0-bit repetition,
+// in the proof-group scalar field F_q, q = tom.order = p256.p.  One thread per item.
+// ---------------------------------------------------------------------------------------------
+struct ItemScalarsTask {
+  ProveCtx c;
+  ZK_HD void job(size_t item, int j, const uint32_t* v_mont, const uint32_t* r_canon) const {
+    uint32_t v[8];
+    Tomq::from_mont(v, v_mont);
+    st<8>(c.s2_jv + c.s2_job(item, j) * 8, v);
+    st<8>(c.s2_jr + c.s2_job(item, j) * 8, r_canon);
+  }
+  ZK_HD void operator()(int it) const {
+    using F = Tomq;
+    const int b = c.item_b[it], i = c.item_i[it], k = c.item_k[it];
+    if (c.pb_T1_inf[it]) ZK_SET_STATUS(c.status + b, ZKA_ERR_T1_INFINITY);  // exp.ts:192-194
+    const int d0 = draws_before_items(c.S) + DRAWS_PER_ITEM * k;
+    // coordinates (Montgomery residues mod p256.p double as F_q elements)
+    uint32_t x1[8], y1[8], x2[8], y2[8], x3[8];
+    ld<8>(x1, c.pb_T1_aff + (size_t)it * 16);
+    ld<8>(y1, c.pb_T1_aff + (size_t)it * 16 + 8);
+    ld<8>(x2, c.pk_aff + (size_t)b * 16);
+    ld<8>(y2, c.pk_aff + (size_t)b * 16 + 8);
+    ld<8>(x3, c.pa_T_aff + ((size_t)b * (c.S + 1) + i) * 16);
+    // blinders (canonical) and their Montgomery forms
+    uint32_t rT1x[8], rT1y[8], rPkx[8], rPky[8], rTx[8], rTy[8];
+    draw_checked<FpP256>(rT1x, c, b, d0 + IT_T1X_R);
+    draw_checked<FpP256>(rT1y, c, b, d0 + IT_T1Y_R);
+    draw_checked<FpP256>(rPkx, c, b, DRAW_PKX_R);
+    draw_checked<FpP256>(rPky, c, b, DRAW_PKY_R);
+    draw_checked<FpP256>(rTx, c, b, DRAW_REP0 + DRAWS_PER_REP * i + 2);
+    draw_checked<FpP256>(rTy, c, b, DRAW_REP0 + DRAWS_PER_REP * i + 3);
+    uint32_t mT1x[8], mT1y[8], mPkx[8], mPky[8], mTx[8], mTy[8];
+    F::to_mont(mT1x, rT1x); F::to_mont(mT1y, rT1y);
+    F::to_mont(mPkx, rPkx); F::to_mont(mPky, rPky);
+    F::to_mont(mTx, rTx);   F::to_mont(mTy, rTy);
+    // pointAdd.ts:130-136
+    uint32_t i7[8], i8[8], i9[8], i10[8], i11[8], i12[8], i13[8];
+    F::sub(i7, x2, x1);
+    F::inv(i8, i7);
+    F::sub(i9, y2, y1);
+    F::mul(i10, i8, i9);
+    F::sqr(i11, i10);
+    F::sub(i12, x1, x3);
+    F::mul(i13, i10, i12);
+    // derived blinders: C7 = C2 - C1, C9 = C5 - C4, C12 = C1 - C3 (pointAdd.ts:137,139,142)
+    uint32_t r7[8], r9[8], r12[8], rcx[8], rcy[8];
+    F::sub(r7, mPkx, mT1x);
+    F::sub(r9, mPky, mT1y);
+    F::sub(r12, mT1x, mTx);
+    F::add(rcx, mTx, mT1x); F::add(rcx, rcx, mPkx);   // Cint = C3 + C1 + C2 (pointAdd.ts:151)
+    F::add(rcy, mTy, mT1y);                           // Cint = C6 + C4      (pointAdd.ts:158)
+    uint32_t r8[8], r10[8], r11[8], r13[8], m8[8], m10[8], m11[8], m13[8];
+    draw_checked<FpP256>(r8, c, b, d0 + IT_C8_R);
+    draw_checked<FpP256>(r10, c, b, d0 + IT_C10_R);
+    draw_checked<FpP256>(r11, c, b, d0 + IT_C11_R);
+    draw_checked<FpP256>(r13, c, b, d0 + IT_C13_R);
+    F::to_mont(m8, r8); F::to_mont(m10, r10); F::to_mont(m11, r11); F::to_mont(m13, r13);
+    job(it, JOB_T1X, x1, rT1x);
+    job(it, JOB_T1Y, y1, rT1y);
+    job(it, JOB_C8, i8, r8);
+    job(it, JOB_C10, i10, r10);
+    job(it, JOB_C11, i11, r11);
+    job(it, JOB_C13, i13, r13);
+    uint32_t one[8], zero[8];
+    F::set_one(one);
+    zero_n<8>(zero);
+    uint32_t* sec = c.secrets + (size_t)it * SECRETS_PER_ITEM * 8;
+    // the four MultProofs (pointAdd.ts:145-149,156): (x, y, z, rx, ry, rz)
+    for (int m = 0; m < 4; m++) {
+      const uint32_t *x, *y, *z, *rx, *ry, *rz;
+      if (m == 0)      { x = i7;  y = i8;  z = one; rx = r7;  ry = m8;  rz = zero; }
+      else if (m == 1) { x = i8;  y = i9;  z = i10; rx = m8;  ry = r9;  rz = m10; }
+      else if (m == 2) { x = i10; y = i10; z = i11; rx = m10; ry = m10; rz = m11; }
+      else             { x = i10; y = i12; z = i13; rx = m10; ry = r12; rz = m13; }
+      const int dm = d0 + item_mult_draw(m);
+      uint32_t kx[8], ky[8], kz[8], ra[8], mkx[8], t[8], u[8], r4[8];
+      draw_checked<FpP256>(kx, c, b, dm + 0);
+      draw_checked<FpP256>(ky, c, b, dm + 1);
+      draw_checked<FpP256>(kz, c, b, dm + 2);
+      F::to_mont(mkx, kx);
+      const int j0 = JOB_MULT0 + 6 * m;
+      // C4 = Cy*x = (x y) g + (x ry) h ; r4 = ry*x   (mult.ts:103-104)
+      F::mul(t, x, y);
+      F::mul(r4, x, ry);
+      F::from_mont(u, r4);
+      job(it, j0 + 0, t, u);
+      // Ax, Ay, Az, A4_1 = commit(k_x), commit(k_y), commit(k_z), commit(k_z) (mult.ts:110-113)
+      draw_checked<FpP256>(ra, c, b, dm + 3);
+      st<8>(c.s2_jv + c.s2_job(it, j0 + 1) * 8, kx); st<8>(c.s2_jr + c.s2_job(it, j0 + 1) * 8, ra);
+      draw_checked<FpP256>(ra, c, b, dm + 4);
+      st<8>(c.s2_jv + c.s2_job(it, j0 + 2) * 8, ky); st<8>(c.s2_jr + c.s2_job(it, j0 + 2) * 8, ra);
+      draw_checked<FpP256>(ra, c, b, dm + 5);
+      st<8>(c.s2_jv + c.s2_job(it, j0 + 3) * 8, kz); st<8>(c.s2_jr + c.s2_job(it, j0 + 3) * 8, ra);
+      draw_checked<FpP256>(ra, c, b, dm + 6);
+      st<8>(c.s2_jv + c.s2_job(it, j0 + 4) * 8, kz); st<8>(c.s2_jr + c.s2_job(it, j0 + 4) * 8, ra);
+      // A4_2 = Cy*k_x = (k_x y) g + (k_x ry) h   (mult.ts:114)
+      F::mul(t, mkx, y);
+      F::mul(u, mkx, ry);
+      F::from_mont(u, u);
+      job(it, j0 + 5, t, u);
+      uint32_t* sm = sec + (size_t)m * 7 * 8;
+      st<8>(sm, x); st<8>(sm + 8, y); st<8>(sm + 16, z);
+      st<8>(sm + 24, rx); st<8>(sm + 32, ry); st<8>(sm + 40, rz); st<8>(sm + 48, r4);
+    }
+    // the two EqualityProofs (pointAdd.ts:151-160): (x, r1, r2)
+    for (int e = 0; e < 2; e++) {
+      const int de = d0 + (e == 0 ? IT_EQ0 : IT_EQ1);
+      uint32_t kk[8], ra[8];
+      draw_checked<FpP256>(kk, c, b, de + 0);
+      draw_checked<FpP256>(ra, c, b, de + 1);
+      st<8>(c.s2_jv + c.s2_job(it, JOB_EQ0 + 2 * e) * 8, kk); st<8>(c.s2_jr + c.s2_job(it, JOB_EQ0 + 2 * e) * 8, ra);
+      draw_checked<FpP256>(ra, c, b, de + 2);
+      st<8>(c.s2_jv + c.s2_job(it, JOB_EQ0 + 2 * e + 1) * 8, kk); st<8>(c.s2_jr + c.s2_job(it, JOB_EQ0 + 2 * e + 1) * 8, ra);
+      uint32_t* se = sec + (size_t)(28 + 3 * e) * 8;
+      st<8>(se, e == 0 ? i11 : i13);
+      st<8>(se + 8, e == 0 ? m11 : m13);
+      st<8>(se + 16, e == 0 ? rcx : rcy);
+    }
+  }
+};
+
+// Stage 6b — derived commitments by point addition (pointAdd.ts:137-159). One thread per item.
+struct DerivedTask {
+  ProveCtx c;
+  ZK_HD void ldaff(TomPt& p, const uint32_t* aff, size_t idx) const {
+    uint32_t x[9], y[9];
+    ld<9>(x, aff + idx * TOM_AFF_WORDS);
+    ld<9>(y, aff + idx * TOM_AFF_WORDS + 9);
+    tom_from_affine(p, x, y);
+  }
+  ZK_HD void stp(size_t idx, const TomPt& p) const {
+    uint32_t* o = c.s2_proj + idx * TOM_PROJ_WORDS;
+    st<9>(o, p.x); st<9>(o + 9, p.y); st<9>(o + 18, p.z);
+  }
+  ZK_HD void operator()(int it) const {
+    const int b = c.item_b[it], i = c.item_i[it];
+    TomPt pkX, pkY, Tx, Ty, T1x, T1y, n, r;
+    ldaff(pkX, c.s1_aff, c.s1_pt(b, 0));
+    ldaff(pkY, c.s1_aff, c.s1_pt(b, 1));
+    ldaff(Tx, c.s1_aff, c.s1_pt(b, 2 + 2 * i));
+    ldaff(Ty, c.s1_aff, c.s1_pt(b, 3 + 2 * i));
+    ldaff(T1x, c.s2_aff, c.s2_job(it, JOB_T1X));
+    ldaff(T1y, c.s2_aff, c.s2_job(it, JOB_T1Y));
+    tom_neg(n, T1x); tom_add(r, pkX, n); stp(c.s2_der(it, DER_C7), r);    // C7 = C2 - C1
+    tom_neg(n, T1y); tom_add(r, pkY, n); stp(c.s2_der(it, DER_C9), r);    // C9 = C5 - C4
+    tom_neg(n, Tx);  tom_add(r, T1x, n); stp(c.s2_der(it, DER_C12), r);   // C12 = C1 - C3
+    tom_add(r, Tx, T1x); tom_add(r, r, pkX); stp(c.s2_der(it, DER_CINTX), r);
+    tom_add(r, Ty, T1y); stp(c.s2_der(it, DER_CINTY), r);
+  }
+};
+
+// Stage 7 — the six Fiat-Shamir challenges of one item (mult.ts:116, equality.ts:69).
+// One thread per (item, h).
+struct ItemHashTask {
+  ProveCtx c;
+  struct Src {
+    const ProveCtx* c;
+    size_t it;
+    int h;
+    ZK_HD const uint8_t* pt(size_t idx) const { return c->s2_bytes + idx * BSTRIDE; }
+    ZK_HD const uint8_t* operator()(int k, int& len) const {
+      len = WP;
+      const ProveCtx& C = *c;
+      if (h < 4) {
+        if (k >= 3) return pt(C.s2_job(it, JOB_MULT0 + 6 * h + (k - 3)));   // C4 Ax Ay Az A4_1 A4_2
+        // Cx, Cy, Cz per MultProof (pointAdd.ts:145-156)
+        if (h == 0) return k == 0 ? pt(C.s2_der(it, DER_C7)) : k == 1 ? pt(C.s2_job(it, JOB_C8)) : C.tg_bytes;
+        if (h == 1) return k == 0 ? pt(C.s2_job(it, JOB_C8)) : k == 1 ? pt(C.s2_der(it, DER_C9)) : pt(C.s2_job(it, JOB_C10));
+        if (h == 2) return k == 2 ? pt(C.s2_job(it, JOB_C11)) : pt(C.s2_job(it, JOB_C10));
+        return k == 0 ? pt(C.s2_job(it, JOB_C10)) : k == 1 ? pt(C.s2_der(it, DER_C12)) : pt(C.s2_job(it, JOB_C13));
+      }
+      const int e = h - 4;
+      if (k == 0) return pt(C.s2_job(it, e == 0 ? JOB_C11 : JOB_C13));
+      if (k == 1) return pt(C.s2_der(it, e == 0 ? DER_CINTX : DER_CINTY));
+      return pt(C.s2_job(it, JOB_EQ0 + 2 * e + (k - 2)));
+    }
+  };
+  ZK_HD void operator()(int t) const {
+    const size_t it = (size_t)t / HASHES_PER_ITEM;
+    const int h = t % HASHES_PER_ITEM;
+    uint32_t c3[3];
+    Src src{&c, it, h};
+    hash_points80(c3, src, h < 4 ? 9 : 4);
+    st<3>(c.item_chal + (size_t)t * 3, c3);
+  }
+};
+
+// response t = k - c*w  (mod q): k canonical, w Montgomery, c canonical 80-bit
+ZK_HD void response(uint8_t* out, const uint32_t* k_canon, const uint32_t* cc, const uint32_t* w_mont) {
+  using F = Tomq;
+  uint32_t cw[8], t[8];
+  F::mul(cw, cc, w_mont);   // c * (w R) / R = c*w, canonical
+  F::sub(t, k_canon, cw);
+  put_scalar(out, t, WS);
+}
+
+// Stage 8 — responses + byte assembly of one 0-bit repetition (exp.ts:212-225,
+// pointAdd.ts:162, mult.ts:122-130, equality.ts:73-77).  One thread per (item, part):
+// part 0..3 MultProof m, 4..5 EqualityProof e, 6 repetition header/tail.
+struct ItemEmitTask {
+  ProveCtx c;
+  ZK_HD void cp(uint8_t* dst, const uint8_t* src, int n) const {
+    for (int i = 0; i < n; i++) dst[i] = src[i];
+  }
+  ZK_HD void operator()(int t) const {
+    const size_t it = (size_t)t / 7;
+    const int part = t % 7;
+    const int b = c.item_b[it], i = c.item_i[it], k = c.item_k[it];
+    uint8_t* rep = c.proofs + (size_t)b * c.proof_stride + c.rep_off[(size_t)b * c.S + i];
+    uint8_t* body = rep + REP_HEAD;            // z z2 PointAddProof r1 r2
+    uint8_t* pa = body + 2 * NS;
+    const int d0 = draws_before_items(c.S) + DRAWS_PER_ITEM * k;
+    const uint32_t* sec = c.secrets + it * SECRETS_PER_ITEM * 8;
+    if (part < 4) {
+      const int m = part;
+      uint8_t* o = pa + 4 * WP + m * MULT_LEN;
+      for (int p = 0; p < 6; p++) cp(o + p * WP, c.s2_bytes + c.s2_job(it, JOB_MULT0 + 6 * m + p) * BSTRIDE, WP);
+      o += 6 * WP;
+      uint32_t cc[8], c3[3], kk[8], w[8];
+      ld<3>(c3, c.item_chal + (it * HASHES_PER_ITEM + m) * 3);
+      challenge_to_limbs(cc, c3);
+      const int dm = d0 + item_mult_draw(m);
+      const uint32_t* sm = sec + (size_t)m * 7 * 8;
+      // t_x t_y t_z t_rx t_ry t_rz t_r4 ; k's: kx ky kz Ax.r Ay.r Az.r A4_1.r ; w: x y z rx ry rz r4
+      for (int q = 0; q < 7; q++) {
+        tape_draw(kk, c.tape_of(b), dm + q);
+        reduce_once<FpP256>(kk);
+        ld<8>(w, sm + q * 8);
+        response(o + q * WS, kk, cc, w);
+      }
+    } else if (part < 6) {
+      const int e = part - 4;
+      uint8_t* o = pa + 4 * WP + 4 * MULT_LEN + e * EQ_LEN;
+      cp(o, c.s2_bytes + c.s2_job(it, JOB_EQ0 + 2 * e) * BSTRIDE, WP);
+      cp(o + WP, c.s2_bytes + c.s2_job(it, JOB_EQ0 + 2 * e + 1) * BSTRIDE, WP);
+      o += 2 * WP;
+      uint32_t cc[8], c3[3], kk[8], w[8];
+      ld<3>(c3, c.item_chal + (it * HASHES_PER_ITEM + 4 + e) * 3);
+      challenge_to_limbs(cc, c3);
+      const int de = d0 + (e == 0 ? IT_EQ0 : IT_EQ1);
+      const uint32_t* se = sec + (size_t)(28 + 3 * e) * 8;
+      for (int q = 0; q < 3; q++) {   // t_x = k - c x ; t_r1 = A1.r - c C1.r ; t_r2 = A2.r - c C2.r
+        tape_draw(kk, c.tape_of(b), de + q);
+        reduce_once<FpP256>(kk);
+        ld<8>(w, se + q * 8);
+        response(o + q * WS, kk, cc, w);
+      }
+    } else {
+      // z = alpha - s1, z2 = r_i - comS1.r  (mod n)  (exp.ts:186,221); r1 = T1x.r, r2 = T1y.r
+      using Fn = P256n;
+      uint32_t alpha[8], s1[8], ri[8], r0[8], z[8];
+      tape_draw(alpha, c.tape_of(b), DRAW_REP0 + DRAWS_PER_REP * i); reduce_once<FnP256>(alpha);
+      tape_draw(ri, c.tape_of(b), DRAW_REP0 + DRAWS_PER_REP * i + 1); reduce_once<FnP256>(ri);
+      tape_draw(r0, c.tape_of(b), DRAW_COMS1_R); reduce_once<FnP256>(r0);
+      ld<8>(s1, c.s1 + (size_t)b * 8);
+      Fn::sub(z, alpha, s1);
+      put_scalar(body, z, NS);
+      Fn::sub(z, ri, r0);
+      put_scalar(body + NS, z, NS);
+      cp(pa, c.s2_bytes + c.s2_job(it, JOB_C8) * BSTRIDE, WP);
+      cp(pa + WP, c.s2_bytes + c.s2_job(it, JOB_C10) * BSTRIDE, WP);
+      cp(pa + 2 * WP, c.s2_bytes + c.s2_job(it, JOB_C11) * BSTRIDE, WP);
+      cp(pa + 3 * WP, c.s2_bytes + c.s2_job(it, JOB_C13) * BSTRIDE, WP);
+      uint32_t r[8];
+      tape_draw(r, c.tape_of(b), d0 + IT_T1X_R); reduce_once<FpP256>(r);
+      put_scalar(pa + PA_LEN, r, WS);
+      tape_draw(r, c.tape_of(b), d0 + IT_T1Y_R); reduce_once<FpP256>(r);
+      put_scalar(pa + PA_LEN + WS, r, WS);
+    }
+  }
+};
+
+// Stage 8b — proof header and per-repetition heads/1-bit bodies.  One thread per (proof, slot),
+// slot in [0, S] (slot S writes the 264-byte header R comS1 keyXcom keyYcom).
+struct RepEmitTask {
+  ProveCtx c;
+  ZK_HD void cp(uint8_t* dst, const uint8_t* src, int n) const {
+    for (int i = 0; i < n; i++) dst[i] = src[i];
+  }
+  ZK_HD void operator()(int t) const {
+    const int S1 = c.S + 1;
+    const int b = t / S1, i = t % S1;
+    uint8_t* proof = c.proofs + (size_t)b * c.proof_stride;
+    if (i == c.S) {
+      cp(proof, c.r_bytes + (size_t)b * BSTRIDE, NP);
+      cp(proof + NP, c.pa_A_bytes + ((size_t)b * S1 + c.S) * BSTRIDE, NP);
+      cp(proof + 2 * NP, c.s1_bytes + c.s1_pt(b, 0) * BSTRIDE, WP);
+      cp(proof + 2 * NP + WP, c.s1_bytes + c.s1_pt(b, 1) * BSTRIDE, WP);
+      if (c.pa_A_inf[(size_t)b * S1 + c.S]) ZK_SET_STATUS(c.status + b, ZKA_ERR_IDENTITY_ENC);
+      return;
+    }
+    uint8_t* rep = proof + c.rep_off[(size_t)b * c.S + i];
+    const uint32_t bit = (c.chal[(size_t)b * 3 + (i >> 5)] >> (i & 31)) & 1u;
+    rep[0] = (uint8_t)bit;
+    cp(rep + 1, c.pa_A_bytes + ((size_t)b * S1 + i) * BSTRIDE, NP);
+    cp(rep + 1 + NP, c.s1_bytes + c.s1_pt(b, 2 + 2 * i) * BSTRIDE, WP);
+    cp(rep + 1 + NP + WP, c.s1_bytes + c.s1_pt(b, 3 + 2 * i) * BSTRIDE, WP);
+    if (bit) {   // exp.ts:170-183: alpha, r, Tx.r, Ty.r
+      uint8_t* o = rep + REP_HEAD;
+      uint32_t r[8];
+      for (int q = 0; q < 4; q++) {
+        tape_draw(r, c.tape_of(b), DRAW_REP0 + DRAWS_PER_REP * i + q);
+        if (q < 2) { reduce_once<FnP256>(r); put_scalar(o, r, NS); o += NS; }
+        else       { reduce_once<FpP256>(r); put_scalar(o, r, WS); o += WS; }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Groth-Kohlweiss membership (gk.ts:94-195), scalar variant over the ring of key x-coordinates.
+// ---------------------------------------------------------------------------------------------
+ZK_HD int gk_draw0(const ProveCtx& c, int b) { return draws_before_items(c.S) + DRAWS_PER_ITEM * (int)c.zcount[b]; }
+
+// jobs cl_i = commit(l_i, r_i), ca_i = commit(a_i, s_i), cb_i = commit(l_i a_i, t_i) (gk.ts:129-133)
+// One thread per (proof, i).
+struct GkJobsTask {
+  ProveCtx c;
+  ZK_HD void operator()(int t) const {
+    const int b = t / c.n, i = t % c.n;
+    const int d = gk_draw0(c, b) + DRAWS_PER_GK_ROUND * i;
+    uint32_t ri[8], ai[8], si[8], ti[8], v[8];
+    draw_checked<FpP256>(ri, c, b, d + 0);
+    draw_checked<FpP256>(ai, c, b, d + 1);
+    draw_checked<FpP256>(si, c, b, d + 2);
+    draw_checked<FpP256>(ti, c, b, d + 3);
+    const uint32_t bit = (c.which[b] >> i) & 1u;
+    zero_n<8>(v);
+    v[0] = bit;
+    size_t j = c.s2_gk(b, i);                        // cl_i
+    st<8>(c.s2_jv + j * 8, v); st<8>(c.s2_jr + j * 8, ri);
+    j = c.s2_gk(b, c.n + i);                         // ca_i
+    st<8>(c.s2_jv + j * 8, ai); st<8>(c.s2_jr + j * 8, si);
+    j = c.s2_gk(b, 2 * c.n + i);                     // cb_i
+    if (bit) copy_n<8>(v, ai); else zero_n<8>(v);
+    st<8>(c.s2_jv + j * 8, v); st<8>(c.s2_jr + j * 8, ti);
+  }
+};
+
+// d(omega_w) = sum_i (v_which - v_i) * prod_j (bit_j(i) ? f1j : f0j)   (gk.ts:141-171),
+// f0j = (1-l_j) w - a_j, f1j = l_j w + a_j.  One thread per (proof, w); O(3 * 2^n) modmuls,
+// products maintained incrementally over the binary counter (no inversions, no p[] array).
+// If some f0j == 0 the reference's ratio trick yields dval = 0 (invMod(0) = 0); reproduced.
+struct GkPolyTask {
+  ProveCtx c;
+  ZK_HD void operator()(int t) const {
+    using F = Tomq;
+    const int b = t / c.n, w = t % c.n;
+    const int n = c.n;
+    const int d0 = gk_draw0(c, b);
+    uint32_t f0[20][8], f1[20][8], P[21][8];
+    uint32_t wm[8], wc[8];
+    zero_n<8>(wc);
+    wc[0] = (uint32_t)w;
+    F::to_mont(wm, wc);
+    bool degenerate = false;
+    for (int j = 0; j < n; j++) {
+      uint32_t a[8], am[8];
+      draw_checked<FpP256>(a, c, b, d0 + DRAWS_PER_GK_ROUND * j + 1);
+      F::to_mont(am, a);
+      const uint32_t bit = (c.which[b] >> j) & 1u;
+      if (bit) { F::neg(f0[j], am); F::add(f1[j], wm, am); }
+      else     { F::sub(f0[j], wm, am); copy_n<8>(f1[j], am); }
+      if (is_zero_n<8>(f0[j])) degenerate = true;
+    }
+    uint32_t dval[8], vw[8];
+    zero_n<8>(dval);
+    ld<8>(vw, c.ring_m + (size_t)c.which[b] * 8);
+    if (!degenerate) {
+      F::set_one(P[n]);
+      for (int j = n - 1; j >= 0; j--) F::mul(P[j], P[j + 1], f0[j]);
+      const uint32_t total = 1u << n;
+      for (uint32_t i = 0;; ) {
+        uint32_t vi[8], df[8], term[8];
+        ld<8>(vi, c.ring_m + (size_t)i * 8);
+        F::sub(df, vw, vi);
+        F::mul(term, df, P[0]);
+        F::add(dval, dval, term);
+        i++;
+        if (i == total) break;
+        // lowest set bit of the new i: bits below it are 0, it is 1, bits above unchanged
+        int tz = 0;
+        while (!((i >> tz) & 1u)) tz++;
+        F::mul(P[tz], P[tz + 1], f1[tz]);
+        for (int j = tz - 1; j >= 0; j--) F::mul(P[j], P[j + 1], f0[j]);
+      }
+    }
+    st<8>(c.gk_dv + ((size_t)b * n + w) * 8, dval);
+  }
+};
+
+// Lagrange matrix for nodes 0..n-1 mod q (interpolate.ts:27-70): coeff_j = sum_i L[j][i] y_i.
+// One thread, once per call.
+struct GkLagrangeTask {
+  uint32_t* lag;  // [n][n][8] Montgomery
+  int n;
+  ZK_HD void operator()(int) const {
+    using F = Tomq;
+    uint32_t s[21][8];
+    uint32_t xs[20][8];
+    for (int i = 0; i < n; i++) {
+      uint32_t cidx[8];
+      zero_n<8>(cidx);
+      cidx[0] = (uint32_t)i;
+      F::to_mont(xs[i], cidx);
+    }
+    for (int i = 0; i <= n; i++) zero_n<8>(s[i]);
+    // s(x) = prod (x - x_i)
+    F::set_one(s[n]);
+    F::neg(s[n - 1], xs[0]);
+    for (int i = 1; i < n; i++) {
+      for (int j = n - i - 1; j < n - 1; j++) {
+        uint32_t t[8];
+        F::mul(t, xs[i], s[j + 1]);
+        F::sub(s[j], s[j], t);
+      }
+      F::sub(s[n - 1], s[n - 1], xs[i]);
+    }
+    for (int i = 0; i < n; i++) {
+      // phi = s'(x_i)
+      uint32_t phi[8], ff[8];
+      zero_n<8>(phi);
+      for (int j = n; j >= 1; j--) {
+        uint32_t jm[8], jc[8], t[8];
+        zero_n<8>(jc);
+        jc[0] = (uint32_t)j;
+        F::to_mont(jm, jc);
+        F::mul(t, jm, s[j]);
+        F::mul(phi, phi, xs[i]);
+        F::add(phi, phi, t);
+      }
+      F::inv(ff, phi);
+      uint32_t bb[8];
+      F::set_one(bb);
+      for (int j = n - 1; j >= 0; j--) {
+        uint32_t t[8];
+        F::mul(t, bb, ff);
+        st<8>(lag + ((size_t)j * n + i) * 8, t);
+        F::mul(t, xs[i], bb);
+        F::add(bb, s[j], t);
+      }
+    }
+  }
+};
+
+// cd_k = commit(d_k, rho_k), d = L * dv  (gk.ts:173-176).  One thread per (proof, k).
+struct GkCdJobsTask {
+  ProveCtx c;
+  ZK_HD void operator()(int t) const {
+    using F = Tomq;
+    const int b = t / c.n, k = t % c.n;
+    uint32_t acc[8];
+    zero_n<8>(acc);
+    for (int i = 0; i < c.n; i++) {
+      uint32_t l[8], y[8], m[8];
+      ld<8>(l, c.gk_lag + ((size_t)k * c.n + i) * 8);
+      ld<8>(y, c.gk_dv + ((size_t)b * c.n + i) * 8);
+      F::mul(m, l, y);
+      F::add(acc, acc, m);
+    }
+    uint32_t v[8], rho[8];
+    F::from_mont(v, acc);
+    draw_checked<FpP256>(rho, c, b, gk_draw0(c, b) + DRAWS_PER_GK_ROUND * k + 4);
+    const size_t j = c.s2_gk(b, 3 * c.n + k);
+    st<8>(c.s2_jv + j * 8, v);
+    st<8>(c.s2_jr + j * 8, rho);
+  }
+};
+
+// x = H(cl, ca, cb, cd) (gk.ts:179-180), responses (gk.ts:184-192) and GK bytes.  Per proof.
+struct GkEmitTask {
+  ProveCtx c;
+  struct Src {
+    const ProveCtx* c;
+    int b;
+    ZK_HD const uint8_t* operator()(int k, int& len) const {
+      len = WP;
+      return c->s2_bytes + c->s2_gk(b, k) * BSTRIDE;
+    }
+  };
+  ZK_HD void operator()(int b) const {
+    using F = Tomq;
+    const int n = c.n;
+    uint32_t c3[3], xc[8], xm[8];
+    Src src{&c, b};
+    hash_points80(c3, src, 4 * n);
+    st<3>(c.gk_x + (size_t)b * 3, c3);
+    challenge_to_limbs(xc, c3);
+    F::to_mont(xm, xc);
+    uint8_t* o = c.proofs + (size_t)b * c.proof_stride + c.gk_off[b];
+    *o++ = (uint8_t)n;
+    for (int k = 0; k < 4 * n; k++) {
+      const uint8_t* s = c.s2_bytes + c.s2_gk(b, k) * BSTRIDE;
+      for (int q = 0; q < WP; q++) o[q] = s[q];
+      o += WP;
+    }
+    uint8_t* of = o;
+    uint8_t* oza = o + (size_t)n * WS;
+    uint8_t* ozb = o + (size_t)2 * n * WS;
+    uint8_t* ozd = o + (size_t)3 * n * WS;
+    const int d0 = gk_draw0(c, b);
+    uint32_t zd[8], xp[8], t[8], u[8];
+    // zd = pkX.r * x^n - sum rho_i x^i
+    F::set_one(xp);
+    zero_n<8>(zd);
+    for (int i = 0; i < n; i++) {
+      uint32_t ri[8], ai[8], si[8], ti[8], rho[8];
+      tape_draw(ri, c.tape_of(b), d0 + 5 * i + 0); reduce_once<FpP256>(ri);
+      tape_draw(ai, c.tape_of(b), d0 + 5 * i + 1); reduce_once<FpP256>(ai);
+      tape_draw(si, c.tape_of(b), d0 + 5 * i + 2); reduce_once<FpP256>(si);
+      tape_draw(ti, c.tape_of(b), d0 + 5 * i + 3); reduce_once<FpP256>(ti);
+      tape_draw(rho, c.tape_of(b), d0 + 5 * i + 4); reduce_once<FpP256>(rho);
+      const uint32_t bit = (c.which[b] >> i) & 1u;
+      // f_i = l_i x + a_i
+      uint32_t f[8];
+      if (bit) F::add(f, xc, ai); else copy_n<8>(f, ai);
+      put_scalar(of + (size_t)i * WS, f, WS);
+      // za_i = r_i x + s_i
+      F::mul(t, ri, xm);          // canonical r_i * x
+      F::add(u, t, si);
+      put_scalar(oza + (size_t)i * WS, u, WS);
+      // zb_i = r_i (x - f_i) + t_i
+      F::sub(u, xc, f);
+      F::to_mont(u, u);
+      F::mul(t, ri, u);
+      F::add(u, t, ti);
+      put_scalar(ozb + (size_t)i * WS, u, WS);
+      // zd -= rho_i x^i   (xp = x^i in Montgomery form)
+      F::mul(t, rho, xp);
+      F::sub(zd, zd, t);
+      F::mul(xp, xp, xm);
+    }
+    uint32_t rpk[8];
+    tape_draw(rpk, c.tape_of(b), DRAW_PKX_R); reduce_once<FpP256>(rpk);
+    F::mul(t, rpk, xp);           // pkX.r * x^n
+    F::add(zd, zd, t);
+    put_scalar(ozd, zd, WS);
+  }
+};
+
+// ring bytes -> Montgomery residues mod q, padded to 2^n with ring[0] (gk.ts:75-86)
+struct RingPrepTask {
+  const uint8_t* ring;  // [N][32]
+  uint32_t* ring_m;     // [2^n][8]
+  int N;
+  ZK_HD void operator()(int i) const {
+    const int src = i < N ? i : 0;
+    uint32_t v[8], m[8];
+    limbs_from_be<8>(v, ring + (size_t)src * 32, 32);
+    reduce_once<FpP256>(v);
+    Tomq::to_mont(m, v);
+    st<8>(ring_m + (size_t)i * 8, m);
+  }
+};
+
+}  // namespace zk

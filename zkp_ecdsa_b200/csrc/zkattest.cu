@@ -1,0 +1,758 @@
+// zkattest.cu — host orchestration + C ABI (include/zkattest.h) of libzkattest.
+//
+// One context = one CUDA device + one stream + a grow-only workspace.  A prove/verify call
+// is a fixed sequence of ~25 batch kernels over flat arrays in HBM; there is no CPU compute
+// path (the ZKA_HOSTSIM build of this file exists only for the CPU unit tests, see
+// zk_launch.cuh).
+#include "zkattest.h"
+
+#include <math.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "zk_launch.cuh"
+#include "zk_prove.cuh"
+#include "zk_verify.cuh"
+
+namespace zk {
+// ---- small helper tasks of the C ABI layer (namespace scope: kernel template arguments) ----
+struct ParsePointsTask {   // host bytes -> affine Montgomery (+ validity), used for params / sub-ops
+  const uint8_t* nist;   // [count][65] or null
+  const uint8_t* tom;    // [count][67] or null
+  uint32_t* nist_aff;    // [count][16]
+  uint32_t* tom_aff;     // [count][18]
+  uint8_t* bad;          // [count]
+  uint8_t* inf;          // [count] (P-256 identity given as 65 zero bytes)
+  ZK_HD void operator()(int t) const {
+    if (nist) {
+      const uint8_t* b = nist + (size_t)t * 65;
+      uint32_t x[8], y[8];
+      limbs_from_be<8>(x, b + 1, 32);
+      limbs_from_be<8>(y, b + 33, 32);
+      bool allz = (b[0] == 0) && is_zero_n<8>(x) && is_zero_n<8>(y);
+      reduce_once<FpP256>(x);
+      reduce_once<FpP256>(y);
+      P256Aff a;
+      P256p::to_mont(a.x, x);
+      P256p::to_mont(a.y, y);
+      bool ok = allz || (b[0] == 0x04 && p256_on_curve(a.x, a.y));
+      if (!ok || allz) p256_set_generator(a);
+      p256_st_aff(nist_aff + (size_t)t * 16, a);
+      if (bad) bad[t] = ok ? 0 : 1;
+      if (inf) inf[t] = allz ? 1 : 0;
+    }
+    if (tom) {
+      const uint8_t* b = tom + (size_t)t * 67;
+      uint32_t x[9], y[9], sa[9];
+      limbs_from_be<9>(x, b + 1, 33);
+      limbs_from_be<9>(y, b + 34, 33);
+      bool ok = (b[0] == 0x04) && lt_p<FpTom>(x) && lt_p<FpTom>(y);   // edwards.ts:75-76 verifyPosRange
+      uint32_t xm[9], ym[9];
+      Tomp::to_mont(xm, x);
+      Tomp::to_mont(ym, y);
+      tom_const(sa, TOM_SQRTA);
+      Tomp::mul(xm, xm, sa);   // to the a'=1 image curve
+      ok = ok && tom_on_curve(xm, ym);
+      if (!ok) { tom_const(xm, TOM_GX1); tom_const(ym, TOM_GY); }
+      st<9>(tom_aff + (size_t)t * 18, xm);
+      st<9>(tom_aff + (size_t)t * 18 + 9, ym);
+      if (bad) bad[t] = ok ? 0 : 1;
+    }
+  }
+};
+
+struct GenAffTask {   // generator constants -> device
+  uint32_t* p256_g;   // [16]
+  uint32_t* tom_g;    // [18]
+  ZK_HD void operator()(int) const {
+    P256Aff g;
+    p256_set_generator(g);
+    p256_st_aff(p256_g, g);
+    uint32_t x[9], y[9];
+    tom_const(x, TOM_GX1);
+    tom_const(y, TOM_GY);
+    st<9>(tom_g, x);
+    st<9>(tom_g + 9, y);
+  }
+};
+
+template <class F, int NB>
+struct FieldOpTask {
+  const uint8_t *a, *b;
+  uint8_t* out;
+  int op;
+  ZK_HD void operator()(int t) const {
+    constexpr int N = F::N;
+    uint32_t x[N], y[N], r[N];
+    limbs_from_be<N>(x, a + (size_t)t * NB, NB);
+    zero_n<N>(y);
+    if (b) limbs_from_be<N>(y, b + (size_t)t * NB, NB);
+    F::to_mont(x, x);
+    F::to_mont(y, y);
+    if (op == 0) F::mul(r, x, y);
+    else if (op == 1) F::add(r, x, y);
+    else if (op == 2) F::sub(r, x, y);
+    else F::inv(r, x);
+    F::from_mont(r, r);
+    limbs_to_be<N>(out + (size_t)t * NB, r, NB);
+  }
+};
+struct GProjTask {
+  const uint32_t* g;
+  uint32_t* proj;
+  ZK_HD void operator()(int) const {
+    uint32_t one[9];
+    Tomp::set_one(one);
+    st<9>(proj, g);
+    st<9>(proj + 9, g + 9);
+    st<9>(proj + 18, one);
+  }
+};
+
+struct CommitConvTask {
+  const uint8_t *v, *r;
+  uint32_t *jv, *jr;
+  ZK_HD void operator()(int t) const {
+    uint32_t a[8];
+    limbs_from_be<8>(a, v + (size_t)t * 32, 32);
+    reduce_once<FpP256>(a);
+    st<8>(jv + (size_t)t * 8, a);
+    limbs_from_be<8>(a, r + (size_t)t * 32, 32);
+    reduce_once<FpP256>(a);
+    st<8>(jr + (size_t)t * 8, a);
+  }
+};
+
+struct PackTomTask {
+  const uint8_t* bytes;
+  uint8_t* out;
+  ZK_HD void operator()(int t) const {
+    for (int i = 0; i < WP; i++) out[(size_t)t * WP + i] = bytes[(size_t)t * BSTRIDE + i];
+  }
+};
+
+struct P256MulTask {
+  const uint8_t* k;
+  const uint32_t* g8;
+  const uint32_t* rtab;
+  const uint8_t* binf;
+  uint32_t* proj;
+  ZK_HD void operator()(int t) const {
+    uint32_t s[8];
+    limbs_from_be<8>(s, k + (size_t)t * 32, 32);
+    reduce_once<FnP256>(s);
+    P256Pt acc;
+    p256_set_identity(acc);
+    if (rtab) {
+      if (!binf[t]) p256_accum_tab4(acc, rtab + (size_t)t * 64 * 16 * P256_AFF_WORDS, s);
+    } else {
+      p256_accum_fixed8(acc, g8, s);
+    }
+    p256_st_proj(proj + (size_t)t * P256_PROJ_WORDS, acc);
+  }
+};
+
+struct PackP256Task {
+  const uint8_t* bytes;
+  uint8_t* out;
+  ZK_HD void operator()(int t) const {
+    for (int i = 0; i < NP; i++) out[(size_t)t * NP + i] = bytes[(size_t)t * BSTRIDE + i];
+  }
+};
+
+struct Hash80Task {
+  const uint8_t* m;
+  size_t stride;
+  const uint32_t* len;
+  uint8_t* out;
+  ZK_HD void operator()(int t) const {
+    Sha256 h;
+    h.init();
+    h.update(m + (size_t)t * stride, (int)len[t]);
+    uint32_t c3[3];
+    h.final80(c3);
+    uint8_t* o = out + (size_t)t * 10;
+    o[0] = (uint8_t)(c3[2] >> 8); o[1] = (uint8_t)c3[2];
+    for (int i = 0; i < 4; i++) { o[2 + i] = (uint8_t)(c3[1] >> (24 - 8 * i)); o[6 + i] = (uint8_t)(c3[0] >> (24 - 8 * i)); }
+  }
+};
+
+struct GenConvTask {
+  const uint8_t* v;
+  uint32_t *jv, *jr;
+  ZK_HD void operator()(int) const {
+    uint32_t a[8];
+    limbs_from_be<8>(a, v, 32);
+    reduce_once<FpP256>(a);
+    st<8>(jv, a);
+    zero_n<8>(a);
+    st<8>(jr, a);
+  }
+};
+
+struct KeyToIntTask {
+  const uint32_t* aff;
+  const uint8_t *bad, *inf;
+  uint8_t* x;
+  int32_t* status;
+  ZK_HD void operator()(int t) const {
+    uint32_t c[8];
+    P256p::from_mont(c, aff + (size_t)t * 16);
+    limbs_to_be<8>(x + (size_t)t * 32, c, 32);
+    status[t] = (bad[t] || inf[t]) ? ZKA_ERR_INVALID_PK : ZKA_OK;
+  }
+};
+
+}  // namespace zk
+
+using namespace zk;
+
+namespace {
+
+struct FixedTable {   // positional table of one base point
+  DevBuf buf;
+  uint32_t* tab = nullptr;
+};
+
+}  // namespace
+
+struct zka_ctx {
+  int device = 0;
+  Stream st;
+  std::string err;
+  int tom_w = 8, tom_nwin = 32;
+  int chunk = 2048;
+  FixedTable g8;          // P-256 generator, w=8 [32][256][16]
+  FixedTable tg;          // tomEdwards256 generator [nwin][2^w][32]
+  DevBuf tg_bytes;        // 67-byte encoding of g
+  // workspace (grow-only)
+  DevBuf w[64];
+  DevBuf in[8], out[4];
+};
+
+struct zka_params {
+  zka_ctx* ctx = nullptr;
+  uint32_t sec_level = 80;
+  FixedTable h8;          // NistGroup.h  w=8 table
+  FixedTable th;          // ProofGroup.h table
+  uint8_t h_nist[65];
+  uint8_t h_proof[67];
+};
+
+namespace {
+
+int fail(zka_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int ceil_log2(uint32_t v) {
+  int n = 0;
+  while ((1ull << n) < v) n++;
+  return n;
+}
+
+// ---- table construction -------------------------------------------------------------------
+// P-256 w=8 positional table from one affine Montgomery base (device pointer, 16 words)
+void build_p256_tab8(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) {
+  Stream& st = ctx->st;
+  DevBuf pows, rows;
+  uint32_t* d_pows = pows.get<uint32_t>((size_t)32 * P256_PROJ_WORDS);
+  uint32_t* d_rows = rows.get<uint32_t>((size_t)32 * 256 * P256_PROJ_WORDS);
+  out.tab = out.buf.get<uint32_t>((size_t)32 * 256 * P256_AFF_WORDS);
+  launch(st, 1, P256PowsTask{base_aff_dev, nullptr, d_pows, 1, 32, 8});
+  launch(st, 32, P256RowsTask{d_pows, d_rows, 8});
+  const int count = 32 * 256;
+  launch(st, (count + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{d_rows, out.tab, nullptr, nullptr, count});
+  sync(st);
+  pows.release();
+  rows.release();
+}
+// tomEdwards256 positional table [nwin][2^w] from one image-curve affine base (18 words, device)
+void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) {
+  Stream& st = ctx->st;
+  const int w = ctx->tom_w, nwin = ctx->tom_nwin;
+  const size_t ne = (size_t)1 << w, count = (size_t)nwin * ne;
+  DevBuf pows, rows, aff;
+  uint32_t* d_pows = pows.get<uint32_t>((size_t)nwin * 36);
+  uint32_t* d_rows = rows.get<uint32_t>(count * TOM_PROJ_WORDS);
+  uint32_t* d_aff = aff.get<uint32_t>(count * TOM_AFF_WORDS);
+  out.tab = out.buf.get<uint32_t>(count * TOM_PRE_WORDS);
+  launch(st, 1, TomPowsTask{base_aff_dev, d_pows, 1, nwin, w});
+  launch(st, nwin, TomRowsTask{d_pows, d_rows, w});
+  launch(st, (long long)(count + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{d_rows, d_aff, nullptr, (int)count});
+  launch(st, (long long)count, TomPreTask{d_aff, out.tab});
+  sync(st);
+  pows.release();
+  rows.release();
+  aff.release();
+}
+
+// stage a caller buffer on the device if it is a host pointer
+template <class T>
+const T* stage_in(zka_ctx* ctx, DevBuf& buf, const T* p, size_t count) {
+  if (!p || count == 0) return p;
+  if (is_device_ptr(p)) return p;
+  T* d = buf.get<T>(count);
+  copy_h2d(ctx->st, d, p, count * sizeof(T));
+  return d;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int zka_version(void) { return 1; }
+
+const char* zka_last_error(const zka_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+uint64_t zka_launch_count(const zka_ctx* ctx) { return ctx ? ctx->st.launches : 0; }
+
+int zka_init(int device, zka_ctx** out) {
+  if (!out) return ZKA_E_ARG;
+  *out = nullptr;
+  zka_ctx* ctx = new zka_ctx();
+  try {
+#if !defined(ZKA_HOSTSIM)
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device >= ndev) {
+      cudaGetLastError();
+      delete ctx;
+      return ZKA_E_CUDA;   // no GPU: fail loudly, there is no CPU fallback
+    }
+    ZK_CUDA_CHECK(cudaSetDevice(device));
+    ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->st.s, cudaStreamNonBlocking));
+#endif
+    ctx->device = device;
+    if (const char* e = getenv("ZKA_TOM_W")) {
+      int w = atoi(e);
+      if (w >= 2 && w <= 14) ctx->tom_w = w;
+    }
+    ctx->tom_nwin = (256 + ctx->tom_w - 1) / ctx->tom_w;
+    if (const char* e = getenv("ZKA_CHUNK")) {
+      int c = atoi(e);
+      if (c >= 1) ctx->chunk = c;
+    }
+    DevBuf gen;
+    uint32_t* d_gen = gen.get<uint32_t>(16 + 18);
+    launch(ctx->st, 1, GenAffTask{d_gen, d_gen + 16});
+    build_p256_tab8(ctx, d_gen, ctx->g8);
+    build_tom_tab(ctx, d_gen + 16, ctx->tg);
+    // encoding of g (C_14 = params.g in pi_8, pointAdd.ts:144,220): normalise the table entry 1*g
+    DevBuf proj, aff;
+    uint32_t* d_proj = proj.get<uint32_t>(TOM_PROJ_WORDS);
+    uint32_t* d_aff = aff.get<uint32_t>(TOM_AFF_WORDS);
+    uint8_t* d_bytes = ctx->tg_bytes.get<uint8_t>(BSTRIDE);
+    launch(ctx->st, 1, GProjTask{d_gen + 16, d_proj});
+    launch(ctx->st, 1, TomNormTask{d_proj, d_aff, d_bytes, 1});
+    sync(ctx->st);
+    gen.release();
+    proj.release();
+    aff.release();
+  } catch (const std::exception& e) {
+    fprintf(stderr, "zka_init: %s\n", e.what());
+    delete ctx;
+    return ZKA_E_CUDA;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void zka_shutdown(zka_ctx* ctx) {
+  if (!ctx) return;
+  ctx->g8.buf.release();
+  ctx->tg.buf.release();
+  ctx->tg_bytes.release();
+  for (auto& b : ctx->w) b.release();
+  for (auto& b : ctx->in) b.release();
+  for (auto& b : ctx->out) b.release();
+#if !defined(ZKA_HOSTSIM)
+  if (ctx->st.s) cudaStreamDestroy(ctx->st.s);
+#endif
+  delete ctx;
+}
+
+int zka_params_create(zka_ctx* ctx, const uint8_t h_nist[65], const uint8_t h_proof[67], uint32_t sec_level,
+                      zka_params** out) {
+  if (!ctx || !h_nist || !h_proof || !out) return ZKA_E_ARG;
+  if (sec_level < 1 || sec_level > MAX_REPS) return fail(ctx, ZKA_E_ARG, "sec_level must be in [1,80]");
+  try {
+    zka_params* P = new zka_params();
+    P->ctx = ctx;
+    P->sec_level = sec_level;
+    memcpy(P->h_nist, h_nist, 65);
+    memcpy(P->h_proof, h_proof, 67);
+    DevBuf bn, bt, an, at, bad, inf;
+    uint8_t* d_bn = bn.get<uint8_t>(65);
+    uint8_t* d_bt = bt.get<uint8_t>(67);
+    uint32_t* d_an = an.get<uint32_t>(16);
+    uint32_t* d_at = at.get<uint32_t>(18);
+    uint8_t* d_bad = bad.get<uint8_t>(2);
+    uint8_t* d_inf = inf.get<uint8_t>(1);
+    copy_h2d(ctx->st, d_bn, h_nist, 65);
+    copy_h2d(ctx->st, d_bt, h_proof, 67);
+    launch(ctx->st, 1, ParsePointsTask{d_bn, nullptr, d_an, nullptr, d_bad, d_inf});
+    launch(ctx->st, 1, ParsePointsTask{nullptr, d_bt, nullptr, d_at, d_bad + 1, nullptr});
+    uint8_t hb[3];
+    copy_d2h(ctx->st, hb, d_bad, 2);
+    copy_d2h(ctx->st, hb + 2, d_inf, 1);
+    sync(ctx->st);
+    if (hb[0] || hb[1] || hb[2]) {
+      delete P;
+      return fail(ctx, ZKA_E_ARG, "params: h point not on its group");
+    }
+    build_p256_tab8(ctx, d_an, P->h8);
+    build_tom_tab(ctx, d_at, P->th);
+    for (DevBuf* b : {&bn, &bt, &an, &at, &bad, &inf}) b->release();
+    *out = P;
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+void zka_params_destroy(zka_params* P) {
+  if (!P) return;
+  P->h8.buf.release();
+  P->th.buf.release();
+  delete P;
+}
+
+size_t zka_proof_max_len(uint32_t ring_size, uint32_t sec_level) {
+  return (size_t)proof_len((int)sec_level, ceil_log2(ring_size), (int)sec_level);
+}
+size_t zka_prove_tape_len(uint32_t ring_size, uint32_t sec_level) {
+  return (size_t)32 * prove_draws((int)sec_level, ceil_log2(ring_size), (int)sec_level);
+}
+size_t zka_verify_tape_len(uint32_t ring_size, uint32_t sec_level) {
+  return verify_tape_len(ceil_log2(ring_size), (int)sec_level);
+}
+
+// ------------------------------------------------------------------------------ sub-ops
+int zka_tom_commit_batch(zka_ctx* ctx, const zka_params* P, uint32_t count, const uint8_t* v, const uint8_t* r,
+                         uint8_t* out) {
+  if (!ctx || !P || !v || !r || !out) return ZKA_E_ARG;
+  if (count == 0) return 0;
+  try {
+    Stream& st = ctx->st;
+    const uint8_t* dv = stage_in(ctx, ctx->in[0], v, (size_t)count * 32);
+    const uint8_t* dr = stage_in(ctx, ctx->in[1], r, (size_t)count * 32);
+    uint32_t* jv = ctx->w[0].get<uint32_t>((size_t)count * 8);
+    uint32_t* jr = ctx->w[1].get<uint32_t>((size_t)count * 8);
+    uint32_t* proj = ctx->w[2].get<uint32_t>((size_t)count * TOM_PROJ_WORDS);
+    uint32_t* aff = ctx->w[3].get<uint32_t>((size_t)count * TOM_AFF_WORDS);
+    uint8_t* bytes = ctx->w[4].get<uint8_t>((size_t)count * BSTRIDE);
+    launch(st, count, CommitConvTask{dv, dr, jv, jr});
+    launch(st, count, TomCommitTask{jv, jr, ctx->tg.tab, P->th.tab, proj, ctx->tom_w, ctx->tom_nwin});
+    launch(st, (count + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{proj, aff, bytes, (int)count});
+    if (is_device_ptr(out)) {
+      launch(st, count, PackTomTask{bytes, out});
+    } else {
+      uint8_t* packed = ctx->out[0].get<uint8_t>((size_t)count * WP);
+      launch(st, count, PackTomTask{bytes, packed});
+      copy_d2h(st, out, packed, (size_t)count * WP);
+    }
+    sync(st);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+int zka_p256_mul_batch(zka_ctx* ctx, uint32_t count, const uint8_t* base, const uint8_t* k, uint8_t* out) {
+  if (!ctx || !k || !out) return ZKA_E_ARG;
+  if (count == 0) return 0;
+  try {
+    Stream& st = ctx->st;
+    const uint8_t* dk = stage_in(ctx, ctx->in[0], k, (size_t)count * 32);
+    const uint8_t* db = base ? stage_in(ctx, ctx->in[1], base, (size_t)count * 65) : nullptr;
+    uint32_t* proj = ctx->w[0].get<uint32_t>((size_t)count * P256_PROJ_WORDS);
+    uint32_t* aff = ctx->w[1].get<uint32_t>((size_t)count * P256_AFF_WORDS);
+    uint8_t* bytes = ctx->w[2].get<uint8_t>((size_t)count * BSTRIDE);
+    uint8_t* inf = ctx->w[3].get<uint8_t>(count);
+    uint32_t* rtab = nullptr;
+    uint8_t* binf = nullptr;
+    if (db) {
+      // per-base w=4 positional tables: the same path the prover uses for R (PhaseAP256Task)
+      uint32_t* baff = ctx->w[4].get<uint32_t>((size_t)count * 16);
+      uint8_t* bad = ctx->w[5].get<uint8_t>(count);
+      binf = ctx->w[6].get<uint8_t>(count);
+      uint32_t* pows = ctx->w[7].get<uint32_t>((size_t)count * 64 * P256_PROJ_WORDS);
+      uint32_t* rows = ctx->w[8].get<uint32_t>((size_t)count * 64 * 16 * P256_PROJ_WORDS);
+      rtab = ctx->w[9].get<uint32_t>((size_t)count * 64 * 16 * P256_AFF_WORDS);
+      launch(st, count, ParsePointsTask{db, nullptr, baff, nullptr, bad, binf});
+      launch(st, count, P256PowsTask{baff, binf, pows, (int)count, 64, 4});
+      launch(st, (long long)count * 64, P256RowsTask{pows, rows, 4});
+      const long long np = (long long)count * 64 * 16;
+      launch(st, (np + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{rows, rtab, nullptr, nullptr, (int)np});
+    }
+    launch(st, count, P256MulTask{dk, ctx->g8.tab, rtab, binf, proj});
+    launch(st, (count + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{proj, aff, bytes, inf, (int)count});
+    if (is_device_ptr(out)) {
+      launch(st, count, PackP256Task{bytes, out});
+    } else {
+      uint8_t* packed = ctx->out[0].get<uint8_t>((size_t)count * NP);
+      launch(st, count, PackP256Task{bytes, packed});
+      copy_d2h(st, out, packed, (size_t)count * NP);
+    }
+    sync(st);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+
+int zka_field_op_batch(zka_ctx* ctx, int field, int op, uint32_t count, const uint8_t* a, const uint8_t* b,
+                       uint8_t* out) {
+  if (!ctx || !a || !out || field < 0 || field > 2 || op < 0 || op > 3 || (op < 3 && !b)) return ZKA_E_ARG;
+  if (count == 0) return 0;
+  try {
+    Stream& st = ctx->st;
+    const int nb = field == 2 ? 33 : 32;
+    const uint8_t* da = stage_in(ctx, ctx->in[0], a, (size_t)count * nb);
+    const uint8_t* db = b ? stage_in(ctx, ctx->in[1], b, (size_t)count * nb) : nullptr;
+    uint8_t* dout = is_device_ptr(out) ? out : ctx->out[0].get<uint8_t>((size_t)count * nb);
+    if (field == 0) launch(st, count, FieldOpTask<P256p, 32>{da, db, dout, op});
+    else if (field == 1) launch(st, count, FieldOpTask<P256n, 32>{da, db, dout, op});
+    else launch(st, count, FieldOpTask<Tomp, 33>{da, db, dout, op});
+    if (dout != out) copy_d2h(st, out, dout, (size_t)count * nb);
+    sync(st);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+int zka_hash80_batch(zka_ctx* ctx, uint32_t count, const uint8_t* msgs, size_t msg_stride, const uint32_t* len,
+                     uint8_t* out) {
+  if (!ctx || !msgs || !len || !out) return ZKA_E_ARG;
+  if (count == 0) return 0;
+  try {
+    Stream& st = ctx->st;
+    const uint8_t* dm = stage_in(ctx, ctx->in[0], msgs, (size_t)count * msg_stride);
+    const uint32_t* dl = stage_in(ctx, ctx->in[1], len, (size_t)count);
+    uint8_t* dout = is_device_ptr(out) ? out : ctx->out[0].get<uint8_t>((size_t)count * 10);
+    launch(st, count, Hash80Task{dm, msg_stride, dl, dout});
+    if (dout != out) copy_d2h(st, out, dout, (size_t)count * 10);
+    sync(st);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+int zka_params_generate(zka_ctx* ctx, const uint8_t rnd[64], uint8_t h_nist[65], uint8_t h_proof[67]) {
+  if (!ctx || !rnd || !h_nist || !h_proof) return ZKA_E_ARG;
+  try {
+    // h_nist = G * rnd0 (pedersen.ts:66-67 on p256); h_proof = g * rnd1 + 0 * g
+    int rc = zka_p256_mul_batch(ctx, 1, nullptr, rnd, h_nist);
+    if (rc) return rc;
+    Stream& st = ctx->st;
+    uint32_t* jv = ctx->w[0].get<uint32_t>(8);
+    uint32_t* jr = ctx->w[1].get<uint32_t>(8);
+    uint32_t* proj = ctx->w[2].get<uint32_t>(TOM_PROJ_WORDS);
+    uint32_t* aff = ctx->w[3].get<uint32_t>(TOM_AFF_WORDS);
+    uint8_t* bytes = ctx->w[4].get<uint8_t>(BSTRIDE);
+    uint8_t* d_rnd = ctx->in[0].get<uint8_t>(32);
+    copy_h2d(st, d_rnd, rnd + 32, 32);
+    launch(st, 1, GenConvTask{d_rnd, jv, jr});
+    // v*g + 0*g: use the g table for both bases
+    launch(st, 1, TomCommitTask{jv, jr, ctx->tg.tab, ctx->tg.tab, proj, ctx->tom_w, ctx->tom_nwin});
+    launch(st, 1, TomNormTask{proj, aff, bytes, 1});
+    copy_d2h(st, h_proof, bytes, 67);
+    sync(st);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+int zka_key_to_int(zka_ctx* ctx, uint32_t count, const uint8_t* pk, uint8_t* x_out, int32_t* status) {
+  if (!ctx || !pk || !x_out) return ZKA_E_ARG;
+  if (count == 0) return 0;
+  try {
+    Stream& st = ctx->st;
+    const uint8_t* dp = stage_in(ctx, ctx->in[0], pk, (size_t)count * 65);
+    uint32_t* aff = ctx->w[0].get<uint32_t>((size_t)count * 16);
+    uint8_t* bad = ctx->w[1].get<uint8_t>(count);
+    uint8_t* inf = ctx->w[2].get<uint8_t>(count);
+    uint8_t* dx = ctx->out[0].get<uint8_t>((size_t)count * 32);
+    int32_t* ds = ctx->out[1].get<int32_t>(count);
+    launch(st, count, ParsePointsTask{dp, nullptr, aff, nullptr, bad, inf});
+    launch(st, count, KeyToIntTask{aff, bad, inf, dx, ds});
+    if (is_device_ptr(x_out)) copy_d2d(st, x_out, dx, (size_t)count * 32); else copy_d2h(st, x_out, dx, (size_t)count * 32);
+    if (status) {
+      if (is_device_ptr(status)) copy_d2d(st, status, ds, (size_t)count * 4); else copy_d2h(st, status, ds, (size_t)count * 4);
+    }
+    sync(st);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+// ------------------------------------------------------------------------------- prove
+int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* sig,
+                    const uint8_t* pk, const uint32_t* which, const uint8_t* ring, uint32_t N, const uint8_t* tape,
+                    size_t tape_stride, uint8_t* proofs, size_t proof_stride, uint32_t* proof_len_out,
+                    int32_t* status) {
+  if (!ctx || !P || !msg_hash || !sig || !pk || !which || !ring || !tape || !proofs || !proof_len_out || !status)
+    return ZKA_E_ARG;
+  if (B == 0) return 0;
+  // N = 1 makes hashPoints([]) throw in the reference (group.ts:223 reduce of an empty array)
+  if (N < 2 || N > (1u << 20)) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
+  const int S = (int)P->sec_level;
+  const int n = ceil_log2(N);
+  if (proof_stride < zka_proof_max_len(N, S)) return fail(ctx, ZKA_E_ARG, "proof_stride < zka_proof_max_len");
+  if (tape_stride < (size_t)32 * prove_draws(0, n, S)) return fail(ctx, ZKA_E_ARG, "tape_stride too small");
+  try {
+    Stream& st = ctx->st;
+    DevBuf* W = ctx->w;
+    // ring: once per call
+    const uint8_t* d_ring = stage_in(ctx, ctx->in[5], ring, (size_t)N * 32);
+    uint32_t* ring_m = W[40].get<uint32_t>(((size_t)1 << n) * 8);
+    launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
+    uint32_t* lag = W[41].get<uint32_t>((size_t)n * n * 8);
+    launch(st, 1, GkLagrangeTask{lag, n});
+
+    const bool out_dev = is_device_ptr(proofs);
+    for (uint32_t b0 = 0; b0 < B; b0 += (uint32_t)ctx->chunk) {
+      const int Bc = (int)std::min<uint32_t>((uint32_t)ctx->chunk, B - b0);
+      ProveCtx c;
+      memset(&c, 0, sizeof(c));
+      c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.M = 0;
+      c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
+      c.msg_hash = stage_in(ctx, ctx->in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
+      c.sig = stage_in(ctx, ctx->in[1], sig + (size_t)b0 * 64, (size_t)Bc * 64);
+      c.pk = stage_in(ctx, ctx->in[2], pk + (size_t)b0 * 65, (size_t)Bc * 65);
+      c.which = stage_in(ctx, ctx->in[3], which + b0, (size_t)Bc);
+      c.tape = stage_in(ctx, ctx->in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      c.tape_stride = tape_stride;
+      c.tape_draws = (uint32_t)(tape_stride / 32);
+      c.ring_m = ring_m;
+      c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab;
+      c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
+      c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
+      const size_t S1 = (size_t)S + 1;
+      const size_t nA = (size_t)Bc * S1;
+      const size_t n1 = (size_t)Bc * (2 + 2 * S);
+      c.s1 = W[0].get<uint32_t>((size_t)Bc * 8);
+      c.pk_aff = W[1].get<uint32_t>((size_t)Bc * 16);
+      c.q_aff = W[2].get<uint32_t>((size_t)Bc * 16);
+      c.q_inf = W[3].get<uint8_t>(Bc);
+      c.r_aff = W[4].get<uint32_t>((size_t)Bc * 16);
+      c.r_bytes = W[5].get<uint8_t>((size_t)Bc * BSTRIDE);
+      c.rpows = W[6].get<uint32_t>((size_t)Bc * 64 * P256_PROJ_WORDS);
+      c.rrows = W[7].get<uint32_t>((size_t)Bc * 64 * 16 * P256_PROJ_WORDS);
+      c.rtab = W[8].get<uint32_t>((size_t)Bc * 64 * 16 * P256_AFF_WORDS);
+      c.pa_T = W[9].get<uint32_t>(nA * P256_PROJ_WORDS);
+      c.pa_A = W[10].get<uint32_t>(nA * P256_PROJ_WORDS);
+      c.pa_T_aff = W[11].get<uint32_t>(nA * 16);
+      c.pa_T_inf = W[12].get<uint8_t>(nA);
+      c.pa_A_aff = W[13].get<uint32_t>(nA * 16);
+      c.pa_A_bytes = W[14].get<uint8_t>(nA * BSTRIDE);
+      c.pa_A_inf = W[15].get<uint8_t>(nA);
+      c.s1_jv = W[16].get<uint32_t>(n1 * 8);
+      c.s1_jr = W[17].get<uint32_t>(n1 * 8);
+      c.s1_proj = W[18].get<uint32_t>(n1 * TOM_PROJ_WORDS);
+      c.s1_aff = W[19].get<uint32_t>(n1 * TOM_AFF_WORDS);
+      c.s1_bytes = W[20].get<uint8_t>(n1 * BSTRIDE);
+      c.chal = W[21].get<uint32_t>((size_t)Bc * 3);
+      c.zcount = W[22].get<uint32_t>(Bc);
+      c.item_base = W[23].get<uint32_t>(Bc);
+      c.item_total = W[24].get<uint32_t>(1);
+      c.rep_off = W[25].get<uint32_t>((size_t)Bc * S);
+      c.gk_off = W[26].get<uint32_t>(Bc);
+      c.gk_dv = W[27].get<uint32_t>((size_t)Bc * n * 8);
+      c.gk_lag = lag;
+      c.gk_x = W[28].get<uint32_t>((size_t)Bc * 3);
+      c.proof_stride = proof_stride;
+      c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ctx->out[0].get<uint8_t>((size_t)Bc * proof_stride);
+      c.proof_len = is_device_ptr(proof_len_out) ? proof_len_out + b0 : ctx->out[1].get<uint32_t>(Bc);
+      c.status = is_device_ptr(status) ? status + b0 : ctx->out[2].get<int32_t>(Bc);
+
+      // --- statement + per-proof tables of R
+      launch(st, Bc, PreTask{c});
+      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, 64, 4});
+      launch(st, (long long)Bc * 64, P256RowsTask{c.rpows, c.rrows, 4});
+      {
+        const long long np = (long long)Bc * 64 * 16;
+        launch(st, (np + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np});
+      }
+      // --- phase A
+      launch(st, (long long)nA, PhaseAP256Task{c});
+      launch(st, (long long)(nA + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (int)nA});
+      launch(st, (long long)(nA + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (int)nA});
+      launch(st, (long long)n1, JobsATask{c});
+      launch(st, (long long)n1, TomCommitTask{c.s1_jv, c.s1_jr, c.tg_tab, c.th_tab, c.s1_proj, c.tom_w, c.tom_nwin});
+      launch(st, (long long)(n1 + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{c.s1_proj, c.s1_aff, c.s1_bytes, (int)n1});
+      // --- challenge, layout
+      launch(st, Bc, ExpChallengeTask{c});
+      launch(st, 1, ScanTask{c});
+      uint32_t M = 0;
+      copy_d2h(st, &M, c.item_total, 4);
+      sync(st);
+      c.M = (int)M;
+      c.item_b = W[29].get<uint32_t>(M);
+      c.item_i = W[30].get<uint32_t>(M);
+      c.item_k = W[31].get<uint32_t>(M);
+      c.pb_T1 = W[32].get<uint32_t>((size_t)M * P256_PROJ_WORDS);
+      c.pb_T1_aff = W[33].get<uint32_t>((size_t)M * 16);
+      c.pb_T1_inf = W[34].get<uint8_t>(M);
+      const size_t n2 = c.s2_count();
+      c.s2_jv = W[35].get<uint32_t>(n2 * 8);
+      c.s2_jr = W[36].get<uint32_t>(n2 * 8);
+      c.s2_proj = W[37].get<uint32_t>(n2 * TOM_PROJ_WORDS);
+      c.s2_aff = W[38].get<uint32_t>(n2 * TOM_AFF_WORDS);
+      c.s2_bytes = W[39].get<uint8_t>(n2 * BSTRIDE);
+      c.secrets = W[42].get<uint32_t>((size_t)M * SECRETS_PER_ITEM * 8);
+      c.item_chal = W[43].get<uint32_t>((size_t)M * HASHES_PER_ITEM * 3);
+      launch(st, Bc, ItemsTask{c});
+      // --- phase B
+      launch(st, M, PhaseBP256Task{c});
+      launch(st, ((long long)M + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.pb_T1, c.pb_T1_aff, nullptr, c.pb_T1_inf, (int)M});
+      launch(st, M, ItemScalarsTask{c});
+      launch(st, (long long)Bc * n, GkJobsTask{c});
+      launch(st, (long long)Bc * n, GkPolyTask{c});
+      launch(st, (long long)Bc * n, GkCdJobsTask{c});
+      {
+        const size_t nj = (size_t)M * JOBS_PER_ITEM, nd = (size_t)M * DERS_PER_ITEM, ng = (size_t)Bc * 4 * n;
+        const size_t g0 = nj + nd;
+        launch(st, (long long)nj, TomCommitTask{c.s2_jv, c.s2_jr, c.tg_tab, c.th_tab, c.s2_proj, c.tom_w, c.tom_nwin});
+        launch(st, (long long)ng, TomCommitTask{c.s2_jv + g0 * 8, c.s2_jr + g0 * 8, c.tg_tab, c.th_tab,
+                                                 c.s2_proj + g0 * TOM_PROJ_WORDS, c.tom_w, c.tom_nwin});
+        launch(st, (long long)(nj + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{c.s2_proj, c.s2_aff, c.s2_bytes, (int)nj});
+        launch(st, M, DerivedTask{c});
+        launch(st, (long long)(nd + ng + NORM_CHUNK - 1) / NORM_CHUNK,
+               TomNormTask{c.s2_proj + nj * TOM_PROJ_WORDS, c.s2_aff + nj * TOM_AFF_WORDS, c.s2_bytes + nj * BSTRIDE, (int)(nd + ng)});
+      }
+      launch(st, (long long)M * HASHES_PER_ITEM, ItemHashTask{c});
+      launch(st, (long long)M * 7, ItemEmitTask{c});
+      launch(st, (long long)nA, RepEmitTask{c});
+      launch(st, Bc, GkEmitTask{c});
+      // --- results
+      if (!out_dev) copy_d2h(st, proofs + (size_t)b0 * proof_stride, c.proofs, (size_t)Bc * proof_stride);
+      if (!is_device_ptr(proof_len_out)) copy_d2h(st, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
+      if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
+      sync(st);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring,
+                     uint32_t N, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
+                     const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status) {
+  if (!ctx || !P || !msg_hash || !ring || !proofs || !proof_len || !tape || !ok || !status) return ZKA_E_ARG;
+  return fail(ctx, ZKA_E_ARG, "zka_verify_batch: not implemented yet");
+}
+
+}  // extern "C"
