@@ -122,6 +122,18 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* params, uint32_t B,
                      const uint8_t* tape /* B x tape_stride */, size_t tape_stride,
                      uint8_t* ok /* B */, int32_t* status /* B */);
 
+/* ---- measurement hooks (bench.py) ----
+ * zka_get_stream: the cudaStream_t every kernel of this context is launched on (so callers can
+ * record CUDA events on the launching stream).  zka_set_profiling(1) brackets every launch with a
+ * CUDA-event pair; zka_profile_json writes {"<task>": {"launches":n,"ms":t,"items":k}, ...}. */
+void* zka_get_stream(zka_ctx* ctx);
+int zka_set_profiling(zka_ctx* ctx, int enable);
+int zka_profile_reset(zka_ctx* ctx);
+size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap);
+/* tuning knobs read at zka_init from the environment: ZKA_TOM_W (window bits of the fixed-base
+ * tables, default 8), ZKA_CHUNK (proofs per pipeline pass).  zka_config reports them. */
+int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk);
+
 /* ---- layer-wise entry points (parity tests of the arithmetic underneath) ---- */
 /* Pedersen commit in the proof group: out[i] = v[i]*g + r[i]*h  (pedersen.ts:53-58 with r given) */
 int zka_tom_commit_batch(zka_ctx* ctx, const zka_params* params, uint32_t count,

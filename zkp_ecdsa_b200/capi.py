@@ -24,6 +24,7 @@ SYMBOLS = [
     'zka_proof_max_len', 'zka_prove_tape_len', 'zka_verify_tape_len',
     'zka_prove_batch', 'zka_verify_batch',
     'zka_tom_commit_batch', 'zka_p256_mul_batch', 'zka_field_op_batch', 'zka_hash80_batch',
+    'zka_get_stream', 'zka_set_profiling', 'zka_profile_reset', 'zka_profile_json', 'zka_config',
 ]
 
 STATUS_MESSAGES = {
@@ -93,6 +94,13 @@ class ZkaLib:
         L.zka_p256_mul_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.zka_field_op_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.zka_hash80_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.zka_get_stream.restype = C.c_void_p
+        L.zka_get_stream.argtypes = [C.c_void_p]
+        L.zka_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.zka_profile_reset.argtypes = [C.c_void_p]
+        L.zka_profile_json.restype = C.c_size_t
+        L.zka_profile_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.zka_config.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         ctx = C.c_void_p()
         rc = L.zka_init(device, C.byref(ctx))
         if rc != 0 or not ctx:
@@ -113,6 +121,27 @@ class ZkaLib:
 
     def launch_count(self) -> int:
         return int(self.lib.zka_launch_count(self.ctx))
+
+    def stream_ptr(self) -> int:
+        return int(self.lib.zka_get_stream(self.ctx) or 0)
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.zka_set_profiling(self.ctx, 1 if on else 0), 'zka_set_profiling')
+
+    def profile_reset(self):
+        self._check(self.lib.zka_profile_reset(self.ctx), 'zka_profile_reset')
+
+    def profile(self) -> dict:
+        import json
+        n = self.lib.zka_profile_json(self.ctx, None, 0)
+        buf = C.create_string_buffer(int(n) + 16)
+        self.lib.zka_profile_json(self.ctx, buf, len(buf))
+        return json.loads(buf.value.decode())
+
+    def config(self) -> dict:
+        w, nw, ch = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.zka_config(self.ctx, C.byref(w), C.byref(nw), C.byref(ch)), 'zka_config')
+        return {'tom_w': w.value, 'tom_nwin': nw.value, 'chunk': ch.value}
 
     def proof_max_len(self, ring_size, sec_level=80): return int(self.lib.zka_proof_max_len(ring_size, sec_level))
     def prove_tape_len(self, ring_size, sec_level=80): return int(self.lib.zka_prove_tape_len(ring_size, sec_level))

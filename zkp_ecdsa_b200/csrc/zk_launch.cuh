@@ -10,8 +10,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <stdexcept>
 #include <string>
+#include <typeinfo>
+#include <vector>
+
+#include <cxxabi.h>
 
 #if !defined(ZKA_HOSTSIM)
 #include <cuda_runtime.h>
@@ -35,10 +40,42 @@ __global__ void __launch_bounds__(128) zk_task_kernel(int n, Task task) {
   if (t < n) task(t);
 }
 
+struct ProfEntry {
+  uint64_t launches = 0;
+  double ms = 0.0;
+  uint64_t items = 0;
+};
 struct Stream {
   cudaStream_t s = nullptr;
   uint64_t launches = 0;
+  // optional live profiling: one CUDA-event pair per launch on this stream
+  bool profiling = false;
+  struct Pending { const char* name; cudaEvent_t e0, e1; long long n; };
+  std::vector<Pending> pending;
+  std::map<std::string, ProfEntry> prof;
 };
+
+inline std::string demangle(const char* n) {
+  int status = 0;
+  char* d = abi::__cxa_demangle(n, nullptr, nullptr, &status);
+  std::string r = (status == 0 && d) ? d : n;
+  free(d);
+  return r;
+}
+// fold finished event pairs into the per-task table (stream must be idle)
+inline void prof_collect(Stream& st) {
+  for (auto& p : st.pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    ProfEntry& e = st.prof[demangle(p.name)];
+    e.launches++;
+    e.ms += ms;
+    e.items += (uint64_t)p.n;
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
+  }
+  st.pending.clear();
+}
 
 template <class Task>
 inline void launch(Stream& st, long long n, const Task& task) {
@@ -46,8 +83,18 @@ inline void launch(Stream& st, long long n, const Task& task) {
   if (n > 0x7fffffffLL) throw std::runtime_error("launch too large");
   const int threads = 128;
   const int blocks = (int)((n + threads - 1) / threads);
+  Stream::Pending pd{typeid(Task).name(), nullptr, nullptr, n};
+  if (st.profiling) {
+    ZK_CUDA_CHECK(cudaEventCreate(&pd.e0));
+    ZK_CUDA_CHECK(cudaEventCreate(&pd.e1));
+    ZK_CUDA_CHECK(cudaEventRecord(pd.e0, st.s));
+  }
   zk_task_kernel<Task><<<blocks, threads, 0, st.s>>>((int)n, task);
   ZK_CUDA_CHECK(cudaGetLastError());
+  if (st.profiling) {
+    ZK_CUDA_CHECK(cudaEventRecord(pd.e1, st.s));
+    st.pending.push_back(pd);
+  }
   st.launches++;
 }
 
@@ -71,7 +118,10 @@ inline void copy_d2d(Stream& st, void* d, const void* s, size_t n) {
 inline void dev_memset(Stream& st, void* d, int v, size_t n) {
   if (n) ZK_CUDA_CHECK(cudaMemsetAsync(d, v, n, st.s));
 }
-inline void sync(Stream& st) { ZK_CUDA_CHECK(cudaStreamSynchronize(st.s)); }
+inline void sync(Stream& st) {
+  ZK_CUDA_CHECK(cudaStreamSynchronize(st.s));
+  if (!st.pending.empty()) prof_collect(st);
+}
 // is `p` a device-accessible pointer that kernels may dereference directly?
 inline bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
@@ -85,8 +135,15 @@ inline bool is_device_ptr(const void* p) {
 
 #else  // ------------------------------------------------------------------ host simulator
 
+struct ProfEntry {
+  uint64_t launches = 0;
+  double ms = 0.0;
+  uint64_t items = 0;
+};
 struct Stream {
   uint64_t launches = 0;
+  bool profiling = false;
+  std::map<std::string, ProfEntry> prof;
 };
 template <class Task>
 inline void launch(Stream& st, long long n, const Task& task) {

@@ -312,6 +312,54 @@ const char* zka_last_error(const zka_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 uint64_t zka_launch_count(const zka_ctx* ctx) { return ctx ? ctx->st.launches : 0; }
 
+void* zka_get_stream(zka_ctx* ctx) {
+#if !defined(ZKA_HOSTSIM)
+  return ctx ? (void*)ctx->st.s : nullptr;
+#else
+  return nullptr;
+#endif
+}
+int zka_set_profiling(zka_ctx* ctx, int enable) {
+  if (!ctx) return ZKA_E_ARG;
+  try { sync(ctx->st); } catch (...) { return ZKA_E_CUDA; }
+  ctx->st.profiling = enable != 0;
+  return 0;
+}
+int zka_profile_reset(zka_ctx* ctx) {
+  if (!ctx) return ZKA_E_ARG;
+  try { sync(ctx->st); } catch (...) { return ZKA_E_CUDA; }
+  ctx->st.prof.clear();
+  return 0;
+}
+size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx) return 0;
+  try { sync(ctx->st); } catch (...) { return 0; }
+  std::string j = "{";
+  bool first = true;
+  for (auto& kv : ctx->st.prof) {
+    char tmp[512];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"items\": %llu}", first ? "" : ", ",
+             kv.first.c_str(), (unsigned long long)kv.second.launches, kv.second.ms,
+             (unsigned long long)kv.second.items);
+    j += tmp;
+    first = false;
+  }
+  j += "}";
+  if (buf && cap) {
+    size_t n = std::min(cap - 1, j.size());
+    memcpy(buf, j.data(), n);
+    buf[n] = 0;
+  }
+  return j.size() + 1;
+}
+int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk) {
+  if (!ctx) return ZKA_E_ARG;
+  if (tom_w) *tom_w = ctx->tom_w;
+  if (tom_nwin) *tom_nwin = ctx->tom_nwin;
+  if (chunk) *chunk = ctx->chunk;
+  return 0;
+}
+
 int zka_init(int device, zka_ctx** out) {
   if (!out) return ZKA_E_ARG;
   *out = nullptr;
