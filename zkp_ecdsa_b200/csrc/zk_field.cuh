@@ -135,6 +135,13 @@ ZK_HD void csel_n(uint32_t* r, bool c, const uint32_t* a, const uint32_t* b) {  
   for (int i = 0; i < N; i++) r[i] = c ? a[i] : b[i];
 }
 
+}  // namespace zk
+#include "zk_field_ptx.cuh"   // sm_100a multiplier kernels (device only)
+namespace zk {
+
+template <class A, class B> struct same_t { static constexpr bool value = false; };
+template <class A> struct same_t<A, A> { static constexpr bool value = true; };
+
 // ------------------------------------------------------------------------------------
 // Field operations
 // ------------------------------------------------------------------------------------
@@ -204,6 +211,11 @@ struct Field {
 
   // Montgomery product r = a*b/R mod p  (CIOS).  r may alias a or b.
   ZK_HD static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__) && !defined(ZKA_NO_PTX_MUL)
+    // product-scanning PTX kernels for the two hot moduli (zk_field_ptx.cuh)
+    if (same_t<F, FpTom>::value) { ptx::tom_mul(r, a, b); return; }
+    if (same_t<F, FpP256>::value) { ptx::p256_mul(r, a, b); return; }
+#endif
     uint32_t t[N + 2];
 #pragma unroll
     for (int i = 0; i < N + 2; i++) t[i] = 0;
