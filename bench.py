@@ -36,9 +36,9 @@ WORKLOADS = {
 }
 SEC_LEVEL = 80
 # executed field multiplications per tomEdwards256 commitment: 2*nwin mixed additions x 8 modmul,
-# each modmul = 9x9 product + 9x9 Montgomery reduction + 9 quotient digits = 171 32x32 MACs
+# each modmul = 9x9 product + 5 generic modulus limbs x 9 quotient digits = 126 32x32 MACs
 MODMUL_PER_MADD = 8
-MAC_PER_TOM_MODMUL = 171
+MAC_PER_TOM_MODMUL = 126   # 81 products + 45 quotient-digit products (zk_field_ptx.cuh); the generic CIOS needs 171
 W_PROVE_REF = {8: 6861088, 256: 6942368, 1024: 6974880}   # reference-algorithm modmuls/proof
 
 
@@ -58,9 +58,24 @@ def _oracle_one(args):
     return time.time() - t
 
 
+def usable_cores() -> int:
+    """Host threads this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(N: int, rounds: int = 1):
     """Oracle port on all host cores: `rounds` proofs per core, one process per core."""
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     jobs = [(1000 + i, N) for i in range(cores * rounds)]
     t = time.time()
     with mp.get_context('spawn').Pool(cores) as pool:

@@ -131,7 +131,7 @@ int zka_set_profiling(zka_ctx* ctx, int enable);
 int zka_profile_reset(zka_ctx* ctx);
 size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap);
 /* tuning knobs read at zka_init from the environment: ZKA_TOM_W (window bits of the fixed-base
- * tables, default 8), ZKA_CHUNK (proofs per pipeline pass).  zka_config reports them. */
+ * tables, default 13), ZKA_CHUNK (proofs per pipeline pass, default 8192).  zka_config reports them. */
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk);
 
 /* ---- layer-wise entry points (parity tests of the arithmetic underneath) ---- */

@@ -54,7 +54,7 @@ __device__ __forceinline__ void subw(uint32_t& a0, uint32_t& a1, uint32_t& a2, u
 }
 
 // r = a*b/2^288 mod tom.p, lazy: inputs < 2^13 p, output < 2p (no final subtraction).
-__device__ __forceinline__ void tom_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+__device__ __forceinline__ void tom_mul_body(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int N = 9;
   constexpr uint32_t P0 = FpTom::p(0), P1 = FpTom::p(1), P2 = FpTom::p(2), P3 = FpTom::p(3), P7 = FpTom::p(7);
   static_assert(FpTom::p(4) == 2 && FpTom::p(5) == 0 && FpTom::p(6) == 4 && FpTom::p(8) == 3, "tom.p limb structure");
@@ -95,7 +95,7 @@ __device__ __forceinline__ void tom_mul(uint32_t* r, const uint32_t* a, const ui
 }
 
 // r = a*b/2^256 mod p256.p, strict: inputs < p, output < p.
-__device__ __forceinline__ void p256_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+__device__ __forceinline__ void p256_mul_body(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int N = 8;
   uint32_t m[N], t[N + 1];
   uint32_t a0 = 0, a1 = 0, a2 = 0;   // signed 96-bit column accumulator (two's complement)
@@ -125,6 +125,47 @@ __device__ __forceinline__ void p256_mul(uint32_t* r, const uint32_t* a, const u
   const bool ge = (t[N] != 0) || (br == 0);
 #pragma unroll
   for (int i = 0; i < N; i++) r[i] = ge ? u[i] : t[i];
+}
+
+// The multipliers are real (non-inlined) functions: operands and result travel in registers
+// (by-value structs; the device ABI keeps them in R4..), and every warp of the SM executes the
+// same ~5 KB body.  Fully inlining them made the commitment kernel ~130 KB of straight-line
+// code and the warps stalled on instruction fetch (ncu: stall_no_instruction 2.7 per issue).
+struct V9 { uint32_t v[9]; };
+struct V8 { uint32_t v[8]; };
+static __device__ __noinline__ V9 tom_mul_fn(V9 a, V9 b) {
+  V9 r;
+  tom_mul_body(r.v, a.v, b.v);
+  return r;
+}
+static __device__ __noinline__ V8 p256_mul_fn(V8 a, V8 b) {
+  V8 r;
+  p256_mul_body(r.v, a.v, b.v);
+  return r;
+}
+__device__ __forceinline__ void tom_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if defined(ZKA_INLINE_MUL)
+  tom_mul_body(r, a, b);
+#else
+  V9 x, y;
+#pragma unroll
+  for (int i = 0; i < 9; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+  V9 z = tom_mul_fn(x, y);
+#pragma unroll
+  for (int i = 0; i < 9; i++) r[i] = z.v[i];
+#endif
+}
+__device__ __forceinline__ void p256_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if defined(ZKA_INLINE_MUL)
+  p256_mul_body(r, a, b);
+#else
+  V8 x, y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+  V8 z = p256_mul_fn(x, y);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = z.v[i];
+#endif
 }
 
 }  // namespace ptx

@@ -46,7 +46,7 @@ enum : int {
   TOM_PROJ_WORDS = 27,   // X, Y, Z (T is not needed after the last addition)
   TOM_AFF_WORDS = 18,    // x', y on the a'=1 image curve, Montgomery
   TOM_PRE_WORDS = 32,    // x', y, k = d' x' y + 5 pad words: one 128-byte line per entry
-  NORM_CHUNK = 8,
+  NORM_CHUNK = 16,       // points per Montgomery-trick chunk (one Fermat inversion each)
 };
 
 ZK_HD void p256_ld_proj(P256Pt& p, const uint32_t* m) {

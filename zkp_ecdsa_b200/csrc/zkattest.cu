@@ -223,8 +223,8 @@ struct zka_ctx {
   int device = 0;
   Stream st;
   std::string err;
-  int tom_w = 8, tom_nwin = 32;
-  int chunk = 2048;
+  int tom_w = 13, tom_nwin = 20;   // 2 x 20 x 8192 x 128 B = 42 MB of tables: L2-resident
+  int chunk = 8192;
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
   FixedTable tg;          // tomEdwards256 generator [nwin][2^w][32]
   DevBuf tg_bytes;        // 67-byte encoding of g
