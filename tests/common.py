@@ -107,3 +107,75 @@ def check_prove_parity(L, B=2, N=6, seed=3, sec_level=80):
         assert plen[b] == flat.proof_len(z, n, sec_level)
     L.params_destroy(P)
     return proofs, plen
+
+
+# ------------------------------------------------------------------------------------- verify
+def run_verify(L, P, msg_hash, ring, proofs, plen, vtape):
+    B = msg_hash.shape[0]
+    ok = np.zeros(B, np.uint8)
+    st = np.zeros(B, np.int32)
+    L.verify_batch(P, B, msg_hash, ring, ring.shape[0], proofs, proofs.shape[1], plen, vtape, vtape.shape[1], ok, st)
+    return ok, st
+
+
+def oracle_verdict(po, msg, ring_ints, proof_bytes, vtape_row, N, sec_level=80):
+    """'err' (the reference would throw), True or False — with the SAME randomness as the GPU."""
+    from zkp_ecdsa_b200 import verify_tape as VT
+    try:
+        prf = flat.de_proof(proof_bytes, sec_level)
+        return OZ.verify_signature_list(po, msg, ring_ints, prf, Tape(VT.oracle_stream(vtape_row, N, sec_level)))
+    except ValueError:
+        return 'err'
+
+
+def check_verify_parity(L, N=6, seed=3, tampers=24, sec_level=80):
+    """Valid proofs verify; tampered inputs give the oracle's decision (throw / false / true)."""
+    from zkp_ecdsa_b200 import verify_tape as VT
+    P, po = make_params(L, seed, sec_level)
+    wl = synth.Workload(B=2, N=N, seed=seed)
+    tape = synth.random_tape(2, L.prove_tape_len(N, sec_level), seed=seed + 100)
+    proofs, plen, status = run_prove(L, P, wl, tape, sec_level)
+    assert (status == 0).all()
+    vts = L.verify_tape_len(N, sec_level)
+    vt = VT.random_verify_tape(2, vts, N, sec_level, seed=seed + 7)
+    ok, st = run_verify(L, P, wl.msg_hash, wl.ring, proofs, plen, vt)
+    assert list(ok) == [1, 1] and list(st) == [0, 0]
+    ring_ints = wl.ring_ints()
+    for b in range(2):
+        assert oracle_verdict(po, wl.msg_hash[b].tobytes(), ring_ints, proofs[b, :plen[b]].tobytes(),
+                              vt[b].tobytes(), N, sec_level) is True
+    # tampering: proofs / message / ring, decisions compared with the oracle on identical randomness
+    good = proofs[0, :plen[0]].copy()
+    ln = len(good)
+    rng = np.random.default_rng(seed)
+    cases = []
+    for k in range(tampers):
+        p, msg, ring = good.copy(), wl.msg_hash[0].copy(), wl.ring.copy()
+        kind = k % 8
+        if kind < 3:
+            p[int(rng.integers(0, ln))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 3:
+            p = p[:ln - 1 - int(rng.integers(0, 40))]                 # truncated
+        elif kind == 4:
+            p[ln - 1 - 33 * int(rng.integers(0, 5))] ^= 1              # a GK response scalar
+        elif kind == 5:
+            msg[int(rng.integers(0, 32))] ^= 1
+        elif kind == 6:
+            ring[int(wl.which[0]), 31] ^= 1
+        else:
+            p[int(rng.integers(264, ln - 1200))] ^= 1
+        cases.append((p, msg, ring))
+    T = len(cases)
+    vt2 = VT.random_verify_tape(T, vts, N, sec_level, seed=seed + 9)
+    agree = 0
+    for k, (p, msg, ring) in enumerate(cases):
+        arr = np.zeros((1, max(len(p), 1)), np.uint8)
+        arr[0, :len(p)] = p
+        ok, st = run_verify(L, P, msg.reshape(1, 32).copy(), ring, arr, np.array([len(p)], np.uint32), vt2[k:k + 1].copy())
+        got = 'err' if st[0] else bool(ok[0])
+        exp = oracle_verdict(po, msg.tobytes(), [int.from_bytes(ring[i].tobytes(), 'big') for i in range(N)],
+                             p.tobytes(), vt2[k].tobytes(), N, sec_level)
+        assert got == exp, (k, k % 8, got, int(st[0]), exp)
+        agree += 1
+    L.params_destroy(P)
+    return agree

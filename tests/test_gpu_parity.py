@@ -73,3 +73,32 @@ def test_error_statuses(gpu_engine):
     _, _, status = common.run_prove(L, P, wl, tape)
     assert list(status) == [0, 1, 6, 5]
     L.params_destroy(P)
+
+
+def test_verify_decisions_match_oracle(gpu_engine):
+    common.check_verify_parity(gpu_engine.lib, N=6, seed=3, tampers=32)
+
+
+def test_verify_ring_256(gpu_engine):
+    common.check_verify_parity(gpu_engine.lib, N=256, seed=12, tampers=8)
+
+
+def test_prove_verify_roundtrip_batch(gpu_engine):
+    """encode -> verify round trip at batch 512, ring 1024 (size-independent property)."""
+    from zkp_ecdsa_b200 import verify_tape as VT
+    L = gpu_engine.lib
+    P, po = common.make_params(L, seed=41)
+    B, N = 512, 1024
+    wl = synth.Workload(B=B, N=N, seed=41)
+    tape = synth.random_tape(B, L.prove_tape_len(N), seed=42)
+    proofs, plen, status = common.run_prove(L, P, wl, tape)
+    assert (status == 0).all()
+    vt = VT.random_verify_tape(B, L.verify_tape_len(N), N, seed=43)
+    ok, st = common.run_verify(L, P, wl.msg_hash, wl.ring, proofs, plen, vt)
+    assert (st == 0).all() and (ok == 1).all()
+    # swap two messages: exactly those two verifications must fail
+    msg = wl.msg_hash.copy()
+    msg[[3, 4]] = msg[[4, 3]]
+    ok, st = common.run_verify(L, P, msg, wl.ring, proofs, plen, vt)
+    assert (st == 0).all() and list(np.nonzero(ok == 0)[0]) == [3, 4]
+    L.params_destroy(P)

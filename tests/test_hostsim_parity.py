@@ -32,3 +32,7 @@ def test_prove_bit_exact_small_ring(hostsim):
 def test_prove_bit_exact_sec_level_16(hostsim):
     # smaller SecLevel keeps the oracle fast while exercising every code path
     common.check_prove_parity(hostsim, B=3, N=17, seed=4, sec_level=16)
+
+
+def test_verify_decisions_match_oracle(hostsim):
+    common.check_verify_parity(hostsim, N=6, seed=3, tampers=16)

@@ -800,7 +800,126 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
                      uint32_t N, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
                      const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status) {
   if (!ctx || !P || !msg_hash || !ring || !proofs || !proof_len || !tape || !ok || !status) return ZKA_E_ARG;
-  return fail(ctx, ZKA_E_ARG, "zka_verify_batch: not implemented yet");
+  if (B == 0) return 0;
+  if (N < 2 || N > (1u << 20)) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
+  const int S = (int)P->sec_level;
+  // verifyExp throws 'security level not achieved' when 20 > pi.length (exp.ts:243-245)
+  if (S < V_SAMPLES) return fail(ctx, ZKA_E_ARG, "security level not achieved");
+  const int n = ceil_log2(N);
+  if (tape_stride < verify_tape_len(n, S)) return fail(ctx, ZKA_E_ARG, "tape_stride < zka_verify_tape_len");
+  try {
+    Stream& st = ctx->st;
+    DevBuf* W = ctx->w;
+    const uint8_t* d_ring = stage_in(ctx, ctx->in[5], ring, (size_t)N * 32);
+    uint32_t* ring_m = W[40].get<uint32_t>(((size_t)1 << n) * 8);
+    launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
+    const int vchunk = std::min(ctx->chunk, 4096);
+    for (uint32_t b0 = 0; b0 < B; b0 += (uint32_t)vchunk) {
+      const int Bc = (int)std::min<uint32_t>((uint32_t)vchunk, B - b0);
+      VerifyCtx c;
+      memset(&c, 0, sizeof(c));
+      c.B = Bc; c.S = S; c.N = (int)N; c.n = n;
+      c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
+      c.msg_hash = stage_in(ctx, ctx->in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
+      c.proofs = stage_in(ctx, ctx->in[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
+      c.proof_stride = proof_stride;
+      c.proof_len = stage_in(ctx, ctx->in[2], proof_len + b0, (size_t)Bc);
+      c.tape = stage_in(ctx, ctx->in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      c.tape_stride = tape_stride;
+      c.ring_m = ring_m;
+      c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab;
+      c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
+      c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
+      const size_t ns = (size_t)Bc * V_SAMPLES;
+      const int ngk = 4 * n + 1;
+      c.rep_off = W[0].get<uint32_t>((size_t)Bc * S);
+      c.gk_off = W[1].get<uint32_t>(Bc);
+      c.tagbits = W[2].get<uint32_t>((size_t)Bc * 3);
+      c.chal = W[3].get<uint32_t>((size_t)Bc * 3);
+      c.gk_ok_len = W[4].get<uint8_t>(Bc);
+      c.r_aff = W[5].get<uint32_t>((size_t)Bc * 16);
+      c.q_aff = W[6].get<uint32_t>((size_t)Bc * 16);
+      c.q_inf = W[7].get<uint8_t>(Bc);
+      c.rpows = W[8].get<uint32_t>((size_t)Bc * 64 * P256_PROJ_WORDS);
+      c.rrows = W[9].get<uint32_t>((size_t)Bc * 64 * 16 * P256_PROJ_WORDS);
+      c.rtab = W[10].get<uint32_t>((size_t)Bc * 64 * 16 * P256_AFF_WORDS);
+      c.samp_idx = W[11].get<uint32_t>(ns);
+      c.samp_draw = W[12].get<uint32_t>(ns);
+      c.sp_T = W[13].get<uint32_t>(ns * P256_PROJ_WORDS);
+      c.sp_T_aff = W[14].get<uint32_t>(ns * 16);
+      c.sp_T_inf = W[15].get<uint8_t>(ns);
+      c.ta_jv = W[16].get<uint32_t>(ns * 2 * 8);
+      c.ta_jr = W[17].get<uint32_t>(ns * 2 * 8);
+      c.ta_proj = W[18].get<uint32_t>(ns * 2 * TOM_PROJ_WORDS);
+      c.ta_aff = W[19].get<uint32_t>(ns * 2 * TOM_AFF_WORDS);
+      c.td_proj = W[20].get<uint32_t>(ns * DERS_PER_ITEM * TOM_PROJ_WORDS);
+      c.td_aff = W[21].get<uint32_t>(ns * DERS_PER_ITEM * TOM_AFF_WORDS);
+      c.td_bytes = W[22].get<uint8_t>(ns * DERS_PER_ITEM * BSTRIDE);
+      c.item_chal = W[23].get<uint32_t>(ns * HASHES_PER_ITEM * 3);
+      c.ent_scalar = W[24].get<uint32_t>((size_t)Bc * V_ENT_TOM * 8);
+      c.ent_off = W[25].get<uint32_t>((size_t)Bc * V_ENT_TOM);
+      c.ent_pre = W[26].get<uint32_t>((size_t)Bc * V_ENT_TOM * TOM_PRE_WORDS);
+      c.ent_cnt = W[27].get<uint32_t>(ns);
+      c.part = W[28].get<uint32_t>(ns * V_PART_WORDS);
+      c.nent_scalar = W[29].get<uint32_t>((size_t)Bc * V_ENT_NIST * 8);
+      c.nent_aff = W[30].get<uint32_t>((size_t)Bc * V_ENT_NIST * 16);
+      c.nent_skip = W[31].get<uint8_t>((size_t)Bc * V_ENT_NIST);
+      c.gk_scalar = W[32].get<uint32_t>((size_t)Bc * ngk * 8);
+      c.gk_pre = W[33].get<uint32_t>((size_t)Bc * ngk * TOM_PRE_WORDS);
+      uint32_t* gk_offs = W[34].get<uint32_t>((size_t)Bc * ngk);
+      c.fx_jv = W[35].get<uint32_t>((size_t)Bc * 2 * 8);
+      c.fx_jr = W[36].get<uint32_t>((size_t)Bc * 2 * 8);
+      c.fx_proj = W[37].get<uint32_t>((size_t)Bc * 2 * TOM_PROJ_WORDS);
+      c.nfix = W[38].get<uint32_t>((size_t)Bc * P256_PROJ_WORDS);
+      c.win_w = W[39].get<uint32_t>((size_t)Bc * MSM_NWIN * 36);
+      c.win_g = W[42].get<uint32_t>((size_t)Bc * MSM_NWIN * 36);
+      c.win_n = W[43].get<uint32_t>((size_t)Bc * MSM_NWIN_N * P256_PROJ_WORDS);
+      c.id_flags = W[44].get<uint8_t>((size_t)Bc * 3);
+      c.ok = is_device_ptr(ok) ? ok + b0 : ctx->out[0].get<uint8_t>(Bc);
+      c.status = is_device_ptr(status) ? status + b0 : ctx->out[1].get<int32_t>(Bc);
+
+      launch(st, Bc, VLayoutTask{c});
+      launch(st, (long long)Bc * (S + 1), VValidateTask{c});
+      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, 64, 4});
+      launch(st, (long long)Bc * 64, P256RowsTask{c.rpows, c.rrows, 4});
+      {
+        const long long np = (long long)Bc * 64 * 16;
+        launch(st, (np + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np});
+      }
+      launch(st, Bc, VChallengeTask{c});
+      launch(st, (long long)ns, VSampleP256Task{c});
+      launch(st, (long long)(ns + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.sp_T, c.sp_T_aff, nullptr, c.sp_T_inf, (int)ns});
+      launch(st, (long long)ns, VSampleJobsTask{c});
+      launch(st, (long long)ns * 2, TomCommitTask{c.ta_jv, c.ta_jr, c.tg_tab, c.th_tab, c.ta_proj, c.tom_w, c.tom_nwin});
+      launch(st, (long long)(ns * 2 + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{c.ta_proj, c.ta_aff, nullptr, (int)(ns * 2)});
+      launch(st, (long long)ns, VDerivedTask{c});
+      launch(st, (long long)(ns * DERS_PER_ITEM + NORM_CHUNK - 1) / NORM_CHUNK,
+             TomNormTask{c.td_proj, c.td_aff, c.td_bytes, (int)(ns * DERS_PER_ITEM)});
+      launch(st, (long long)ns * HASHES_PER_ITEM, VItemHashTask{c});
+      dev_memset(st, c.ent_off, 0, (size_t)Bc * V_ENT_TOM * 4);
+      launch(st, (long long)ns, VRelationsTask{c});
+      launch(st, Bc, VGkTask{c});
+      launch(st, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
+      launch(st, Bc, VReduceTask{c});
+      launch(st, (long long)Bc * V_ENT_TOM, VParseEntriesTask{c.proofs, proof_stride, c.ent_off, c.ent_pre, V_ENT_TOM});
+      launch(st, (long long)Bc * ngk, VParseEntriesTask{c.proofs, proof_stride, gk_offs, c.gk_pre, ngk});
+      launch(st, (long long)Bc * 2, TomCommitTask{c.fx_jv, c.fx_jr, c.tg_tab, c.th_tab, c.fx_proj, c.tom_w, c.tom_nwin});
+      launch(st, (long long)Bc * MSM_NWIN,
+             MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, V_ENT_TOM, V_SAMPLES, V_ENT_PER_SAMPLE, 2, c.win_w});
+      launch(st, (long long)Bc * MSM_NWIN, MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, c.win_g});
+      launch(st, Bc, MsmTomCombineTask{c.win_g, c.fx_proj, c.id_flags, 2, 0, 0});
+      launch(st, Bc, MsmTomCombineTask{c.win_w, c.fx_proj, c.id_flags, 2, 1, 1});
+      launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n});
+      launch(st, Bc, MsmP256CombineTask{c.win_n, c.nfix, c.id_flags});
+      launch(st, Bc, VFinalTask{c});
+      if (!is_device_ptr(ok)) copy_d2h(st, ok + b0, c.ok, (size_t)Bc);
+      if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
+      sync(st);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
 }
 
 }  // extern "C"
