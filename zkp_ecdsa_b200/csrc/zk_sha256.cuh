@@ -37,6 +37,7 @@ struct Sha256 {
     for (int i = 0; i < 16; i++) w[i] = 0;
     fill = 0;
     total = 0;
+    cur = 0;
   }
 
   ZK_HD void compress() {
@@ -70,22 +71,38 @@ struct Sha256 {
     fill = 0;
   }
 
+  // The block buffer is a 16-word FIFO with static indices only (w[15] is the newest word), so it
+  // stays in registers; `fill` counts bytes of the current block, `cur` gathers 4 bytes.
+  uint32_t cur;
+  ZK_HD void push_word(uint32_t v) {
+#pragma unroll
+    for (int i = 0; i < 15; i++) w[i] = w[i + 1];
+    w[15] = v;
+  }
   ZK_HD void put(uint8_t byte) {
-    w[fill >> 2] |= (uint32_t)byte << (24 - 8 * (fill & 3));
+    cur = (cur << 8) | byte;
     fill++;
     total++;
-    if (fill == 64) compress();
+    if ((fill & 3) == 0) {
+      push_word(cur);
+      if (fill == 64) compress();
+    }
   }
   ZK_HD void update(const uint8_t* p, int n) {
     for (int i = 0; i < n; i++) put(p[i]);
   }
   // digest[0..9] as (hi16, lo64): challenge = hi16 * 2^64 + lo64
   ZK_HD void final80(uint32_t* c3) {  // c3[0] = low 32, c3[1] = mid 32, c3[2] = top 16 bits
-    uint64_t bits = total * 8;
+    const uint64_t bits = total * 8;
     put(0x80);
-    while (fill != 56) put(0);
-    w[14] = (uint32_t)(bits >> 32);
-    w[15] = (uint32_t)bits;
+    while ((fill & 3) != 0) put(0);
+    // now `fill` is a multiple of 4; pad with zero words up to byte 56, then the length
+    if (fill > 56) {
+      while (fill != 0) { push_word(0); fill += 4; if (fill == 64) compress(); }
+    }
+    while (fill != 56) { push_word(0); fill += 4; }
+    push_word((uint32_t)(bits >> 32));
+    push_word((uint32_t)bits);
     compress();
     // digest bytes 0..9 = h0 (4) h1 (4) top half of h2 (2)  -> 80-bit big-endian integer
     uint32_t top16 = h[0] >> 16;

@@ -228,6 +228,8 @@ struct zka_ctx {
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
   FixedTable tg;          // tomEdwards256 generator [nwin][2^w][32]
   DevBuf tg_bytes;        // 67-byte encoding of g
+  DevBuf lag;             // GK Lagrange matrix cache
+  int lag_n = -1;
   // workspace (grow-only)
   DevBuf w[64];
   DevBuf in[8], out[4];
@@ -379,7 +381,7 @@ int zka_init(int device, zka_ctx** out) {
     ctx->device = device;
     if (const char* e = getenv("ZKA_TOM_W")) {
       int w = atoi(e);
-      if (w >= 2 && w <= 14) ctx->tom_w = w;
+      if (w >= 2 && w <= 16) ctx->tom_w = w;
     }
     ctx->tom_nwin = (256 + ctx->tom_w - 1) / ctx->tom_w;
     if (const char* e = getenv("ZKA_CHUNK")) {
@@ -416,6 +418,7 @@ void zka_shutdown(zka_ctx* ctx) {
   ctx->g8.buf.release();
   ctx->tg.buf.release();
   ctx->tg_bytes.release();
+  ctx->lag.release();
   for (auto& b : ctx->w) b.release();
   for (auto& b : ctx->in) b.release();
   for (auto& b : ctx->out) b.release();
@@ -666,8 +669,13 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
     const uint8_t* d_ring = stage_in(ctx, ctx->in[5], ring, (size_t)N * 32);
     uint32_t* ring_m = W[40].get<uint32_t>(((size_t)1 << n) * 8);
     launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
-    uint32_t* lag = W[41].get<uint32_t>((size_t)n * n * 8);
-    launch(st, 1, GkLagrangeTask{lag, n});
+    // Lagrange matrix for nodes 0..n-1: depends only on n, cached per context
+    if (ctx->lag_n != n) {
+      uint32_t* l = ctx->lag.get<uint32_t>((size_t)n * n * 8);
+      launch(st, 1, GkLagrangeTask{l, n});
+      ctx->lag_n = n;
+    }
+    uint32_t* lag = (uint32_t*)ctx->lag.p;
 
     const bool out_dev = is_device_ptr(proofs);
     for (uint32_t b0 = 0; b0 < B; b0 += (uint32_t)ctx->chunk) {
