@@ -1,0 +1,95 @@
+"""World-size-2 gloo test of the N>1 host logic: shard-by-proof + one all-gather of proof bytes.
+
+Each rank proves its shard with the host-simulator build (CPU), the gathered buffer must equal
+the single-process result for the whole batch byte for byte (proofs are independent, so
+sharding must not change any proof).
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B, N, SEC = 4, 5, 8
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _prove(lib, lo, hi):
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import common
+    from zkp_ecdsa_b200 import synth
+    P, _ = common.make_params(lib, seed=9, sec_level=SEC)
+    wl = synth.Workload(B=B, N=N, seed=9)
+    tape = synth.random_tape(B, lib.prove_tape_len(N, SEC), seed=10)
+    for name in ('msg_hash', 'sig', 'pk', 'which'):
+        setattr(wl, name, np.ascontiguousarray(getattr(wl, name)[lo:hi]))
+    wl.B = hi - lo
+    proofs, plen, status = common.run_prove(lib, P, wl, np.ascontiguousarray(tape[lo:hi]), SEC)
+    assert (status == 0).all()
+    return proofs, plen
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import __graft_entry__ as g
+    from zkp_ecdsa_b200 import sharding
+    from zkp_ecdsa_b200.capi import ZkaLib
+    lib = ZkaLib(g.HOSTSIM)
+    lo, hi = sharding.shard_range(B, rank, world)
+    per = (B + world - 1) // world
+    proofs, plen = _prove(lib, lo, hi)
+    stride = proofs.shape[1]
+    lp = torch.zeros((per, stride), dtype=torch.uint8)
+    ll = torch.zeros(per, dtype=torch.int32)
+    lp[:hi - lo] = torch.from_numpy(proofs)
+    ll[:hi - lo] = torch.from_numpy(plen.astype(np.int32))
+    allp, alll = sharding.all_gather_proofs(lp, ll, world, rank, per)
+    if rank == 0:
+        q.put((allp.numpy(), alll.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_batch():
+    from zkp_ecdsa_b200 import sharding
+    for total in (1, 7, 8, 65536):
+        for world in (1, 2, 3, 8):
+            r = [sharding.shard_range(total, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+def test_two_rank_gather_equals_single_process():
+    import __graft_entry__ as g
+    g.build_hostsim()
+    from zkp_ecdsa_b200.capi import ZkaLib
+    ref_proofs, ref_len = _prove(ZkaLib(g.HOSTSIM), 0, B)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    allp, alll = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert list(alll[:B]) == list(ref_len)
+    for b in range(B):
+        assert allp[b, :alll[b]].tobytes() == ref_proofs[b, :ref_len[b]].tobytes()

@@ -78,15 +78,18 @@ class Workload:
     """B signing instances sharing one ring of N key x-coordinates."""
 
     def __init__(self, B: int, N: int, seed: int = 0, distinct_signers: int | None = None):
-        from cryptography.hazmat.primitives import hashes, serialization
+        from cryptography.hazmat.primitives import serialization
         from cryptography.hazmat.primitives.asymmetric import ec
-        from cryptography.hazmat.primitives.asymmetric.utils import decode_dss_signature
         self.B, self.N, self.seed = B, N, seed
         ns = min(B, N) if distinct_signers is None else min(distinct_signers, B, N)
         d = Drbg(seed, 'signers')
-        sks = [ec.derive_private_key(d.below(P256_N - 1) + 1, ec.SECP256R1()) for _ in range(ns)]
-        pks = [sk.public_key().public_bytes(serialization.Encoding.X962, serialization.PublicFormat.UncompressedPoint)
-               for sk in sks]
+        dn = Drbg(seed, 'nonces')
+        sk_ints = [d.below(P256_N - 1) + 1 for _ in range(ns)]
+
+        def pub(k):   # k*G as 65 raw bytes (OpenSSL does the scalar multiplication)
+            return ec.derive_private_key(k, ec.SECP256R1()).public_key().public_bytes(
+                serialization.Encoding.X962, serialization.PublicFormat.UncompressedPoint)
+        pks = [pub(k) for k in sk_ints]
         # ring: signer j sits at slot slot[j]; filler entries are arbitrary 256-bit values
         dr = Drbg(seed, 'ring')
         ring = [dr.bytes(32) for _ in range(N)]
@@ -101,8 +104,15 @@ class Workload:
         for b in range(B):
             j = b % ns
             msg = b'zkattest-bench-%d' % b
-            r, s = decode_dss_signature(sks[j].sign(msg, ec.ECDSA(hashes.SHA256())))
-            self.msg_hash[b] = np.frombuffer(hashlib.sha256(msg).digest(), np.uint8)
+            digest = hashlib.sha256(msg).digest()
+            # deterministic ECDSA: nonce from the DRBG; r = (kG).x mod n, s = (z + r d)/k
+            while True:
+                k = dn.below(P256_N - 1) + 1
+                r = int.from_bytes(pub(k)[1:33], 'big') % P256_N
+                s = pow(k, -1, P256_N) * (int.from_bytes(digest, 'big') + r * sk_ints[j]) % P256_N
+                if r and s:
+                    break
+            self.msg_hash[b] = np.frombuffer(digest, np.uint8)
             self.sig[b] = np.frombuffer(r.to_bytes(32, 'big') + s.to_bytes(32, 'big'), np.uint8)
             self.pk[b] = np.frombuffer(pks[j], np.uint8)
             self.which[b] = int(perm[j])
