@@ -18,7 +18,17 @@ def hostsim():
     import __graft_entry__ as g
     g.build_hostsim()
     from zkp_ecdsa_b200.capi import ZkaLib
-    return ZkaLib(g.HOSTSIM)
+    # the CPU simulator builds its tables with plain loops: keep them small (13-bit windows also
+    # exercise the unaligned digit extraction); the GPU tests run the default 16-bit windows
+    old = os.environ.get('ZKA_TOM_W')
+    os.environ['ZKA_TOM_W'] = '13'
+    try:
+        return ZkaLib(g.HOSTSIM)
+    finally:
+        if old is None:
+            os.environ.pop('ZKA_TOM_W', None)
+        else:
+            os.environ['ZKA_TOM_W'] = old
 
 
 @pytest.fixture(scope='session')

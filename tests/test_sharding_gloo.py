@@ -49,6 +49,7 @@ def _worker(rank, world, port, q):
     import __graft_entry__ as g
     from zkp_ecdsa_b200 import sharding
     from zkp_ecdsa_b200.capi import ZkaLib
+    os.environ['ZKA_TOM_W'] = '10'
     lib = ZkaLib(g.HOSTSIM)
     lo, hi = sharding.shard_range(B, rank, world)
     per = (B + world - 1) // world
@@ -79,7 +80,9 @@ def test_two_rank_gather_equals_single_process():
     import __graft_entry__ as g
     g.build_hostsim()
     from zkp_ecdsa_b200.capi import ZkaLib
+    os.environ['ZKA_TOM_W'] = '10'
     ref_proofs, ref_len = _prove(ZkaLib(g.HOSTSIM), 0, B)
+    os.environ.pop('ZKA_TOM_W', None)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()

@@ -46,7 +46,7 @@ enum : int {
   TOM_PROJ_WORDS = 27,   // X, Y, Z (T is not needed after the last addition)
   TOM_AFF_WORDS = 18,    // x', y on the a'=1 image curve, Montgomery
   TOM_PRE_WORDS = 32,    // x', y, k = d' x' y + 5 pad words: one 128-byte line per entry
-  NORM_CHUNK = 16,       // points per Montgomery-trick chunk (one Fermat inversion each)
+  NORM_CHUNK_MAX = 64,   // max points per Montgomery-trick chunk (one Fermat inversion each)
 };
 
 ZK_HD void p256_ld_proj(P256Pt& p, const uint32_t* m) {
@@ -142,13 +142,14 @@ struct P256NormTask {
   uint8_t* bytes;        // [count][BSTRIDE] or null
   uint8_t* inf;          // [count] or null
   int count;
+  int chunk;             // points per thread (<= NORM_CHUNK_MAX)
   ZK_HD void operator()(int t) const {
     using F = P256p;
-    const int lo = t * NORM_CHUNK;
+    const int lo = t * chunk;
     int n = count - lo;
-    if (n > NORM_CHUNK) n = NORM_CHUNK;
+    if (n > chunk) n = chunk;
     if (n <= 0) return;
-    uint32_t pre[NORM_CHUNK][8];
+    uint32_t pre[NORM_CHUNK_MAX][8];
     uint32_t acc[8], z[8], one[8];
     F::set_one(one);
     copy_n<8>(acc, one);
@@ -265,6 +266,48 @@ struct TomRowsTask {
     }
   }
 };
+// Two-level construction of the same rows for wide windows (w > 8): first the 2^(w-8) "high"
+// multiples m * 2^8 * P_j (one thread per window), then one thread per (window, m) walks the
+// 256 entries below it.  2^(w-8) + 256 sequential additions instead of 2^w.
+struct TomRowsHiTask {
+  const uint32_t* pows;   // [nwin][36]
+  uint32_t* hi;           // [nwin][2^(w-8)][36]
+  int w;
+  ZK_HD void operator()(int t) const {
+    TomPt p, acc;
+    const uint32_t* s = pows + (size_t)t * 36;
+    ld<9>(p.x, s); ld<9>(p.y, s + 9); ld<9>(p.t, s + 18); ld<9>(p.z, s + 27);
+    for (int k = 0; k < 8; k++) tom_dbl(p, p);
+    tom_set_identity(acc);
+    const int nh = 1 << (w - 8);
+    for (int m = 0; m < nh; m++) {
+      uint32_t* o = hi + ((size_t)t * nh + m) * 36;
+      st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.t); st<9>(o + 27, acc.z);
+      tom_add(acc, acc, p);
+    }
+  }
+};
+struct TomRowsLoTask {
+  const uint32_t* pows;   // [nwin][36]
+  const uint32_t* hi;     // [nwin][2^(w-8)][36]
+  uint32_t* rows;         // [nwin][2^w][27]
+  int w;
+  ZK_HD void operator()(int t) const {
+    const int nh = 1 << (w - 8);
+    const int j = t / nh, m = t % nh;
+    TomPt p, acc;
+    const uint32_t* s = pows + (size_t)j * 36;
+    ld<9>(p.x, s); ld<9>(p.y, s + 9); ld<9>(p.t, s + 18); ld<9>(p.z, s + 27);
+    const uint32_t* h = hi + (size_t)t * 36;
+    ld<9>(acc.x, h); ld<9>(acc.y, h + 9); ld<9>(acc.t, h + 18); ld<9>(acc.z, h + 27);
+    uint32_t* out = rows + (((size_t)j << w) + ((size_t)m << 8)) * TOM_PROJ_WORDS;
+    for (int d = 0; d < 256; d++) {
+      uint32_t* o = out + (size_t)d * TOM_PROJ_WORDS;
+      st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.z);
+      tom_add(acc, acc, p);
+    }
+  }
+};
 // aff (x', y) -> table entry (x', y, d' x' y), canonical residues, 128-byte stride
 struct TomPreTask {
   const uint32_t* aff;  // [count][18]
@@ -291,13 +334,14 @@ struct TomNormTask {
   uint32_t* aff;         // [count][18]
   uint8_t* bytes;        // [count][BSTRIDE] or null
   int count;
+  int chunk;             // points per thread (<= NORM_CHUNK_MAX)
   ZK_HD void operator()(int t) const {
     using F = Tomp;
-    const int lo = t * NORM_CHUNK;
+    const int lo = t * chunk;
     int n = count - lo;
-    if (n > NORM_CHUNK) n = NORM_CHUNK;
+    if (n > chunk) n = chunk;
     if (n <= 0) return;
-    uint32_t pre[NORM_CHUNK][9];
+    uint32_t pre[NORM_CHUNK_MAX][9];
     uint32_t acc[9], z[9];
     F::set_one(acc);
     for (int k = 0; k < n; k++) {

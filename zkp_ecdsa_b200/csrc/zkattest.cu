@@ -223,7 +223,8 @@ struct zka_ctx {
   int device = 0;
   Stream st;
   std::string err;
-  int tom_w = 13, tom_nwin = 20;   // 2 x 20 x 8192 x 128 B = 42 MB of tables: L2-resident
+  int tom_w = 16, tom_nwin = 16;   // 2 bases x 16 windows x 65536 entries x 128 B = 268 MB in HBM/L2
+                                   // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 8192;
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
   FixedTable tg;          // tomEdwards256 generator [nwin][2^w][32]
@@ -257,6 +258,26 @@ int ceil_log2(uint32_t v) {
   return n;
 }
 
+
+// normalisation launches: points per thread (= per Fermat inversion) grow with the batch so the
+// inversion cost is amortised while at least ~150k threads stay in flight
+inline int norm_chunk_for(long long count) {
+  long long c = count / 150000;
+  if (c < 8) c = 8;
+  if (c > NORM_CHUNK_MAX) c = NORM_CHUNK_MAX;
+  return (int)c;
+}
+inline void launch_p256_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uint8_t* bytes, uint8_t* inf, long long count) {
+  if (count <= 0) return;
+  const int ch = norm_chunk_for(count);
+  launch(st, (count + ch - 1) / ch, P256NormTask{proj, aff, bytes, inf, (int)count, ch});
+}
+inline void launch_tom_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uint8_t* bytes, long long count) {
+  if (count <= 0) return;
+  const int ch = norm_chunk_for(count);
+  launch(st, (count + ch - 1) / ch, TomNormTask{proj, aff, bytes, (int)count, ch});
+}
+
 // ---- table construction -------------------------------------------------------------------
 // P-256 w=8 positional table from one affine Montgomery base (device pointer, 16 words)
 void build_p256_tab8(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) {
@@ -268,7 +289,7 @@ void build_p256_tab8(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out
   launch(st, 1, P256PowsTask{base_aff_dev, nullptr, d_pows, 1, 32, 8});
   launch(st, 32, P256RowsTask{d_pows, d_rows, 8});
   const int count = 32 * 256;
-  launch(st, (count + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{d_rows, out.tab, nullptr, nullptr, count});
+  launch_p256_norm(st, d_rows, out.tab, nullptr, nullptr, (long long)(count));
   sync(st);
   pows.release();
   rows.release();
@@ -284,8 +305,18 @@ void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) 
   uint32_t* d_aff = aff.get<uint32_t>(count * TOM_AFF_WORDS);
   out.tab = out.buf.get<uint32_t>(count * TOM_PRE_WORDS);
   launch(st, 1, TomPowsTask{base_aff_dev, d_pows, 1, nwin, w});
-  launch(st, nwin, TomRowsTask{d_pows, d_rows, w});
-  launch(st, (long long)(count + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{d_rows, d_aff, nullptr, (int)count});
+  if (w > 8) {
+    DevBuf hi;
+    const int nh = 1 << (w - 8);
+    uint32_t* d_hi = hi.get<uint32_t>((size_t)nwin * nh * 36);
+    launch(st, nwin, TomRowsHiTask{d_pows, d_hi, w});
+    launch(st, (long long)nwin * nh, TomRowsLoTask{d_pows, d_hi, d_rows, w});
+    sync(st);
+    hi.release();
+  } else {
+    launch(st, nwin, TomRowsTask{d_pows, d_rows, w});
+  }
+  launch_tom_norm(st, d_rows, d_aff, nullptr, (long long)(count));
   launch(st, (long long)count, TomPreTask{d_aff, out.tab});
   sync(st);
   pows.release();
@@ -399,7 +430,7 @@ int zka_init(int device, zka_ctx** out) {
     uint32_t* d_aff = aff.get<uint32_t>(TOM_AFF_WORDS);
     uint8_t* d_bytes = ctx->tg_bytes.get<uint8_t>(BSTRIDE);
     launch(ctx->st, 1, GProjTask{d_gen + 16, d_proj});
-    launch(ctx->st, 1, TomNormTask{d_proj, d_aff, d_bytes, 1});
+    launch_tom_norm(ctx->st, d_proj, d_aff, d_bytes, 1);
     sync(ctx->st);
     gen.release();
     proj.release();
@@ -500,7 +531,7 @@ int zka_tom_commit_batch(zka_ctx* ctx, const zka_params* P, uint32_t count, cons
     uint8_t* bytes = ctx->w[4].get<uint8_t>((size_t)count * BSTRIDE);
     launch(st, count, CommitConvTask{dv, dr, jv, jr});
     launch(st, count, TomCommitTask{jv, jr, ctx->tg.tab, P->th.tab, proj, ctx->tom_w, ctx->tom_nwin});
-    launch(st, (count + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{proj, aff, bytes, (int)count});
+    launch_tom_norm(st, proj, aff, bytes, (long long)(count));
     if (is_device_ptr(out)) {
       launch(st, count, PackTomTask{bytes, out});
     } else {
@@ -540,10 +571,10 @@ int zka_p256_mul_batch(zka_ctx* ctx, uint32_t count, const uint8_t* base, const 
       launch(st, count, P256PowsTask{baff, binf, pows, (int)count, 64, 4});
       launch(st, (long long)count * 64, P256RowsTask{pows, rows, 4});
       const long long np = (long long)count * 64 * 16;
-      launch(st, (np + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{rows, rtab, nullptr, nullptr, (int)np});
+      launch_p256_norm(st, rows, rtab, nullptr, nullptr, (long long)(np));
     }
     launch(st, count, P256MulTask{dk, ctx->g8.tab, rtab, binf, proj});
-    launch(st, (count + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{proj, aff, bytes, inf, (int)count});
+    launch_p256_norm(st, proj, aff, bytes, inf, (long long)(count));
     if (is_device_ptr(out)) {
       launch(st, count, PackP256Task{bytes, out});
     } else {
@@ -615,7 +646,7 @@ int zka_params_generate(zka_ctx* ctx, const uint8_t rnd[64], uint8_t h_nist[65],
     launch(st, 1, GenConvTask{d_rnd, jv, jr});
     // v*g + 0*g: use the g table for both bases
     launch(st, 1, TomCommitTask{jv, jr, ctx->tg.tab, ctx->tg.tab, proj, ctx->tom_w, ctx->tom_nwin});
-    launch(st, 1, TomNormTask{proj, aff, bytes, 1});
+    launch_tom_norm(st, proj, aff, bytes, (long long)(1));
     copy_d2h(st, h_proof, bytes, 67);
     sync(st);
     return 0;
@@ -739,15 +770,15 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch(st, (long long)Bc * 64, P256RowsTask{c.rpows, c.rrows, 4});
       {
         const long long np = (long long)Bc * 64 * 16;
-        launch(st, (np + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np});
+        launch_p256_norm(st, c.rrows, c.rtab, nullptr, nullptr, (long long)(np));
       }
       // --- phase A
       launch(st, (long long)nA, PhaseAP256Task{c});
-      launch(st, (long long)(nA + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (int)nA});
-      launch(st, (long long)(nA + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (int)nA});
+      launch_p256_norm(st, c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (long long)(nA));
+      launch_p256_norm(st, c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (long long)(nA));
       launch(st, (long long)n1, JobsATask{c});
       launch(st, (long long)n1, TomCommitTask{c.s1_jv, c.s1_jr, c.tg_tab, c.th_tab, c.s1_proj, c.tom_w, c.tom_nwin});
-      launch(st, (long long)(n1 + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{c.s1_proj, c.s1_aff, c.s1_bytes, (int)n1});
+      launch_tom_norm(st, c.s1_proj, c.s1_aff, c.s1_bytes, (long long)(n1));
       // --- challenge, layout
       launch(st, Bc, ExpChallengeTask{c});
       launch(st, 1, ScanTask{c});
@@ -772,7 +803,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch(st, Bc, ItemsTask{c});
       // --- phase B
       launch(st, M, PhaseBP256Task{c});
-      launch(st, ((long long)M + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.pb_T1, c.pb_T1_aff, nullptr, c.pb_T1_inf, (int)M});
+      launch_p256_norm(st, c.pb_T1, c.pb_T1_aff, nullptr, c.pb_T1_inf, (long long)(M));
       launch(st, M, ItemScalarsTask{c});
       launch(st, (long long)Bc * n, GkJobsTask{c});
       launch(st, (long long)Bc * n, GkPolyTask{c});
@@ -783,10 +814,9 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         launch(st, (long long)nj, TomCommitTask{c.s2_jv, c.s2_jr, c.tg_tab, c.th_tab, c.s2_proj, c.tom_w, c.tom_nwin});
         launch(st, (long long)ng, TomCommitTask{c.s2_jv + g0 * 8, c.s2_jr + g0 * 8, c.tg_tab, c.th_tab,
                                                  c.s2_proj + g0 * TOM_PROJ_WORDS, c.tom_w, c.tom_nwin});
-        launch(st, (long long)(nj + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{c.s2_proj, c.s2_aff, c.s2_bytes, (int)nj});
+        launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)(nj));
         launch(st, M, DerivedTask{c});
-        launch(st, (long long)(nd + ng + NORM_CHUNK - 1) / NORM_CHUNK,
-               TomNormTask{c.s2_proj + nj * TOM_PROJ_WORDS, c.s2_aff + nj * TOM_AFF_WORDS, c.s2_bytes + nj * BSTRIDE, (int)(nd + ng)});
+        launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, c.s2_aff + nj * TOM_AFF_WORDS, c.s2_bytes + nj * BSTRIDE, (long long)(nd + ng));
       }
       launch(st, (long long)M * HASHES_PER_ITEM, ItemHashTask{c});
       launch(st, (long long)M * 7, ItemEmitTask{c});
@@ -892,17 +922,16 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch(st, (long long)Bc * 64, P256RowsTask{c.rpows, c.rrows, 4});
       {
         const long long np = (long long)Bc * 64 * 16;
-        launch(st, (np + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np});
+        launch_p256_norm(st, c.rrows, c.rtab, nullptr, nullptr, (long long)(np));
       }
       launch(st, Bc, VChallengeTask{c});
       launch(st, (long long)ns, VSampleP256Task{c});
-      launch(st, (long long)(ns + NORM_CHUNK - 1) / NORM_CHUNK, P256NormTask{c.sp_T, c.sp_T_aff, nullptr, c.sp_T_inf, (int)ns});
+      launch_p256_norm(st, c.sp_T, c.sp_T_aff, nullptr, c.sp_T_inf, (long long)(ns));
       launch(st, (long long)ns, VSampleJobsTask{c});
       launch(st, (long long)ns * 2, TomCommitTask{c.ta_jv, c.ta_jr, c.tg_tab, c.th_tab, c.ta_proj, c.tom_w, c.tom_nwin});
-      launch(st, (long long)(ns * 2 + NORM_CHUNK - 1) / NORM_CHUNK, TomNormTask{c.ta_proj, c.ta_aff, nullptr, (int)(ns * 2)});
+      launch_tom_norm(st, c.ta_proj, c.ta_aff, nullptr, (long long)(ns * 2));
       launch(st, (long long)ns, VDerivedTask{c});
-      launch(st, (long long)(ns * DERS_PER_ITEM + NORM_CHUNK - 1) / NORM_CHUNK,
-             TomNormTask{c.td_proj, c.td_aff, c.td_bytes, (int)(ns * DERS_PER_ITEM)});
+      launch_tom_norm(st, c.td_proj, c.td_aff, c.td_bytes, (long long)(ns * DERS_PER_ITEM));
       launch(st, (long long)ns * HASHES_PER_ITEM, VItemHashTask{c});
       dev_memset(st, c.ent_off, 0, (size_t)Bc * V_ENT_TOM * 4);
       launch(st, (long long)ns, VRelationsTask{c});
