@@ -270,7 +270,19 @@ struct Field {
     zero_n<N>(o);
     o[0] = 1;
     mul(r, a, o);
-    reduce(r);
+    if (F::kLazy) {
+      // a*1/R + p < 2p for any legal lazy input (a < 2^13 p << R): two conditional subtractions
+      // (2p, p) are more than enough; the generic 14-step ladder of reduce() is not needed here
+      uint32_t t[N], p2[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) p2[i] = (F::p(i) << 1) | (i > 0 ? (F::p(i - 1) >> 31) : 0u);
+      uint32_t br = sub_n<N>(t, r, p2);
+      csel_n<N>(r, br == 0, t, r);
+      br = sub_p<F>(t, r);
+      csel_n<N>(r, br == 0, t, r);
+    } else {
+      reduce(r);
+    }
   }
   // canonical zero test of a (possibly lazy) Montgomery value
   ZK_HD static bool is_zero(const uint32_t* a) {
@@ -330,6 +342,7 @@ ZK_HD void limbs_from_be(uint32_t* r, const uint8_t* b, int nbytes) {
 }
 template <int N>
 ZK_HD void limbs_to_be(uint8_t* b, const uint32_t* a, int nbytes) {
+#pragma unroll
   for (int k = 0; k < nbytes; k++) {
     int pos = nbytes - 1 - k;
     b[k] = ((pos >> 2) < N) ? (uint8_t)(a[pos >> 2] >> (8 * (pos & 3))) : 0;
