@@ -75,6 +75,28 @@ ZK_HD void tom_ld_pre(TomPre& q, const uint32_t* m) {
 #endif
 }
 
+// Encoded point (tag || x || y, big-endian coordinates of CB bytes) written as 32-bit words into a
+// 4-byte aligned BSTRIDE slot: 17 word stores instead of 65/67 byte stores (the byte index of
+// every output position is a compile-time constant after unrolling).
+template <int N, int CB>
+ZK_HD uint32_t enc_byte(int i, uint32_t tag, const uint32_t* x, const uint32_t* y) {
+  if (i == 0) return tag;
+  if (i >= 1 + 2 * CB) return 0u;
+  const uint32_t* c = i <= CB ? x : y;
+  const int pos = CB - 1 - (i <= CB ? i - 1 : i - 1 - CB);   // byte significance
+  return (pos >> 2) < N ? ((c[pos >> 2] >> (8 * (pos & 3))) & 0xffu) : 0u;
+}
+template <int N, int CB>
+ZK_HD void store_point_words(uint8_t* o, uint32_t tag, const uint32_t* x, const uint32_t* y) {
+  uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+  for (int j = 0; j < BSTRIDE / 4; j++) {
+    const uint32_t w = enc_byte<N, CB>(4 * j, tag, x, y) | (enc_byte<N, CB>(4 * j + 1, tag, x, y) << 8) |
+                       (enc_byte<N, CB>(4 * j + 2, tag, x, y) << 16) | (enc_byte<N, CB>(4 * j + 3, tag, x, y) << 24);
+    ow[j] = w;
+  }
+}
+
 // digit j of width w (w in {4, 8}) of a canonical 256-bit scalar
 ZK_HD uint32_t digit4(const uint32_t* k, int j) { return (k[j >> 3] >> (4 * (j & 7))) & 15u; }
 ZK_HD uint32_t digit8(const uint32_t* k, int j) { return (k[j >> 2] >> (8 * (j & 3))) & 255u; }
@@ -179,16 +201,11 @@ struct P256NormTask {
       if (inf) inf[lo + k] = isinf ? 1 : 0;
       if (bytes) {
         uint8_t* o = bytes + (size_t)(lo + k) * BSTRIDE;
-        if (isinf) {
-          for (int i = 0; i < NP; i++) o[i] = 0;
-        } else {
-          uint32_t c[8];
-          o[0] = 0x04;
-          F::from_mont(c, a.x);
-          limbs_to_be<8>(o + 1, c, 32);
-          F::from_mont(c, a.y);
-          limbs_to_be<8>(o + 33, c, 32);
-        }
+        uint32_t cx[8], cy[8];
+        F::from_mont(cx, a.x);
+        F::from_mont(cy, a.y);
+        if (isinf) { zero_n<8>(cx); zero_n<8>(cy); }
+        store_point_words<8, 32>(o, isinf ? 0x00u : 0x04u, cx, cy);
       }
     }
   }
@@ -368,13 +385,11 @@ struct TomNormTask {
       st<9>(a + 9, y);
       if (bytes) {
         uint8_t* o = bytes + (size_t)(lo + k) * BSTRIDE;
-        uint32_t c[9];
-        o[0] = 0x04;
-        F::mul(c, x, isa);      // back to the reference curve: x = x' / sqrt(a)
-        F::from_mont(c, c);
-        limbs_to_be<9>(o + 1, c, 33);
-        F::from_mont(c, y);
-        limbs_to_be<9>(o + 34, c, 33);
+        uint32_t cx[9], cy[9];
+        F::mul(cx, x, isa);      // back to the reference curve: x = x' / sqrt(a)
+        F::from_mont(cx, cx);
+        F::from_mont(cy, y);
+        store_point_words<9, 33>(o, 0x04u, cx, cy);
       }
     }
   }
@@ -430,7 +445,55 @@ ZK_HD void challenge_to_limbs(uint32_t* r, const uint32_t* c3) {
   r[0] = c3[0]; r[1] = c3[1]; r[2] = c3[2];
 }
 
-// write a canonical 8-limb scalar as a big-endian field of `len` bytes (32 or 33)
-ZK_HD void put_scalar(uint8_t* o, const uint32_t* c, int len) { limbs_to_be<8>(o, c, len); }
+// Store the first n bytes of a little-endian byte stream held in words w[0..NW) to an arbitrarily
+// aligned destination: <= 3 head bytes, aligned 32-bit stores built with 64-bit funnel shifts,
+// <= 3 tail bytes.  All register indices are static (the proof layout has odd field offsets, so
+// byte-wise copies were 65/67 single-byte stores per point).
+template <int NW>
+ZK_HD void store_stream(uint8_t* dst, const uint32_t* w, int n) {
+  const int head = (int)((4 - ((size_t)dst & 3)) & 3);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (i < head && i < n) dst[i] = (uint8_t)(w[0] >> (8 * i));
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  const int nw = (n - head) >> 2;
+#pragma unroll
+  for (int j = 0; j < NW; j++) {
+    const uint64_t pair = ((uint64_t)(j + 1 < NW ? w[j + 1] : 0u) << 32) | w[j];
+    const uint32_t v = (uint32_t)(pair >> (8 * head));
+    if (j < nw) {
+      dw[j] = v;
+    } else if (j == nw) {
+#pragma unroll
+      for (int t = 0; t < 3; t++)
+        if (head + 4 * nw + t < n) dst[head + 4 * nw + t] = (uint8_t)(v >> (8 * t));
+    }
+  }
+}
+// copy an encoded point (n = 65 or 67 bytes) from a 4-byte aligned BSTRIDE slot
+ZK_HD void copy_point(uint8_t* dst, const uint8_t* src, int n) {
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
+  uint32_t w[BSTRIDE / 4];
+#pragma unroll
+  for (int i = 0; i < BSTRIDE / 4; i++) w[i] = sw[i];
+  store_stream<BSTRIDE / 4>(dst, w, n);
+}
+// write a canonical 8-limb scalar as a big-endian field of LEN bytes (32 or 33)
+template <int LEN>
+ZK_HD void put_scalar(uint8_t* o, const uint32_t* c) {
+  uint32_t w[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int k = 4 * j + t;               // stream position
+      const int pos = LEN - 1 - k;           // byte significance
+      if (k < LEN && pos >= 0 && pos < 32) v |= ((c[pos >> 2] >> (8 * (pos & 3))) & 0xffu) << (8 * t);
+    }
+    w[j] = v;
+  }
+  store_stream<9>(o, w, LEN);
+}
 
 }  // namespace zk

@@ -558,7 +558,7 @@ ZK_HD void response(uint8_t* out, const uint32_t* k_canon, const uint32_t* cc, c
   uint32_t cw[8], t[8];
   F::mul(cw, cc, w_mont);   // c * (w R) / R = c*w, canonical
   F::sub(t, k_canon, cw);
-  put_scalar(out, t, WS);
+  put_scalar<WS>(out, t);
 }
 
 // Stage 8 — responses + byte assembly of one 0-bit repetition (exp.ts:212-225,
@@ -566,9 +566,7 @@ ZK_HD void response(uint8_t* out, const uint32_t* k_canon, const uint32_t* cc, c
 // part 0..3 MultProof m, 4..5 EqualityProof e, 6 repetition header/tail.
 struct ItemEmitTask {
   ProveCtx c;
-  ZK_HD void cp(uint8_t* dst, const uint8_t* src, int n) const {
-    for (int i = 0; i < n; i++) dst[i] = src[i];
-  }
+  ZK_HD void cp(uint8_t* dst, const uint8_t* src, int n) const { copy_point(dst, src, n); }
   ZK_HD void operator()(int t) const {
     const size_t it = (size_t)t / 7;
     const int part = t % 7;
@@ -621,18 +619,18 @@ struct ItemEmitTask {
       tape_draw(r0, c.tape_of(b), DRAW_COMS1_R); reduce_once<FnP256>(r0);
       ld<8>(s1, c.s1 + (size_t)b * 8);
       Fn::sub(z, alpha, s1);
-      put_scalar(body, z, NS);
+      put_scalar<NS>(body, z);
       Fn::sub(z, ri, r0);
-      put_scalar(body + NS, z, NS);
+      put_scalar<NS>(body + NS, z);
       cp(pa, c.s2_bytes + c.s2_job(it, JOB_C8) * BSTRIDE, WP);
       cp(pa + WP, c.s2_bytes + c.s2_job(it, JOB_C10) * BSTRIDE, WP);
       cp(pa + 2 * WP, c.s2_bytes + c.s2_job(it, JOB_C11) * BSTRIDE, WP);
       cp(pa + 3 * WP, c.s2_bytes + c.s2_job(it, JOB_C13) * BSTRIDE, WP);
       uint32_t r[8];
       tape_draw(r, c.tape_of(b), d0 + IT_T1X_R); reduce_once<FpP256>(r);
-      put_scalar(pa + PA_LEN, r, WS);
+      put_scalar<WS>(pa + PA_LEN, r);
       tape_draw(r, c.tape_of(b), d0 + IT_T1Y_R); reduce_once<FpP256>(r);
-      put_scalar(pa + PA_LEN + WS, r, WS);
+      put_scalar<WS>(pa + PA_LEN + WS, r);
     }
   }
 };
@@ -641,9 +639,7 @@ struct ItemEmitTask {
 // slot in [0, S] (slot S writes the 264-byte header R comS1 keyXcom keyYcom).
 struct RepEmitTask {
   ProveCtx c;
-  ZK_HD void cp(uint8_t* dst, const uint8_t* src, int n) const {
-    for (int i = 0; i < n; i++) dst[i] = src[i];
-  }
+  ZK_HD void cp(uint8_t* dst, const uint8_t* src, int n) const { copy_point(dst, src, n); }
   ZK_HD void operator()(int t) const {
     const int S1 = c.S + 1;
     const int b = t / S1, i = t % S1;
@@ -667,8 +663,8 @@ struct RepEmitTask {
       uint32_t r[8];
       for (int q = 0; q < 4; q++) {
         tape_draw(r, c.tape_of(b), DRAW_REP0 + DRAWS_PER_REP * i + q);
-        if (q < 2) { reduce_once<FnP256>(r); put_scalar(o, r, NS); o += NS; }
-        else       { reduce_once<FpP256>(r); put_scalar(o, r, WS); o += WS; }
+        if (q < 2) { reduce_once<FnP256>(r); put_scalar<NS>(o, r); o += NS; }
+        else       { reduce_once<FpP256>(r); put_scalar<WS>(o, r); o += WS; }
       }
     }
   }
@@ -857,8 +853,7 @@ struct GkEmitTask {
     uint8_t* o = c.proofs + (size_t)b * c.proof_stride + c.gk_off[b];
     *o++ = (uint8_t)n;
     for (int k = 0; k < 4 * n; k++) {
-      const uint8_t* s = c.s2_bytes + c.s2_gk(b, k) * BSTRIDE;
-      for (int q = 0; q < WP; q++) o[q] = s[q];
+      copy_point(o, c.s2_bytes + c.s2_gk(b, k) * BSTRIDE, WP);
       o += WP;
     }
     uint8_t* of = o;
@@ -881,17 +876,17 @@ struct GkEmitTask {
       // f_i = l_i x + a_i
       uint32_t f[8];
       if (bit) F::add(f, xc, ai); else copy_n<8>(f, ai);
-      put_scalar(of + (size_t)i * WS, f, WS);
+      put_scalar<WS>(of + (size_t)i * WS, f);
       // za_i = r_i x + s_i
       F::mul(t, ri, xm);          // canonical r_i * x
       F::add(u, t, si);
-      put_scalar(oza + (size_t)i * WS, u, WS);
+      put_scalar<WS>(oza + (size_t)i * WS, u);
       // zb_i = r_i (x - f_i) + t_i
       F::sub(u, xc, f);
       F::to_mont(u, u);
       F::mul(t, ri, u);
       F::add(u, t, ti);
-      put_scalar(ozb + (size_t)i * WS, u, WS);
+      put_scalar<WS>(ozb + (size_t)i * WS, u);
       // zd -= rho_i x^i   (xp = x^i in Montgomery form)
       F::mul(t, rho, xp);
       F::sub(zd, zd, t);
@@ -901,7 +896,7 @@ struct GkEmitTask {
     tape_draw(rpk, c.tape_of(b), DRAW_PKX_R); reduce_once<FpP256>(rpk);
     F::mul(t, rpk, xp);           // pkX.r * x^n
     F::add(zd, zd, t);
-    put_scalar(ozd, zd, WS);
+    put_scalar<WS>(ozd, zd);
   }
 };
 

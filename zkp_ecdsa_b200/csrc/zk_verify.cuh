@@ -822,10 +822,25 @@ struct VGkOffsetsTask {   // byte offsets of cl, ca, cb, cd, com for VParseEntri
 // One thread per (instance, window): 2^c - 1 buckets in local memory, mixed additions into
 // buckets, then the running-sum reduction.  Instances: GK (4n+1 entries) and multiW.
 // ---------------------------------------------------------------------------------------------
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+ZK_HD void bk_load(TomPt& p, const U4* b) {
+  uint32_t w[36];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { const U4 u = b[i]; w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) { p.x[i] = w[i]; p.y[i] = w[9 + i]; p.t[i] = w[18 + i]; p.z[i] = w[27 + i]; }
+}
+ZK_HD void bk_store(U4* b, const TomPt& p) {
+  uint32_t w[36];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { w[i] = p.x[i]; w[9 + i] = p.y[i]; w[18 + i] = p.t[i]; w[27 + i] = p.z[i]; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) { U4 u; u.x = w[4 * i]; u.y = w[4 * i + 1]; u.z = w[4 * i + 2]; u.w = w[4 * i + 3]; b[i] = u; }
+}
 struct MsmTomWindowTask {
   // Sorted-bucket Pippenger: a thread first counting-sorts the indices of its window's entries by
-  // digit (2 bytes of local memory per entry), then walks the buckets from the highest digit down,
-  // summing each bucket in REGISTERS and folding it into the running sums
+  // digit (2 bytes of local memory per entry), then walks the sorted entries in one flat loop,
+  // summing each bucket in REGISTERS, and finally folds the bucket sums into the running sums
   //   run += S_d ; tot += run      =>   tot = sum_d d * S_d .
   // (The first version kept 31 extended points per thread in local memory and read-modify-wrote
   // one per addition: 4.5 KB/thread thrashed L1/L2 — ncu: 26 GB of DRAM reads per launch, 5 % L1
@@ -844,7 +859,7 @@ struct MsmTomWindowTask {
     const int width = (256 - pos) < MSM_C ? (256 - pos) : MSM_C;
     const int wi = pos >> 5, sh = pos & 31;
     const uint32_t mask = (1u << width) - 1u;
-    uint16_t order[V_ENT_TOM];
+    uint16_t order[V_ENT_TOM];     // (digit << 10) | entry index, sorted by digit
     uint16_t start[NB + 1];
     for (int d = 0; d <= NB; d++) start[d] = 0;
     // pass 1: histogram of digits
@@ -859,11 +874,10 @@ struct MsmTomWindowTask {
         start[dgt + 1]++;
       }
     }
-    // exclusive prefix: start[d] = first slot of digit d
     for (int d = 1; d <= NB; d++) start[d] = (uint16_t)(start[d] + start[d - 1]);
     uint16_t fillp[NB];
     for (int d = 0; d < NB; d++) fillp[d] = start[d];
-    // pass 2: scatter entry indices
+    // pass 2: scatter
     for (int gidx = 0; gidx <= groups; gidx++) {
       const int base = gidx * group_len;
       const int m = gidx < groups ? (cnt ? (int)cnt[(size_t)inst * groups + gidx] : group_len) : tail;
@@ -872,22 +886,40 @@ struct MsmTomWindowTask {
         uint64_t v = k[wi];
         if (wi + 1 < 8) v |= (uint64_t)k[wi + 1] << 32;
         const uint32_t dgt = (uint32_t)(v >> sh) & mask;
-        order[fillp[dgt]++] = (uint16_t)(base + e);
+        order[fillp[dgt]++] = (uint16_t)((dgt << 10) | (uint32_t)(base + e));
       }
     }
-    // pass 3: buckets from the top digit down, each summed in registers
-    TomPt run, tot, acc;
+    // pass 3: ONE flat loop over the entries with a non-zero digit (the trip count is the same for
+    // every window of an instance up to +-3, so the warp does not diverge); a finished bucket sum
+    // is parked in local memory exactly once
+    U4 S[NB][9];
+    uint32_t present = 0;
+    TomPt acc;
+    tom_set_identity(acc);
+    int curd = NB - 1;
+    const int total = start[NB], first = start[1];
+    for (int q = total - 1; q >= first; q--) {
+      const uint32_t oe = order[q];
+      const int d = (int)(oe >> 10);
+      if (d != curd) {
+        bk_store(S[curd], acc);
+        present |= 1u << curd;
+        tom_set_identity(acc);
+        curd = d;
+      }
+      TomPre pt;
+      tom_ld_pre(pt, pp + (size_t)(oe & 1023u) * TOM_PRE_WORDS);
+      tom_madd<true>(acc, acc, pt);
+    }
+    bk_store(S[curd], acc);
+    present |= 1u << curd;
+    // pass 4: running sums  tot = sum_d d * S_d
+    TomPt run, tot;
     tom_set_identity(run);
     tom_set_identity(tot);
     for (int d = NB - 1; d >= 1; d--) {
-      const int lo = start[d], hi = start[d + 1];
-      if (hi > lo) {
-        tom_set_identity(acc);
-        for (int q = lo; q < hi; q++) {
-          TomPre pt;
-          tom_ld_pre(pt, pp + (size_t)order[q] * TOM_PRE_WORDS);
-          tom_madd<true>(acc, acc, pt);
-        }
+      if ((present >> d) & 1u) {
+        bk_load(acc, S[d]);
         tom_add(run, run, acc);
       }
       tom_add(tot, tot, run);
