@@ -115,6 +115,10 @@ inline void copy_d2h(Stream& st, void* h, const void* d, size_t n) {
 inline void copy_d2d(Stream& st, void* d, const void* s, size_t n) {
   if (n) ZK_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s));
 }
+// strided rows: only the first `width` bytes of each of `height` rows cross PCIe
+inline void copy_d2h_2d(Stream& st, void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height) {
+  if (width && height) ZK_CUDA_CHECK(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, height, cudaMemcpyDefault, st.s));
+}
 inline void dev_memset(Stream& st, void* d, int v, size_t n) {
   if (n) ZK_CUDA_CHECK(cudaMemsetAsync(d, v, n, st.s));
 }
@@ -155,6 +159,9 @@ inline void dev_free(void* p) { free(p); }
 inline void copy_h2d(Stream&, void* d, const void* h, size_t n) { if (n) memcpy(d, h, n); }
 inline void copy_d2h(Stream&, void* h, const void* d, size_t n) { if (n) memcpy(h, d, n); }
 inline void copy_d2d(Stream&, void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
+inline void copy_d2h_2d(Stream&, void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height) {
+  for (size_t r = 0; r < height; r++) memcpy((char*)h + r * hpitch, (const char*)d + r * dpitch, width);
+}
 inline void dev_memset(Stream&, void* d, int v, size_t n) { if (n) memset(d, v, n); }
 inline void sync(Stream&) {}
 inline bool is_device_ptr(const void*) { return false; }

@@ -310,12 +310,14 @@ struct ExpChallengeTask {
 struct ScanTask {
   ProveCtx c;
   ZK_HD void operator()(int) const {
-    uint32_t acc = 0;
+    uint32_t acc = 0, mx = 0;
     for (int b = 0; b < c.B; b++) {
       c.item_base[b] = acc;
       acc += c.zcount[b];
+      if (c.zcount[b] > mx) mx = c.zcount[b];
     }
     c.item_total[0] = acc;
+    c.item_total[1] = mx;   // longest proof of the chunk (bounds the D2H row width)
   }
 };
 struct ItemsTask {

@@ -753,7 +753,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.chal = W[21].get<uint32_t>((size_t)Bc * 3);
       c.zcount = W[22].get<uint32_t>(Bc);
       c.item_base = W[23].get<uint32_t>(Bc);
-      c.item_total = W[24].get<uint32_t>(1);
+      c.item_total = W[24].get<uint32_t>(2);
       c.rep_off = W[25].get<uint32_t>((size_t)Bc * S);
       c.gk_off = W[26].get<uint32_t>(Bc);
       c.gk_dv = W[27].get<uint32_t>((size_t)Bc * n * 8);
@@ -782,9 +782,11 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       // --- challenge, layout
       launch(st, Bc, ExpChallengeTask{c});
       launch(st, 1, ScanTask{c});
-      uint32_t M = 0;
-      copy_d2h(st, &M, c.item_total, 4);
+      uint32_t tot2[2] = {0, 0};
+      copy_d2h(st, tot2, c.item_total, 8);
       sync(st);
+      const uint32_t M = tot2[0];
+      const size_t max_len = (size_t)proof_len((int)tot2[1], n, S);
       c.M = (int)M;
       c.item_b = W[29].get<uint32_t>(M);
       c.item_i = W[30].get<uint32_t>(M);
@@ -823,7 +825,8 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch(st, (long long)nA, RepEmitTask{c});
       launch(st, Bc, GkEmitTask{c});
       // --- results
-      if (!out_dev) copy_d2h(st, proofs + (size_t)b0 * proof_stride, c.proofs, (size_t)Bc * proof_stride);
+      // only the bytes up to the longest proof of the chunk are copied back (rows are stride-padded)
+      if (!out_dev) copy_d2h_2d(st, proofs + (size_t)b0 * proof_stride, proof_stride, c.proofs, proof_stride, max_len, Bc);
       if (!is_device_ptr(proof_len_out)) copy_d2h(st, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
       if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
       sync(st);
