@@ -360,7 +360,13 @@ def run_ours(args):
             'hbm': {'achieved': alg_bytes / (avg_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak,
                     'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6.65 TB/s'},
-            'traffic': None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+            # (profiles/ncu_tomcommit_r1d_w16_noinline.md: 3.486 GB + 0.237 GB for 1 392 640 commitments =
+            # 2 674 B/commitment, w=16 tables), scaled to this run's commitments per launch
+            'traffic': commits_per_launch * 2674.0 if cfg['tom_w'] == 16 else None,
+            'traffic_unit': 'bytes/launch',
+            'traffic_note': 'algorithmic bytes are 172 B/commitment; the rest is the 32 random 128-byte table lookups per '
+                            'commitment (268 MB of tables, 44 % L2 hit rate) — HBM stays ~7 % busy',
         }
     kernels = {k.replace('zk::', ''): {'ms_per_step': v['ms'] / args.steps, 'launches_per_step': v['launches'] / args.steps}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
