@@ -102,3 +102,13 @@ def test_prove_verify_roundtrip_batch(gpu_engine):
     ok, st = common.run_verify(L, P, msg, wl.ring, proofs, plen, vt)
     assert (st == 0).all() and list(np.nonzero(ok == 0)[0]) == [3, 4]
     L.params_destroy(P)
+
+
+def test_edge_cases_on_gpu(gpu_engine):
+    import test_edge_cases as E
+    L = gpu_engine.lib
+    E.test_ring_of_two(L)
+    E.test_ragged_ring_signer_last(L)
+    E.test_zero_message_hash(L)
+    E.test_zero_r_and_zero_s(L)
+    E.test_key_to_int(L)
