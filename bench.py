@@ -37,7 +37,7 @@ WORKLOADS = {
 SEC_LEVEL = 80
 # executed field multiplications per tomEdwards256 commitment: 2*nwin mixed additions x 8 modmul,
 # each modmul = 9x9 product + 5 generic modulus limbs x 9 quotient digits = 126 32x32 MACs
-MODMUL_PER_MADD = 8
+MODMUL_PER_MADD = 7      # a = -1 image curve, mixed addition with (v-w, v+w, 2 d2 w v) entries (zk_curves.cuh)
 MAC_PER_TOM_MODMUL = 126   # 81 products + 45 quotient-digit products (zk_field_ptx.cuh); the generic CIOS needs 171
 W_PROVE_REF = {8: 6861088, 256: 6942368, 1024: 6974880}   # reference-algorithm modmuls/proof
 

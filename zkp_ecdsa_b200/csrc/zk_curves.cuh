@@ -204,11 +204,40 @@ ZK_HD void tom_const(uint32_t* r, int which) {
   constexpr uint32_t d1[9] = ZK_TOM_D1_MONT;
   constexpr uint32_t gx[9] = ZK_TOM_GX1_MONT;
   constexpr uint32_t gy[9] = ZK_TOM_GY_MONT;
+  constexpr uint32_t s2[9] = ZK_TOM_SQRTND1_MONT;
+  constexpr uint32_t is2[9] = ZK_TOM_INVSQRTND1_MONT;
+  constexpr uint32_t dd2[9] = ZK_TOM_2D2_MONT;
 #pragma unroll
   for (int i = 0; i < 9; i++)
-    r[i] = which == 0 ? sa[i] : which == 1 ? isa[i] : which == 2 ? d1[i] : which == 3 ? gx[i] : gy[i];
+    r[i] = which == 0 ? sa[i] : which == 1 ? isa[i] : which == 2 ? d1[i] : which == 3 ? gx[i] : which == 4 ? gy[i]
+           : which == 5 ? s2[i] : which == 6 ? is2[i] : dd2[i];
 }
-enum { TOM_SQRTA = 0, TOM_INVSQRTA = 1, TOM_D1 = 2, TOM_GX1 = 3, TOM_GY = 4 };
+enum { TOM_SQRTA = 0, TOM_INVSQRTA = 1, TOM_D1 = 2, TOM_GX1 = 3, TOM_GY = 4, TOM_SQRTND1 = 5, TOM_INVSQRTND1 = 6,
+       TOM_2D2 = 7 };
+
+// ---- second image curve E2: -w^2 + v^2 = 1 + d2 w^2 v^2, (w, v) = (sqrt(-d1) x', 1/y) -------------
+// Used ONLY by the prover's fixed-base commitment kernel (all its points lie in the prime-order
+// subgroup generated by g, where the a = -1 formulas have no exceptional cases; gen_consts.py).
+// Table entry: (v - w, v + w, 2 d2 w v).  Mixed addition "madd-2008-hwcd-3": 7M.
+template <bool kNeedT>
+ZK_HD void tom2_madd(TomPt& r, const TomPt& p, const TomPre& q) {   // q.x = v-w, q.y = v+w, q.k = 2 d2 w v
+  using F = Tomp;
+  uint32_t A[9], B[9], C[9], D[9], E[9], Fv[9], G[9], H[9];
+  F::sub(A, p.y, p.x);
+  F::mul(A, A, q.x);
+  F::add(B, p.y, p.x);
+  F::mul(B, B, q.y);
+  F::mul(C, p.t, q.k);
+  F::add(D, p.z, p.z);
+  F::sub(E, B, A);
+  F::sub(Fv, D, C);
+  F::add(G, D, C);
+  F::add(H, B, A);
+  F::mul(r.x, E, Fv);
+  F::mul(r.y, G, H);
+  if (kNeedT) F::mul(r.t, E, H);
+  F::mul(r.z, Fv, G);
+}
 
 ZK_HD void tom_set_identity(TomPt& p) {
   zero_n<9>(p.x);

@@ -344,14 +344,71 @@ struct TomPreTask {
   }
 };
 
-// Batched normalisation of tomEdwards256 points: proj (X,Y,Z) -> image-curve affine (x', y)
-// Montgomery (+ optional 67-byte reference encoding of (x = x'/sqrt(a), y)).
+// Rows of a fixed-base table (E1 projective X:Y:Z) -> entries of the prover's a = -1 image curve
+// E2 (zk_curves.cuh): (w, v) = (sqrt(-d1) X/Z, Z/Y), stored as (v - w, v + w, 2 d2 w v), canonical,
+// one 128-byte line each.  Montgomery's trick over chunks of 16 entries on the products Y*Z.
+struct TomTabE2Task {
+  const uint32_t* proj;  // [count][27]
+  uint32_t* pre;         // [count][32]
+  int count;
+  ZK_HD void operator()(int t) const {
+    using F = Tomp;
+    constexpr int CH = 16;
+    const int lo = t * CH;
+    int n = count - lo;
+    if (n > CH) n = CH;
+    if (n <= 0) return;
+    uint32_t pf[CH][9];
+    uint32_t acc[9], y[9], z[9], den[9];
+    F::set_one(acc);
+    for (int k = 0; k < n; k++) {
+      const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
+      ld<9>(y, src + 9);
+      ld<9>(z, src + 18);
+      F::mul(den, y, z);
+      F::mul(acc, acc, den);
+      copy_n<9>(pf[k], acc);
+    }
+    uint32_t inv[9], s2[9], dd2[9];
+    F::inv(inv, acc);
+    tom_const(s2, TOM_SQRTND1);
+    tom_const(dd2, TOM_2D2);
+    for (int k = n - 1; k >= 0; k--) {
+      const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
+      uint32_t x[9], di[9], w[9], v[9], kk[9], ym[9], yp[9];
+      ld<9>(x, src);
+      ld<9>(y, src + 9);
+      ld<9>(z, src + 18);
+      F::mul(den, y, z);
+      if (k > 0) F::mul(di, inv, pf[k - 1]); else copy_n<9>(di, inv);   // 1 / (Y Z)
+      F::mul(inv, inv, den);
+      F::mul(w, x, y);      // X Y
+      F::mul(w, w, di);     // X / Z
+      F::mul(w, w, s2);     // w
+      F::sqr(v, z);
+      F::mul(v, v, di);     // Z / Y
+      F::mul(kk, w, v);
+      F::mul(kk, kk, dd2);
+      F::sub(ym, v, w);
+      F::add(yp, v, w);
+      F::reduce(ym); F::reduce(yp); F::reduce(kk);
+      uint32_t* o = pre + (size_t)(lo + k) * TOM_PRE_WORDS;
+      st<9>(o, ym); st<9>(o + 9, yp); st<9>(o + 18, kk);
+      for (int i = 27; i < 32; i++) o[i] = 0;
+    }
+  }
+};
+
+// Batched normalisation of tomEdwards256 points -> E1 affine (x', y) Montgomery (+ optional 67-byte
+// reference encoding of (x = x'/sqrt(a), y)).  e2 == 0: input is E1 projective (X:Y:Z);
+// e2 == 1: input is an E2 point (W:V:Z) from the commitment kernel: x' = W / (Z sqrt(-d1)), y = Z / V.
 struct TomNormTask {
   const uint32_t* proj;  // [count][27]
   uint32_t* aff;         // [count][18]
   uint8_t* bytes;        // [count][BSTRIDE] or null
   int count;
   int chunk;             // points per thread (<= NORM_CHUNK_MAX)
+  int e2;
   ZK_HD void operator()(int t) const {
     using F = Tomp;
     const int lo = t * chunk;
@@ -359,27 +416,39 @@ struct TomNormTask {
     if (n > chunk) n = chunk;
     if (n <= 0) return;
     uint32_t pre[NORM_CHUNK_MAX][9];
-    uint32_t acc[9], z[9];
+    uint32_t acc[9], z[9], v[9], den[9];
     F::set_one(acc);
     for (int k = 0; k < n; k++) {
-      ld<9>(z, proj + (size_t)(lo + k) * TOM_PROJ_WORDS + 18);
-      F::mul(acc, acc, z);   // Z != 0 always on a complete Edwards curve
-      copy_n<9>(pre[k], acc);
-    }
-    uint32_t inv[9], isa[9];
-    F::inv(inv, acc);
-    tom_const(isa, TOM_INVSQRTA);
-    for (int k = n - 1; k >= 0; k--) {
       const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
       ld<9>(z, src + 18);
-      uint32_t zi[9];
-      if (k > 0) F::mul(zi, inv, pre[k - 1]); else copy_n<9>(zi, inv);
-      F::mul(inv, inv, z);
-      uint32_t X[9], Y[9], x[9], y[9];
+      if (e2) { ld<9>(v, src + 9); F::mul(den, z, v); } else copy_n<9>(den, z);
+      F::mul(acc, acc, den);   // Z != 0 (complete curve); V != 0 inside the prime-order subgroup
+      copy_n<9>(pre[k], acc);
+    }
+    uint32_t inv[9], isa[9], is2[9];
+    F::inv(inv, acc);
+    tom_const(isa, TOM_INVSQRTA);
+    tom_const(is2, TOM_INVSQRTND1);
+    for (int k = n - 1; k >= 0; k--) {
+      const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
+      uint32_t X[9], Y[9], x[9], y[9], di[9];
       ld<9>(X, src);
       ld<9>(Y, src + 9);
-      F::mul(x, X, zi);
-      F::mul(y, Y, zi);
+      ld<9>(z, src + 18);
+      if (e2) F::mul(den, z, Y); else copy_n<9>(den, z);
+      if (k > 0) F::mul(di, inv, pre[k - 1]); else copy_n<9>(di, inv);
+      F::mul(inv, inv, den);
+      if (e2) {
+        uint32_t zi[9], vi[9];
+        F::mul(zi, di, Y);       // 1/Z
+        F::mul(vi, di, z);       // 1/V
+        F::mul(x, X, zi);
+        F::mul(x, x, is2);       // x' = W / (Z sqrt(-d1))
+        F::mul(y, z, vi);        // y = Z / V
+      } else {
+        F::mul(x, X, di);
+        F::mul(y, Y, di);
+      }
       uint32_t* a = aff + (size_t)(lo + k) * TOM_AFF_WORDS;
       st<9>(a, x);
       st<9>(a + 9, y);
@@ -402,7 +471,7 @@ struct TomCommitTask {
   const uint32_t* jr;    // [count][8] canonical blinders
   const uint32_t* gtab;  // [nwin][2^w][32]
   const uint32_t* htab;
-  uint32_t* proj;        // [count][27]
+  uint32_t* proj;        // [count][27]  E2 point (W:V:Z) -> TomNormTask{e2 = 1}
   int w, nwin;
   ZK_HD void operator()(int t) const {
     uint32_t v[8], r[8];
@@ -416,9 +485,9 @@ struct TomCommitTask {
       int width = (256 - j * w) < w ? (256 - j * w) : w;
       uint32_t dv = digit_w(v, j * w, width), dr = digit_w(r, j * w, width);
       tom_ld_pre(q, gtab + ((size_t)j * ne + dv) * TOM_PRE_WORDS);
-      tom_madd<true>(acc, acc, q);
+      tom2_madd<true>(acc, acc, q);     // a = -1 image curve E2: 7M per lookup
       tom_ld_pre(q, htab + ((size_t)j * ne + dr) * TOM_PRE_WORDS);
-      tom_madd<true>(acc, acc, q);
+      tom2_madd<true>(acc, acc, q);
     }
     uint32_t* o = proj + (size_t)t * TOM_PROJ_WORDS;
     st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.z);

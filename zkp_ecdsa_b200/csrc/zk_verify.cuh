@@ -946,11 +946,17 @@ struct MsmTomCombineTask {
     TomPt f;
     const uint32_t* fp = fixed + ((size_t)inst * fix_stride + fix_off) * TOM_PROJ_WORDS;
     ld<9>(f.x, fp); ld<9>(f.y, fp + 9); ld<9>(f.z, fp + 18);
-    // T = X*Y/Z is not stored for commitment outputs; rebuild an extended point with Z' = Z^2:
-    // (XZ : YZ : XY : Z^2) represents the same point.
-    uint32_t xz[9], yz[9], xy[9], zz[9];
-    Tomp::mul(xz, f.x, f.z); Tomp::mul(yz, f.y, f.z); Tomp::mul(xy, f.x, f.y); Tomp::sqr(zz, f.z);
-    copy_n<9>(f.x, xz); copy_n<9>(f.y, yz); copy_n<9>(f.t, xy); copy_n<9>(f.z, zz);
+    // The commitment kernel works on the a = -1 image curve E2 and stores (W : V : Z) with
+    // x' = W / (Z sqrt(-d1)), y = Z / V.  Same point in E1 extended coordinates with Z' = Z V:
+    //   X = c W V,  Y = Z^2,  T = X Y / Z' = c W Z,   c = 1/sqrt(-d1).
+    uint32_t cw[9], X[9], Y[9], Tt[9], Zp[9], c1[9];
+    tom_const(c1, TOM_INVSQRTND1);
+    Tomp::mul(cw, f.x, c1);
+    Tomp::mul(X, cw, f.y);
+    Tomp::sqr(Y, f.z);
+    Tomp::mul(Tt, cw, f.z);
+    Tomp::mul(Zp, f.z, f.y);
+    copy_n<9>(f.x, X); copy_n<9>(f.y, Y); copy_n<9>(f.t, Tt); copy_n<9>(f.z, Zp);
     tom_add(acc, acc, f);
     // identity <=> X == 0 and Y == Z (edwards.ts:117-125 in projective form)
     const bool id = Tomp::is_zero(acc.x) && Tomp::eq(acc.y, acc.z);

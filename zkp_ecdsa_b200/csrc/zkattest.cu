@@ -272,10 +272,11 @@ inline void launch_p256_norm(Stream& st, const uint32_t* proj, uint32_t* aff, ui
   const int ch = norm_chunk_for(count);
   launch(st, (count + ch - 1) / ch, P256NormTask{proj, aff, bytes, inf, (int)count, ch});
 }
-inline void launch_tom_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uint8_t* bytes, long long count) {
+// e2 = 1: the points come from TomCommitTask (a = -1 image curve E2); e2 = 0: E1 projective
+inline void launch_tom_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uint8_t* bytes, long long count, int e2) {
   if (count <= 0) return;
   const int ch = norm_chunk_for(count);
-  launch(st, (count + ch - 1) / ch, TomNormTask{proj, aff, bytes, (int)count, ch});
+  launch(st, (count + ch - 1) / ch, TomNormTask{proj, aff, bytes, (int)count, ch, e2});
 }
 
 // ---- table construction -------------------------------------------------------------------
@@ -316,8 +317,9 @@ void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) 
   } else {
     launch(st, nwin, TomRowsTask{d_pows, d_rows, w});
   }
-  launch_tom_norm(st, d_rows, d_aff, nullptr, (long long)(count));
-  launch(st, (long long)count, TomPreTask{d_aff, out.tab});
+  // rows (E1 projective) -> entries of the prover's a = -1 image curve (v - w, v + w, 2 d2 w v)
+  launch(st, (long long)(count + 15) / 16, TomTabE2Task{d_rows, out.tab, (int)count});
+  (void)d_aff;
   sync(st);
   pows.release();
   rows.release();
@@ -430,7 +432,7 @@ int zka_init(int device, zka_ctx** out) {
     uint32_t* d_aff = aff.get<uint32_t>(TOM_AFF_WORDS);
     uint8_t* d_bytes = ctx->tg_bytes.get<uint8_t>(BSTRIDE);
     launch(ctx->st, 1, GProjTask{d_gen + 16, d_proj});
-    launch_tom_norm(ctx->st, d_proj, d_aff, d_bytes, 1);
+    launch_tom_norm(ctx->st, d_proj, d_aff, d_bytes, 1, 0);
     sync(ctx->st);
     gen.release();
     proj.release();
@@ -531,7 +533,7 @@ int zka_tom_commit_batch(zka_ctx* ctx, const zka_params* P, uint32_t count, cons
     uint8_t* bytes = ctx->w[4].get<uint8_t>((size_t)count * BSTRIDE);
     launch(st, count, CommitConvTask{dv, dr, jv, jr});
     launch(st, count, TomCommitTask{jv, jr, ctx->tg.tab, P->th.tab, proj, ctx->tom_w, ctx->tom_nwin});
-    launch_tom_norm(st, proj, aff, bytes, (long long)(count));
+    launch_tom_norm(st, proj, aff, bytes, (long long)(count), 1);
     if (is_device_ptr(out)) {
       launch(st, count, PackTomTask{bytes, out});
     } else {
@@ -646,7 +648,7 @@ int zka_params_generate(zka_ctx* ctx, const uint8_t rnd[64], uint8_t h_nist[65],
     launch(st, 1, GenConvTask{d_rnd, jv, jr});
     // v*g + 0*g: use the g table for both bases
     launch(st, 1, TomCommitTask{jv, jr, ctx->tg.tab, ctx->tg.tab, proj, ctx->tom_w, ctx->tom_nwin});
-    launch_tom_norm(st, proj, aff, bytes, (long long)(1));
+    launch_tom_norm(st, proj, aff, bytes, (long long)(1), 1);
     copy_d2h(st, h_proof, bytes, 67);
     sync(st);
     return 0;
@@ -778,7 +780,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch_p256_norm(st, c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (long long)(nA));
       launch(st, (long long)n1, JobsATask{c});
       launch(st, (long long)n1, TomCommitTask{c.s1_jv, c.s1_jr, c.tg_tab, c.th_tab, c.s1_proj, c.tom_w, c.tom_nwin});
-      launch_tom_norm(st, c.s1_proj, c.s1_aff, c.s1_bytes, (long long)(n1));
+      launch_tom_norm(st, c.s1_proj, c.s1_aff, c.s1_bytes, (long long)(n1), 1);
       // --- challenge, layout
       launch(st, Bc, ExpChallengeTask{c});
       launch(st, 1, ScanTask{c});
@@ -816,9 +818,11 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         launch(st, (long long)nj, TomCommitTask{c.s2_jv, c.s2_jr, c.tg_tab, c.th_tab, c.s2_proj, c.tom_w, c.tom_nwin});
         launch(st, (long long)ng, TomCommitTask{c.s2_jv + g0 * 8, c.s2_jr + g0 * 8, c.tg_tab, c.th_tab,
                                                  c.s2_proj + g0 * TOM_PROJ_WORDS, c.tom_w, c.tom_nwin});
-        launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)(nj));
+        launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)(nj), 1);
         launch(st, M, DerivedTask{c});
-        launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, c.s2_aff + nj * TOM_AFF_WORDS, c.s2_bytes + nj * BSTRIDE, (long long)(nd + ng));
+        // derived points come from complete E1 additions, the GK commitments from the commit kernel (E2)
+        launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, c.s2_aff + nj * TOM_AFF_WORDS, c.s2_bytes + nj * BSTRIDE, (long long)nd, 0);
+        launch_tom_norm(st, c.s2_proj + g0 * TOM_PROJ_WORDS, c.s2_aff + g0 * TOM_AFF_WORDS, c.s2_bytes + g0 * BSTRIDE, (long long)ng, 1);
       }
       launch(st, (long long)M * HASHES_PER_ITEM, ItemHashTask{c});
       launch(st, (long long)M * 7, ItemEmitTask{c});
@@ -932,9 +936,9 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch_p256_norm(st, c.sp_T, c.sp_T_aff, nullptr, c.sp_T_inf, (long long)(ns));
       launch(st, (long long)ns, VSampleJobsTask{c});
       launch(st, (long long)ns * 2, TomCommitTask{c.ta_jv, c.ta_jr, c.tg_tab, c.th_tab, c.ta_proj, c.tom_w, c.tom_nwin});
-      launch_tom_norm(st, c.ta_proj, c.ta_aff, nullptr, (long long)(ns * 2));
+      launch_tom_norm(st, c.ta_proj, c.ta_aff, nullptr, (long long)(ns * 2), 1);
       launch(st, (long long)ns, VDerivedTask{c});
-      launch_tom_norm(st, c.td_proj, c.td_aff, c.td_bytes, (long long)(ns * DERS_PER_ITEM));
+      launch_tom_norm(st, c.td_proj, c.td_aff, c.td_bytes, (long long)(ns * DERS_PER_ITEM), 0);
       launch(st, (long long)ns * HASHES_PER_ITEM, VItemHashTask{c});
       dev_memset(st, c.ent_off, 0, (size_t)Bc * V_ENT_TOM * 4);
       launch(st, (long long)ns, VRelationsTask{c});
