@@ -107,6 +107,63 @@ ZK_HD void p256_dbl(P256Pt& r, const P256Pt& p) {
   copy_n<8>(r.z, z3);
 }
 
+// Jacobian doubling for a = -3 ("dbl-2001-b", 3M + 5S = 8 multiplications instead of 13): used only
+// in the long DOUBLING CHAINS (16^j R for the per-proof table, the one-shot ladder u2*pk), which
+// are latency-bound with one thread per proof.  Doubling has no exceptional case on a prime-order
+// curve (no points of order 2) and maps the identity (Z = 0) to itself.
+struct P256Jac {
+  uint32_t x[8], y[8], z[8];   // x = X/Z^2, y = Y/Z^3
+};
+ZK_HD void p256_jac_dbl(P256Jac& r, const P256Jac& p) {
+  using F = P256p;
+  uint32_t delta[8], gamma[8], beta[8], alpha[8], t0[8], t1[8];
+  F::sqr(delta, p.z);
+  F::sqr(gamma, p.y);
+  F::mul(beta, p.x, gamma);
+  F::sub(t0, p.x, delta);
+  F::add(t1, p.x, delta);
+  F::mul(alpha, t0, t1);
+  F::add(t0, alpha, alpha);
+  F::add(alpha, t0, alpha);            // 3 (X - delta)(X + delta)
+  F::add(t0, p.y, p.z);
+  F::sqr(t0, t0);
+  F::sub(t0, t0, gamma);
+  F::sub(r.z, t0, delta);              // Z3 = (Y + Z)^2 - gamma - delta
+  F::add(t0, beta, beta);
+  F::add(t0, t0, t0);                  // 4 beta
+  F::add(t1, t0, t0);                  // 8 beta
+  F::sqr(r.x, alpha);
+  F::sub(r.x, r.x, t1);                // X3 = alpha^2 - 8 beta
+  F::sub(t0, t0, r.x);
+  F::mul(t0, alpha, t0);
+  F::sqr(t1, gamma);
+  F::add(t1, t1, t1);
+  F::add(t1, t1, t1);
+  F::add(t1, t1, t1);                  // 8 gamma^2
+  F::sub(r.y, t0, t1);                 // Y3 = alpha (4 beta - X3) - 8 gamma^2
+}
+// Jacobian (X:Y:Z) -> homogeneous (X Z : Y : Z^3);  homogeneous (X:Y:Z) -> Jacobian (X Z : Y Z^2 : Z)
+ZK_HD void p256_jac_to_hom(P256Pt& r, const P256Jac& p) {
+  using F = P256p;
+  uint32_t z2[8];
+  F::sqr(z2, p.z);
+  F::mul(r.x, p.x, p.z);
+  copy_n<8>(r.y, p.y);
+  F::mul(r.z, z2, p.z);
+}
+ZK_HD void p256_hom_to_jac(P256Jac& r, const P256Pt& p) {
+  using F = P256p;
+  uint32_t z2[8];
+  F::sqr(z2, p.z);
+  F::mul(r.x, p.x, p.z);
+  F::mul(r.y, p.y, z2);
+  copy_n<8>(r.z, p.z);
+  if (is_zero_n<8>(p.z)) {   // identity (0:Y:0) -> (1:1:0); (0:0:0) would not survive the way back
+    F::set_one(r.x);
+    F::set_one(r.y);
+  }
+}
+
 // shared tail of RCB15 Alg. 4 / Alg. 5 after t0,t1,t2,t3,t4,y3 are formed:
 //   t0 = X1X2, t1 = Y1Y2, t2 = Z1Z2, t3 = X1Y2+X2Y1, t4 = Y1Z2+Y2Z1, y3 = X1Z2+X2Z1
 ZK_HD void p256_add_tail(P256Pt& r, uint32_t* t0, uint32_t* t1, uint32_t* t2, uint32_t* t3, uint32_t* t4,
@@ -207,13 +264,14 @@ ZK_HD void tom_const(uint32_t* r, int which) {
   constexpr uint32_t s2[9] = ZK_TOM_SQRTND1_MONT;
   constexpr uint32_t is2[9] = ZK_TOM_INVSQRTND1_MONT;
   constexpr uint32_t dd2[9] = ZK_TOM_2D2_MONT;
+  constexpr uint32_t isd[9] = ZK_TOM_INVSQRTND_MONT;
 #pragma unroll
   for (int i = 0; i < 9; i++)
     r[i] = which == 0 ? sa[i] : which == 1 ? isa[i] : which == 2 ? d1[i] : which == 3 ? gx[i] : which == 4 ? gy[i]
-           : which == 5 ? s2[i] : which == 6 ? is2[i] : dd2[i];
+           : which == 5 ? s2[i] : which == 6 ? is2[i] : which == 7 ? dd2[i] : isd[i];
 }
 enum { TOM_SQRTA = 0, TOM_INVSQRTA = 1, TOM_D1 = 2, TOM_GX1 = 3, TOM_GY = 4, TOM_SQRTND1 = 5, TOM_INVSQRTND1 = 6,
-       TOM_2D2 = 7 };
+       TOM_2D2 = 7, TOM_INVSQRTND = 8 };
 
 // ---- second image curve E2: -w^2 + v^2 = 1 + d2 w^2 v^2, (w, v) = (sqrt(-d1) x', 1/y) -------------
 // Used ONLY by the prover's fixed-base commitment kernel (all its points lie in the prime-order

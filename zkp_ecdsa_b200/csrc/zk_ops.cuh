@@ -131,9 +131,13 @@ struct P256PowsTask {
     P256Pt p;
     p256_from_affine(p, a);
     if (base_inf && base_inf[t]) p256_set_identity(p);
+    // the doubling chain runs in Jacobian coordinates (8 instead of 13 multiplications per step)
+    P256Jac q;
+    p256_hom_to_jac(q, p);
     for (int j = 0; j < nwin; j++) {
+      p256_jac_to_hom(p, q);
       p256_st_proj(pows + ((size_t)t * nwin + j) * P256_PROJ_WORDS, p);
-      for (int k = 0; k < w; k++) p256_dbl(p, p);
+      for (int k = 0; k < w; k++) p256_jac_dbl(q, q);
     }
   }
 };
@@ -241,7 +245,11 @@ ZK_HD void p256_mul_var(P256Pt& r, const P256Aff& base, const uint32_t* k) {
   for (int d = 2; d < 16; d++) p256_madd(tb[d], tb[d - 1], base);
   p256_set_identity(r);
   for (int j = 63; j >= 0; j--) {
-    p256_dbl(r, r); p256_dbl(r, r); p256_dbl(r, r); p256_dbl(r, r);
+    // four doublings in Jacobian coordinates, the (complete) table addition in homogeneous ones
+    P256Jac q;
+    p256_hom_to_jac(q, r);
+    p256_jac_dbl(q, q); p256_jac_dbl(q, q); p256_jac_dbl(q, q); p256_jac_dbl(q, q);
+    p256_jac_to_hom(r, q);
     p256_add(r, r, tb[digit4(k, j)]);
   }
 }
@@ -404,11 +412,21 @@ struct TomTabE2Task {
 // e2 == 1: input is an E2 point (W:V:Z) from the commitment kernel: x' = W / (Z sqrt(-d1)), y = Z / V.
 struct TomNormTask {
   const uint32_t* proj;  // [count][27]
-  uint32_t* aff;         // [count][18]
+  uint32_t* aff;         // [count][18] or null
   uint8_t* bytes;        // [count][BSTRIDE] or null
   int count;
   int chunk;             // points per thread (<= NORM_CHUNK_MAX)
   int e2;
+  int aff_mod, aff_lim;  // the E1 affine pair is produced only for points with (index % aff_mod) < aff_lim
+  ZK_HD static void canon2p(uint32_t* r) {   // value < 4p -> [0, p)
+    uint32_t t[9], p2[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) p2[i] = (FpTom::p(i) << 1) | (i > 0 ? (FpTom::p(i - 1) >> 31) : 0u);
+    uint32_t br = sub_n<9>(t, r, p2);
+    csel_n<9>(r, br == 0, t, r);
+    br = sub_p<FpTom>(t, r);
+    csel_n<9>(r, br == 0, t, r);
+  }
   ZK_HD void operator()(int t) const {
     using F = Tomp;
     const int lo = t * chunk;
@@ -425,40 +443,58 @@ struct TomNormTask {
       F::mul(acc, acc, den);   // Z != 0 (complete curve); V != 0 inside the prime-order subgroup
       copy_n<9>(pre[k], acc);
     }
-    uint32_t inv[9], isa[9], is2[9];
+    uint32_t inv[9], isa[9], is2[9], isd[9], one_plain[9];
     F::inv(inv, acc);
     tom_const(isa, TOM_INVSQRTA);
     tom_const(is2, TOM_INVSQRTND1);
+    tom_const(isd, TOM_INVSQRTND);
+    zero_n<9>(one_plain);
+    one_plain[0] = 1;
     for (int k = n - 1; k >= 0; k--) {
       const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
-      uint32_t X[9], Y[9], x[9], y[9], di[9];
+      uint32_t X[9], Y[9], di[9];
       ld<9>(X, src);
       ld<9>(Y, src + 9);
       ld<9>(z, src + 18);
       if (e2) F::mul(den, z, Y); else copy_n<9>(den, z);
-      if (k > 0) F::mul(di, inv, pre[k - 1]); else copy_n<9>(di, inv);
+      if (k > 0) F::mul(di, inv, pre[k - 1]); else copy_n<9>(di, inv);   // Montgomery residue of 1/den
       F::mul(inv, inv, den);
-      if (e2) {
-        uint32_t zi[9], vi[9];
-        F::mul(zi, di, Y);       // 1/Z
-        F::mul(vi, di, z);       // 1/V
-        F::mul(x, X, zi);
-        F::mul(x, x, is2);       // x' = W / (Z sqrt(-d1))
-        F::mul(y, z, vi);        // y = Z / V
-      } else {
-        F::mul(x, X, di);
-        F::mul(y, Y, di);
-      }
-      uint32_t* a = aff + (size_t)(lo + k) * TOM_AFF_WORDS;
-      st<9>(a, x);
-      st<9>(a + 9, y);
       if (bytes) {
-        uint8_t* o = bytes + (size_t)(lo + k) * BSTRIDE;
-        uint32_t cx[9], cy[9];
-        F::mul(cx, x, isa);      // back to the reference curve: x = x' / sqrt(a)
-        F::from_mont(cx, cx);
-        F::from_mont(cy, y);
-        store_point_words<9, 33>(o, 0x04u, cx, cy);
+        // D = 1/den as a PLAIN integer: a Montgomery product with it leaves Montgomery form, so the
+        // reference coordinates come out without separate from_mont multiplications
+        uint32_t Dp[9], cx[9], cy[9];
+        F::mul(Dp, di, one_plain);
+        if (e2) {                       // x = W V D / sqrt(-d),  y = Z^2 D
+          F::mul(cx, X, Y);
+          F::mul(cx, cx, isd);
+          F::mul(cx, cx, Dp);
+          F::sqr(cy, z);
+          F::mul(cy, cy, Dp);
+        } else {                        // x = X D / sqrt(a),  y = Y D
+          F::mul(cx, X, isa);
+          F::mul(cx, cx, Dp);
+          F::mul(cy, Y, Dp);
+        }
+        canon2p(cx);
+        canon2p(cy);
+        store_point_words<9, 33>(bytes + (size_t)(lo + k) * BSTRIDE, 0x04u, cx, cy);
+      }
+      if (aff && ((lo + k) % aff_mod) < aff_lim) {
+        uint32_t x[9], y[9];
+        if (e2) {
+          uint32_t zi[9], vi[9];
+          F::mul(zi, di, Y);       // 1/Z
+          F::mul(vi, di, z);       // 1/V
+          F::mul(x, X, zi);
+          F::mul(x, x, is2);       // x' = W / (Z sqrt(-d1))
+          F::mul(y, z, vi);        // y = Z / V
+        } else {
+          F::mul(x, X, di);
+          F::mul(y, Y, di);
+        }
+        uint32_t* a = aff + (size_t)(lo + k) * TOM_AFF_WORDS;
+        st<9>(a, x);
+        st<9>(a + 9, y);
       }
     }
   }

@@ -66,9 +66,7 @@ struct Sha256 {
       hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
-#pragma unroll
-    for (int i = 0; i < 16; i++) w[i] = 0;
-    fill = 0;
+    fill -= 64;   // bytes still pending in `cur` (0..3) belong to the next block
   }
 
   // The block buffer is a 16-word FIFO with static indices only (w[15] is the newest word), so it
@@ -88,8 +86,22 @@ struct Sha256 {
       if (fill == 64) compress();
     }
   }
+  // four stream bytes at once, given as the little-endian word loaded from memory
+  ZK_HD void put4(uint32_t lw) {
+    const uint32_t bw = (lw << 24) | ((lw & 0xff00u) << 8) | ((lw >> 8) & 0xff00u) | (lw >> 24);
+    const int nb = (int)(fill & 3);                       // bytes pending in `cur`
+    const uint64_t v = ((uint64_t)cur << 32) | bw;
+    push_word((uint32_t)(v >> (8 * nb)));
+    cur = bw;                                             // its low nb bytes are the new pending bytes
+    fill += 4;
+    total += 4;
+    if (fill >= 64) compress();
+  }
   ZK_HD void update(const uint8_t* p, int n) {
-    for (int i = 0; i < n; i++) put(p[i]);
+    int i = 0;
+    while (i < n && (((size_t)(p + i)) & 3)) put(p[i++]);
+    for (; i + 4 <= n; i += 4) put4(*reinterpret_cast<const uint32_t*>(p + i));
+    for (; i < n; i++) put(p[i]);
   }
   // digest[0..9] as (hi16, lo64): challenge = hi16 * 2^64 + lo64
   ZK_HD void final80(uint32_t* c3) {  // c3[0] = low 32, c3[1] = mid 32, c3[2] = top 16 bits

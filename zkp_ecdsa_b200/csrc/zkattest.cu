@@ -273,10 +273,12 @@ inline void launch_p256_norm(Stream& st, const uint32_t* proj, uint32_t* aff, ui
   launch(st, (count + ch - 1) / ch, P256NormTask{proj, aff, bytes, inf, (int)count, ch});
 }
 // e2 = 1: the points come from TomCommitTask (a = -1 image curve E2); e2 = 0: E1 projective
-inline void launch_tom_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uint8_t* bytes, long long count, int e2) {
+// aff may be null; otherwise the E1 affine pair is written for points with (index % aff_mod) < aff_lim
+inline void launch_tom_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uint8_t* bytes, long long count, int e2,
+                            int aff_mod = 1, int aff_lim = 1) {
   if (count <= 0) return;
   const int ch = norm_chunk_for(count);
-  launch(st, (count + ch - 1) / ch, TomNormTask{proj, aff, bytes, (int)count, ch, e2});
+  launch(st, (count + ch - 1) / ch, TomNormTask{proj, aff, bytes, (int)count, ch, e2, aff_mod, aff_lim});
 }
 
 // ---- table construction -------------------------------------------------------------------
@@ -818,11 +820,12 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         launch(st, (long long)nj, TomCommitTask{c.s2_jv, c.s2_jr, c.tg_tab, c.th_tab, c.s2_proj, c.tom_w, c.tom_nwin});
         launch(st, (long long)ng, TomCommitTask{c.s2_jv + g0 * 8, c.s2_jr + g0 * 8, c.tg_tab, c.th_tab,
                                                  c.s2_proj + g0 * TOM_PROJ_WORDS, c.tom_w, c.tom_nwin});
-        launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)(nj), 1);
+        // only T1x, T1y (jobs 0, 1 of each item) are needed again as points (DerivedTask)
+        launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)(nj), 1, JOBS_PER_ITEM, 2);
         launch(st, M, DerivedTask{c});
         // derived points come from complete E1 additions, the GK commitments from the commit kernel (E2)
-        launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, c.s2_aff + nj * TOM_AFF_WORDS, c.s2_bytes + nj * BSTRIDE, (long long)nd, 0);
-        launch_tom_norm(st, c.s2_proj + g0 * TOM_PROJ_WORDS, c.s2_aff + g0 * TOM_AFF_WORDS, c.s2_bytes + g0 * BSTRIDE, (long long)ng, 1);
+        launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, nullptr, c.s2_bytes + nj * BSTRIDE, (long long)nd, 0);
+        launch_tom_norm(st, c.s2_proj + g0 * TOM_PROJ_WORDS, nullptr, c.s2_bytes + g0 * BSTRIDE, (long long)ng, 1);
       }
       launch(st, (long long)M * HASHES_PER_ITEM, ItemHashTask{c});
       launch(st, (long long)M * 7, ItemEmitTask{c});
@@ -938,7 +941,7 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch(st, (long long)ns * 2, TomCommitTask{c.ta_jv, c.ta_jr, c.tg_tab, c.th_tab, c.ta_proj, c.tom_w, c.tom_nwin});
       launch_tom_norm(st, c.ta_proj, c.ta_aff, nullptr, (long long)(ns * 2), 1);
       launch(st, (long long)ns, VDerivedTask{c});
-      launch_tom_norm(st, c.td_proj, c.td_aff, c.td_bytes, (long long)(ns * DERS_PER_ITEM), 0);
+      launch_tom_norm(st, c.td_proj, nullptr, c.td_bytes, (long long)(ns * DERS_PER_ITEM), 0);
       launch(st, (long long)ns * HASHES_PER_ITEM, VItemHashTask{c});
       dev_memset(st, c.ent_off, 0, (size_t)Bc * V_ENT_TOM * 4);
       launch(st, (long long)ns, VRelationsTask{c});
