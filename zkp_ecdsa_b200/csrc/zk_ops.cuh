@@ -43,7 +43,7 @@ ZK_HD void st(uint32_t* p, const uint32_t* r) {
 enum : int {
   P256_PROJ_WORDS = 24,
   P256_AFF_WORDS = 16,
-  TOM_PROJ_WORDS = 27,   // X, Y, Z (T is not needed after the last addition)
+  TOM_PROJ_WORDS = 28,   // X, Y, Z (T is not needed after the last addition) + 1 pad word: 7 x 16 bytes
   TOM_AFF_WORDS = 18,    // x', y on the a'=1 image curve, Montgomery
   TOM_PRE_WORDS = 32,    // x', y, k = d' x' y + 5 pad words: one 128-byte line per entry
   NORM_CHUNK_MAX = 64,   // max points per Montgomery-trick chunk (one Fermat inversion each)
@@ -57,6 +57,37 @@ ZK_HD void p256_st_proj(uint32_t* m, const P256Pt& p) {
 }
 ZK_HD void p256_ld_aff(P256Aff& a, const uint32_t* m) { ld<8>(a.x, m); ld<8>(a.y, m + 8); }
 ZK_HD void p256_st_aff(uint32_t* m, const P256Aff& a) { st<8>(m, a.x); st<8>(m + 8, a.y); }
+
+// staged tomEdwards256 points (X, Y, Z at words 0, 9, 18 of a 112-byte, 16-byte aligned slot):
+// seven 16-byte transactions instead of 27 four-byte ones (the slots are strided per thread)
+ZK_HD void tom_st_xyz(uint32_t* m, const uint32_t* x, const uint32_t* y, const uint32_t* z) {
+  uint32_t w[28];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { w[i] = x[i]; w[9 + i] = y[i]; w[18 + i] = z[i]; }
+  w[27] = 0;
+#if defined(__CUDA_ARCH__)
+  uint4* v = reinterpret_cast<uint4*>(m);
+#pragma unroll
+  for (int i = 0; i < 7; i++) v[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+#else
+  for (int i = 0; i < 28; i++) m[i] = w[i];
+#endif
+}
+ZK_HD void tom_ld_xyz(uint32_t* x, uint32_t* y, uint32_t* z, const uint32_t* m) {
+  uint32_t w[28];
+#if defined(__CUDA_ARCH__)
+  const uint4* v = reinterpret_cast<const uint4*>(m);
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const uint4 u = v[i];
+    w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
+  }
+#else
+  for (int i = 0; i < 28; i++) w[i] = m[i];
+#endif
+#pragma unroll
+  for (int i = 0; i < 9; i++) { x[i] = w[i]; y[i] = w[9 + i]; z[i] = w[18 + i]; }
+}
 
 ZK_HD void tom_ld_pre(TomPre& q, const uint32_t* m) {
 #if defined(__CUDA_ARCH__)
@@ -286,7 +317,7 @@ struct TomRowsTask {
     uint32_t* out = rows + (size_t)t * ne * TOM_PROJ_WORDS;
     for (int d = 0; d < ne; d++) {
       uint32_t* o = out + (size_t)d * TOM_PROJ_WORDS;
-      st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.z);
+      tom_st_xyz(o, acc.x, acc.y, acc.z);
       tom_add(acc, acc, p);
     }
   }
@@ -328,7 +359,7 @@ struct TomRowsLoTask {
     uint32_t* out = rows + (((size_t)j << w) + ((size_t)m << 8)) * TOM_PROJ_WORDS;
     for (int d = 0; d < 256; d++) {
       uint32_t* o = out + (size_t)d * TOM_PROJ_WORDS;
-      st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.z);
+      tom_st_xyz(o, acc.x, acc.y, acc.z);
       tom_add(acc, acc, p);
     }
   }
@@ -371,8 +402,8 @@ struct TomTabE2Task {
     F::set_one(acc);
     for (int k = 0; k < n; k++) {
       const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
-      ld<9>(y, src + 9);
-      ld<9>(z, src + 18);
+      uint32_t xx[9];
+      tom_ld_xyz(xx, y, z, src);
       F::mul(den, y, z);
       F::mul(acc, acc, den);
       copy_n<9>(pf[k], acc);
@@ -384,9 +415,7 @@ struct TomTabE2Task {
     for (int k = n - 1; k >= 0; k--) {
       const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
       uint32_t x[9], di[9], w[9], v[9], kk[9], ym[9], yp[9];
-      ld<9>(x, src);
-      ld<9>(y, src + 9);
-      ld<9>(z, src + 18);
+      tom_ld_xyz(x, y, z, src);
       F::mul(den, y, z);
       if (k > 0) F::mul(di, inv, pf[k - 1]); else copy_n<9>(di, inv);   // 1 / (Y Z)
       F::mul(inv, inv, den);
@@ -438,8 +467,9 @@ struct TomNormTask {
     F::set_one(acc);
     for (int k = 0; k < n; k++) {
       const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
-      ld<9>(z, src + 18);
-      if (e2) { ld<9>(v, src + 9); F::mul(den, z, v); } else copy_n<9>(den, z);
+      uint32_t xx[9];
+      tom_ld_xyz(xx, v, z, src);
+      if (e2) F::mul(den, z, v); else copy_n<9>(den, z);
       F::mul(acc, acc, den);   // Z != 0 (complete curve); V != 0 inside the prime-order subgroup
       copy_n<9>(pre[k], acc);
     }
@@ -453,9 +483,7 @@ struct TomNormTask {
     for (int k = n - 1; k >= 0; k--) {
       const uint32_t* src = proj + (size_t)(lo + k) * TOM_PROJ_WORDS;
       uint32_t X[9], Y[9], di[9];
-      ld<9>(X, src);
-      ld<9>(Y, src + 9);
-      ld<9>(z, src + 18);
+      tom_ld_xyz(X, Y, z, src);
       if (e2) F::mul(den, z, Y); else copy_n<9>(den, z);
       if (k > 0) F::mul(di, inv, pre[k - 1]); else copy_n<9>(di, inv);   // Montgomery residue of 1/den
       F::mul(inv, inv, den);
@@ -526,7 +554,77 @@ struct TomCommitTask {
       tom2_madd<true>(acc, acc, q);
     }
     uint32_t* o = proj + (size_t)t * TOM_PROJ_WORDS;
-    st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.z);
+    tom_st_xyz(o, acc.x, acc.y, acc.z);
+  }
+};
+
+// Split commitments for the 34 jobs of a 0-bit repetition.  Several of them commit to the SAME value
+// with different blinders (proveMult: A_z and A_4_1 both commit k_z, mult.ts:112-113; proveEquality:
+// A_1 and A_2 both commit k, equality.ts:67-68), so the g-parts v*g are computed once per distinct
+// value (28 per item) and every job continues from its g-part with the 16 lookups of r*h:
+//   34 x 32 = 1088 lookups  ->  28 x 16 + 34 x 16 = 992.
+enum : int { GJOBS_PER_ITEM = 28, TOM_EXT_WORDS = 36 };
+// job index (0..33) -> index of its g-part (0..27)
+ZK_HD int item_gpart_of_job(int j) {
+  if (j < 6) return j;                       // T1x T1y C8 C10 C11 C13
+  if (j < 30) {                              // MultProof m: C4 Ax Ay Az A4_1 A4_2 -> 0 1 2 3 3 4
+    const int m = (j - 6) / 6, u = (j - 6) % 6;
+    return 6 + 5 * m + (u < 4 ? u : u - 1);
+  }
+  return 26 + ((j - 30) >> 1);               // EqualityProof e: A1, A2 share k
+}
+// g-part index (0..27) -> a job that carries its value scalar
+ZK_HD int item_job_of_gpart(int g) {
+  if (g < 6) return g;
+  if (g < 26) {
+    const int m = (g - 6) / 5, u = (g - 6) % 5;
+    return 6 + 6 * m + (u < 4 ? u : 5);
+  }
+  return 30 + 2 * (g - 26);
+}
+struct TomCommitGTask {   // one thread per (item, g-part): K = v*g as an extended E2 point
+  const uint32_t* jv;     // [items*34][8]
+  const uint32_t* gtab;
+  uint32_t* ext;          // [items*28][36]
+  int w, nwin;
+  ZK_HD void operator()(int t) const {
+    const int item = t / GJOBS_PER_ITEM, g = t % GJOBS_PER_ITEM;
+    uint32_t v[8];
+    ld<8>(v, jv + ((size_t)item * JOBS_PER_ITEM + item_job_of_gpart(g)) * 8);
+    TomPt acc;
+    tom_set_identity(acc);
+    const size_t ne = (size_t)1 << w;
+    for (int j = 0; j < nwin; j++) {
+      TomPre q;
+      int width = (256 - j * w) < w ? (256 - j * w) : w;
+      tom_ld_pre(q, gtab + ((size_t)j * ne + digit_w(v, j * w, width)) * TOM_PRE_WORDS);
+      tom2_madd<true>(acc, acc, q);
+    }
+    uint32_t* o = ext + (size_t)t * TOM_EXT_WORDS;
+    st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.t); st<9>(o + 27, acc.z);
+  }
+};
+struct TomCommitHTask {   // one thread per job: C = K + r*h
+  const uint32_t* jr;     // [items*34][8]
+  const uint32_t* htab;
+  const uint32_t* ext;    // [items*28][36]
+  uint32_t* proj;         // [items*34][28]
+  int w, nwin;
+  ZK_HD void operator()(int t) const {
+    const int item = t / JOBS_PER_ITEM, jb = t % JOBS_PER_ITEM;
+    uint32_t r[8];
+    ld<8>(r, jr + (size_t)t * 8);
+    TomPt acc;
+    const uint32_t* s = ext + ((size_t)item * GJOBS_PER_ITEM + item_gpart_of_job(jb)) * TOM_EXT_WORDS;
+    ld<9>(acc.x, s); ld<9>(acc.y, s + 9); ld<9>(acc.t, s + 18); ld<9>(acc.z, s + 27);
+    const size_t ne = (size_t)1 << w;
+    for (int j = 0; j < nwin; j++) {
+      TomPre q;
+      int width = (256 - j * w) < w ? (256 - j * w) : w;
+      tom_ld_pre(q, htab + ((size_t)j * ne + digit_w(r, j * w, width)) * TOM_PRE_WORDS);
+      tom2_madd<true>(acc, acc, q);
+    }
+    tom_st_xyz(proj + (size_t)t * TOM_PROJ_WORDS, acc.x, acc.y, acc.z);
   }
 };
 

@@ -499,7 +499,7 @@ struct DerivedTask {
   }
   ZK_HD void stp(size_t idx, const TomPt& p) const {
     uint32_t* o = c.s2_proj + idx * TOM_PROJ_WORDS;
-    st<9>(o, p.x); st<9>(o + 9, p.y); st<9>(o + 18, p.z);
+    tom_st_xyz(o, p.x, p.y, p.z);
   }
   ZK_HD void operator()(int it) const {
     const int b = c.item_b[it], i = c.item_i[it];

@@ -396,7 +396,7 @@ struct VDerivedTask {
   }
   ZK_HD void stp(size_t idx, const TomPt& p) const {
     uint32_t* o = c.td_proj + idx * TOM_PROJ_WORDS;
-    st<9>(o, p.x); st<9>(o + 9, p.y); st<9>(o + 18, p.z);
+    tom_st_xyz(o, p.x, p.y, p.z);
   }
   ZK_HD void operator()(int t) const {
     const int b = t / V_SAMPLES;
@@ -945,7 +945,7 @@ struct MsmTomCombineTask {
     }
     TomPt f;
     const uint32_t* fp = fixed + ((size_t)inst * fix_stride + fix_off) * TOM_PROJ_WORDS;
-    ld<9>(f.x, fp); ld<9>(f.y, fp + 9); ld<9>(f.z, fp + 18);
+    tom_ld_xyz(f.x, f.y, f.z, fp);
     // The commitment kernel works on the a = -1 image curve E2 and stores (W : V : Z) with
     // x' = W / (Z sqrt(-d1)), y = Z / V.  Same point in E1 extended coordinates with Z' = Z V:
     //   X = c W V,  Y = Z^2,  T = X Y / Z' = c W Z,   c = 1/sqrt(-d1).

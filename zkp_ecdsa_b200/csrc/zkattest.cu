@@ -817,7 +817,10 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       {
         const size_t nj = (size_t)M * JOBS_PER_ITEM, nd = (size_t)M * DERS_PER_ITEM, ng = (size_t)Bc * 4 * n;
         const size_t g0 = nj + nd;
-        launch(st, (long long)nj, TomCommitTask{c.s2_jv, c.s2_jr, c.tg_tab, c.th_tab, c.s2_proj, c.tom_w, c.tom_nwin});
+        // item jobs: g-parts once per distinct committed value, then r*h on top (TomCommitG/HTask)
+        uint32_t* gext = W[45].get<uint32_t>((size_t)M * GJOBS_PER_ITEM * TOM_EXT_WORDS);
+        launch(st, (long long)M * GJOBS_PER_ITEM, TomCommitGTask{c.s2_jv, c.tg_tab, gext, c.tom_w, c.tom_nwin});
+        launch(st, (long long)nj, TomCommitHTask{c.s2_jr, c.th_tab, gext, c.s2_proj, c.tom_w, c.tom_nwin});
         launch(st, (long long)ng, TomCommitTask{c.s2_jv + g0 * 8, c.s2_jr + g0 * 8, c.tg_tab, c.th_tab,
                                                  c.s2_proj + g0 * TOM_PROJ_WORDS, c.tom_w, c.tom_nwin});
         // only T1x, T1y (jobs 0, 1 of each item) are needed again as points (DerivedTask)
