@@ -339,29 +339,24 @@ struct ItemsTask {
   }
 };
 
-// Stage 4 — exp.ts:186-190: z = alpha_i - s1, T1 = z*R (+ Q).  One thread per item.
+// Stage 4 — exp.ts:186-190: z = alpha_i - s1, T1 = z*R + Q.  Because the statement was built as
+// R = (z/s) G + (r/s) pk, s1 = s/r, Q = (z/r) G, the identity s1*R - Q = pk holds whenever r and s
+// are invertible (otherwise PreTask has already flagged the proof), hence
+//     T1 = alpha_i*R - (s1*R - Q) = T_i - pk :
+// one complete mixed addition per item instead of a 64-lookup scalar multiplication.
 struct PhaseBP256Task {
   ProveCtx c;
   ZK_HD void operator()(int it) const {
+    using F = P256p;
     const int b = c.item_b[it], i = c.item_i[it];
-    uint32_t alpha[8], s1[8], z[8];
-    draw_checked<FnP256>(alpha, c, b, DRAW_REP0 + DRAWS_PER_REP * i);
-    ld<8>(s1, c.s1 + (size_t)b * 8);
-    uint32_t br = sub_n<8>(z, alpha, s1);
-    if (br) {
-      uint32_t nn[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) nn[k] = FnP256::p(k);
-      add_n<8>(z, z, nn);
-    }
+    const size_t slot = (size_t)b * (c.S + 1) + i;
+    P256Aff T, npk;
+    p256_ld_aff(T, c.pa_T_aff + slot * 16);
+    p256_ld_aff(npk, c.pk_aff + (size_t)b * 16);
+    F::neg(npk.y, npk.y);
     P256Pt T1;
-    p256_set_identity(T1);
-    p256_accum_tab4(T1, c.rtab + (size_t)b * 64 * 16 * P256_AFF_WORDS, z);
-    if (!c.q_inf[b]) {
-      P256Aff Q;
-      p256_ld_aff(Q, c.q_aff + (size_t)b * 16);
-      p256_madd(T1, T1, Q);
-    }
+    if (c.pa_T_inf[slot]) p256_set_identity(T1); else p256_from_affine(T1, T);
+    p256_madd(T1, T1, npk);
     p256_st_proj(c.pb_T1 + (size_t)it * P256_PROJ_WORDS, T1);
   }
 };
