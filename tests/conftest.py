@@ -22,6 +22,7 @@ def hostsim():
     # exercise the unaligned digit extraction); the GPU tests run the default 16-bit windows
     old = os.environ.get('ZKA_TOM_W')
     os.environ['ZKA_TOM_W'] = '13'
+    os.environ['ZKA_P256_HW'] = '8'
     try:
         return ZkaLib(g.HOSTSIM)
     finally:
@@ -29,6 +30,7 @@ def hostsim():
             os.environ.pop('ZKA_TOM_W', None)
         else:
             os.environ['ZKA_TOM_W'] = old
+        os.environ.pop('ZKA_P256_HW', None)
 
 
 @pytest.fixture(scope='session')

@@ -191,6 +191,60 @@ struct P256RowsTask {
     }
   }
 };
+// Per-base SIGNED 5-bit table (the per-proof table of R): k = sum_j d_j 32^j with d_j in [-16, 16],
+// 52 windows x 16 entries (1..16 multiples); a negative digit negates y of the affine entry.
+// 52 mixed additions per scalar multiplication instead of 64 with unsigned 4-bit windows, and the
+// table is smaller (832 entries instead of 960).
+enum : int { RT_W = 5, RT_NWIN = 52, RT_ROW = 16, RT_ENTRIES = RT_NWIN * RT_ROW };
+struct P256RowsSignedTask {
+  const uint32_t* pows;  // [nbase*RT_NWIN][24]
+  uint32_t* rows;        // [nbase*RT_NWIN][RT_ROW][24]: entry d-1 = d * pows
+  ZK_HD void operator()(int t) const {
+    P256Pt p, acc;
+    p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
+    acc = p;
+    uint32_t* out = rows + (size_t)t * RT_ROW * P256_PROJ_WORDS;
+    for (int d = 1; d <= RT_ROW; d++) {
+      p256_st_proj(out + (size_t)(d - 1) * P256_PROJ_WORDS, acc);
+      if (d < RT_ROW) p256_add(acc, acc, p);
+    }
+  }
+};
+// Two-level rows for a wide fixed-base table (w > 8), same idea as TomRowsHi/LoTask
+struct P256RowsHiTask {
+  const uint32_t* pows;   // [nwin][24]
+  uint32_t* hi;           // [nwin][2^(w-8)][24]
+  int w;
+  ZK_HD void operator()(int t) const {
+    P256Pt p, acc;
+    p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
+    for (int k = 0; k < 8; k++) p256_dbl(p, p);
+    p256_set_identity(acc);
+    const int nh = 1 << (w - 8);
+    for (int m = 0; m < nh; m++) {
+      p256_st_proj(hi + ((size_t)t * nh + m) * P256_PROJ_WORDS, acc);
+      p256_add(acc, acc, p);
+    }
+  }
+};
+struct P256RowsLoTask {
+  const uint32_t* pows;
+  const uint32_t* hi;
+  uint32_t* rows;         // [nwin][2^w][24]  (entry 0 of each window is the identity: never read)
+  int w;
+  ZK_HD void operator()(int t) const {
+    const int nh = 1 << (w - 8);
+    const int j = t / nh, m = t % nh;
+    P256Pt p, acc;
+    p256_ld_proj(p, pows + (size_t)j * P256_PROJ_WORDS);
+    p256_ld_proj(acc, hi + (size_t)t * P256_PROJ_WORDS);
+    uint32_t* out = rows + (((size_t)j << w) + ((size_t)m << 8)) * P256_PROJ_WORDS;
+    for (int d = 0; d < 256; d++) {
+      p256_st_proj(out + (size_t)d * P256_PROJ_WORDS, acc);
+      p256_add(acc, acc, p);
+    }
+  }
+};
 
 // Batched normalisation: proj[count] -> affine Montgomery (+ optional 65-byte encodings)
 struct P256NormTask {
@@ -257,13 +311,31 @@ ZK_HD void p256_accum_fixed8(P256Pt& acc, const uint32_t* tab, const uint32_t* k
     }
   }
 }
-// acc += sum_j T[j][digit_j(k)] for a w=4 table [64][16] of affine entries
-ZK_HD void p256_accum_tab4(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
-  for (int j = 0; j < 64; j++) {
-    uint32_t d = digit4(k, j);
+// acc += sum_j T[j][digit_j(k)] for a fixed table [nwin][2^w] of affine entries, w in {8, 16}
+ZK_HD void p256_accum_fixed(P256Pt& acc, const uint32_t* tab, const uint32_t* k, int w) {
+  const int nwin = 256 / w;
+  for (int j = 0; j < nwin; j++) {
+    const uint32_t d = digit_w(k, j * w, w);
     if (d) {
       P256Aff q;
-      p256_ld_aff(q, tab + ((size_t)j * 16 + d) * P256_AFF_WORDS);
+      p256_ld_aff(q, tab + (((size_t)j << w) + d) * P256_AFF_WORDS);
+      p256_madd(acc, acc, q);
+    }
+  }
+}
+// acc += k * base on the signed 5-bit per-base table [RT_NWIN][RT_ROW] (P256RowsSignedTask)
+ZK_HD void p256_accum_rtab(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
+  uint32_t carry = 0;
+  for (int j = 0; j < RT_NWIN; j++) {
+    const int pos = j * RT_W;
+    uint32_t d = (pos < 256 ? digit_w(k, pos, (256 - pos) < RT_W ? (256 - pos) : RT_W) : 0u) + carry;
+    carry = d > 16 ? 1u : 0u;
+    const bool neg = d > 16;
+    if (neg) d = 32 - d;
+    if (d) {
+      P256Aff q;
+      p256_ld_aff(q, tab + ((size_t)j * RT_ROW + (d - 1)) * P256_AFF_WORDS);
+      if (neg) P256p::neg(q.y, q.y);
       p256_madd(acc, acc, q);
     }
   }

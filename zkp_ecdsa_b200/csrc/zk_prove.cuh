@@ -41,7 +41,8 @@ struct ProveCtx {
   const uint32_t* ring_m;    // [2^n] ring values mod tom.order, Montgomery, padded with ring[0]
   // parameters / tables
   const uint32_t* g_tab8;    // P-256 generator, w=8 affine table [32][256][16]
-  const uint32_t* h_tab8;    // NistGroup.h,     w=8 affine table
+  const uint32_t* h_tab8;    // NistGroup.h, fixed-base affine table with h_w-bit windows
+  int h_w;
   const uint32_t* tg_tab;    // ProofGroup.g table [nwin][2^w][32]
   const uint32_t* th_tab;    // ProofGroup.h table
   const uint8_t* tg_bytes;   // 67-byte encoding of ProofGroup.g (C_14, pointAdd.ts:144)
@@ -52,9 +53,9 @@ struct ProveCtx {
   uint8_t* q_inf;      // [B]
   uint32_t* r_aff;     // [B][16] R
   uint8_t* r_bytes;    // [B][BSTRIDE]
-  uint32_t* rpows;     // [B][64][24]
-  uint32_t* rrows;     // [B][64][16][24]
-  uint32_t* rtab;      // [B][64][16][16] affine
+  uint32_t* rpows;     // [B][RT_NWIN][24]
+  uint32_t* rrows;     // [B][RT_NWIN][RT_ROW][24]
+  uint32_t* rtab;      // [B][RT_NWIN][RT_ROW][16] affine
   // phase A (P-256): slot i in [0,S] per proof; slot S is comS1
   uint32_t* pa_T;      // [B][S+1][24]
   uint32_t* pa_A;      // [B][S+1][24]
@@ -180,13 +181,13 @@ struct PreTask {
     // R = u1*G + u2*pk
     P256Pt R, U;
     p256_set_identity(R);
-    p256_accum_fixed8(R, c.g_tab8, u1);
+    p256_accum_fixed(R, c.g_tab8, u1, 8);
     p256_mul_var(U, pk, u2);
     p256_add(R, R, U);
     // Q = z1*G
     P256Pt Q;
     p256_set_identity(Q);
-    p256_accum_fixed8(Q, c.g_tab8, z1);
+    p256_accum_fixed(Q, c.g_tab8, z1, 8);
 
     // affine R, Q (own Fermat inversions: once per proof)
     uint32_t zi[8];
@@ -240,9 +241,9 @@ struct PhaseAP256Task {
     }
     P256Pt T, A;
     p256_set_identity(T);
-    p256_accum_tab4(T, c.rtab + (size_t)b * 64 * 16 * P256_AFF_WORDS, alpha);
+    p256_accum_rtab(T, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, alpha);
     A = T;
-    p256_accum_fixed8(A, c.h_tab8, r);
+    p256_accum_fixed(A, c.h_tab8, r, c.h_w);
     p256_st_proj(c.pa_T + (size_t)t * P256_PROJ_WORDS, T);
     p256_st_proj(c.pa_A + (size_t)t * P256_PROJ_WORDS, A);
   }

@@ -60,6 +60,7 @@ struct VerifyCtx {
   const uint32_t* ring_m;      // [2^n][8] Montgomery mod q
   const uint32_t* g_tab8;
   const uint32_t* h_tab8;
+  int h_w;
   const uint32_t* tg_tab;
   const uint32_t* th_tab;
   const uint8_t* tg_bytes;
@@ -72,9 +73,9 @@ struct VerifyCtx {
   uint32_t* r_aff;      // [B][16]
   uint32_t* q_aff;      // [B][16]
   uint8_t* q_inf;       // [B]
-  uint32_t* rpows;      // [B][64][24]
-  uint32_t* rrows;      // [B][64][16][24]
-  uint32_t* rtab;       // [B][64][16][16]
+  uint32_t* rpows;      // [B][RT_NWIN][24]
+  uint32_t* rrows;      // [B][RT_NWIN][RT_ROW][24]
+  uint32_t* rtab;       // [B][RT_NWIN][RT_ROW][16]
   uint32_t* samp_idx;   // [B][20] sampled repetition index
   uint32_t* samp_draw;  // [B][20] first exp draw of the sample (32-byte units from the exp area)
   // per sample (B*20)
@@ -219,7 +220,7 @@ struct VLayoutTask {
     Fn::from_mont(z1, t);
     P256Pt Q;
     p256_set_identity(Q);
-    p256_accum_fixed8(Q, c.g_tab8, z1);
+    p256_accum_fixed(Q, c.g_tab8, z1, 8);
     P256Aff Qa;
     const bool qinf = p256_is_identity(Q);
     if (qinf) {
@@ -353,7 +354,7 @@ struct VSampleP256Task {
     reduce_once<FnP256>(s);
     P256Pt T;
     p256_set_identity(T);
-    p256_accum_tab4(T, c.rtab + (size_t)b * 64 * 16 * P256_AFF_WORDS, s);
+    p256_accum_rtab(T, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, s);
     if (!rep[0] && !c.q_inf[b]) {
       P256Aff Q;
       p256_ld_aff(Q, c.q_aff + (size_t)b * 16);
@@ -691,8 +692,8 @@ struct VReduceTask {
     Fn::from_mont(kH, sH);
     P256Pt acc;
     p256_set_identity(acc);
-    p256_accum_tab4(acc, c.rtab + (size_t)b * 64 * 16 * P256_AFF_WORDS, kR);
-    p256_accum_fixed8(acc, c.h_tab8, kH);
+    p256_accum_rtab(acc, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, kR);
+    p256_accum_fixed(acc, c.h_tab8, kH, c.h_w);
     p256_st_proj(c.nfix + (size_t)b * P256_PROJ_WORDS, acc);
   }
 };
@@ -969,7 +970,7 @@ struct MsmP256WindowTask {
   const uint32_t* scalar;   // [B][21][8]
   const uint32_t* aff;      // [B][21][16]
   const uint8_t* skip;      // [B][21]
-  uint32_t* win;            // [B][64][24]
+  uint32_t* win;            // [B][RT_NWIN][24]
   ZK_HD void operator()(int t) const {
     const int b = t / MSM_NWIN_N, w = t % MSM_NWIN_N;
     P256Pt bucket[15];

@@ -147,9 +147,9 @@ struct P256MulTask {
     P256Pt acc;
     p256_set_identity(acc);
     if (rtab) {
-      if (!binf[t]) p256_accum_tab4(acc, rtab + (size_t)t * 64 * 16 * P256_AFF_WORDS, s);
+      if (!binf[t]) p256_accum_rtab(acc, rtab + (size_t)t * RT_ENTRIES * P256_AFF_WORDS, s);
     } else {
-      p256_accum_fixed8(acc, g8, s);
+      p256_accum_fixed(acc, g8, s, 8);
     }
     p256_st_proj(proj + (size_t)t * P256_PROJ_WORDS, acc);
   }
@@ -226,6 +226,7 @@ struct zka_ctx {
   int tom_w = 16, tom_nwin = 16;   // 2 bases x 16 windows x 65536 entries x 128 B = 268 MB in HBM/L2
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 8192;
+  int p256_hw = 16;       // window bits of the per-params NistGroup.h table
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
   FixedTable tg;          // tomEdwards256 generator [nwin][2^w][32]
   DevBuf tg_bytes;        // 67-byte encoding of g
@@ -239,7 +240,8 @@ struct zka_ctx {
 struct zka_params {
   zka_ctx* ctx = nullptr;
   uint32_t sec_level = 80;
-  FixedTable h8;          // NistGroup.h  w=8 table
+  FixedTable h8;          // NistGroup.h fixed-base table, h_w-bit windows (16 x 65536 x 64 B = 67 MB)
+  int h_w = 16;
   FixedTable th;          // ProofGroup.h table
   uint8_t h_nist[65];
   uint8_t h_proof[67];
@@ -283,15 +285,26 @@ inline void launch_tom_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uin
 
 // ---- table construction -------------------------------------------------------------------
 // P-256 w=8 positional table from one affine Montgomery base (device pointer, 16 words)
-void build_p256_tab8(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) {
+void build_p256_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out, int w) {
   Stream& st = ctx->st;
+  const int nwin = 256 / w;
+  const size_t count = (size_t)nwin << w;
   DevBuf pows, rows;
-  uint32_t* d_pows = pows.get<uint32_t>((size_t)32 * P256_PROJ_WORDS);
-  uint32_t* d_rows = rows.get<uint32_t>((size_t)32 * 256 * P256_PROJ_WORDS);
-  out.tab = out.buf.get<uint32_t>((size_t)32 * 256 * P256_AFF_WORDS);
-  launch(st, 1, P256PowsTask{base_aff_dev, nullptr, d_pows, 1, 32, 8});
-  launch(st, 32, P256RowsTask{d_pows, d_rows, 8});
-  const int count = 32 * 256;
+  uint32_t* d_pows = pows.get<uint32_t>((size_t)nwin * P256_PROJ_WORDS);
+  uint32_t* d_rows = rows.get<uint32_t>(count * P256_PROJ_WORDS);
+  out.tab = out.buf.get<uint32_t>(count * P256_AFF_WORDS);
+  launch(st, 1, P256PowsTask{base_aff_dev, nullptr, d_pows, 1, nwin, w});
+  if (w > 8) {
+    DevBuf hi;
+    const int nh = 1 << (w - 8);
+    uint32_t* d_hi = hi.get<uint32_t>((size_t)nwin * nh * P256_PROJ_WORDS);
+    launch(st, nwin, P256RowsHiTask{d_pows, d_hi, w});
+    launch(st, (long long)nwin * nh, P256RowsLoTask{d_pows, d_hi, d_rows, w});
+    sync(st);
+    hi.release();
+  } else {
+    launch(st, nwin, P256RowsTask{d_pows, d_rows, w});
+  }
   launch_p256_norm(st, d_rows, out.tab, nullptr, nullptr, (long long)(count));
   sync(st);
   pows.release();
@@ -423,10 +436,14 @@ int zka_init(int device, zka_ctx** out) {
       int c = atoi(e);
       if (c >= 1) ctx->chunk = c;
     }
+    if (const char* e = getenv("ZKA_P256_HW")) {   // window bits of the NistGroup.h table: 8 or 16
+      int w = atoi(e);
+      if (w == 8 || w == 16) ctx->p256_hw = w;
+    }
     DevBuf gen;
     uint32_t* d_gen = gen.get<uint32_t>(16 + 18);
     launch(ctx->st, 1, GenAffTask{d_gen, d_gen + 16});
-    build_p256_tab8(ctx, d_gen, ctx->g8);
+    build_p256_tab(ctx, d_gen, ctx->g8, 8);
     build_tom_tab(ctx, d_gen + 16, ctx->tg);
     // encoding of g (C_14 = params.g in pi_8, pointAdd.ts:144,220): normalise the table entry 1*g
     DevBuf proj, aff;
@@ -471,6 +488,7 @@ int zka_params_create(zka_ctx* ctx, const uint8_t h_nist[65], const uint8_t h_pr
     zka_params* P = new zka_params();
     P->ctx = ctx;
     P->sec_level = sec_level;
+    P->h_w = ctx->p256_hw;
     memcpy(P->h_nist, h_nist, 65);
     memcpy(P->h_proof, h_proof, 67);
     DevBuf bn, bt, an, at, bad, inf;
@@ -492,7 +510,7 @@ int zka_params_create(zka_ctx* ctx, const uint8_t h_nist[65], const uint8_t h_pr
       delete P;
       return fail(ctx, ZKA_E_ARG, "params: h point not on its group");
     }
-    build_p256_tab8(ctx, d_an, P->h8);
+    build_p256_tab(ctx, d_an, P->h8, P->h_w);
     build_tom_tab(ctx, d_at, P->th);
     for (DevBuf* b : {&bn, &bt, &an, &at, &bad, &inf}) b->release();
     *out = P;
@@ -568,13 +586,13 @@ int zka_p256_mul_batch(zka_ctx* ctx, uint32_t count, const uint8_t* base, const 
       uint32_t* baff = ctx->w[4].get<uint32_t>((size_t)count * 16);
       uint8_t* bad = ctx->w[5].get<uint8_t>(count);
       binf = ctx->w[6].get<uint8_t>(count);
-      uint32_t* pows = ctx->w[7].get<uint32_t>((size_t)count * 64 * P256_PROJ_WORDS);
-      uint32_t* rows = ctx->w[8].get<uint32_t>((size_t)count * 64 * 16 * P256_PROJ_WORDS);
-      rtab = ctx->w[9].get<uint32_t>((size_t)count * 64 * 16 * P256_AFF_WORDS);
+      uint32_t* pows = ctx->w[7].get<uint32_t>((size_t)count * RT_NWIN * P256_PROJ_WORDS);
+      uint32_t* rows = ctx->w[8].get<uint32_t>((size_t)count * RT_ENTRIES * P256_PROJ_WORDS);
+      rtab = ctx->w[9].get<uint32_t>((size_t)count * RT_ENTRIES * P256_AFF_WORDS);
       launch(st, count, ParsePointsTask{db, nullptr, baff, nullptr, bad, binf});
-      launch(st, count, P256PowsTask{baff, binf, pows, (int)count, 64, 4});
-      launch(st, (long long)count * 64, P256RowsTask{pows, rows, 4});
-      const long long np = (long long)count * 64 * 16;
+      launch(st, count, P256PowsTask{baff, binf, pows, (int)count, RT_NWIN, RT_W});
+      launch(st, (long long)count * RT_NWIN, P256RowsSignedTask{pows, rows});
+      const long long np = (long long)count * RT_ENTRIES;
       launch_p256_norm(st, rows, rtab, nullptr, nullptr, (long long)(np));
     }
     launch(st, count, P256MulTask{dk, ctx->g8.tab, rtab, binf, proj});
@@ -727,7 +745,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.tape_stride = tape_stride;
       c.tape_draws = (uint32_t)(tape_stride / 32);
       c.ring_m = ring_m;
-      c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab;
+      c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
       c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
       c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
       const size_t S1 = (size_t)S + 1;
@@ -739,9 +757,9 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.q_inf = W[3].get<uint8_t>(Bc);
       c.r_aff = W[4].get<uint32_t>((size_t)Bc * 16);
       c.r_bytes = W[5].get<uint8_t>((size_t)Bc * BSTRIDE);
-      c.rpows = W[6].get<uint32_t>((size_t)Bc * 64 * P256_PROJ_WORDS);
-      c.rrows = W[7].get<uint32_t>((size_t)Bc * 64 * 16 * P256_PROJ_WORDS);
-      c.rtab = W[8].get<uint32_t>((size_t)Bc * 64 * 16 * P256_AFF_WORDS);
+      c.rpows = W[6].get<uint32_t>((size_t)Bc * RT_NWIN * P256_PROJ_WORDS);
+      c.rrows = W[7].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_PROJ_WORDS);
+      c.rtab = W[8].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_AFF_WORDS);
       c.pa_T = W[9].get<uint32_t>(nA * P256_PROJ_WORDS);
       c.pa_A = W[10].get<uint32_t>(nA * P256_PROJ_WORDS);
       c.pa_T_aff = W[11].get<uint32_t>(nA * 16);
@@ -770,10 +788,10 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
 
       // --- statement + per-proof tables of R
       launch(st, Bc, PreTask{c});
-      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, 64, 4});
-      launch(st, (long long)Bc * 64, P256RowsTask{c.rpows, c.rrows, 4});
+      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
+      launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows});
       {
-        const long long np = (long long)Bc * 64 * 16;
+        const long long np = (long long)Bc * RT_ENTRIES;
         launch_p256_norm(st, c.rrows, c.rtab, nullptr, nullptr, (long long)(np));
       }
       // --- phase A
@@ -878,7 +896,7 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.tape = stage_in(ctx, ctx->in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
       c.tape_stride = tape_stride;
       c.ring_m = ring_m;
-      c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab;
+      c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
       c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
       c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
       const size_t ns = (size_t)Bc * V_SAMPLES;
@@ -891,9 +909,9 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.r_aff = W[5].get<uint32_t>((size_t)Bc * 16);
       c.q_aff = W[6].get<uint32_t>((size_t)Bc * 16);
       c.q_inf = W[7].get<uint8_t>(Bc);
-      c.rpows = W[8].get<uint32_t>((size_t)Bc * 64 * P256_PROJ_WORDS);
-      c.rrows = W[9].get<uint32_t>((size_t)Bc * 64 * 16 * P256_PROJ_WORDS);
-      c.rtab = W[10].get<uint32_t>((size_t)Bc * 64 * 16 * P256_AFF_WORDS);
+      c.rpows = W[8].get<uint32_t>((size_t)Bc * RT_NWIN * P256_PROJ_WORDS);
+      c.rrows = W[9].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_PROJ_WORDS);
+      c.rtab = W[10].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_AFF_WORDS);
       c.samp_idx = W[11].get<uint32_t>(ns);
       c.samp_draw = W[12].get<uint32_t>(ns);
       c.sp_T = W[13].get<uint32_t>(ns * P256_PROJ_WORDS);
@@ -931,10 +949,10 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
 
       launch(st, Bc, VLayoutTask{c});
       launch(st, (long long)Bc * (S + 1), VValidateTask{c});
-      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, 64, 4});
-      launch(st, (long long)Bc * 64, P256RowsTask{c.rpows, c.rrows, 4});
+      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
+      launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows});
       {
-        const long long np = (long long)Bc * 64 * 16;
+        const long long np = (long long)Bc * RT_ENTRIES;
         launch_p256_norm(st, c.rrows, c.rtab, nullptr, nullptr, (long long)(np));
       }
       launch(st, Bc, VChallengeTask{c});
