@@ -144,7 +144,8 @@ int zka_tom_commit_batch(zka_ctx* ctx, const zka_params* params, uint32_t count,
 int zka_p256_mul_batch(zka_ctx* ctx, uint32_t count, const uint8_t* base /* count x 65 or NULL */,
                        const uint8_t* k /* count x 32 */, uint8_t* out /* count x 65 */);
 /* field arithmetic: field 0 = p256.p (= tom.order), 1 = p256.n, 2 = tom.p (33-byte operands);
- * op 0 = a*b, 1 = a+b, 2 = a-b, 3 = a^-1 (0 -> 0).  Operands/results big-endian, canonical. */
+ * op 0 = a*b, 1 = a+b, 2 = a-b, 3 = a^-1 (0 -> 0; binary almost-inverse), 4 = a^(p-2) (Fermat ladder, the
+ * cross-check of op 3).  Operands/results big-endian, canonical. */
 int zka_field_op_batch(zka_ctx* ctx, int field, int op, uint32_t count, const uint8_t* a, const uint8_t* b,
                        uint8_t* out);
 /* hashPoints (group.ts:221-233): 80-bit challenge (10 bytes) of `len[i]` message bytes each */

@@ -21,8 +21,8 @@ def check_field_ops(L, seed=0, count=24):
         va = [int.from_bytes(d.bytes(40), 'big') % mod for _ in range(count)] + [0, 1, mod - 1, mod - 1]
         vb = [int.from_bytes(d.bytes(40), 'big') % mod for _ in range(count)] + [mod - 1, 0, mod - 1, 1]
         a, b = be(va, nb), be(vb, nb)
-        fns = [lambda x, y: x * y % mod, lambda x, y: (x + y) % mod, lambda x, y: (x - y) % mod,
-               lambda x, y: pow(x, -1, mod) if x else 0]
+        inv = lambda x, y: pow(x, -1, mod) if x else 0  # noqa: E731
+        fns = [lambda x, y: x * y % mod, lambda x, y: (x + y) % mod, lambda x, y: (x - y) % mod, inv, inv]
         for op, fn in enumerate(fns):
             out = L.field_op_batch(field, op, a, b)
             for i in range(len(va)):

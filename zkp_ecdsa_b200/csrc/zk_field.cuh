@@ -300,9 +300,9 @@ struct Field {
     return eq_n<N>(t, u);
   }
 
-  // r = a^(p-2) (Fermat inverse), a in Montgomery form; returns 0 for a == 0.
-  // Not inlined: called once per batch-inversion chunk.
-  static ZK_HDN void inv(uint32_t* r, const uint32_t* a) {
+  // r = a^(p-2) (Fermat inverse), a in Montgomery form; returns 0 for a == 0.  Kept as the
+  // cross-check of inv() in the field-op tests (zka_field_op_batch op 4).
+  static ZK_HDN void inv_fermat(uint32_t* r, const uint32_t* a) {
     uint32_t e[N];
 #pragma unroll
     for (int i = 0; i < N; i++) e[i] = F::p(i);
@@ -310,8 +310,6 @@ struct Field {
     uint32_t acc[N], base[N];
     set_one(acc);
     copy_n<N>(base, a);
-    // left-to-right binary with 4-bit fixed window would be faster; the plain
-    // square-and-multiply ladder keeps code size small (one mul + one sqr site).
     int top = N * 32 - 1;
     while (top > 0 && !((e[top >> 5] >> (top & 31)) & 1)) top--;
 #pragma unroll 1
@@ -320,6 +318,80 @@ struct Field {
       if ((e[bit >> 5] >> (bit & 31)) & 1) mul(acc, acc, base);
     }
     copy_n<N>(r, acc);
+  }
+
+  // Modular inverse of a Montgomery residue (0 -> 0, like the reference's invEuclid,
+  // /root/reference/src/bignum/big.ts:112-119).  Kaliski's binary "almost inverse"
+  // (u, v, r, s) iteration, written branch-free so a warp stays converged inside an iteration:
+  // ~1.4 * bitlen(p) rounds of shifts / adds / selects on N+1 limbs — ALU-pipe work worth about a
+  // quarter of the 380-multiplication Fermat ladder — followed by four Montgomery products that
+  // turn  A^-1 2^k  (A = a = xR)  into  x^-1 R.
+  static ZK_HDN void inv(uint32_t* out, const uint32_t* a) {
+    constexpr int L = N + 1;
+    uint32_t u[L], v[L], r[L], s[L];
+    {
+      uint32_t t[N];
+      copy_n<N>(t, a);
+      reduce(t);                       // canonical A in [0, p)
+#pragma unroll
+      for (int i = 0; i < N; i++) { u[i] = F::p(i); v[i] = t[i]; r[i] = 0; s[i] = 0; }
+      u[N] = 0; v[N] = 0; r[N] = 0; s[N] = 0;
+      s[0] = 1;
+    }
+    if (is_zero_n<L>(v)) { zero_n<N>(out); return; }
+    int k = 0;
+#pragma unroll 1
+    while (!is_zero_n<L>(v)) {
+      uint32_t dm[L], dn[L], sm[L];
+      const uint32_t bor = sub_n<L>(dm, u, v);     // u - v
+      sub_n<L>(dn, v, u);                          // v - u
+      add_n<L>(sm, r, s);
+      const bool ue = (u[0] & 1u) == 0, ve = (v[0] & 1u) == 0;
+      const bool gt = (bor == 0) && !is_zero_n<L>(dm);
+      const bool cA = ue, cB = !ue && ve, cC = !ue && !ve && gt, cD = !ue && !ve && !gt;
+      const bool su = cA || cC;                    // the u side is halved, s doubled
+      const bool sv = cB || cD;                    // the v side is halved, r doubled
+      uint32_t nu[L], nv[L], nr[L], ns[L];
+#pragma unroll
+      for (int i = 0; i < L; i++) {
+        const uint32_t uu = cC ? dm[i] : u[i], uh = cC ? (i + 1 < L ? dm[i + 1] : 0u) : (i + 1 < L ? u[i + 1] : 0u);
+        const uint32_t vv = cD ? dn[i] : v[i], vh = cD ? (i + 1 < L ? dn[i + 1] : 0u) : (i + 1 < L ? v[i + 1] : 0u);
+        nu[i] = su ? ((uu >> 1) | (uh << 31)) : u[i];
+        nv[i] = sv ? ((vv >> 1) | (vh << 31)) : v[i];
+        const uint32_t rl = i > 0 ? r[i - 1] : 0u, sl = i > 0 ? s[i - 1] : 0u;
+        nr[i] = cC ? sm[i] : (sv ? ((r[i] << 1) | (rl >> 31)) : r[i]);
+        ns[i] = cD ? sm[i] : (su ? ((s[i] << 1) | (sl >> 31)) : s[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < L; i++) { u[i] = nu[i]; v[i] = nv[i]; r[i] = nr[i]; s[i] = ns[i]; }
+      k++;
+    }
+    // r < 2p:  r -= p if r >= p;  result rr = p - r = A^-1 2^k mod p
+    uint32_t pp[L], t[L];
+#pragma unroll
+    for (int i = 0; i < N; i++) pp[i] = F::p(i);
+    pp[N] = 0;
+    uint32_t br = sub_n<L>(t, r, pp);
+    csel_n<L>(r, br == 0, t, r);
+    sub_n<L>(t, pp, r);
+    uint32_t rr[N];
+    copy_n<N>(rr, t);
+    // x^-1 R = rr * 2^(2m - k), m = 32 N:  two (R^2, 2^e) pairs of Montgomery products
+    int e = 2 * 32 * N - k;
+    const int emax = (F::p(N - 1) >> 31) ? 32 * N - 1 : 32 * (N - 1);   // 2^emax < p for our moduli
+    int e1 = e < emax ? e : emax, e2 = e - e1;
+    uint32_t rr2[N], pw[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) rr2[i] = F::rr(i);
+    mul(rr, rr, rr2);
+    zero_n<N>(pw);
+    pw[e1 >> 5] = 1u << (e1 & 31);
+    mul(rr, rr, pw);
+    mul(rr, rr, rr2);
+    zero_n<N>(pw);
+    pw[e2 >> 5] = 1u << (e2 & 31);
+    mul(rr, rr, pw);
+    copy_n<N>(out, rr);
   }
 };
 

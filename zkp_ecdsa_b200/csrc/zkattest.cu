@@ -95,7 +95,8 @@ struct FieldOpTask {
     if (op == 0) F::mul(r, x, y);
     else if (op == 1) F::add(r, x, y);
     else if (op == 2) F::sub(r, x, y);
-    else F::inv(r, x);
+    else if (op == 3) F::inv(r, x);
+    else F::inv_fermat(r, x);
     F::from_mont(r, r);
     limbs_to_be<N>(out + (size_t)t * NB, r, NB);
   }
@@ -264,7 +265,7 @@ int ceil_log2(uint32_t v) {
 // normalisation launches: points per thread (= per Fermat inversion) grow with the batch so the
 // inversion cost is amortised while at least ~150k threads stay in flight
 inline int norm_chunk_for(long long count) {
-  long long c = count / 150000;
+  long long c = count / 100000;
   if (c < 8) c = 8;
   if (c > NORM_CHUNK_MAX) c = NORM_CHUNK_MAX;
   return (int)c;
@@ -614,7 +615,7 @@ int zka_p256_mul_batch(zka_ctx* ctx, uint32_t count, const uint8_t* base, const 
 
 int zka_field_op_batch(zka_ctx* ctx, int field, int op, uint32_t count, const uint8_t* a, const uint8_t* b,
                        uint8_t* out) {
-  if (!ctx || !a || !out || field < 0 || field > 2 || op < 0 || op > 3 || (op < 3 && !b)) return ZKA_E_ARG;
+  if (!ctx || !a || !out || field < 0 || field > 2 || op < 0 || op > 4 || (op < 3 && !b)) return ZKA_E_ARG;
   if (count == 0) return 0;
   try {
     Stream& st = ctx->st;
