@@ -103,3 +103,36 @@ def test_key_to_int(hostsim):
     assert list(st) == [0, 0, 1]
     for b in range(2):
         assert int.from_bytes(x[b].tobytes(), 'big') == OZ.key_to_int(wl.pk[b].tobytes())
+
+
+def test_multi_chunk_batches_equal_single_chunk():
+    """A batch larger than the pipeline chunk is processed in several passes: same bytes."""
+    import os
+    import __graft_entry__ as g
+    from zkp_ecdsa_b200.capi import ZkaLib
+    g.build_hostsim()
+    os.environ.update(ZKA_TOM_W='10', ZKA_P256_HW='8', ZKA_CHUNK='2')
+    try:
+        small = ZkaLib(g.HOSTSIM)
+    finally:
+        os.environ.pop('ZKA_CHUNK', None)
+    try:
+        big = ZkaLib(g.HOSTSIM)
+    finally:
+        os.environ.pop('ZKA_TOM_W', None)
+        os.environ.pop('ZKA_P256_HW', None)
+    assert small.config()['chunk'] == 2 and big.config()['chunk'] > 2
+    wl = synth.Workload(B=5, N=4, seed=61)
+    outs = []
+    for L in (small, big):
+        P, _ = common.make_params(L, 61, 20)
+        tape = synth.random_tape(5, L.prove_tape_len(4, 20), seed=62)
+        proofs, plen, status = common.run_prove(L, P, wl, tape, 20)
+        assert (status == 0).all()
+        vt = VT.random_verify_tape(5, L.verify_tape_len(4, 20), 4, 20, seed=63)
+        ok, st = common.run_verify(L, P, wl.msg_hash, wl.ring, proofs, plen, vt)
+        assert (ok == 1).all() and (st == 0).all()
+        outs.append((proofs.copy(), plen.copy()))
+    assert (outs[0][1] == outs[1][1]).all()
+    for b in range(5):
+        assert outs[0][0][b, :outs[0][1][b]].tobytes() == outs[1][0][b, :outs[1][1][b]].tobytes()
