@@ -114,7 +114,7 @@ def run_reference(args):
         'e2e': {'value': v, 'unit': 'proofs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -410,12 +410,32 @@ def run_ours(args):
                                for k, v in sorted(vprof.items(), key=lambda kv: -kv[1]['ms'])[:10]}},
         'kernels': kernels,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr while the run is in progress: NCCL (version banner) and other native
+    libraries write to stdout, but the contract is ONE JSON line there."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
