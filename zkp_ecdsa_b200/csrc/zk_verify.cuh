@@ -38,8 +38,8 @@ enum : int {
   V_ENT_NIST = V_SAMPLES + 1,  // A_j + comS1
   V_IDX_PAD = 96,
   V_PART_WORDS = 7 * 8,        // per-sample partial sums: gW hW pkX pkY | sR shN sCom
-  MSM_C = 5,                   // bucket window bits (tom);  52 windows cover 260 bits
-  MSM_NWIN = 52,
+  MSM_C = 6,                   // SIGNED 6-bit bucket windows (tom): digits in [-32, 31], 32 buckets,
+  MSM_NWIN = 43,               // 43 windows cover the 258 bits of k + offset (msm_digit6)
   MSM_C_N = 4,                 // P-256 MSM: 64 windows
   MSM_NWIN_N = 64,
 };
@@ -838,9 +838,35 @@ ZK_HD void bk_store(U4* b, const TomPt& p) {
 #pragma unroll
   for (int i = 0; i < 9; i++) { U4 u; u.x = w[4 * i]; u.y = w[4 * i + 1]; u.z = w[4 * i + 2]; u.w = w[4 * i + 3]; b[i] = u; }
 }
+// Signed window digits without a carry chain: with OFFS = sum_j 32 * 64^j the unsigned 6-bit windows of
+// k' = k + OFFS, minus 32, are digits d_j in [-32, 31] with sum_j d_j 64^j = k.  Returns |d_j| (the
+// bucket, 0..32) and its sign.  Half the buckets of an unsigned 6-bit window, one window fewer per
+// 6 bits than the 5-bit version: 43 x (n + 64) instead of 52 x (n + 62) point operations.
+ZK_HD uint32_t msm_digit6(const uint32_t* k, int w, bool& neg) {
+  constexpr uint32_t OFFS[9] = {0x20820820u, 0x08208208u, 0x82082082u, 0x20820820u, 0x08208208u,
+                                0x82082082u, 0x20820820u, 0x08208208u, 0x00000002u};
+  uint32_t kp[9];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    c += (uint64_t)(i < 8 ? k[i] : 0u) + OFFS[i];
+    kp[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  const int pos = w * MSM_C, wi = pos >> 5, sh = pos & 31;
+  uint64_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {     // static indexing: select the two limbs the window touches
+    if (i == wi) v |= kp[i];
+    if (i == wi + 1) v |= (uint64_t)kp[i] << 32;
+  }
+  const int d = (int)((uint32_t)(v >> sh) & 63u) - 32;
+  neg = d < 0;
+  return (uint32_t)(d < 0 ? -d : d);
+}
 struct MsmTomWindowTask {
   // Sorted-bucket Pippenger: a thread first counting-sorts the indices of its window's entries by
-  // digit (2 bytes of local memory per entry), then walks the sorted entries in one flat loop,
+  // |digit| (2 bytes of local memory per entry), then walks the sorted entries in one flat loop,
   // summing each bucket in REGISTERS, and finally folds the bucket sums into the running sums
   //   run += S_d ; tot += run      =>   tot = sum_d d * S_d .
   // (The first version kept 31 extended points per thread in local memory and read-modify-wrote
@@ -853,26 +879,20 @@ struct MsmTomWindowTask {
   uint32_t* win;            // [inst][MSM_NWIN][36]
   ZK_HD void operator()(int t) const {
     const int inst = t / MSM_NWIN, w = t % MSM_NWIN;
-    constexpr int NB = 1 << MSM_C;
+    constexpr int NB = 33;          // bucket 0 (skipped) .. 32
     const uint32_t* sc = scalar + (size_t)inst * stride * 8;
     const uint32_t* pp = pre + (size_t)inst * stride * TOM_PRE_WORDS;
-    const int pos = w * MSM_C;
-    const int width = (256 - pos) < MSM_C ? (256 - pos) : MSM_C;
-    const int wi = pos >> 5, sh = pos & 31;
-    const uint32_t mask = (1u << width) - 1u;
-    uint16_t order[V_ENT_TOM];     // (digit << 10) | entry index, sorted by digit
+    uint16_t order[V_ENT_TOM];     // sign << 15 | (bucket - 1) << 10 | entry index, sorted by bucket
     uint16_t start[NB + 1];
     for (int d = 0; d <= NB; d++) start[d] = 0;
-    // pass 1: histogram of digits
+    // pass 1: histogram of buckets
     for (int gidx = 0; gidx <= groups; gidx++) {
       const int base = gidx * group_len;
       const int m = gidx < groups ? (cnt ? (int)cnt[(size_t)inst * groups + gidx] : group_len) : tail;
       for (int e = 0; e < m; e++) {
-        const uint32_t* k = sc + (size_t)(base + e) * 8;
-        uint64_t v = k[wi];
-        if (wi + 1 < 8) v |= (uint64_t)k[wi + 1] << 32;
-        const uint32_t dgt = (uint32_t)(v >> sh) & mask;
-        start[dgt + 1]++;
+        bool neg;
+        const uint32_t bk = msm_digit6(sc + (size_t)(base + e) * 8, w, neg);
+        start[bk + 1]++;
       }
     }
     for (int d = 1; d <= NB; d++) start[d] = (uint16_t)(start[d] + start[d - 1]);
@@ -883,43 +903,46 @@ struct MsmTomWindowTask {
       const int base = gidx * group_len;
       const int m = gidx < groups ? (cnt ? (int)cnt[(size_t)inst * groups + gidx] : group_len) : tail;
       for (int e = 0; e < m; e++) {
-        const uint32_t* k = sc + (size_t)(base + e) * 8;
-        uint64_t v = k[wi];
-        if (wi + 1 < 8) v |= (uint64_t)k[wi + 1] << 32;
-        const uint32_t dgt = (uint32_t)(v >> sh) & mask;
-        order[fillp[dgt]++] = (uint16_t)((dgt << 10) | (uint32_t)(base + e));
+        bool neg;
+        const uint32_t bk = msm_digit6(sc + (size_t)(base + e) * 8, w, neg);
+        const uint32_t enc = bk ? (((neg ? 1u : 0u) << 15) | ((bk - 1) << 10) | (uint32_t)(base + e)) : (uint32_t)(base + e);
+        order[fillp[bk]++] = (uint16_t)enc;
       }
     }
     // pass 3: ONE flat loop over the entries with a non-zero digit (the trip count is the same for
-    // every window of an instance up to +-3, so the warp does not diverge); a finished bucket sum
-    // is parked in local memory exactly once
+    // every window of an instance up to a few entries, so the warp does not diverge); a finished
+    // bucket sum is parked in local memory exactly once
     U4 S[NB][9];
-    uint32_t present = 0;
+    uint64_t present = 0;
     TomPt acc;
     tom_set_identity(acc);
     int curd = NB - 1;
     const int total = start[NB], first = start[1];
     for (int q = total - 1; q >= first; q--) {
       const uint32_t oe = order[q];
-      const int d = (int)(oe >> 10);
+      const int d = (int)((oe >> 10) & 31u) + 1;
       if (d != curd) {
         bk_store(S[curd], acc);
-        present |= 1u << curd;
+        present |= 1ull << curd;
         tom_set_identity(acc);
         curd = d;
       }
       TomPre pt;
       tom_ld_pre(pt, pp + (size_t)(oe & 1023u) * TOM_PRE_WORDS);
+      if (oe & 0x8000u) {            // negative digit: -(x, y) = (-x, y), k = d x y changes sign too
+        Tomp::neg(pt.x, pt.x);
+        Tomp::neg(pt.k, pt.k);
+      }
       tom_madd<true>(acc, acc, pt);
     }
     bk_store(S[curd], acc);
-    present |= 1u << curd;
+    present |= 1ull << curd;
     // pass 4: running sums  tot = sum_d d * S_d
     TomPt run, tot;
     tom_set_identity(run);
     tom_set_identity(tot);
     for (int d = NB - 1; d >= 1; d--) {
-      if ((present >> d) & 1u) {
+      if ((present >> d) & 1ull) {
         bk_load(acc, S[d]);
         tom_add(run, run, acc);
       }
