@@ -37,6 +37,9 @@ WORKLOADS = {
 SEC_LEVEL = 80
 # executed field multiplications per tomEdwards256 commitment: 2*nwin mixed additions x 8 modmul,
 # each modmul = 9x9 product + 5 generic modulus limbs x 9 quotient digits = 126 32x32 MACs
+# DRAM bytes per table lookup of the commitment kernels, from `ncu --set full` captures (profiles/):
+# window bits -> (dram read + write bytes per launch - algorithmic bytes) / lookups
+NCU_DRAM_BYTES_PER_LOOKUP = {16: 78.0}
 MODMUL_PER_MADD = 7      # a = -1 image curve, mixed addition with (v-w, v+w, 2 d2 w v) entries (zk_curves.cuh)
 MAC_PER_TOM_MODMUL = 126   # 81 products + 45 quotient-digit products (zk_field_ptx.cuh); the generic CIOS needs 171
 W_PROVE_REF = {8: 6861088, 256: 6942368, 1024: 6974880}   # reference-algorithm modmuls/proof
@@ -365,7 +368,7 @@ def run_ours(args):
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         roof = {
             'kernel': 'zk_task_kernel<TomCommitHTask> (fixed-base Pedersen commitments C = v*g + r*h, 258-bit field, '
-                      'a=-1 image curve: 16 lookups x 7 modmul x 126 MAC per launch item)',
+                      f"a=-1 image curve: {lookups['TomCommitHTask']} lookups x 7 modmul x 126 MAC per launch item)",
             'bound': 'int32-multiplier pipe (IMAD.WIDE.U32) — not hbm/tensor: ~30 modmul per HBM byte',
             'achieved': ach, 'peak': peak_gmac, 'unit': 'G(32x32+64 MAC)/s', 'frac': ach / peak_gmac,
             'peak_source': how,
@@ -380,10 +383,11 @@ def run_ours(args):
             # dram__bytes_read.sum + dram__bytes_write.sum from the `ncu --set full` capture of the commitment
             # kernel (profiles/ncu_tomcommit_r1d_w16_noinline.md: 3.72 GB for 1 392 640 commitments x 32 lookups
             # = 78 B of table traffic per lookup on top of the algorithmic bytes), scaled to this launch
-            'traffic': per_launch * (284.0 + 78.0 * lookups['TomCommitHTask']) if cfg['tom_w'] == 16 else None,
+            'traffic': (per_launch * (284.0 + NCU_DRAM_BYTES_PER_LOOKUP[cfg['tom_w']] * lookups['TomCommitHTask'])
+                        if cfg['tom_w'] in NCU_DRAM_BYTES_PER_LOOKUP else None),
             'traffic_unit': 'bytes/launch',
             'traffic_note': 'algorithmic bytes are 284 B/commitment; the rest is the random 128-byte table lookups '
-                            '(134 MB table per base, ~44 % L2 hit rate) — HBM stays < 10 % busy',
+                            f"({cfg['tom_nwin'] * (1 << cfg['tom_w']) * 128 / 1e6:.0f} MB table per base) — HBM stays < 10 % busy",
         }
     kernels = {k.replace('zk::', ''): {'ms_per_step': v['ms'] / args.steps, 'launches_per_step': v['launches'] / args.steps}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}

@@ -224,7 +224,7 @@ struct zka_ctx {
   int device = 0;
   Stream st;
   std::string err;
-  int tom_w = 16, tom_nwin = 16;   // 2 bases x 16 windows x 65536 entries x 128 B = 268 MB in HBM/L2
+  int tom_w = 22, tom_nwin = 12;   // per base: 12 windows x 2^22 entries x 128 B = 6.4 GB of HBM (ZKA_TOM_W)
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 8192;
   int p256_hw = 16;       // window bits of the per-params NistGroup.h table
@@ -316,10 +316,9 @@ void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) 
   Stream& st = ctx->st;
   const int w = ctx->tom_w, nwin = ctx->tom_nwin;
   const size_t ne = (size_t)1 << w, count = (size_t)nwin * ne;
-  DevBuf pows, rows, aff;
+  DevBuf pows, rows;
   uint32_t* d_pows = pows.get<uint32_t>((size_t)nwin * 36);
   uint32_t* d_rows = rows.get<uint32_t>(count * TOM_PROJ_WORDS);
-  uint32_t* d_aff = aff.get<uint32_t>(count * TOM_AFF_WORDS);
   out.tab = out.buf.get<uint32_t>(count * TOM_PRE_WORDS);
   launch(st, 1, TomPowsTask{base_aff_dev, d_pows, 1, nwin, w});
   if (w > 8) {
@@ -335,11 +334,9 @@ void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) 
   }
   // rows (E1 projective) -> entries of the prover's a = -1 image curve (v - w, v + w, 2 d2 w v)
   launch(st, (long long)(count + 15) / 16, TomTabE2Task{d_rows, out.tab, (int)count});
-  (void)d_aff;
   sync(st);
   pows.release();
   rows.release();
-  aff.release();
 }
 
 // stage a caller buffer on the device if it is a host pointer
@@ -430,7 +427,7 @@ int zka_init(int device, zka_ctx** out) {
     ctx->device = device;
     if (const char* e = getenv("ZKA_TOM_W")) {
       int w = atoi(e);
-      if (w >= 2 && w <= 16) ctx->tom_w = w;
+      if (w >= 2 && w <= 24) ctx->tom_w = w;
     }
     ctx->tom_nwin = (256 + ctx->tom_w - 1) / ctx->tom_w;
     if (const char* e = getenv("ZKA_CHUNK")) {
