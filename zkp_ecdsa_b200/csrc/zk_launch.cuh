@@ -126,6 +126,26 @@ inline void sync(Stream& st) {
   ZK_CUDA_CHECK(cudaStreamSynchronize(st.s));
   if (!st.pending.empty()) prof_collect(st);
 }
+// auxiliary (copy) streams and the events that order them against the compute stream
+struct Event { cudaEvent_t e = nullptr; };
+inline void stream_create(Stream& st) {
+  if (!st.s) ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+}
+inline void stream_destroy(Stream& st) {
+  if (st.s) cudaStreamDestroy(st.s);
+  st.s = nullptr;
+}
+inline void ev_record(Event& ev, Stream& st) {
+  if (!ev.e) ZK_CUDA_CHECK(cudaEventCreateWithFlags(&ev.e, cudaEventDisableTiming));
+  ZK_CUDA_CHECK(cudaEventRecord(ev.e, st.s));
+}
+inline void ev_wait(Stream& st, Event& ev) {   // no-op for an event that was never recorded
+  if (ev.e) ZK_CUDA_CHECK(cudaStreamWaitEvent(st.s, ev.e, 0));
+}
+inline void ev_destroy(Event& ev) {
+  if (ev.e) cudaEventDestroy(ev.e);
+  ev.e = nullptr;
+}
 // is `p` a device-accessible pointer that kernels may dereference directly?
 inline bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
@@ -164,6 +184,12 @@ inline void copy_d2h_2d(Stream&, void* h, size_t hpitch, const void* d, size_t d
 }
 inline void dev_memset(Stream&, void* d, int v, size_t n) { if (n) memset(d, v, n); }
 inline void sync(Stream&) {}
+struct Event {};
+inline void stream_create(Stream&) {}
+inline void stream_destroy(Stream&) {}
+inline void ev_record(Event&, Stream&) {}
+inline void ev_wait(Stream&, Event&) {}
+inline void ev_destroy(Event&) {}
 inline bool is_device_ptr(const void*) { return false; }
 
 #endif

@@ -43,6 +43,8 @@ struct ProveCtx {
   const uint32_t* g_tab8;    // P-256 generator, w=8 affine table [32][256][16]
   const uint32_t* h_tab8;    // NistGroup.h, fixed-base affine table with h_w-bit windows
   int h_w;
+  const uint32_t* g_tabw;    // P-256 generator again, with g_w-bit windows (phase A)
+  int g_w;
   const uint32_t* tg_tab;    // ProofGroup.g table [nwin][2^w][32]
   const uint32_t* th_tab;    // ProofGroup.h table
   const uint8_t* tg_bytes;   // 67-byte encoding of ProofGroup.g (C_14, pointAdd.ts:144)
@@ -53,9 +55,10 @@ struct ProveCtx {
   uint8_t* q_inf;      // [B]
   uint32_t* r_aff;     // [B][16] R
   uint8_t* r_bytes;    // [B][BSTRIDE]
-  uint32_t* rpows;     // [B][RT_NWIN][24]
-  uint32_t* rrows;     // [B][RT_NWIN][RT_ROW][24]
-  uint32_t* rtab;      // [B][RT_NWIN][RT_ROW][16] affine
+  uint32_t* u12;       // [B][16] u1 = z/s, u2 = r/s (Montgomery mod n): R = u1*G + u2*pk
+  uint32_t* rpows;     // [B][RT_NWIN][24]          per-proof signed 5-bit table of pk:
+  uint32_t* rrows;     // [B][RT_NWIN][RT_ROW][24]    every alpha*R of the proof is evaluated as
+  uint32_t* rtab;      // [B][RT_NWIN][RT_ROW][16]    (alpha u1)*G + (alpha u2)*pk, so no table of R is needed
   // phase A (P-256): slot i in [0,S] per proof; slot S is comS1
   uint32_t* pa_T;      // [B][S+1][24]
   uint32_t* pa_A;      // [B][S+1][24]
@@ -131,7 +134,10 @@ ZK_HD void reduce_once(uint32_t* a) {
 
 // ---------------------------------------------------------------------------------------------
 // Stage 0 — ECDSA statement (zkpAttestList.ts:112-136): one thread per proof.
-//   R = u1*G + u2*pk, Q = z1*G, s1 = s/r;   sinv, rinv by Fermat (invMod(0) = 0 as in big.ts).
+//   u1 = z/s, u2 = r/s, s1 = s/r, Q = z1*G  (invMod(0) = 0 as in big.ts).
+// R = u1*G + u2*pk is NOT computed here with a variable-base ladder (a 256-doubling latency chain per
+// proof).  The pipeline builds ONE positional table per proof, of pk, and evaluates R (RPointTask) and
+// every alpha*R of phase A on the G table and that pk table.
 // ---------------------------------------------------------------------------------------------
 struct PreTask {
   ProveCtx c;
@@ -171,43 +177,19 @@ struct PreTask {
     Fn::to_mont(sm, s);
     Fn::inv(sinv, sm);
     Fn::inv(rinv, rm);
-    uint32_t u1[8], u2[8], s1[8], z1[8];
-    Fn::mul(t, sinv, zm); Fn::from_mont(u1, t);
-    Fn::mul(t, sinv, rm); Fn::from_mont(u2, t);
+    uint32_t s1[8], z1[8];
+    Fn::mul(t, sinv, zm); st<8>(c.u12 + (size_t)b * 16, t);
+    Fn::mul(t, sinv, rm); st<8>(c.u12 + (size_t)b * 16 + 8, t);
     Fn::mul(t, rinv, sm); Fn::from_mont(s1, t);
     Fn::mul(t, rinv, zm); Fn::from_mont(z1, t);
     st<8>(c.s1 + (size_t)b * 8, s1);
 
-    // R = u1*G + u2*pk
-    P256Pt R, U;
-    p256_set_identity(R);
-    p256_accum_fixed(R, c.g_tab8, u1, 8);
-    p256_mul_var(U, pk, u2);
-    p256_add(R, R, U);
-    // Q = z1*G
+    // Q = z1*G, affine (own inversion: once per proof)
     P256Pt Q;
     p256_set_identity(Q);
     p256_accum_fixed(Q, c.g_tab8, z1, 8);
-
-    // affine R, Q (own Fermat inversions: once per proof)
     uint32_t zi[8];
-    P256Aff Ra, Qa;
-    bool rinf = p256_is_identity(R);
-    if (rinf) {
-      ZK_SET_STATUS(c.status + b, ZKA_ERR_T_INFINITY);  // T_i = R*alpha is the identity (exp.ts:151)
-      p256_set_generator(Ra);
-    } else {
-      Fp::inv(zi, R.z);
-      Fp::mul(Ra.x, R.x, zi);
-      Fp::mul(Ra.y, R.y, zi);
-    }
-    if (is_zero_n<8>(r)) ZK_SET_STATUS(c.status + b, ZKA_ERR_POINTS_DONT_ADD);  // rinv = 0: T1 + pk != T (pointAdd.ts:105)
-    p256_st_aff(c.r_aff + (size_t)b * 16, Ra);
-    uint8_t* rb = c.r_bytes + (size_t)b * BSTRIDE;
-    uint32_t cv[8];
-    rb[0] = 0x04;
-    Fp::from_mont(cv, Ra.x); limbs_to_be<8>(rb + 1, cv, 32);
-    Fp::from_mont(cv, Ra.y); limbs_to_be<8>(rb + 33, cv, 32);
+    P256Aff Qa;
     bool qinf = p256_is_identity(Q);
     if (qinf) {
       p256_set_generator(Qa);
@@ -218,6 +200,42 @@ struct PreTask {
     }
     p256_st_aff(c.q_aff + (size_t)b * 16, Qa);
     c.q_inf[b] = qinf ? 1 : 0;
+  }
+};
+
+// Stage 0b — R = u1*G + u2*pk on the tables, affine + encoded; per-proof checks in the reference's order.
+struct RPointTask {
+  ProveCtx c;
+  ZK_HD void operator()(int b) const {
+    using Fp = P256p;
+    using Fn = P256n;
+    uint32_t m[8], u1[8], u2[8];
+    ld<8>(m, c.u12 + (size_t)b * 16);     Fn::from_mont(u1, m);
+    ld<8>(m, c.u12 + (size_t)b * 16 + 8); Fn::from_mont(u2, m);
+    P256Pt R;
+    p256_set_identity(R);
+    p256_accum_fixed(R, c.g_tabw, u1, c.g_w);
+    p256_accum_rtab(R, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, u2);
+    uint32_t zi[8];
+    P256Aff Ra;
+    if (p256_is_identity(R)) {
+      ZK_SET_STATUS(c.status + b, ZKA_ERR_T_INFINITY);  // T_i = R*alpha is the identity (exp.ts:151)
+      p256_set_generator(Ra);
+    } else {
+      Fp::inv(zi, R.z);
+      Fp::mul(Ra.x, R.x, zi);
+      Fp::mul(Ra.y, R.y, zi);
+    }
+    uint32_t r[8];
+    limbs_from_be<8>(r, c.sig + (size_t)b * 64, 32);
+    reduce_once<FnP256>(r);
+    if (is_zero_n<8>(r)) ZK_SET_STATUS(c.status + b, ZKA_ERR_POINTS_DONT_ADD);  // rinv = 0: T1 + pk != T (pointAdd.ts:105)
+    p256_st_aff(c.r_aff + (size_t)b * 16, Ra);
+    uint8_t* rb = c.r_bytes + (size_t)b * BSTRIDE;
+    uint32_t cv[8];
+    rb[0] = 0x04;
+    Fp::from_mont(cv, Ra.x); limbs_to_be<8>(rb + 1, cv, 32);
+    Fp::from_mont(cv, Ra.y); limbs_to_be<8>(rb + 33, cv, 32);
     if (c.which[b] >= (uint32_t)c.N) ZK_SET_STATUS(c.status + b, ZKA_ERR_BAD_INDEX);
   }
 };
@@ -225,10 +243,12 @@ struct PreTask {
 // ---------------------------------------------------------------------------------------------
 // Stage 1 — exp.ts:144-148: T_i = alpha_i*R, A_i = T_i + r_i*h; slot S: comS1 = s1*R + r*h
 // (zkpAttestList.ts:137-138).  One thread per (proof, slot).
+//   alpha*R = (alpha u1 mod n)*G + (alpha u2 mod n)*pk
 // ---------------------------------------------------------------------------------------------
 struct PhaseAP256Task {
   ProveCtx c;
   ZK_HD void operator()(int t) const {
+    using Fn = P256n;
     const int S1 = c.S + 1;
     const int b = t / S1, i = t % S1;
     uint32_t alpha[8], r[8];
@@ -239,9 +259,14 @@ struct PhaseAP256Task {
       ld<8>(alpha, c.s1 + (size_t)b * 8);
       draw_checked<FnP256>(r, c, b, DRAW_COMS1_R);
     }
+    uint32_t am[8], um[8], pm[8], a1[8], a2[8];
+    Fn::to_mont(am, alpha);
+    ld<8>(um, c.u12 + (size_t)b * 16);     Fn::mul(pm, am, um); Fn::from_mont(a1, pm);
+    ld<8>(um, c.u12 + (size_t)b * 16 + 8); Fn::mul(pm, am, um); Fn::from_mont(a2, pm);
     P256Pt T, A;
     p256_set_identity(T);
-    p256_accum_rtab(T, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, alpha);
+    p256_accum_fixed(T, c.g_tabw, a1, c.g_w);
+    p256_accum_rtab(T, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, a2);
     A = T;
     p256_accum_fixed(A, c.h_tab8, r, c.h_w);
     p256_st_proj(c.pa_T + (size_t)t * P256_PROJ_WORDS, T);

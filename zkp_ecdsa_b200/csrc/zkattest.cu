@@ -227,15 +227,20 @@ struct zka_ctx {
   int tom_w = 22, tom_nwin = 12;   // per base: 12 windows x 2^22 entries x 128 B = 6.4 GB of HBM (ZKA_TOM_W)
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 8192;
+  int host_chunk = 4096;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
+  // copy streams + events of the host-buffer pipeline (zka_prove_batch); slot = chunk index & 1
+  Stream cs_in, cs_out;
+  Event ev_small[2], ev_tape[2], ev_done[2], ev_out[2];
   int p256_hw = 16;       // window bits of the per-params NistGroup.h table
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
+  FixedTable gw;          // P-256 generator, p256_hw-bit windows (prover phase A)
   FixedTable tg;          // tomEdwards256 generator [nwin][2^w][32]
   DevBuf tg_bytes;        // 67-byte encoding of g
   DevBuf lag;             // GK Lagrange matrix cache
   int lag_n = -1;
   // workspace (grow-only)
   DevBuf w[64];
-  DevBuf in[8], out[4];
+  DevBuf in[16], out[8];
 };
 
 struct zka_params {
@@ -341,12 +346,16 @@ void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) 
 
 // stage a caller buffer on the device if it is a host pointer
 template <class T>
-const T* stage_in(zka_ctx* ctx, DevBuf& buf, const T* p, size_t count) {
+const T* stage_in(Stream& st, DevBuf& buf, const T* p, size_t count) {
   if (!p || count == 0) return p;
   if (is_device_ptr(p)) return p;
   T* d = buf.get<T>(count);
-  copy_h2d(ctx->st, d, p, count * sizeof(T));
+  copy_h2d(st, d, p, count * sizeof(T));
   return d;
+}
+template <class T>
+const T* stage_in(zka_ctx* ctx, DevBuf& buf, const T* p, size_t count) {
+  return stage_in(ctx->st, buf, p, count);
 }
 
 }  // namespace
@@ -434,6 +443,12 @@ int zka_init(int device, zka_ctx** out) {
       int c = atoi(e);
       if (c >= 1) ctx->chunk = c;
     }
+    if (const char* e = getenv("ZKA_HOST_CHUNK")) {
+      int c = atoi(e);
+      if (c >= 1) ctx->host_chunk = c;
+    }
+    stream_create(ctx->cs_in);
+    stream_create(ctx->cs_out);
     if (const char* e = getenv("ZKA_P256_HW")) {   // window bits of the NistGroup.h table: 8 or 16
       int w = atoi(e);
       if (w == 8 || w == 16) ctx->p256_hw = w;
@@ -442,6 +457,7 @@ int zka_init(int device, zka_ctx** out) {
     uint32_t* d_gen = gen.get<uint32_t>(16 + 18);
     launch(ctx->st, 1, GenAffTask{d_gen, d_gen + 16});
     build_p256_tab(ctx, d_gen, ctx->g8, 8);
+    build_p256_tab(ctx, d_gen, ctx->gw, ctx->p256_hw);
     build_tom_tab(ctx, d_gen + 16, ctx->tg);
     // encoding of g (C_14 = params.g in pi_8, pointAdd.ts:144,220): normalise the table entry 1*g
     DevBuf proj, aff;
@@ -466,12 +482,18 @@ int zka_init(int device, zka_ctx** out) {
 void zka_shutdown(zka_ctx* ctx) {
   if (!ctx) return;
   ctx->g8.buf.release();
+  ctx->gw.buf.release();
   ctx->tg.buf.release();
   ctx->tg_bytes.release();
   ctx->lag.release();
   for (auto& b : ctx->w) b.release();
   for (auto& b : ctx->in) b.release();
   for (auto& b : ctx->out) b.release();
+  for (int i = 0; i < 2; i++) {
+    ev_destroy(ctx->ev_small[i]); ev_destroy(ctx->ev_tape[i]); ev_destroy(ctx->ev_done[i]); ev_destroy(ctx->ev_out[i]);
+  }
+  stream_destroy(ctx->cs_in);
+  stream_destroy(ctx->cs_out);
 #if !defined(ZKA_HOSTSIM)
   if (ctx->st.s) cudaStreamDestroy(ctx->st.s);
 #endif
@@ -717,7 +739,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
     Stream& st = ctx->st;
     DevBuf* W = ctx->w;
     // ring: once per call
-    const uint8_t* d_ring = stage_in(ctx, ctx->in[5], ring, (size_t)N * 32);
+    const uint8_t* d_ring = stage_in(ctx, ctx->in[10], ring, (size_t)N * 32);
     uint32_t* ring_m = W[40].get<uint32_t>(((size_t)1 << n) * 8);
     launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
     // Lagrange matrix for nodes 0..n-1: depends only on n, cached per context
@@ -728,22 +750,55 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
     }
     uint32_t* lag = (uint32_t*)ctx->lag.p;
 
+    // Chunks are software-pipelined over three streams when buffers live in host memory: the inputs of
+    // chunk k+1 travel on cs_in and the proofs of chunk k-1 on cs_out while chunk k computes on st
+    // (staging buffers double-buffered by slot = k & 1).  Inside a chunk the tape (97 % of the input
+    // bytes) is only awaited by phase A, so it also overlaps the latency-bound statement stage.
     const bool out_dev = is_device_ptr(proofs);
-    for (uint32_t b0 = 0; b0 < B; b0 += (uint32_t)ctx->chunk) {
-      const int Bc = (int)std::min<uint32_t>((uint32_t)ctx->chunk, B - b0);
+    const bool len_dev = is_device_ptr(proof_len_out), st_dev = is_device_ptr(status);
+    const uint32_t chunk = (uint32_t)((out_dev && is_device_ptr(tape)) ? ctx->chunk : std::min(ctx->chunk, ctx->host_chunk));
+    const uint32_t nchunks = (B + chunk - 1) / chunk;
+    struct ChunkIn { const uint8_t *msg_hash, *sig, *pk, *tape; const uint32_t* which; } cin[2];
+    auto issue_inputs = [&](uint32_t k) {
+      const int slot = (int)(k & 1);
+      const uint32_t b0 = k * chunk;
+      const size_t Bc = std::min<uint32_t>(chunk, B - b0);
+      Stream& ci = ctx->cs_in;
+      DevBuf* in = ctx->in + 5 * slot;
+      ev_wait(ci, ctx->ev_done[slot]);   // chunk k-2 has finished reading these staging buffers
+      cin[slot].msg_hash = stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32);
+      cin[slot].sig = stage_in(ci, in[1], sig + (size_t)b0 * 64, Bc * 64);
+      cin[slot].pk = stage_in(ci, in[2], pk + (size_t)b0 * 65, Bc * 65);
+      cin[slot].which = stage_in(ci, in[3], which + b0, Bc);
+      ev_record(ctx->ev_small[slot], ci);
+      cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
+      ev_record(ctx->ev_tape[slot], ci);
+    };
+    ev_record(ctx->ev_done[0], st);      // the ring / Lagrange launches above precede every copy stream
+    ev_wait(ctx->cs_in, ctx->ev_done[0]);
+    ev_wait(ctx->cs_out, ctx->ev_done[0]);
+    issue_inputs(0);
+    for (uint32_t k = 0; k < nchunks; k++) {
+      const uint32_t b0 = k * chunk;
+      const int slot = (int)(k & 1);
+      const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
+      if (k + 1 < nchunks) issue_inputs(k + 1);
+      ev_wait(st, ctx->ev_small[slot]);
+      ev_wait(st, ctx->ev_out[slot]);    // the proofs of chunk k-2 have left the output staging buffers
       ProveCtx c;
       memset(&c, 0, sizeof(c));
       c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.M = 0;
       c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
-      c.msg_hash = stage_in(ctx, ctx->in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
-      c.sig = stage_in(ctx, ctx->in[1], sig + (size_t)b0 * 64, (size_t)Bc * 64);
-      c.pk = stage_in(ctx, ctx->in[2], pk + (size_t)b0 * 65, (size_t)Bc * 65);
-      c.which = stage_in(ctx, ctx->in[3], which + b0, (size_t)Bc);
-      c.tape = stage_in(ctx, ctx->in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      c.msg_hash = cin[slot].msg_hash;
+      c.sig = cin[slot].sig;
+      c.pk = cin[slot].pk;
+      c.which = cin[slot].which;
+      c.tape = cin[slot].tape;
       c.tape_stride = tape_stride;
       c.tape_draws = (uint32_t)(tape_stride / 32);
       c.ring_m = ring_m;
       c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
+      c.g_tabw = ctx->gw.tab; c.g_w = ctx->p256_hw;
       c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
       c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
       const size_t S1 = (size_t)S + 1;
@@ -779,20 +834,24 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.gk_dv = W[27].get<uint32_t>((size_t)Bc * n * 8);
       c.gk_lag = lag;
       c.gk_x = W[28].get<uint32_t>((size_t)Bc * 3);
+      c.u12 = W[46].get<uint32_t>((size_t)Bc * 16);
       c.proof_stride = proof_stride;
-      c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ctx->out[0].get<uint8_t>((size_t)Bc * proof_stride);
-      c.proof_len = is_device_ptr(proof_len_out) ? proof_len_out + b0 : ctx->out[1].get<uint32_t>(Bc);
-      c.status = is_device_ptr(status) ? status + b0 : ctx->out[2].get<int32_t>(Bc);
+      DevBuf* ob = ctx->out + 3 * slot;
+      c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ob[0].get<uint8_t>((size_t)Bc * proof_stride);
+      c.proof_len = len_dev ? proof_len_out + b0 : ob[1].get<uint32_t>(Bc);
+      c.status = st_dev ? status + b0 : ob[2].get<int32_t>(Bc);
 
-      // --- statement + per-proof tables of R
+      // --- statement + per-proof tables of pk, then R = u1*G + u2*pk on the tables
       launch(st, Bc, PreTask{c});
-      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
+      launch(st, Bc, P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
       launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows});
       {
         const long long np = (long long)Bc * RT_ENTRIES;
         launch_p256_norm(st, c.rrows, c.rtab, nullptr, nullptr, (long long)(np));
       }
-      // --- phase A
+      launch(st, Bc, RPointTask{c});
+      // --- phase A (first consumer of the tape)
+      ev_wait(st, ctx->ev_tape[slot]);
       launch(st, (long long)nA, PhaseAP256Task{c});
       launch_p256_norm(st, c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (long long)(nA));
       launch_p256_norm(st, c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (long long)(nA));
@@ -850,13 +909,21 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch(st, (long long)M * 7, ItemEmitTask{c});
       launch(st, (long long)nA, RepEmitTask{c});
       launch(st, Bc, GkEmitTask{c});
-      // --- results
-      // only the bytes up to the longest proof of the chunk are copied back (rows are stride-padded)
-      if (!out_dev) copy_d2h_2d(st, proofs + (size_t)b0 * proof_stride, proof_stride, c.proofs, proof_stride, max_len, Bc);
-      if (!is_device_ptr(proof_len_out)) copy_d2h(st, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
-      if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
-      sync(st);
+      // --- results: on the output stream, behind this chunk's last kernel
+      ev_record(ctx->ev_done[slot], st);
+      if (!out_dev || !len_dev || !st_dev) {
+        Stream& co = ctx->cs_out;
+        ev_wait(co, ctx->ev_done[slot]);
+        // only the bytes up to the longest proof of the chunk are copied back (rows are stride-padded)
+        if (!out_dev) copy_d2h_2d(co, proofs + (size_t)b0 * proof_stride, proof_stride, c.proofs, proof_stride, max_len, Bc);
+        if (!len_dev) copy_d2h(co, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
+        if (!st_dev) copy_d2h(co, status + b0, c.status, (size_t)Bc * 4);
+        ev_record(ctx->ev_out[slot], co);
+      }
     }
+    sync(ctx->cs_in);
+    sync(ctx->cs_out);
+    sync(st);
     return 0;
   } catch (const std::exception& e) {
     return fail(ctx, ZKA_E_CUDA, e.what());
@@ -877,7 +944,7 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
   try {
     Stream& st = ctx->st;
     DevBuf* W = ctx->w;
-    const uint8_t* d_ring = stage_in(ctx, ctx->in[5], ring, (size_t)N * 32);
+    const uint8_t* d_ring = stage_in(ctx, ctx->in[10], ring, (size_t)N * 32);
     uint32_t* ring_m = W[40].get<uint32_t>(((size_t)1 << n) * 8);
     launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
     const int vchunk = std::min(ctx->chunk, 4096);
