@@ -39,7 +39,7 @@ SEC_LEVEL = 80
 # each modmul = 9x9 product + 5 generic modulus limbs x 9 quotient digits = 126 32x32 MACs
 # DRAM bytes per table lookup of the commitment kernels, from `ncu --set full` captures (profiles/):
 # window bits -> (dram read + write bytes per launch - algorithmic bytes) / lookups
-NCU_DRAM_BYTES_PER_LOOKUP = {16: 78.0}
+NCU_DRAM_BYTES_PER_LOOKUP = {16: 78.0, 22: 118.0}
 MODMUL_PER_MADD = 7      # a = -1 image curve, mixed addition with (v-w, v+w, 2 d2 w v) entries (zk_curves.cuh)
 MAC_PER_TOM_MODMUL = 126   # 81 products + 45 quotient-digit products (zk_field_ptx.cuh); the generic CIOS needs 171
 W_PROVE_REF = {8: 6861088, 256: 6942368, 1024: 6974880}   # reference-algorithm modmuls/proof
