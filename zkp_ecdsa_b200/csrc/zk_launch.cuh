@@ -34,8 +34,12 @@ namespace zk {
                                __FILE__ + ":" + std::to_string(__LINE__));                    \
   } while (0)
 
+// resident CTAs per SM a task asks the register allocator for (specialise per task; default: no bound)
 template <class Task>
-__global__ void __launch_bounds__(128) zk_task_kernel(int n, Task task) {
+struct TaskMinBlocks { static constexpr int value = 1; };
+
+template <class Task>
+__global__ void __launch_bounds__(128, TaskMinBlocks<Task>::value) zk_task_kernel(int n, Task task) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) task(t);
 }

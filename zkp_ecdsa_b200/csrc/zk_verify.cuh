@@ -1038,6 +1038,22 @@ struct MsmP256CombineTask {
   }
 };
 
+// The three Horner passes of a proof (GK, multiW, multiN) are 250-doubling latency chains run by one
+// thread each; launched as ONE grid they overlap instead of queueing (3 B threads are still few).
+struct MsmCombineAllTask {
+  MsmTomCombineTask gk, w;
+  MsmP256CombineTask n;
+  int B, Bp;   // Bp = B rounded up to a warp multiple: the P-256 chain never shares a warp with a Tom chain
+  ZK_HD void operator()(int t) const {
+    const int kind = t / Bp, i = t % Bp;
+    if (i >= B) return;
+    if (kind == 0) gk(i);
+    else if (kind == 1) w(i);
+    else n(i);
+  }
+};
+
+
 // final verdict (zkpAttestList.ts:165-183): GK first, then exp
 struct VFinalTask {
   VerifyCtx c;

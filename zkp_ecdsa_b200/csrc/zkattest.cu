@@ -1040,10 +1040,13 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch(st, (long long)Bc * MSM_NWIN,
              MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, V_ENT_TOM, V_SAMPLES, V_ENT_PER_SAMPLE, 2, c.win_w});
       launch(st, (long long)Bc * MSM_NWIN, MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, c.win_g});
-      launch(st, Bc, MsmTomCombineTask{c.win_g, c.fx_proj, c.id_flags, 2, 0, 0});
-      launch(st, Bc, MsmTomCombineTask{c.win_w, c.fx_proj, c.id_flags, 2, 1, 1});
       launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n});
-      launch(st, Bc, MsmP256CombineTask{c.win_n, c.nfix, c.id_flags});
+      {
+        const int Bp = (Bc + 31) & ~31;
+        launch(st, 3ll * Bp, MsmCombineAllTask{MsmTomCombineTask{c.win_g, c.fx_proj, c.id_flags, 2, 0, 0},
+                                               MsmTomCombineTask{c.win_w, c.fx_proj, c.id_flags, 2, 1, 1},
+                                               MsmP256CombineTask{c.win_n, c.nfix, c.id_flags}, Bc, Bp});
+      }
       launch(st, Bc, VFinalTask{c});
       if (!is_device_ptr(ok)) copy_d2h(st, ok + b0, c.ok, (size_t)Bc);
       if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
