@@ -305,6 +305,39 @@ def run_ours(args):
     valid = col < plen_d.unsqueeze(1)
     same = bool(torch.equal(plen_h.to(dev), plen_d)) and bool(((proofs_h.to(dev) == proofs_d) | ~valid).all().item())
 
+    # ---- the same host-buffer call issued by TWO caller threads, each with its own context (own streams,
+    # workspace and tables): the copies of one caller overlap the kernels of the other, which is how a
+    # service with more than one request in flight keeps the device busy.  Reported beside e2e, not as e2e.
+    two = None
+    if world == 1 and not args.no_two_callers:
+        import threading
+        eng2 = api.Engine(device=local)
+        params2 = eng2.load_params(params.h_nist, params.h_proof, SEC_LEVEL)
+        outs2 = (torch.empty((B, ps), dtype=torch.uint8).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory(),
+                 torch.zeros(B, dtype=torch.int32).pin_memory())
+
+        def caller(lib, ph, outs, n):
+            for _ in range(n):
+                lib.prove_batch(ph, B, h['msg'].data_ptr(), h['sig'].data_ptr(), h['pk'].data_ptr(),
+                                h['which'].data_ptr(), h['ring'].data_ptr(), N, tape_h.data_ptr(), ts,
+                                outs[0].data_ptr(), ps, outs[1].data_ptr(), outs[2].data_ptr())
+        caller(eng2.lib, params2.handle, outs2, 2)          # warm-up of the second context
+        nsteps = max(2, min(args.steps, 4))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=caller, args=(L, params.handle, (proofs_h, plen_h, stat_h), nsteps)),
+              threading.Thread(target=caller, args=(eng2.lib, params2.handle, outs2, nsteps))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        assert int((outs2[2] != 0).sum().item()) == 0 and bool(torch.equal(outs2[1], plen_h))
+        two = {'value': 2 * nsteps * B / wall, 'unit': 'proofs/s', 'callers': 2, 'steps_per_caller': nsteps,
+               'note': 'two host threads, one zka context each, same host buffers in / separate pinned buffers out'}
+        eng2.close()
+
     # ---- verifySignatureList over the proofs just produced (device resident), verifies/s
     from zkp_ecdsa_b200 import verify_tape as VT
     vts = L.verify_tape_len(N, SEC_LEVEL)
@@ -402,7 +435,8 @@ def run_ours(args):
                    'tom_window_bits': cfg['tom_w'], 'chunk': cfg['chunk'],
                    'collective': 'none' if world == 1 else 'one NCCL all-gather of stride-padded proof bytes per step'},
         'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'proofs/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms, 'bit_identical_to_device_arm': same},
+                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms, 'bit_identical_to_device_arm': same,
+                'two_callers': two},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roof,
@@ -449,6 +483,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--ring', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-two-callers', action='store_true', help='skip the two-caller host-buffer leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -700,6 +700,12 @@ struct TomCommitHTask {   // one thread per job: C = K + r*h
   }
 };
 
+#if !defined(ZKA_HOSTSIM) && defined(ZKA_COMMIT_MINBLOCKS)
+template <> struct TaskMinBlocks<TomCommitHTask> { static constexpr int value = ZKA_COMMIT_MINBLOCKS; };
+template <> struct TaskMinBlocks<TomCommitGTask> { static constexpr int value = ZKA_COMMIT_MINBLOCKS; };
+template <> struct TaskMinBlocks<TomCommitTask> { static constexpr int value = ZKA_COMMIT_MINBLOCKS; };
+#endif
+
 // ================================================================================== hashing
 // Streams `npts` encoded points (given as (pointer, length) by a functor) through SHA-256.
 // Encodings in 4-byte aligned slots are fetched one point ahead (17 independent word loads).
