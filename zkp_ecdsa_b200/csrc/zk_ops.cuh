@@ -311,11 +311,11 @@ ZK_HD void p256_accum_fixed8(P256Pt& acc, const uint32_t* tab, const uint32_t* k
     }
   }
 }
-// acc += sum_j T[j][digit_j(k)] for a fixed table [nwin][2^w] of affine entries, w in {8, 16}
+// acc += sum_j T[j][digit_j(k)] for a fixed table [ceil(256/w)][2^w] of affine entries
 ZK_HD void p256_accum_fixed(P256Pt& acc, const uint32_t* tab, const uint32_t* k, int w) {
-  const int nwin = 256 / w;
+  const int nwin = (256 + w - 1) / w;
   for (int j = 0; j < nwin; j++) {
-    const uint32_t d = digit_w(k, j * w, w);
+    const uint32_t d = digit_w(k, j * w, (256 - j * w) < w ? (256 - j * w) : w);
     if (d) {
       P256Aff q;
       p256_ld_aff(q, tab + (((size_t)j << w) + d) * P256_AFF_WORDS);
