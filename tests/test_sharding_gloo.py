@@ -50,6 +50,7 @@ def _worker(rank, world, port, q):
     from zkp_ecdsa_b200 import sharding
     from zkp_ecdsa_b200.capi import ZkaLib
     os.environ['ZKA_TOM_W'] = '10'
+    os.environ['ZKA_P256_HW'] = '8'   # small tables: the host simulator builds them on one CPU core
     lib = ZkaLib(g.HOSTSIM)
     lo, hi = sharding.shard_range(B, rank, world)
     per = (B + world - 1) // world
@@ -60,6 +61,11 @@ def _worker(rank, world, port, q):
     lp[:hi - lo] = torch.from_numpy(proofs)
     ll[:hi - lo] = torch.from_numpy(plen.astype(np.int32))
     allp, alll = sharding.all_gather_proofs(lp, ll, world, rank, per)
+    # trimmed variant: same rows, cut at the longest proof of the whole job (rounded up to 16 bytes)
+    trimmed, tlen = sharding.all_gather_proofs(lp, ll, world, rank, per, trim=True)
+    w = trimmed.shape[1]
+    assert w <= stride and w >= int(alll.max()) and w - int(alll.max()) < 16
+    assert torch.equal(trimmed, allp[:, :w]) and torch.equal(tlen, alll)
     if rank == 0:
         q.put((allp.numpy(), alll.numpy()))
     dist.barrier()
@@ -81,8 +87,10 @@ def test_two_rank_gather_equals_single_process():
     g.build_hostsim()
     from zkp_ecdsa_b200.capi import ZkaLib
     os.environ['ZKA_TOM_W'] = '10'
+    os.environ['ZKA_P256_HW'] = '8'
     ref_proofs, ref_len = _prove(ZkaLib(g.HOSTSIM), 0, B)
     os.environ.pop('ZKA_TOM_W', None)
+    os.environ.pop('ZKA_P256_HW', None)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
