@@ -122,16 +122,57 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region: an NVML polling thread (every 5 ms;
+    a timed region of a few steps is < 100 ms), `nvidia-smi -lms` as the fallback."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    REASON_BITS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.samples = []
+        self.samples = []          # (sm_mhz, max_mhz, power_w, reason_mask)
         self.proc = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            if not uuid.startswith('GPU-'):
+                uuid = 'GPU-' + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+
+    def _poll(self):
+        nv, h = self.nvml
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while True:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), float(mx), pw, int(mask)))
+            except Exception:
+                pass
+            if self.stop_flag.wait(0.005):
+                break
 
     def start(self):
+        try:
+            self.nvml = self._nvml_handle()
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-i', str(self.idx), '-lms', '100'], stdout=subprocess.PIPE, text=True)
@@ -142,31 +183,39 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for s in self.samples:
-            f = [x.strip() for x in s.split(',')]
+            f = [x.strip() for x in line.strip().split(',')]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                mask = 0
+                for bit, v in zip((0x8, 0x40, 0x20, 0x4), f[4:8]):
+                    if v.lower().startswith('active'):
+                        mask |= bit
+                self.samples.append((float(f[1]), float(f[2]), float(f[3]), mask))
             except ValueError:
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
-                if v.lower().startswith('active'):
+
+    def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.th.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML / nvidia-smi']}
+        sm = sorted(x[0] for x in self.samples)
+        reasons = set()
+        for x in self.samples:
+            for bit, name in self.REASON_BITS.items():
+                if x[3] & bit:
                     reasons.add(name)
-        sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max((x[1] for x in self.samples), default=None),
+                'power_w_max': max((x[2] for x in self.samples), default=None), 'samples': len(sm),
+                'source': 'nvml' if self.nvml else 'nvidia-smi', 'reasons': sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------------------- our arm

@@ -130,8 +130,13 @@ void* zka_get_stream(zka_ctx* ctx);
 int zka_set_profiling(zka_ctx* ctx, int enable);
 int zka_profile_reset(zka_ctx* ctx);
 size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap);
-/* tuning knobs read at zka_init from the environment: ZKA_TOM_W (window bits of the fixed-base
- * tables, default 13), ZKA_CHUNK (proofs per pipeline pass, default 8192).  zka_config reports them. */
+/* tuning knobs read at zka_init from the environment (zka_config reports the first three):
+ *   ZKA_TOM_W       window bits of the tomEdwards256 fixed-base tables, 2..24, default 22
+ *                   (ceil(256/w) windows x 2^w entries x 128 B per base: 6.4 GB at 22, 134 MB at 16)
+ *   ZKA_P256_HW     window bits of the P-256 G / NistGroup.h tables, 8..24, default 20 (872 MB per base)
+ *   ZKA_CHUNK       proofs per pipeline pass when all buffers are device memory, default 8192
+ *   ZKA_HOST_CHUNK  proofs per pass when buffers are host memory (copies of one pass overlap the
+ *                   kernels of the next), default 4096 */
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk);
 
 /* ---- layer-wise entry points (parity tests of the arithmetic underneath) ---- */

@@ -136,3 +136,21 @@ def test_multi_chunk_batches_equal_single_chunk():
     assert (outs[0][1] == outs[1][1]).all()
     for b in range(5):
         assert outs[0][0][b, :outs[0][1][b]].tobytes() == outs[1][0][b, :outs[1][1][b]].tobytes()
+
+
+def test_ragged_table_windows_bit_exact():
+    """Table window widths that do not divide 256 (the defaults, 22 and 20 bits, do not): the last
+    window is narrower.  Same proof bytes and verdicts as the oracle with 11- and 9-bit windows."""
+    import os
+    import __graft_entry__ as g
+    from zkp_ecdsa_b200.capi import ZkaLib
+    g.build_hostsim()
+    os.environ.update(ZKA_TOM_W='11', ZKA_P256_HW='9')
+    try:
+        L = ZkaLib(g.HOSTSIM)
+    finally:
+        os.environ.pop('ZKA_TOM_W', None)
+        os.environ.pop('ZKA_P256_HW', None)
+    assert L.config()['tom_w'] == 11 and L.config()['tom_nwin'] == 24
+    common.check_prove_parity(L, B=2, N=5, sec_level=20, seed=71)
+    common.check_verify_parity(L, N=5, sec_level=20, seed=72, tampers=6)
