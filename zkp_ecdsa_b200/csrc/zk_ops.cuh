@@ -156,12 +156,16 @@ struct P256PowsTask {
   const uint8_t* base_inf;   // [nbase] or null
   uint32_t* pows;            // [nbase][nwin][24]
   int nbase, nwin, w;
+  const uint32_t* index = nullptr;      // optional: base t is base_aff[index[t]]
+  const uint32_t* count_dev = nullptr;  // optional: number of bases actually present (<= nbase)
   ZK_HD void operator()(int t) const {
+    if (count_dev && (uint32_t)t >= *count_dev) return;
+    const size_t src = index ? index[t] : (size_t)t;
     P256Aff a;
-    p256_ld_aff(a, base_aff + (size_t)t * P256_AFF_WORDS);
+    p256_ld_aff(a, base_aff + src * P256_AFF_WORDS);
     P256Pt p;
     p256_from_affine(p, a);
-    if (base_inf && base_inf[t]) p256_set_identity(p);
+    if (base_inf && base_inf[src]) p256_set_identity(p);
     // the doubling chain runs in Jacobian coordinates (8 instead of 13 multiplications per step)
     P256Jac q;
     p256_hom_to_jac(q, p);
@@ -199,7 +203,9 @@ enum : int { RT_W = 5, RT_NWIN = 52, RT_ROW = 16, RT_ENTRIES = RT_NWIN * RT_ROW 
 struct P256RowsSignedTask {
   const uint32_t* pows;  // [nbase*RT_NWIN][24]
   uint32_t* rows;        // [nbase*RT_NWIN][RT_ROW][24]: entry d-1 = d * pows
+  const uint32_t* count_dev = nullptr;   // optional: number of bases actually present
   ZK_HD void operator()(int t) const {
+    if (count_dev && (uint32_t)(t / RT_NWIN) >= *count_dev) return;
     P256Pt p, acc;
     p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
     acc = p;
@@ -254,10 +260,17 @@ struct P256NormTask {
   uint8_t* inf;          // [count] or null
   int count;
   int chunk;             // points per thread (<= NORM_CHUNK_MAX)
+  const uint32_t* groups_dev = nullptr;  // optional: only the first *groups_dev * group_size points exist
+  int group_size = 0;
   ZK_HD void operator()(int t) const {
     using F = P256p;
     const int lo = t * chunk;
-    int n = count - lo;
+    int total = count;
+    if (groups_dev) {
+      const long long present = (long long)*groups_dev * group_size;
+      if (present < total) total = (int)present;
+    }
+    int n = total - lo;
     if (n > chunk) n = chunk;
     if (n <= 0) return;
     uint32_t pre[NORM_CHUNK_MAX][8];

@@ -56,7 +56,10 @@ struct ProveCtx {
   uint32_t* r_aff;     // [B][16] R
   uint8_t* r_bytes;    // [B][BSTRIDE]
   uint32_t* u12;       // [B][16] u1 = z/s, u2 = r/s (Montgomery mod n): R = u1*G + u2*pk
-  uint32_t* rpows;     // [B][RT_NWIN][24]          per-proof signed 5-bit table of pk:
+  uint32_t* tab_of;    // [B]   table index of the proof's pk (equal keys of a batch share one table)
+  uint32_t* tab_rep;   // [B]   proof index that owns table t; tab_count[0] = number of tables
+  uint32_t* tab_count; // [1]
+  uint32_t* rpows;     // [B][RT_NWIN][24]          per-KEY signed 5-bit table of pk:
   uint32_t* rrows;     // [B][RT_NWIN][RT_ROW][24]    every alpha*R of the proof is evaluated as
   uint32_t* rtab;      // [B][RT_NWIN][RT_ROW][16]    (alpha u1)*G + (alpha u2)*pk, so no table of R is needed
   // phase A (P-256): slot i in [0,S] per proof; slot S is comS1
@@ -87,6 +90,7 @@ struct ProveCtx {
   // Tom store 2 (post-challenge): [34 M jobs][5 M derived][4n B GK]
   uint32_t *s2_jv, *s2_jr, *s2_proj, *s2_aff;
   uint8_t* s2_bytes;
+  uint32_t* item_inv;  // [M][8]     1 / (x2 - x1) of the item's point addition (Montgomery mod q; 0 for 0)
   uint32_t* secrets;   // [M][34][8] Montgomery mod tom.order
   uint32_t* item_chal; // [M][6][3]
   // GK
@@ -203,6 +207,47 @@ struct PreTask {
   }
 };
 
+// Stage 0a — equal public keys share one table.  All proofs of a call prove membership in ONE ring, so a
+// batch holds at most N distinct keys; tables (a 255-doubling chain, 780 additions and 832
+// normalisations each) are built per distinct key.  Thread b looks for the first proof with the same
+// (validated, Montgomery-form) key; KeyRankTask turns first occurrences into dense table indices.
+struct KeyDedupTask {
+  ProveCtx c;
+  ZK_HD void operator()(int b) const {
+    uint32_t mine[16];
+    ld<16>(mine, c.pk_aff + (size_t)b * 16);
+    int rep = b;
+    for (int o = 0; o < b; o++) {
+      const uint32_t* q = c.pk_aff + (size_t)o * 16;
+      if (q[0] != mine[0]) continue;
+      bool same = true;
+      for (int i = 1; i < 16; i++) same = same && (q[i] == mine[i]);
+      if (same) { rep = o; break; }
+    }
+    c.tab_of[b] = (uint32_t)rep;      // provisional: index of the first proof with this key
+  }
+};
+struct KeyRankTask {
+  ProveCtx c;
+  ZK_HD void operator()(int b) const {
+    const uint32_t rep = c.tab_of[b];
+    // (tab_of is only rewritten by the follow-up KeyAssignTask, so every thread sees first occurrences)
+    uint32_t rank = 0;
+    for (uint32_t o = 0; o < rep; o++) rank += (c.tab_of[o] == o) ? 1u : 0u;
+    c.tab_rep[c.B + b] = rank;        // scratch half of tab_rep: rank of this proof's table
+    if (rep == (uint32_t)b) c.tab_rep[rank] = (uint32_t)b;
+    if (b == c.B - 1) {
+      uint32_t total = 0;
+      for (uint32_t o = 0; o < (uint32_t)c.B; o++) total += (c.tab_of[o] == o) ? 1u : 0u;
+      c.tab_count[0] = total;
+    }
+  }
+};
+struct KeyAssignTask {
+  ProveCtx c;
+  ZK_HD void operator()(int b) const { c.tab_of[b] = c.tab_rep[c.B + b]; }
+};
+
 // Stage 0b — R = u1*G + u2*pk on the tables, affine + encoded; per-proof checks in the reference's order.
 struct RPointTask {
   ProveCtx c;
@@ -215,7 +260,7 @@ struct RPointTask {
     P256Pt R;
     p256_set_identity(R);
     p256_accum_fixed(R, c.g_tabw, u1, c.g_w);
-    p256_accum_rtab(R, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, u2);
+    p256_accum_rtab(R, c.rtab + (size_t)c.tab_of[b] * RT_ENTRIES * P256_AFF_WORDS, u2);
     uint32_t zi[8];
     P256Aff Ra;
     if (p256_is_identity(R)) {
@@ -266,7 +311,7 @@ struct PhaseAP256Task {
     P256Pt T, A;
     p256_set_identity(T);
     p256_accum_fixed(T, c.g_tabw, a1, c.g_w);
-    p256_accum_rtab(T, c.rtab + (size_t)b * RT_ENTRIES * P256_AFF_WORDS, a2);
+    p256_accum_rtab(T, c.rtab + (size_t)c.tab_of[b] * RT_ENTRIES * P256_AFF_WORDS, a2);
     A = T;
     p256_accum_fixed(A, c.h_tab8, r, c.h_w);
     p256_st_proj(c.pa_T + (size_t)t * P256_PROJ_WORDS, T);
@@ -390,6 +435,51 @@ struct PhaseBP256Task {
   }
 };
 
+// Stage 5a — the one inversion of every item, i8 = 1 / (x2 - x1) (pointAdd.ts:131), batched:
+// one thread runs Montgomery's trick over ITEM_INV_CHUNK items (one binary inversion instead of 8).
+// invMod(0) = 0 as in big.ts: a zero difference is replaced by 1 inside the product and yields 0.
+enum : int { ITEM_INV_CHUNK = 8 };
+struct ItemInvTask {
+  ProveCtx c;
+  ZK_HD void operator()(int t) const {
+    using F = Tomq;
+    const int lo = t * ITEM_INV_CHUNK;
+    int n = c.M - lo;
+    if (n > ITEM_INV_CHUNK) n = ITEM_INV_CHUNK;
+    uint32_t d[ITEM_INV_CHUNK][8], pre[ITEM_INV_CHUNK][8], acc[8];
+    bool z[ITEM_INV_CHUNK];
+    F::set_one(acc);
+#pragma unroll
+    for (int k = 0; k < ITEM_INV_CHUNK; k++) {
+      if (k < n) {
+        const int it = lo + k;
+        uint32_t x1[8], x2[8], one[8];
+        ld<8>(x1, c.pb_T1_aff + (size_t)it * 16);
+        ld<8>(x2, c.pk_aff + (size_t)c.item_b[it] * 16);
+        F::sub(d[k], x2, x1);
+        z[k] = is_zero_n<8>(d[k]);
+        F::set_one(one);
+        csel_n<8>(d[k], z[k], one, d[k]);
+        F::mul(acc, acc, d[k]);
+        copy_n<8>(pre[k], acc);
+      }
+    }
+    uint32_t inv[8];
+    F::inv(inv, acc);
+#pragma unroll
+    for (int k = ITEM_INV_CHUNK - 1; k >= 0; k--) {
+      if (k < n) {
+        uint32_t r[8], zero[8];
+        if (k > 0) F::mul(r, inv, pre[k - 1]); else copy_n<8>(r, inv);
+        F::mul(inv, inv, d[k]);
+        zero_n<8>(zero);
+        csel_n<8>(r, z[k], zero, r);
+        st<8>(c.item_inv + (size_t)(lo + k) * 8, r);
+      }
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Stage 5 — pointAdd.ts:125-160 witnesses + every commitment opening of one 0-bit repetition,
 // in the proof-group scalar field F_q, q = tom.order = p256.p.  One thread per item.
@@ -429,7 +519,7 @@ struct ItemScalarsTask {
     // pointAdd.ts:130-136
     uint32_t i7[8], i8[8], i9[8], i10[8], i11[8], i12[8], i13[8];
     F::sub(i7, x2, x1);
-    F::inv(i8, i7);
+    ld<8>(i8, c.item_inv + (size_t)it * 8);   // 1 / i7 (ItemInvTask)
     F::sub(i9, y2, y1);
     F::mul(i10, i8, i9);
     F::sqr(i11, i10);

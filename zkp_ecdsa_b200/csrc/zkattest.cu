@@ -836,6 +836,9 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.gk_lag = lag;
       c.gk_x = W[28].get<uint32_t>((size_t)Bc * 3);
       c.u12 = W[46].get<uint32_t>((size_t)Bc * 16);
+      c.tab_of = W[48].get<uint32_t>(Bc);
+      c.tab_rep = W[49].get<uint32_t>((size_t)Bc * 2);
+      c.tab_count = W[50].get<uint32_t>(1);
       c.proof_stride = proof_stride;
       DevBuf* ob = ctx->out + 3 * slot;
       c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ob[0].get<uint8_t>((size_t)Bc * proof_stride);
@@ -844,11 +847,16 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
 
       // --- statement + per-proof tables of pk, then R = u1*G + u2*pk on the tables
       launch(st, Bc, PreTask{c});
-      launch(st, Bc, P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
-      launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows});
+      // one table per DISTINCT key of the chunk (grids are sized for Bc tables, surplus threads return)
+      launch(st, Bc, KeyDedupTask{c});
+      launch(st, Bc, KeyRankTask{c});
+      launch(st, Bc, KeyAssignTask{c});
+      launch(st, Bc, P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count});
+      launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows, c.tab_count});
       {
         const long long np = (long long)Bc * RT_ENTRIES;
-        launch_p256_norm(st, c.rrows, c.rtab, nullptr, nullptr, (long long)(np));
+        const int ch = norm_chunk_for(np);
+        launch(st, (np + ch - 1) / ch, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np, ch, c.tab_count, RT_ENTRIES});
       }
       launch(st, Bc, RPointTask{c});
       // --- phase A (first consumer of the tape)
@@ -881,11 +889,13 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.s2_aff = W[38].get<uint32_t>(n2 * TOM_AFF_WORDS);
       c.s2_bytes = W[39].get<uint8_t>(n2 * BSTRIDE);
       c.secrets = W[42].get<uint32_t>((size_t)M * SECRETS_PER_ITEM * 8);
+      c.item_inv = W[47].get<uint32_t>((size_t)M * 8);
       c.item_chal = W[43].get<uint32_t>((size_t)M * HASHES_PER_ITEM * 3);
       launch(st, Bc, ItemsTask{c});
       // --- phase B
       launch(st, M, PhaseBP256Task{c});
       launch_p256_norm(st, c.pb_T1, c.pb_T1_aff, nullptr, c.pb_T1_inf, (long long)(M));
+      launch(st, ((long long)M + ITEM_INV_CHUNK - 1) / ITEM_INV_CHUNK, ItemInvTask{c});
       launch(st, M, ItemScalarsTask{c});
       launch(st, (long long)Bc * n, GkJobsTask{c});
       launch(st, (long long)Bc * n, GkPolyTask{c});
