@@ -32,17 +32,28 @@ __device__ __noinline__ W mul_ps(V a, V b) {   // product scanning
   return r;
 }
 
-// row: lanes (acc[2t], acc[2t+1]) += x * b[j0 + 2t], t = 0..cnt-1, one carry chain; returns carry-out
-template <int CNT>
-__device__ __forceinline__ uint32_t row_chain(uint32_t* acc, uint32_t x, const uint32_t* b, int j0) {
-  asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(x), "r"(b[j0]));
-#pragma unroll
-  for (int t = 1; t < CNT; t++)
-    asm("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-        : "+r"(acc[2 * t]), "+r"(acc[2 * t + 1]) : "r"(x), "r"(b[j0 + 2 * t]));
-  uint32_t c;
-  asm("addc.u32 %0, 0, 0;" : "=r"(c));
-  return c;
+// row: lanes (acc[2t], acc[2t+1]) += x * b[j0 + 2t], t = 0..CNT-1, ONE carry chain in ONE asm statement
+// (the carry flag must not live across asm statements); the carry-out is added to acc[2*CNT].
+__device__ __forceinline__ void row_chain5(uint32_t* acc, uint32_t x, const uint32_t* b) {
+  asm("mad.lo.cc.u32 %0, %11, %12, %0;\n\tmadc.hi.cc.u32 %1, %11, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %11, %13, %2;\n\tmadc.hi.cc.u32 %3, %11, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %14, %4;\n\tmadc.hi.cc.u32 %5, %11, %14, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %15, %6;\n\tmadc.hi.cc.u32 %7, %11, %15, %7;\n\t"
+      "madc.lo.cc.u32 %8, %11, %16, %8;\n\tmadc.hi.cc.u32 %9, %11, %16, %9;\n\t"
+      "addc.u32 %10, %10, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+        "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10])
+      : "r"(x), "r"(b[0]), "r"(b[2]), "r"(b[4]), "r"(b[6]), "r"(b[8]));
+}
+__device__ __forceinline__ void row_chain4(uint32_t* acc, uint32_t x, const uint32_t* b) {
+  asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+        "+r"(acc[8])
+      : "r"(x), "r"(b[1]), "r"(b[3]), "r"(b[5]), "r"(b[7]));
 }
 __device__ __noinline__ W mul_os(V a, V b) {   // operand scanning, even/odd arrays: T = E + (O << 32)
   uint32_t E[2 * N + 2], O[2 * N + 2];
@@ -52,22 +63,23 @@ __device__ __noinline__ W mul_os(V a, V b) {   // operand scanning, even/odd arr
   for (int i = 0; i < N; i++) {
     // a_i * b_j lands at limbs (i+j, i+j+1): even i+j -> E lanes, odd i+j -> O lanes (O offset by one limb)
     if ((i & 1) == 0) {
-      uint32_t c = row_chain<5>(E + i, a.v[i], b.v, 0);       // j = 0,2,4,6,8
-      E[i + 10] += c;
-      c = row_chain<4>(O + i, a.v[i], b.v, 1);                // j = 1,3,5,7 -> T limbs i+j = O index i+j-1
-      O[i + 8] += c;
+      row_chain5(E + i, a.v[i], b.v);       // j = 0,2,4,6,8: positions i+j even
+      row_chain4(O + i, a.v[i], b.v);       // j = 1,3,5,7: T limb i+j = O index i+j-1
     } else {
-      uint32_t c = row_chain<5>(O + i - 1, a.v[i], b.v, 0);   // i+j odd for even j
-      O[i + 9] += c;
-      c = row_chain<4>(E + i + 1, a.v[i], b.v, 1);            // i+j even for odd j
-      E[i + 9] += c;
+      row_chain5(O + i - 1, a.v[i], b.v);   // i+j odd for even j
+      row_chain4(E + i + 1, a.v[i], b.v);   // i+j even for odd j
     }
   }
   W r;
   r.v[0] = E[0];
-  asm("add.cc.u32 %0, %1, %2;" : "=r"(r.v[1]) : "r"(E[1]), "r"(O[0]));
+  // T = E + (O << 32): one ripple add (kept out of asm: it is not what is being measured)
+  uint64_t carry = 0;
 #pragma unroll
-  for (int k = 2; k < 2 * N; k++) asm("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(E[k]), "r"(O[k - 1]));
+  for (int k = 1; k < 2 * N; k++) {
+    const uint64_t t = (uint64_t)E[k] + O[k - 1] + carry;
+    r.v[k] = (uint32_t)t;
+    carry = t >> 32;
+  }
   return r;
 }
 

@@ -143,11 +143,10 @@ ZK_HD void reduce_once(uint32_t* a) {
 // proof).  The pipeline builds ONE positional table per proof, of pk, and evaluates R (RPointTask) and
 // every alpha*R of phase A on the G table and that pk table.
 // ---------------------------------------------------------------------------------------------
-struct PreTask {
+struct PreKeyTask {   // validate and store the public key (everything the key tables depend on)
   ProveCtx c;
   ZK_HD void operator()(int b) const {
     using Fp = P256p;
-    using Fn = P256n;
     c.status[b] = ZKA_OK;
     const uint8_t* pkb = c.pk + (size_t)b * 65;
     uint32_t px[8], py[8];
@@ -167,7 +166,13 @@ struct PreTask {
       p256_set_generator(pk);
     }
     p256_st_aff(c.pk_aff + (size_t)b * 16, pk);
-
+  }
+};
+struct PreTask {      // the scalars of the statement and Q = z1*G
+  ProveCtx c;
+  ZK_HD void operator()(int b) const {
+    using Fp = P256p;
+    using Fn = P256n;
     uint32_t z[8], r[8], s[8];
     limbs_from_be<8>(z, c.msg_hash + (size_t)b * 32, 32);   // truncateToN is the identity for 32 bytes
     limbs_from_be<8>(r, c.sig + (size_t)b * 64, 32);
@@ -246,6 +251,21 @@ struct KeyRankTask {
 struct KeyAssignTask {
   ProveCtx c;
   ZK_HD void operator()(int b) const { c.tab_of[b] = c.tab_rep[c.B + b]; }
+};
+
+// The doubling chains of the (few) distinct keys and the per-proof scalar stage are both latency bound
+// and independent of each other: one grid runs them side by side.
+struct PowsAndPreTask {
+  P256PowsTask pows;
+  PreTask pre;
+  int Bp;   // pows.nbase rounded up to a warp multiple
+  ZK_HD void operator()(int t) const {
+    if (t < Bp) {
+      if (t < pows.nbase) pows(t);
+    } else if (t - Bp < pre.c.B) {
+      pre(t - Bp);
+    }
+  }
 };
 
 // Stage 0b — R = u1*G + u2*pk on the tables, affine + encoded; per-proof checks in the reference's order.

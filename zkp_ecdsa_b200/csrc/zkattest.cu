@@ -846,12 +846,16 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.status = st_dev ? status + b0 : ob[2].get<int32_t>(Bc);
 
       // --- statement + per-proof tables of pk, then R = u1*G + u2*pk on the tables
-      launch(st, Bc, PreTask{c});
+      launch(st, Bc, PreKeyTask{c});
       // one table per DISTINCT key of the chunk (grids are sized for Bc tables, surplus threads return)
       launch(st, Bc, KeyDedupTask{c});
       launch(st, Bc, KeyRankTask{c});
       launch(st, Bc, KeyAssignTask{c});
-      launch(st, Bc, P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count});
+      {
+        const int Bp = (Bc + 31) & ~31;
+        launch(st, (long long)Bp + Bc,
+               PowsAndPreTask{P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count}, PreTask{c}, Bp});
+      }
       launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows, c.tab_count});
       {
         const long long np = (long long)Bc * RT_ENTRIES;
