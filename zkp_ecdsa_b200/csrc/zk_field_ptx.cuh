@@ -111,10 +111,10 @@ __device__ __forceinline__ void tom_mul_body_ps(uint32_t* r, const uint32_t* a, 
 
 // ---------------------------------------------------------------------------------------------
 // tom.p, operand scanning with even/odd accumulator arrays (the layout sppark / CGBN-style code uses).
-// tools/mac_patterns.cu: the 81 products of a 9x9 multiplication run at 0.79 of the IMAD.WIDE peak when
-// every product goes through one 96-bit column accumulator (product scanning: each MAC waits for the
-// previous one's registers) and at 0.88-0.93 when each row is two carry chains of mad.lo.cc/madc.hi.cc
-// pairs over DISTINCT accumulators (only the carry flag links consecutive instructions).
+// In product scanning every product goes through one 96-bit column accumulator, so each MAC reads the
+// registers the previous MAC wrote; here each row is two carry chains of mad.lo.cc/madc.hi.cc pairs over
+// DISTINCT accumulators and only the carry flag links consecutive instructions.  tools/mul_peak.cu (this
+// multiplier alone, registers only): 0.67 -> 0.77 of the IMAD.WIDE peak at the commit kernels' occupancy.
 //
 // T = E + O: E holds 64-bit lanes at even limb positions (0,1),(2,3).., O at odd positions (1,2),(3,4)..
 // Row i adds a_i*b (5 lanes into the array whose lanes start at position i, 4 into the other one), then
