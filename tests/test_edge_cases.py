@@ -154,3 +154,11 @@ def test_ragged_table_windows_bit_exact():
     assert L.config()['tom_w'] == 11 and L.config()['tom_nwin'] == 24
     common.check_prove_parity(L, B=2, N=5, sec_level=20, seed=71)
     common.check_verify_parity(L, N=5, sec_level=20, seed=72, tampers=6)
+
+
+def test_equal_keys_share_tables_bit_exact(hostsim):
+    """Six proofs over a ring of three: several signers repeat, so the per-key tables are shared
+    (KeyDedupTask); every proof still equals the oracle's byte for byte."""
+    wl = synth.Workload(B=6, N=3, seed=81)
+    assert len({bytes(k) for k in wl.pk}) < 6
+    common.check_prove_parity(hostsim, B=6, N=3, sec_level=12, seed=81)

@@ -353,23 +353,6 @@ ZK_HD void p256_accum_rtab(P256Pt& acc, const uint32_t* tab, const uint32_t* k) 
     }
   }
 }
-// r = k * base, 4-bit fixed window, one-shot variable base (used once per proof for u2*pk)
-ZK_HD void p256_mul_var(P256Pt& r, const P256Aff& base, const uint32_t* k) {
-  P256Pt tb[16];
-  p256_set_identity(tb[0]);
-  p256_from_affine(tb[1], base);
-  for (int d = 2; d < 16; d++) p256_madd(tb[d], tb[d - 1], base);
-  p256_set_identity(r);
-  for (int j = 63; j >= 0; j--) {
-    // four doublings in Jacobian coordinates, the (complete) table addition in homogeneous ones
-    P256Jac q;
-    p256_hom_to_jac(q, r);
-    p256_jac_dbl(q, q); p256_jac_dbl(q, q); p256_jac_dbl(q, q); p256_jac_dbl(q, q);
-    p256_jac_to_hom(r, q);
-    p256_add(r, r, tb[digit4(k, j)]);
-  }
-}
-
 // ===================================================================== tomEdwards256 tables
 struct TomPowsTask {
   const uint32_t* base_aff;  // [nbase][18] image-curve affine (x', y), Montgomery
@@ -449,25 +432,6 @@ struct TomRowsLoTask {
     }
   }
 };
-// aff (x', y) -> table entry (x', y, d' x' y), canonical residues, 128-byte stride
-struct TomPreTask {
-  const uint32_t* aff;  // [count][18]
-  uint32_t* pre;        // [count][32]
-  ZK_HD void operator()(int t) const {
-    using F = Tomp;
-    uint32_t x[9], y[9], k[9], d1[9];
-    ld<9>(x, aff + (size_t)t * TOM_AFF_WORDS);
-    ld<9>(y, aff + (size_t)t * TOM_AFF_WORDS + 9);
-    tom_const(d1, TOM_D1);
-    F::mul(k, x, y);
-    F::mul(k, k, d1);
-    F::reduce(x); F::reduce(y); F::reduce(k);
-    uint32_t* o = pre + (size_t)t * TOM_PRE_WORDS;
-    st<9>(o, x); st<9>(o + 9, y); st<9>(o + 18, k);
-    for (int i = 27; i < 32; i++) o[i] = 0;
-  }
-};
-
 // Rows of a fixed-base table (E1 projective X:Y:Z) -> entries of the prover's a = -1 image curve
 // E2 (zk_curves.cuh): (w, v) = (sqrt(-d1) X/Z, Z/Y), stored as (v - w, v + w, 2 d2 w v), canonical,
 // one 128-byte line each.  Montgomery's trick over chunks of 16 entries on the products Y*Z.
