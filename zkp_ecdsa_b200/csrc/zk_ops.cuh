@@ -21,7 +21,18 @@ namespace zk {
 
 #if defined(__CUDA_ARCH__)
 #define ZK_SET_STATUS(ptr, code) atomicCAS((int*)(ptr), 0, (int)(code))
+// first error wins, except that `code` also replaces the later-stage error `over` (used when the two
+// stages run side by side in one grid: the outcome equals running this stage first)
+#define ZK_SET_STATUS_OVER(ptr, code, over) \
+  do {                                      \
+    atomicCAS((int*)(ptr), 0, (int)(code)); \
+    atomicCAS((int*)(ptr), (int)(over), (int)(code)); \
+  } while (0)
 #else
+#define ZK_SET_STATUS_OVER(ptr, code, over)              \
+  do {                                                   \
+    if (*(ptr) == 0 || *(ptr) == (over)) *(ptr) = (code); \
+  } while (0)
 #define ZK_SET_STATUS(ptr, code) \
   do {                           \
     if (*(ptr) == 0) *(ptr) = (code); \

@@ -284,7 +284,7 @@ struct RPointTask {
     uint32_t zi[8];
     P256Aff Ra;
     if (p256_is_identity(R)) {
-      ZK_SET_STATUS(c.status + b, ZKA_ERR_T_INFINITY);  // T_i = R*alpha is the identity (exp.ts:151)
+      ZK_SET_STATUS_OVER(c.status + b, ZKA_ERR_T_INFINITY, ZKA_ERR_TAPE_RANGE);  // T_i = R*alpha is the identity (exp.ts:151)
       p256_set_generator(Ra);
     } else {
       Fp::inv(zi, R.z);
@@ -294,14 +294,14 @@ struct RPointTask {
     uint32_t r[8];
     limbs_from_be<8>(r, c.sig + (size_t)b * 64, 32);
     reduce_once<FnP256>(r);
-    if (is_zero_n<8>(r)) ZK_SET_STATUS(c.status + b, ZKA_ERR_POINTS_DONT_ADD);  // rinv = 0: T1 + pk != T (pointAdd.ts:105)
+    if (is_zero_n<8>(r)) ZK_SET_STATUS_OVER(c.status + b, ZKA_ERR_POINTS_DONT_ADD, ZKA_ERR_TAPE_RANGE);  // rinv = 0: T1 + pk != T (pointAdd.ts:105)
     p256_st_aff(c.r_aff + (size_t)b * 16, Ra);
     uint8_t* rb = c.r_bytes + (size_t)b * BSTRIDE;
     uint32_t cv[8];
     rb[0] = 0x04;
     Fp::from_mont(cv, Ra.x); limbs_to_be<8>(rb + 1, cv, 32);
     Fp::from_mont(cv, Ra.y); limbs_to_be<8>(rb + 33, cv, 32);
-    if (c.which[b] >= (uint32_t)c.N) ZK_SET_STATUS(c.status + b, ZKA_ERR_BAD_INDEX);
+    if (c.which[b] >= (uint32_t)c.N) ZK_SET_STATUS_OVER(c.status + b, ZKA_ERR_BAD_INDEX, ZKA_ERR_TAPE_RANGE);
   }
 };
 
@@ -341,6 +341,22 @@ struct PhaseAP256Task {
 
 // (TaskMinBlocks<PhaseAP256Task> = 5, i.e. <= 102 registers so that 81 x 1024 threads fit one wave, was
 //  measured: 135 spill accesses, no gain at 1024 proofs, 1.5 % slower at 8192 — left at the default.)
+
+// R itself is only needed after phase A (its encoding goes into the proof header), and phase A works on
+// the tables: both run in one grid.  RPointTask's errors precede phase A's tape-range error in the
+// pipeline order, hence ZK_SET_STATUS_OVER there.
+struct PhaseAAndRPointTask {
+  PhaseAP256Task pa;
+  RPointTask rp;
+  int nA, nAp;   // phase-A threads, rounded up to a warp multiple
+  ZK_HD void operator()(int t) const {
+    if (t < nAp) {
+      if (t < nA) pa(t);
+    } else if (t - nAp < rp.c.B) {
+      rp(t - nAp);
+    }
+  }
+};
 
 // Stage 2a — commitment jobs for pkX, pkY (zkpAttestList.ts:139-140) and Tx_i, Ty_i
 // (exp.ts:154-155).  One thread per (proof, j), j in [0, 2+2S).

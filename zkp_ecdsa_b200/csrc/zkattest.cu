@@ -862,10 +862,12 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         const int ch = norm_chunk_for(np);
         launch(st, (np + ch - 1) / ch, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np, ch, c.tab_count, RT_ENTRIES});
       }
-      launch(st, Bc, RPointTask{c});
-      // --- phase A (first consumer of the tape)
+      // --- phase A (first consumer of the tape) and R = u1*G + u2*pk side by side
       ev_wait(st, ctx->ev_tape[slot]);
-      launch(st, (long long)nA, PhaseAP256Task{c});
+      {
+        const int nAp = (int)((nA + 31) & ~(size_t)31);
+        launch(st, (long long)nAp + Bc, PhaseAAndRPointTask{PhaseAP256Task{c}, RPointTask{c}, (int)nA, nAp});
+      }
       launch_p256_norm(st, c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (long long)(nA));
       launch_p256_norm(st, c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (long long)(nA));
       launch(st, (long long)n1, JobsATask{c});
