@@ -255,14 +255,11 @@ struct VValidateTask {
     for (int i = 0; i < k; i++) ok = wscalar_parse(r, p + (size_t)i * WS) && ok;
     return ok;
   }
-  // One thread per (proof, slot, part): a 0-bit repetition holds 35 points, a 1-bit one 3, so a thread
-  // per repetition left most lanes of a warp waiting for the few heavy ones.  Parts of a repetition:
-  // 0 = head (A, Tx, Ty, z, z2) + C8..C13 + r1 r2, 1..4 = MultProof m, 5..6 = EqualityProof e;
-  // of the header slot: 0 = comS1, keyXcom, keyYcom, 0..7 = the GK points / scalars round robin.
-  enum : int { V_PARTS = 8 };
+  // (one thread per (proof, slot, part-of-repetition) was measured: 2x SLOWER — more threads re-reading
+  //  the same headers; kept at one thread per (proof, slot))
   ZK_HD void operator()(int t) const {
     const int S1 = c.S + 1;
-    const int part = t % V_PARTS, slot = (t / V_PARTS) % S1, b = t / (V_PARTS * S1);
+    const int b = t / S1, slot = t % S1;
     if (c.status[b] == ZKA_ERR_MALFORMED) return;
     const uint8_t* pr = c.proof_of(b);
     bool ok = true;
@@ -270,39 +267,35 @@ struct VValidateTask {
     P256Aff a;
     bool inf;
     if (slot == c.S) {
-      if (part == 0) {
-        ok = p256_parse(a, inf, pr + NP) && ok;             // comS1 (R is checked in VLayoutTask)
-        ok = wpts(pr + 2 * NP, 2) && ok;                    // keyXcom keyYcom
-      }
+      ok = p256_parse(a, inf, pr + NP) && ok;             // comS1 (R is checked in VLayoutTask)
+      ok = wpts(pr + 2 * NP, 2) && ok;                    // keyXcom keyYcom
       const uint8_t* g = pr + c.gk_off[b];
       const int n = g[0];
-      for (int i = part; i < 4 * n; i += V_PARTS) ok = wpts(g + 1 + (size_t)i * WP, 1) && ok;
-      for (int i = part; i < 3 * n + 1; i += V_PARTS) ok = wscs(g + 1 + (size_t)4 * n * WP + (size_t)i * WS, 1) && ok;
+      ok = wpts(g + 1, 4 * n) && ok;
+      ok = wscs(g + 1 + (size_t)4 * n * WP, 3 * n + 1) && ok;
     } else {
       const uint8_t* rep = pr + c.rep_off[(size_t)b * c.S + slot];
+      ok = p256_parse(a, inf, rep + 1) && ok;
+      ok = wpts(rep + 1 + NP, 2) && ok;
       const uint8_t* body = rep + REP_HEAD;
-      if (part == 0) {
-        ok = p256_parse(a, inf, rep + 1) && ok;
-        ok = wpts(rep + 1 + NP, 2) && ok;
-        ok = nscalar_parse(r, body) && ok;
-        ok = nscalar_parse(r, body + NS) && ok;
-      }
+      ok = nscalar_parse(r, body) && ok;
+      ok = nscalar_parse(r, body + NS) && ok;
       if (rep[0]) {
-        if (part == 0) ok = wscs(body + 2 * NS, 2) && ok;
+        ok = wscs(body + 2 * NS, 2) && ok;
       } else {
         const uint8_t* pa = body + 2 * NS;
-        if (part == 0) {
-          ok = wpts(pa, 4) && ok;
-          ok = wscs(pa + PA_LEN, 2) && ok;
-        } else if (part <= 4) {
-          const uint8_t* mp = pa + 4 * WP + (part - 1) * MULT_LEN;
+        ok = wpts(pa, 4) && ok;
+        for (int m = 0; m < 4; m++) {
+          const uint8_t* mp = pa + 4 * WP + m * MULT_LEN;
           ok = wpts(mp, 6) && ok;
           ok = wscs(mp + 6 * WP, 7) && ok;
-        } else if (part <= 6) {
-          const uint8_t* ep = pa + 4 * WP + 4 * MULT_LEN + (part - 5) * EQ_LEN;
+        }
+        for (int e = 0; e < 2; e++) {
+          const uint8_t* ep = pa + 4 * WP + 4 * MULT_LEN + e * EQ_LEN;
           ok = wpts(ep, 2) && ok;
           ok = wscs(ep + 2 * WP, 3) && ok;
         }
+        ok = wscs(pa + PA_LEN, 2) && ok;
       }
     }
     if (!ok) ZK_SET_STATUS(c.status + b, ZKA_ERR_MALFORMED);

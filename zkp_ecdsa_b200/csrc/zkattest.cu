@@ -1030,7 +1030,7 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.status = is_device_ptr(status) ? status + b0 : ctx->out[1].get<int32_t>(Bc);
 
       launch(st, Bc, VLayoutTask{c});
-      launch(st, (long long)Bc * (S + 1) * VValidateTask::V_PARTS, VValidateTask{c});
+      launch(st, (long long)Bc * (S + 1), VValidateTask{c});
       launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
       launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows});
       {
