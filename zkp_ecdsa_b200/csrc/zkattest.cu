@@ -268,17 +268,32 @@ int ceil_log2(uint32_t v) {
 }
 
 
-// normalisation launches: points per thread (= per Fermat inversion) grow with the batch so the
-// inversion cost is amortised while at least ~150k threads stay in flight
-inline int norm_chunk_for(long long count) {
-  long long c = count / 100000;
-  if (c < 8) c = 8;
-  if (c > NORM_CHUNK_MAX) c = NORM_CHUNK_MAX;
-  return (int)c;
+// Normalisation launches: points per thread (= per binary inversion).  A thread costs about
+// per_point * chunk + 70 multiplications in sequence (the inversion is worth ~70), and the grid runs in
+// waves of (SMs x 4 resident CTAs): pick the chunk that minimises waves x thread length.  (The first
+// heuristic, count / 100000, put 1.4 waves on the GPU for a 1024-proof batch.)
+static int g_norm_slots = 148 * 4;
+static bool g_norm_model = true;
+inline int norm_chunk_for(long long count, int per_point = 11) {
+  if (!g_norm_model) {
+    long long c = count / 100000;
+    if (c < 8) c = 8;
+    if (c > NORM_CHUNK_MAX) c = NORM_CHUNK_MAX;
+    return (int)c;
+  }
+  int best = 8;
+  long long best_cost = -1;
+  for (int c = 8; c <= NORM_CHUNK_MAX; c++) {
+    const long long threads = (count + c - 1) / c, ctas = (threads + 127) / 128;
+    const long long waves = (ctas + g_norm_slots - 1) / g_norm_slots;
+    const long long cost = waves * ((long long)per_point * c + 70);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 inline void launch_p256_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uint8_t* bytes, uint8_t* inf, long long count) {
   if (count <= 0) return;
-  const int ch = norm_chunk_for(count);
+  const int ch = norm_chunk_for(count, bytes ? 7 : 5);
   launch(st, (count + ch - 1) / ch, P256NormTask{proj, aff, bytes, inf, (int)count, ch});
 }
 // e2 = 1: the points come from TomCommitTask (a = -1 image curve E2); e2 = 0: E1 projective
@@ -444,6 +459,13 @@ int zka_init(int device, zka_ctx** out) {
       int c = atoi(e);
       if (c >= 1) ctx->chunk = c;
     }
+    if (const char* e = getenv("ZKA_NORM_MODEL")) g_norm_model = atoi(e) != 0;
+#if !defined(ZKA_HOSTSIM)
+    {
+      int sms = 0;
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) g_norm_slots = sms * 4;
+    }
+#endif
     if (const char* e = getenv("ZKA_HOST_CHUNK")) {
       int c = atoi(e);
       if (c >= 1) ctx->host_chunk = c;
@@ -859,7 +881,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows, c.tab_count});
       {
         const long long np = (long long)Bc * RT_ENTRIES;
-        const int ch = norm_chunk_for(np);
+        const int ch = norm_chunk_for(np, 5);
         launch(st, (np + ch - 1) / ch, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np, ch, c.tab_count, RT_ENTRIES});
       }
       // --- phase A (first consumer of the tape) and R = u1*G + u2*pk side by side
