@@ -162,3 +162,11 @@ def test_equal_keys_share_tables_bit_exact(hostsim):
     wl = synth.Workload(B=6, N=3, seed=81)
     assert len({bytes(k) for k in wl.pk}) < 6
     common.check_prove_parity(hostsim, B=6, N=3, sec_level=12, seed=81)
+
+
+def test_large_ring_block_sums_bit_exact(hostsim):
+    """Rings above 1024 entries: the Groth-Kohlweiss ring polynomial is summed in blocks of 1024 entries
+    by separate threads (prover GkPolyTask/GkPolyReduceTask, verifier VGkSumTask).  N = 2100 pads to
+    4096 = 4 blocks; proof bytes and verdicts (incl. tampered proofs) must equal the oracle's."""
+    common.check_prove_parity(hostsim, B=1, N=2100, sec_level=20, seed=91)
+    common.check_verify_parity(hostsim, N=2100, sec_level=20, seed=92, tampers=4)

@@ -694,6 +694,40 @@ template <> struct TaskMinBlocks<TomCommitGTask> { static constexpr int value = 
 template <> struct TaskMinBlocks<TomCommitTask> { static constexpr int value = ZKA_COMMIT_MINBLOCKS; };
 #endif
 
+// ============================================================================ Groth-Kohlweiss sums
+// sum over the 2^k ring entries i of block `blk` of coef_i * prod_j (bit_j(i) ? fo[j] : fz[j]),
+// coef_i = vw ? (vw - v_i) : v_i  (gk.ts:141-171 prover, gk.ts:239-250 verifier).  The product is walked
+// incrementally over the binary counter of the low k bits (about 3 multiplications per entry); the high
+// n-k bits are fixed by the block index.  k = n, blk = 0 is the whole ring in one call; large rings are
+// cut into blocks of 2^GK_BLOCK_BITS entries, one thread each, and summed afterwards.
+enum : int { GK_BLOCK_BITS = 10 };
+ZK_HD int gk_block_bits(int n) { return n < GK_BLOCK_BITS ? n : GK_BLOCK_BITS; }
+ZK_HD void gk_block_sum(uint32_t* acc, const uint32_t* ring_m, const uint32_t (*fz)[8], const uint32_t (*fo)[8], int n,
+                        int k, uint32_t blk, const uint32_t* vw) {
+  using F = Tomq;
+  uint32_t P[21][8];
+  F::set_one(P[n]);
+  for (int j = n - 1; j >= k; j--) F::mul(P[j], P[j + 1], ((blk >> (j - k)) & 1u) ? fo[j] : fz[j]);
+  for (int j = k - 1; j >= 0; j--) F::mul(P[j], P[j + 1], fz[j]);
+  zero_n<8>(acc);
+  const size_t base = (size_t)blk << k;
+  const uint32_t cnt = 1u << k;
+  for (uint32_t l = 0;;) {
+    uint32_t vi[8], term[8];
+    ld<8>(vi, ring_m + (base + l) * 8);
+    if (vw) F::sub(vi, vw, vi);
+    F::mul(term, vi, P[0]);
+    F::add(acc, acc, term);
+    l++;
+    if (l == cnt) break;
+    // lowest set bit of the new l: bits below it are 0, it is 1, bits above unchanged
+    int tz = 0;
+    while (!((l >> tz) & 1u)) tz++;
+    F::mul(P[tz], P[tz + 1], fo[tz]);
+    for (int j = tz - 1; j >= 0; j--) F::mul(P[j], P[j + 1], fz[j]);
+  }
+}
+
 // ================================================================================== hashing
 // Streams `npts` encoded points (given as (pointer, length) by a functor) through SHA-256.
 // Encodings in 4-byte aligned slots are fetched one point ahead (17 independent word loads).

@@ -95,6 +95,7 @@ struct ProveCtx {
   uint32_t* item_chal; // [M][6][3]
   // GK
   uint32_t* gk_dv;     // [B][n][8]  d(omega_w), Montgomery
+  uint32_t* gk_part;   // [B][n][2^(n-k)][8] block sums of d(omega_w) when the ring is cut into blocks (n > k)
   uint32_t* gk_lag;    // [n][n][8]  Lagrange matrix for nodes 0..n-1, Montgomery
   uint32_t* gk_x;      // [B][3]
   // outputs
@@ -856,14 +857,16 @@ struct GkJobsTask {
 // f0j = (1-l_j) w - a_j, f1j = l_j w + a_j.  One thread per (proof, w); O(3 * 2^n) modmuls,
 // products maintained incrementally over the binary counter (no inversions, no p[] array).
 // If some f0j == 0 the reference's ratio trick yields dval = 0 (invMod(0) = 0); reproduced.
-struct GkPolyTask {
+struct GkPolyTask {     // one thread per (proof, w, ring block)
   ProveCtx c;
   ZK_HD void operator()(int t) const {
     using F = Tomq;
-    const int b = t / c.n, w = t % c.n;
-    const int n = c.n;
+    const int n = c.n, k = gk_block_bits(n);
+    const int nblk = 1 << (n - k);
+    const int blk = t % nblk, bw = t / nblk;
+    const int b = bw / n, w = bw % n;
     const int d0 = gk_draw0(c, b);
-    uint32_t f0[20][8], f1[20][8], P[21][8];
+    uint32_t f0[20][8], f1[20][8];
     uint32_t wm[8], wc[8];
     zero_n<8>(wc);
     wc[0] = (uint32_t)w;
@@ -881,26 +884,23 @@ struct GkPolyTask {
     uint32_t dval[8], vw[8];
     zero_n<8>(dval);
     ld<8>(vw, c.ring_m + (size_t)c.which[b] * 8);
-    if (!degenerate) {
-      F::set_one(P[n]);
-      for (int j = n - 1; j >= 0; j--) F::mul(P[j], P[j + 1], f0[j]);
-      const uint32_t total = 1u << n;
-      for (uint32_t i = 0;; ) {
-        uint32_t vi[8], df[8], term[8];
-        ld<8>(vi, c.ring_m + (size_t)i * 8);
-        F::sub(df, vw, vi);
-        F::mul(term, df, P[0]);
-        F::add(dval, dval, term);
-        i++;
-        if (i == total) break;
-        // lowest set bit of the new i: bits below it are 0, it is 1, bits above unchanged
-        int tz = 0;
-        while (!((i >> tz) & 1u)) tz++;
-        F::mul(P[tz], P[tz + 1], f1[tz]);
-        for (int j = tz - 1; j >= 0; j--) F::mul(P[j], P[j + 1], f0[j]);
-      }
+    if (!degenerate) gk_block_sum(dval, c.ring_m, f0, f1, n, k, (uint32_t)blk, vw);
+    uint32_t* out = nblk == 1 ? c.gk_dv + (size_t)bw * 8 : c.gk_part + (size_t)t * 8;
+    st<8>(out, dval);
+  }
+};
+struct GkPolyReduceTask {   // d(omega_w) = sum of the block sums (only launched when n > GK_BLOCK_BITS)
+  ProveCtx c;
+  ZK_HD void operator()(int bw) const {
+    using F = Tomq;
+    const int nblk = 1 << (c.n - gk_block_bits(c.n));
+    uint32_t acc[8], v[8];
+    zero_n<8>(acc);
+    for (int i = 0; i < nblk; i++) {
+      ld<8>(v, c.gk_part + ((size_t)bw * nblk + i) * 8);
+      F::add(acc, acc, v);
     }
-    st<8>(c.gk_dv + ((size_t)b * n + w) * 8, dval);
+    st<8>(c.gk_dv + (size_t)bw * 8, acc);
   }
 };
 

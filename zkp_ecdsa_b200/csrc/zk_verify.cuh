@@ -98,6 +98,7 @@ struct VerifyCtx {
   uint8_t* nent_skip;   // [B][21]
   // GK
   uint32_t* gk_scalar;  // [B][4n+1][8]
+  uint32_t* gk_part;    // [B][2^(n-k)][8] block sums of the ring polynomial (only when n > GK_BLOCK_BITS)
   uint32_t* gk_pre;     // [B][4n+1][32]
   // fixed-base parts: tom jobs [B][2] (0: GK, 1: W) and their points; P-256 fixed part
   uint32_t *fx_jv, *fx_jr, *fx_proj;   // [B*2]
@@ -721,6 +722,42 @@ struct VParseEntriesTask {
   }
 };
 
+// V11a — large rings only (n > GK_BLOCK_BITS): the N*n multiplications of the ring polynomial, one
+// thread per (proof, block of 2^GK_BLOCK_BITS ring entries).  Every thread re-derives the challenge
+// x = H(cl, ca, cb, cd) and the f_j from the proof (cheap next to its 3 * 1024 multiplications).
+struct VGkSumTask {
+  VerifyCtx c;
+  ZK_HD void operator()(int t) const {
+    using F = Tomq;
+    const int n = c.n, k = gk_block_bits(n);
+    const int nblk = 1 << (n - k);
+    const int b = t / nblk, blk = t % nblk;
+    uint32_t acc[8];
+    zero_n<8>(acc);
+    if (c.gk_ok_len[b]) {
+      const uint8_t* g = c.proof_of(b) + c.gk_off[b];
+      const uint8_t* pts = g + 1;
+      const uint8_t* fs = pts + (size_t)4 * n * WP;
+      Sha256 h;
+      h.init();
+      h.update(pts, 4 * n * WP);
+      uint32_t c3[3], xc[8], xm[8];
+      h.final80(c3);
+      challenge_to_limbs(xc, c3);
+      F::to_mont(xm, xc);
+      uint32_t fm[20][8], omf[20][8];
+      for (int i = 0; i < n; i++) {
+        uint32_t f[8];
+        wscalar_parse(f, fs + (size_t)i * WS);
+        F::to_mont(fm[i], f);
+        F::sub(omf[i], xm, fm[i]);
+      }
+      gk_block_sum(acc, c.ring_m, omf, fm, n, k, (uint32_t)blk, nullptr);
+    }
+    st<8>(c.gk_part + (size_t)t * 8, acc);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // V11 — Groth-Kohlweiss relations (gk.ts:220-259).  One thread per proof.
 // ---------------------------------------------------------------------------------------------
@@ -772,22 +809,19 @@ struct VGkTask {
       F::mul(t0, r1, zb); F::sub(hS, hS, t0);
     }
     // total = sum_i v_i prod_j (bit_j(i) ? f_j : x - f_j)   (gk.ts:239-250)
-    uint32_t P[21][8], total[8];
-    zero_n<8>(total);
-    F::set_one(P[n]);
-    for (int j = n - 1; j >= 0; j--) F::mul(P[j], P[j + 1], omf[j]);
-    const uint32_t count = 1u << n;
-    for (uint32_t i = 0;;) {
-      uint32_t vi[8];
-      ld<8>(vi, c.ring_m + (size_t)i * 8);
-      F::mul(t0, vi, P[0]);
-      F::add(total, total, t0);
-      i++;
-      if (i == count) break;
-      int tz = 0;
-      while (!((i >> tz) & 1u)) tz++;
-      F::mul(P[tz], P[tz + 1], fm[tz]);
-      for (int j = tz - 1; j >= 0; j--) F::mul(P[j], P[j + 1], omf[j]);
+    uint32_t total[8];
+    {
+      const int k = gk_block_bits(n), nblk = 1 << (n - k);
+      if (nblk == 1) {
+        gk_block_sum(total, c.ring_m, omf, fm, n, k, 0u, nullptr);
+      } else {               // block sums from VGkSumTask
+        uint32_t v[8];
+        zero_n<8>(total);
+        for (int i = 0; i < nblk; i++) {
+          ld<8>(v, c.gk_part + ((size_t)b * nblk + i) * 8);
+          F::add(total, total, v);
+        }
+      }
     }
     // relFinal: sum_k -x^k cd_k + x^n com - total g - zd h
     uint32_t rf[8], xp[8], zd[8];

@@ -926,7 +926,12 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch(st, ((long long)M + ITEM_INV_CHUNK - 1) / ITEM_INV_CHUNK, ItemInvTask{c});
       launch(st, M, ItemScalarsTask{c});
       launch(st, (long long)Bc * n, GkJobsTask{c});
-      launch(st, (long long)Bc * n, GkPolyTask{c});
+      {
+        const int nblk = 1 << (n - gk_block_bits(n));
+        c.gk_part = nblk > 1 ? W[51].get<uint32_t>((size_t)Bc * n * nblk * 8) : nullptr;
+        launch(st, (long long)Bc * n * nblk, GkPolyTask{c});
+        if (nblk > 1) launch(st, (long long)Bc * n, GkPolyReduceTask{c});
+      }
       launch(st, (long long)Bc * n, GkCdJobsTask{c});
       {
         const size_t nj = (size_t)M * JOBS_PER_ITEM, nd = (size_t)M * DERS_PER_ITEM, ng = (size_t)Bc * 4 * n;
@@ -1070,6 +1075,11 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch(st, (long long)ns * HASHES_PER_ITEM, VItemHashTask{c});
       dev_memset(st, c.ent_off, 0, (size_t)Bc * V_ENT_TOM * 4);
       launch(st, (long long)ns, VRelationsTask{c});
+      {
+        const int nblk = 1 << (n - gk_block_bits(n));
+        c.gk_part = nblk > 1 ? W[51].get<uint32_t>((size_t)Bc * nblk * 8) : nullptr;
+        if (nblk > 1) launch(st, (long long)Bc * nblk, VGkSumTask{c});
+      }
       launch(st, Bc, VGkTask{c});
       launch(st, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
       launch(st, Bc, VReduceTask{c});
