@@ -148,26 +148,30 @@ class ClockSampler:
         except Exception:
             return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
 
-    def _poll(self):
+    def _sample(self, with_power=False):
         nv, h = self.nvml
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        while True:
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
             try:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((float(sm), float(mx), pw, int(mask)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             except Exception:
-                pass
-            if self.stop_flag.wait(0.005):
-                break
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0 if with_power else 0.0
+            self.samples.append((float(sm), float(self.max_mhz), pw, int(mask)))
+        except Exception:
+            pass
+
+    def _poll(self):
+        # clock + event reasons only inside the loop (the power query is the slow one); every 5 ms
+        k = 0
+        while not self.stop_flag.wait(0.005):
+            self._sample(with_power=(k % 8 == 0))
+            k += 1
 
     def start(self):
         try:
             self.nvml = self._nvml_handle()
+            self.max_mhz = self.nvml[0].nvmlDeviceGetMaxClockInfo(self.nvml[1], self.nvml[0].NVML_CLOCK_SM)
             self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
             return
@@ -199,6 +203,8 @@ class ClockSampler:
         if self.nvml:
             self.stop_flag.set()
             self.th.join(timeout=2)
+            if not self.samples:              # never happened so far; better a sample right after than none
+                self._sample(with_power=True)
         elif self.proc:
             self.proc.terminate()
             try:
