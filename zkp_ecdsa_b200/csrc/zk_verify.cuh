@@ -1074,6 +1074,20 @@ struct MsmP256CombineTask {
   }
 };
 
+// The two tomEdwards256 MSM instances of a proof (multiW: up to 682 entries, GK: 4n+1) as one grid: the
+// short GK threads fill the SMs the long multiW threads leave idle (one 1024-proof batch is 0.8 of a wave).
+struct MsmTomWindowBothTask {
+  MsmTomWindowTask w, gk;
+  int nW, nWp;   // multiW threads, rounded up to a warp multiple
+  ZK_HD void operator()(int t) const {
+    if (t < nWp) {
+      if (t < nW) w(t);
+    } else if (t - nWp < nW) {
+      gk(t - nWp);
+    }
+  }
+};
+
 // The three Horner passes of a proof (GK, multiW, multiN) are 250-doubling latency chains run by one
 // thread each; launched as ONE grid they overlap instead of queueing (3 B threads are still few).
 struct MsmCombineAllTask {

@@ -1086,9 +1086,12 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch(st, (long long)Bc * V_ENT_TOM, VParseEntriesTask{c.proofs, proof_stride, c.ent_off, c.ent_pre, V_ENT_TOM});
       launch(st, (long long)Bc * ngk, VParseEntriesTask{c.proofs, proof_stride, gk_offs, c.gk_pre, ngk});
       launch(st, (long long)Bc * 2, TomCommitTask{c.fx_jv, c.fx_jr, c.tg_tab, c.th_tab, c.fx_proj, c.tom_w, c.tom_nwin});
-      launch(st, (long long)Bc * MSM_NWIN,
-             MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, V_ENT_TOM, V_SAMPLES, V_ENT_PER_SAMPLE, 2, c.win_w});
-      launch(st, (long long)Bc * MSM_NWIN, MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, c.win_g});
+      {
+        const int nW = Bc * MSM_NWIN, nWp = (nW + 31) & ~31;
+        launch(st, (long long)nWp + nW,
+               MsmTomWindowBothTask{MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, V_ENT_TOM, V_SAMPLES, V_ENT_PER_SAMPLE, 2, c.win_w},
+                                    MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, c.win_g}, nW, nWp});
+      }
       launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n});
       {
         const int Bp = (Bc + 31) & ~31;
