@@ -42,10 +42,23 @@ class SystemParametersList:
     h_nist: bytes     # 65 B
     h_proof: bytes    # 67 B
     sec_level: int
-    handle: object = None   # device tables (zka_params*)
+    handle: object = None   # device tables (zka_params*): 7.3 GB of HBM with the default window widths
+    _lib: object = None     # the ZkaLib that owns `handle`
 
     def eq(self, o: 'SystemParametersList') -> bool:
         return self.h_nist == o.h_nist and self.h_proof == o.h_proof and self.sec_level == o.sec_level
+
+    def close(self) -> None:
+        """Free the device tables of this parameter set (zka_params_destroy); idempotent."""
+        if self.handle is not None and self._lib is not None and getattr(self._lib, 'ctx', None):
+            self._lib.params_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 @dataclass
@@ -94,7 +107,7 @@ class Engine:
 
     def load_params(self, h_nist: bytes, h_proof: bytes, sec_level: int = 80) -> SystemParametersList:
         h = self.lib.params_create(h_nist, h_proof, sec_level)
-        return SystemParametersList(bytes(h_nist), bytes(h_proof), sec_level, h)
+        return SystemParametersList(bytes(h_nist), bytes(h_proof), sec_level, h, self.lib)
 
     def key_to_int(self, public_key: bytes) -> int:
         """keyToInt (zkpAttestList.ts:94-102) on the raw 65-byte key (WebCrypto exportKey('raw'))."""
