@@ -391,6 +391,7 @@ def run_ours(args):
         assert int((outs2[2] != 0).sum().item()) == 0 and bool(torch.equal(outs2[1], plen_h))
         two = {'value': 2 * nsteps * B / wall, 'unit': 'proofs/s', 'callers': 2, 'steps_per_caller': nsteps,
                'note': 'two host threads, one zka context each, same host buffers in / separate pinned buffers out'}
+        params2.close()
         eng2.close()
 
     # ---- verifySignatureList over the proofs just produced (device resident), verifies/s
