@@ -112,3 +112,22 @@ def test_edge_cases_on_gpu(gpu_engine):
     E.test_zero_message_hash(L)
     E.test_zero_r_and_zero_s(L)
     E.test_key_to_int(L)
+
+
+def test_alternate_code_paths_on_gpu():
+    """Paths the default engine does not take for small batches: one-thread-per-commitment phase A
+    (ZKA_PHASEA_SPLIT=0) and ragged / small table windows; plus a ring above 1024 entries (block sums)."""
+    import os
+    from zkp_ecdsa_b200 import api
+    os.environ.update(ZKA_TOM_W='14', ZKA_P256_HW='11', ZKA_PHASEA_SPLIT='0')
+    try:
+        eng = api.Engine(device=0)
+    finally:
+        for k in ('ZKA_TOM_W', 'ZKA_P256_HW', 'ZKA_PHASEA_SPLIT'):
+            os.environ.pop(k, None)
+    try:
+        common.check_prove_parity(eng.lib, B=3, N=6, sec_level=80, seed=41)
+        common.check_prove_parity(eng.lib, B=1, N=2100, sec_level=20, seed=42)
+        common.check_verify_parity(eng.lib, N=2100, sec_level=20, seed=43, tampers=4)
+    finally:
+        eng.close()
