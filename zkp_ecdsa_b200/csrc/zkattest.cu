@@ -889,11 +889,11 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       // --- phase A (first consumer of the tape) and R = u1*G + u2*pk side by side
       ev_wait(st, ctx->ev_tape[slot]);
       // fewer than two waves of one-thread-per-commitment: two threads per commitment + a combine pass
-      const bool split_a = ctx->phase_a_split >= 0 ? ctx->phase_a_split != 0 : (long long)nA <= 2ll * 128 * g_norm_slots;
+      const bool split_a = ctx->phase_a_split >= 0 ? ctx->phase_a_split != 0 : false;
       if (split_a) {
         c.pa_part = W[52].get<uint32_t>(nA * 3 * P256_PROJ_WORDS);
-        const int nH = (int)(2 * nA), nHp = (nH + 31) & ~31;
-        launch(st, (long long)nHp + Bc, PhaseAHalfAndRPointTask{PhaseAHalfTask{c}, RPointTask{c}, nH, nHp});
+        const int nH = 2 * (int)((nA + 31) & ~(size_t)31), nHp = nH;   // two warps per 32 commitments
+        launch(st, (long long)nHp + Bc, PhaseAHalfAndRPointTask{PhaseAHalfTask{c, (int)nA}, RPointTask{c}, nH, nHp});
         launch(st, (long long)nA, PhaseACombineTask{c});
       } else {
         const int nAp = (int)((nA + 31) & ~(size_t)31);
