@@ -170,20 +170,3 @@ def test_large_ring_block_sums_bit_exact(hostsim):
     4096 = 4 blocks; proof bytes and verdicts (incl. tampered proofs) must equal the oracle's."""
     common.check_prove_parity(hostsim, B=1, N=2100, sec_level=20, seed=91)
     common.check_verify_parity(hostsim, N=2100, sec_level=20, seed=92, tampers=4)
-
-
-@pytest.mark.parametrize('split', ['0', '1'])
-def test_phase_a_variants_bit_exact(split):
-    """Phase A has a one-thread and a two-thread-per-commitment variant (chosen by batch size,
-    ZKA_PHASEA_SPLIT forces one): same proof bytes as the oracle either way."""
-    import os
-    import __graft_entry__ as g
-    from zkp_ecdsa_b200.capi import ZkaLib
-    g.build_hostsim()
-    os.environ.update(ZKA_TOM_W='10', ZKA_P256_HW='8', ZKA_PHASEA_SPLIT=split)
-    try:
-        L = ZkaLib(g.HOSTSIM)
-    finally:
-        for k in ('ZKA_TOM_W', 'ZKA_P256_HW', 'ZKA_PHASEA_SPLIT'):
-            os.environ.pop(k, None)
-    common.check_prove_parity(L, B=2, N=4, sec_level=16, seed=95)

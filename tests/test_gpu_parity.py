@@ -115,15 +115,15 @@ def test_edge_cases_on_gpu(gpu_engine):
 
 
 def test_alternate_code_paths_on_gpu():
-    """Paths the default engine does not take for small batches: one-thread-per-commitment phase A
-    (ZKA_PHASEA_SPLIT=0) and ragged / small table windows; plus a ring above 1024 entries (block sums)."""
+    """Paths the default engine does not take: ragged / small table windows, and a ring above 1024
+    entries (Groth-Kohlweiss block sums)."""
     import os
     from zkp_ecdsa_b200 import api
-    os.environ.update(ZKA_TOM_W='14', ZKA_P256_HW='11', ZKA_PHASEA_SPLIT='0')
+    os.environ.update(ZKA_TOM_W='14', ZKA_P256_HW='11')
     try:
         eng = api.Engine(device=0)
     finally:
-        for k in ('ZKA_TOM_W', 'ZKA_P256_HW', 'ZKA_PHASEA_SPLIT'):
+        for k in ('ZKA_TOM_W', 'ZKA_P256_HW'):
             os.environ.pop(k, None)
     try:
         common.check_prove_parity(eng.lib, B=3, N=6, sec_level=80, seed=41)

@@ -348,26 +348,21 @@ ZK_HD void p256_accum_fixed(P256Pt& acc, const uint32_t* tab, const uint32_t* k,
   }
 }
 // acc += k * base on the signed 5-bit per-base table [RT_NWIN][RT_ROW] (P256RowsSignedTask)
-// windows [j0, j1) only; the signed recoding carries from window to window, so the digits below j0 are
-// re-derived (integer work only) to get the carry into window j0
-ZK_HD void p256_accum_rtab_range(P256Pt& acc, const uint32_t* tab, const uint32_t* k, int j0, int j1) {
+ZK_HD void p256_accum_rtab(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
   uint32_t carry = 0;
-  for (int j = 0; j < j1; j++) {
+  for (int j = 0; j < RT_NWIN; j++) {
     const int pos = j * RT_W;
     uint32_t d = (pos < 256 ? digit_w(k, pos, (256 - pos) < RT_W ? (256 - pos) : RT_W) : 0u) + carry;
     carry = d > 16 ? 1u : 0u;
     const bool neg = d > 16;
     if (neg) d = 32 - d;
-    if (d && j >= j0) {
+    if (d) {
       P256Aff q;
       p256_ld_aff(q, tab + ((size_t)j * RT_ROW + (d - 1)) * P256_AFF_WORDS);
       if (neg) P256p::neg(q.y, q.y);
       p256_madd(acc, acc, q);
     }
   }
-}
-ZK_HD void p256_accum_rtab(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
-  p256_accum_rtab_range(acc, tab, k, 0, RT_NWIN);
 }
 // ===================================================================== tomEdwards256 tables
 struct TomPowsTask {

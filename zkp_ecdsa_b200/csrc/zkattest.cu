@@ -227,7 +227,6 @@ struct zka_ctx {
   int tom_w = 22, tom_nwin = 12;   // per base: 12 windows x 2^22 entries x 128 B = 6.4 GB of HBM (ZKA_TOM_W)
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 8192;
-  int phase_a_split = -1; // ZKA_PHASEA_SPLIT: 1/0 force the two-thread phase A on/off, -1 = by batch size
   int host_chunk = 4096;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
   // copy streams + events of the host-buffer pipeline (zka_prove_batch); slot = chunk index & 1
   Stream cs_in, cs_out;
@@ -461,7 +460,6 @@ int zka_init(int device, zka_ctx** out) {
       if (c >= 1) ctx->chunk = c;
     }
     if (const char* e = getenv("ZKA_NORM_MODEL")) g_norm_model = atoi(e) != 0;
-    if (const char* e = getenv("ZKA_PHASEA_SPLIT")) ctx->phase_a_split = atoi(e) != 0 ? 1 : 0;
 #if !defined(ZKA_HOSTSIM)
     {
       int sms = 0;
@@ -888,14 +886,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       }
       // --- phase A (first consumer of the tape) and R = u1*G + u2*pk side by side
       ev_wait(st, ctx->ev_tape[slot]);
-      // fewer than two waves of one-thread-per-commitment: two threads per commitment + a combine pass
-      const bool split_a = ctx->phase_a_split >= 0 ? ctx->phase_a_split != 0 : false;
-      if (split_a) {
-        c.pa_part = W[52].get<uint32_t>(nA * 3 * P256_PROJ_WORDS);
-        const int nH = 2 * (int)((nA + 31) & ~(size_t)31), nHp = nH;   // two warps per 32 commitments
-        launch(st, (long long)nHp + Bc, PhaseAHalfAndRPointTask{PhaseAHalfTask{c, (int)nA}, RPointTask{c}, nH, nHp});
-        launch(st, (long long)nA, PhaseACombineTask{c});
-      } else {
+      {
         const int nAp = (int)((nA + 31) & ~(size_t)31);
         launch(st, (long long)nAp + Bc, PhaseAAndRPointTask{PhaseAP256Task{c}, RPointTask{c}, (int)nA, nAp});
       }
