@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generate tests/golden/zkattest_v1.npz from the ORACLE (run from the repo root).
+"""Generate tests/golden/zkattest_v1.npz and zkattest_v2.npz from the ORACLE (run from the repo root).
 
 The reference has no proof-byte vectors and cannot run here, so the fixtures
 pin (a) the oracle against its own regressions and (b) the CUDA path against the oracle on
@@ -52,6 +52,11 @@ def main():
     out.update(case('b', B=3, N=17, sec=20, seed=1002))   # ragged ring (padding 17 -> 32), smaller SecLevel
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'zkattest_v1.npz'), **out)
     print({k: v.shape for k, v in out.items()})
+    out2 = {}
+    out2.update(case('c', B=1, N=2100, sec=20, seed=1003))  # ring above 1024 entries: block-parallel ring sums
+    out2.update(case('d', B=4, N=3, sec=20, seed=1004))     # repeated signers: shared per-key tables
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'zkattest_v2.npz'), **out2)
+    print({k: v.shape for k, v in out2.items()})
 
 
 if __name__ == '__main__':

@@ -1,4 +1,4 @@
-"""Committed golden fixtures (tests/golden/zkattest_v1.npz, made by tests/golden/make_golden.py)."""
+"""Committed golden fixtures (tests/golden/zkattest_v{1,2}.npz, made by tests/golden/make_golden.py)."""
 import os
 
 import numpy as np
@@ -10,12 +10,15 @@ from oracle import zkattest as OZ
 from oracle.big import Tape
 from zkp_ecdsa_b200 import verify_tape as VT
 
-G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'zkattest_v1.npz'))
+G = {}
+for _f in ('zkattest_v1.npz', 'zkattest_v2.npz'):
+    _z = np.load(os.path.join(os.path.dirname(__file__), 'golden', _f))
+    G.update({k: _z[k] for k in _z.files})
 
 
 def _case(tag):
     B, N, sec, seed = (int(v) for v in G[f'{tag}_meta'])
-    return B, N, sec, {k[len(tag) + 1:]: G[k] for k in G.files if k.startswith(tag + '_')}
+    return B, N, sec, {k[len(tag) + 1:]: G[k] for k in G if k.startswith(tag + '_')}
 
 
 def _check_lib(L, tag):
@@ -48,12 +51,12 @@ def test_oracle_reproduces_golden_a():
                                     Tape(VT.oracle_stream(d['vtape'][0].tobytes(), N, sec))) == bool(d['verdict'][0])
 
 
-@pytest.mark.parametrize('tag', ['a', 'b'])
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
 def test_hostsim_matches_golden(hostsim, tag):
     _check_lib(hostsim, tag)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('tag', ['a', 'b'])
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
 def test_gpu_matches_golden(gpu_engine, tag):
     _check_lib(gpu_engine.lib, tag)
