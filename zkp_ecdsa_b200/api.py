@@ -123,7 +123,7 @@ class Engine:
         ring = _keys_to_ring(keys)
         ts = self.lib.prove_tape_len(len(keys), params.sec_level)
         if tape is None:
-            t = synth_os_tape(1, ts)
+            t = synth_os_tape(1, ts, params.sec_level)
         else:
             t = np.zeros((1, ts), np.uint8)
             t[0, :min(ts, len(tape))] = np.frombuffer(tape[:ts], np.uint8)
@@ -141,7 +141,7 @@ class Engine:
         ring = _keys_to_ring(keys)
         ts = self.lib.verify_tape_len(len(keys), params.sec_level)
         if tape is None:
-            t = synth_os_verify_tape(1, ts, len(keys))
+            t = synth_os_verify_tape(1, ts, len(keys), params.sec_level)
         else:
             t = np.zeros((1, ts), np.uint8)
             t[0, :min(ts, len(tape))] = np.frombuffer(tape[:ts], np.uint8)
@@ -176,17 +176,47 @@ class Engine:
 
 
 def _rnd_below(m: int) -> bytes:
+    """rnd(m) of the reference (big.ts:171-181): 32 fresh CSPRNG bytes, redrawn while >= m."""
     while True:
         v = int.from_bytes(os.urandom(32), 'big')
         if v < m:
             return v.to_bytes(32, 'big')
 
 
-def synth_os_tape(rows: int, stride: int) -> np.ndarray:
-    """OS-random prover tape, every draw below min(p256.n, tom.order) (see synth.random_tape)."""
-    return synth.random_tape(rows, stride, int.from_bytes(os.urandom(8), 'big'))
+def synth_os_tape(rows: int, stride: int, sec_level: int = 80) -> np.ndarray:
+    """Default prover tape = what crypto.getRandomValues would have produced (big.ts:175): every draw is
+    32 bytes of os.urandom, redrawn while >= the modulus of that draw (rnd()'s rejection loop; the modulus
+    of draw k depends only on k, synth.draw_modulus).  No numpy generator is involved: the revealed
+    (alpha_i, r_i, Tx_i.r, Ty_i.r) of 1-bit repetitions are raw tape draws, so the tape must be a CSPRNG."""
+    assert stride % 32 == 0
+    nd = stride // 32
+    t = np.frombuffer(os.urandom(rows * stride), np.uint8).reshape(rows, nd, 32).copy()
+    # both moduli start 0xffffffff...: only draws whose top word is all ones can be out of range (2^-32 each)
+    cand = np.argwhere((t[:, :, :4] == 255).all(axis=2))
+    for r, k in cand:
+        m = synth.draw_modulus(int(k), sec_level)
+        while int.from_bytes(t[r, k].tobytes(), 'big') >= m:
+            t[r, k] = np.frombuffer(os.urandom(32), np.uint8)
+    return t.reshape(rows, stride)
 
 
 def synth_os_verify_tape(rows: int, stride: int, ring_size: int, sec_level: int = 80) -> np.ndarray:
-    from .verify_tape import random_verify_tape
-    return random_verify_tape(rows, stride, ring_size, sec_level, int.from_bytes(os.urandom(8), 'big'))
+    """Default verifier tape from the OS CSPRNG: Relation.drain scalars (multimult.ts:168-173) and the
+    generateIndices bytes rnd(limit - i) (exp.ts:101-106) via secrets.randbelow.  The modulus of a packed
+    exp drain depends on the challenge bits, which the host does not know yet, so every 32-byte draw is
+    taken uniformly below 0xffffffff * 2^224 (< p256.n < tom.order): 2^-32 short of rnd()'s range, which
+    does not affect the soundness of the random linear combination."""
+    import secrets
+    from .verify_tape import IDX_PAD, ceil_log2, verify_tape_len
+    assert stride % 32 == 0 and stride >= verify_tape_len(ring_size)
+    t = np.frombuffer(os.urandom(rows * stride), np.uint8).reshape(rows, stride // 32, 32).copy()
+    for r, k in np.argwhere((t[:, :, :4] == 255).all(axis=2)):
+        while (t[r, k, :4] == 255).all():
+            t[r, k] = np.frombuffer(os.urandom(32), np.uint8)
+    t = t.reshape(rows, stride)
+    g = 32 * (2 * ceil_log2(ring_size) + 1)
+    for r in range(rows):
+        for i in range(sec_level - 2):
+            t[r, g + i] = secrets.randbelow(sec_level - i)
+    t[:, g + sec_level - 2:g + IDX_PAD] = 0
+    return t

@@ -34,7 +34,8 @@ struct ProveCtx {
   const uint8_t* msg_hash;   // [B][32]
   const uint8_t* sig;        // [B][64]
   const uint8_t* pk;         // [B][65]
-  const uint32_t* which;     // [B]
+  const uint32_t* which;     // [B]  caller's index (only range-checked: RPointTask)
+  uint32_t* which_s;         // [B]  sanitised copy (0 when outside the ring): every ring_m / bit access uses this one
   const uint8_t* tape;       // [B][tape_stride]
   size_t tape_stride;
   uint32_t tape_draws;       // draws available per proof
@@ -167,6 +168,10 @@ struct PreKeyTask {   // validate and store the public key (everything the key t
       p256_set_generator(pk);
     }
     p256_st_aff(c.pk_aff + (size_t)b * 16, pk);
+    // an index outside the ring is flagged by RPointTask (ZKA_ERR_BAD_INDEX); the Groth-Kohlweiss tasks
+    // must still stay inside ring_m[2^n], so they read this clamped copy
+    const uint32_t w = c.which[b];
+    c.which_s[b] = w < (uint32_t)c.N ? w : 0u;
   }
 };
 struct PreTask {      // the scalars of the statement and Q = z1*G
@@ -843,7 +848,7 @@ struct GkJobsTask {
     draw_checked<FpP256>(ai, c, b, d + 1);
     draw_checked<FpP256>(si, c, b, d + 2);
     draw_checked<FpP256>(ti, c, b, d + 3);
-    const uint32_t bit = (c.which[b] >> i) & 1u;
+    const uint32_t bit = (c.which_s[b] >> i) & 1u;
     zero_n<8>(v);
     v[0] = bit;
     size_t j = c.s2_gk(b, i);                        // cl_i
@@ -879,14 +884,14 @@ struct GkPolyTask {     // one thread per (proof, w, ring block)
       uint32_t a[8], am[8];
       draw_checked<FpP256>(a, c, b, d0 + DRAWS_PER_GK_ROUND * j + 1);
       F::to_mont(am, a);
-      const uint32_t bit = (c.which[b] >> j) & 1u;
+      const uint32_t bit = (c.which_s[b] >> j) & 1u;
       if (bit) { F::neg(f0[j], am); F::add(f1[j], wm, am); }
       else     { F::sub(f0[j], wm, am); copy_n<8>(f1[j], am); }
       if (is_zero_n<8>(f0[j])) degenerate = true;
     }
     uint32_t dval[8], vw[8];
     zero_n<8>(dval);
-    ld<8>(vw, c.ring_m + (size_t)c.which[b] * 8);
+    ld<8>(vw, c.ring_m + (size_t)c.which_s[b] * 8);
     if (!degenerate) gk_block_sum(dval, c.ring_m, f0, f1, n, k, (uint32_t)blk, vw);
     uint32_t* out = nblk == 1 ? c.gk_dv + (size_t)bw * 8 : c.gk_part + (size_t)t * 8;
     st<8>(out, dval);
@@ -1027,7 +1032,7 @@ struct GkEmitTask {
       tape_draw(si, c.tape_of(b), d0 + 5 * i + 2); reduce_once<FpP256>(si);
       tape_draw(ti, c.tape_of(b), d0 + 5 * i + 3); reduce_once<FpP256>(ti);
       tape_draw(rho, c.tape_of(b), d0 + 5 * i + 4); reduce_once<FpP256>(rho);
-      const uint32_t bit = (c.which[b] >> i) & 1u;
+      const uint32_t bit = (c.which_s[b] >> i) & 1u;
       // f_i = l_i x + a_i
       uint32_t f[8];
       if (bit) F::add(f, xc, ai); else copy_n<8>(f, ai);
@@ -1052,6 +1057,24 @@ struct GkEmitTask {
     F::mul(t, rpk, xp);           // pkX.r * x^n
     F::add(zd, zd, t);
     put_scalar<WS>(ozd, zd);
+  }
+};
+
+// Last stage: a proof whose status is not ZKA_OK must not leave the library (its blinders may have been
+// replaced by zeros or reduced values, which would open the commitments): the row is zeroed and its
+// length set to 0.  FIN_PARTS threads per proof, each clears its share of the row with 16-byte stores.
+enum : int { FIN_PARTS = 64 };
+struct FinalizeTask {
+  ProveCtx c;
+  ZK_HD void operator()(int t) const {
+    const int b = t / FIN_PARTS, part = t % FIN_PARTS;
+    if (c.status[b] == ZKA_OK) return;
+    uint8_t* row = c.proofs + (size_t)b * c.proof_stride;
+    const size_t per = (c.proof_stride + FIN_PARTS - 1) / FIN_PARTS;
+    size_t lo = per * part, hi = lo + per;
+    if (hi > c.proof_stride) hi = c.proof_stride;
+    for (size_t i = lo; i < hi; i++) row[i] = 0;
+    if (part == 0) c.proof_len[b] = 0;
   }
 };
 

@@ -861,6 +861,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       c.tab_of = W[48].get<uint32_t>(Bc);
       c.tab_rep = W[49].get<uint32_t>((size_t)Bc * 2);
       c.tab_count = W[50].get<uint32_t>(1);
+      c.which_s = W[52].get<uint32_t>(Bc);
       c.proof_stride = proof_stride;
       DevBuf* ob = ctx->out + 3 * slot;
       c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ob[0].get<uint8_t>((size_t)Bc * proof_stride);
@@ -953,6 +954,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       launch(st, (long long)M * 7, ItemEmitTask{c});
       launch(st, (long long)nA, RepEmitTask{c});
       launch(st, Bc, GkEmitTask{c});
+      launch(st, (long long)Bc * FIN_PARTS, FinalizeTask{c});
       // --- results: on the output stream, behind this chunk's last kernel
       ev_record(ctx->ev_done[slot], st);
       if (!out_dev || !len_dev || !st_dev) {
