@@ -7,7 +7,9 @@
 
 A "step" = one zka_prove_batch pass over one batch of synthetic signatures (per rank), followed,
 for N > 1, by ONE NCCL all-gather of the serialized proof bytes (BASELINE.json north_star).
-Workload at N=1: BASELINE.json configs[1] = batch 1024 proofs, ring N=8 (per GPU; weak scaling).
+Workload at N=1: BASELINE.json configs[2] = batch 8192 proofs, ring N=256, the largest single-GPU
+configuration; under torchrun (N>1): 8192 proofs per GPU, ring N=1024 = configs[3] (prove) and
+configs[4] (verify) at 8 GPUs, weak scaling.  `--workload config1|config2|config3` overrides.
 `value`  : proofs/s, inputs resident in HBM, device pointers through the C ABI.
 `e2e`    : proofs/s through the same C-ABI call with pinned HOST buffers (H2D tape/inputs and
            D2H proofs inside the timed region).
@@ -18,7 +20,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import multiprocessing as mp
 import os
 import subprocess
 import sys
@@ -41,26 +42,19 @@ SEC_LEVEL = 80
 # window bits -> (dram read + write bytes per launch - algorithmic bytes) / lookups
 NCU_DRAM_BYTES_PER_LOOKUP = {16: 78.0, 22: 118.0}
 MODMUL_PER_MADD = 7      # a = -1 image curve, mixed addition with (v-w, v+w, 2 d2 w v) entries (zk_curves.cuh)
-MAC_PER_TOM_MODMUL = 126   # 81 products + 45 quotient-digit products (zk_field_ptx.cuh); the generic CIOS needs 171
+MAC_PER_TOM_MODMUL = 117   # EXECUTED IMAD.WIDE per 258-bit product: 9 rows x (9 + 4) (zk_field_ptx.cuh tom_row;
+                           # profiles/sass_tom_mul_r2.txt); the generic CIOS needs 171
+MAC_PER_P256_MODMUL = 64   # p256.p product scanning: 8 x 8, the reduction is additions only
+MAC_PER_N256_MODMUL = 136  # p256.n generic CIOS: 64 + 64 + 8
 W_PROVE_REF = {8: 6861088, 256: 6942368, 1024: 6974880}   # reference-algorithm modmuls/proof
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
-def _oracle_one(args):
-    seed, N = args
-    from oracle import zkattest as OZ
-    from oracle.big import Tape
-    from zkp_ecdsa_b200 import synth
-    rnd = synth.params_rnd(0)
-    params = OZ.generate_params_list(Tape(rnd))
-    wl = synth.Workload(B=1, N=N, seed=seed)
-    tape = synth.random_tape(1, 32 * (3 + 4 * SEC_LEVEL + 40 * SEC_LEVEL + 5 * 20), seed=seed + 1)
-    t = time.time()
-    OZ.prove_signature_list(params, wl.msg_hash[0].tobytes(), wl.sig[0].tobytes(), wl.pk[0].tobytes(),
-                            int(wl.which[0]), wl.ring_ints(), Tape(tape[0].tobytes()))
-    return time.time() - t
-
-
+# The reference itself (TypeScript on node) cannot run in this image.  The CPU arm is oracle/cpu: a C++
+# restatement of the reference's OWN algorithms (4-bit-window mul/dblmul, RCB / Hisil formulas, one inversion
+# per toBytes, Bos-Coster verification) behind the same C ABI, byte-identical to the Python oracle and the
+# golden fixtures (tests/test_cpu_port.py).  Native 64-bit-limb Montgomery code is several times faster than
+# BigInt arithmetic in V8 would be, so ratios against it are conservative.
 def usable_cores() -> int:
     """Host threads this process may actually use: affinity mask capped by the cgroup CPU quota."""
     try:
@@ -76,44 +70,97 @@ def usable_cores() -> int:
     return n
 
 
-def cpu_baseline(N: int, rounds: int = 1):
-    """Oracle port on all host cores: `rounds` proofs per core, one process per core."""
+class CpuPort:
+    """oracle/_ref/libzkattest_cpu.so on `threads` host threads, fed with the synthetic workload of bench.py."""
+
+    def __init__(self, N: int, threads: int):
+        import numpy as np
+        import __graft_entry__ as g
+        from zkp_ecdsa_b200 import synth, verify_tape as VT
+        from zkp_ecdsa_b200.capi import ZkaLib
+        if not os.path.exists(g.ORACLE_CPU):
+            g.build_oracle_cpu()
+        os.environ['ZKA_CPU_THREADS'] = str(threads)
+        self.np, self.N, self.threads = np, N, threads
+        self.L = ZkaLib(g.ORACLE_CPU)
+        hn, hp = self.L.params_generate(synth.params_rnd(0))
+        self.P = self.L.params_create(hn, hp, SEC_LEVEL)
+        self.synth, self.VT = synth, VT
+
+    def sample(self, B: int, seed: int):
+        np, L = self.np, self.L
+        wl = self.synth.Workload(B, self.N, seed=seed, distinct_signers=min(B, self.N))
+        tape = self.synth.random_tape(B, L.prove_tape_len(self.N, SEC_LEVEL), seed=seed + 1)
+        vt = self.VT.random_verify_tape(B, L.verify_tape_len(self.N, SEC_LEVEL), self.N, SEC_LEVEL, seed=seed + 2)
+        ps = L.proof_max_len(self.N, SEC_LEVEL)
+        return wl, tape, vt, np.zeros((B, ps), np.uint8), np.zeros(B, np.uint32), np.zeros(B, np.int32), ps
+
+    def prove(self, smp):
+        wl, tape, vt, proofs, plen, st, ps = smp
+        t = time.perf_counter()
+        self.L.prove_batch(self.P, wl.B, wl.msg_hash, wl.sig, wl.pk, wl.which, wl.ring, self.N, tape, tape.shape[1], proofs, ps, plen, st)
+        dt = time.perf_counter() - t
+        assert not st.any(), st
+        return dt
+
+    def verify(self, smp):
+        wl, tape, vt, proofs, plen, st, ps = smp
+        ok = self.np.zeros(wl.B, self.np.uint8)
+        t = time.perf_counter()
+        self.L.verify_batch(self.P, wl.B, wl.msg_hash, wl.ring, self.N, proofs, ps, plen, vt, vt.shape[1], ok, st)
+        dt = time.perf_counter() - t
+        assert ok.all() and not st.any()
+        return dt
+
+
+def cpu_baseline(N: int, per_core: int = 2):
+    """oracle/cpu on all usable host cores (threads inside one process), plus the single-thread figure."""
     cores = usable_cores()
-    jobs = [(1000 + i, N) for i in range(cores * rounds)]
-    t = time.time()
-    with mp.get_context('spawn').Pool(cores) as pool:
-        per = pool.map(_oracle_one, jobs)
-    wall = time.time() - t
-    return {'value': len(jobs) / wall, 'unit': 'proofs/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{len(jobs)} proofs (ring {N}, SecLevel {SEC_LEVEL}), one oracle process per core; '
-                      f'mean {sum(per) / len(per):.2f} s/proof/core',
-            'wall_s': wall}
+    port = CpuPort(N, cores)
+    smp = port.sample(cores * per_core, 1000)
+    dt = port.prove(smp)
+    dv = port.verify(smp)
+    one = CpuPort(N, 1)
+    s1 = one.sample(1, 2000)
+    d1 = one.prove(s1)
+    v1 = one.verify(s1)
+    B = cores * per_core
+    return {'value': B / dt, 'unit': 'proofs/s', 'cores': cores, 'kind': 'port-c++',
+            'sample': f'{B} proofs (ring {N}, SecLevel {SEC_LEVEL}) on {cores} threads of oracle/cpu (C++ restatement of the '
+                      f'reference algorithms; the TypeScript reference cannot run here: no node), {dt:.2f} s wall',
+            'single_thread': {'value': 1.0 / d1, 'unit': 'proofs/s', 's_per_proof': d1},
+            'verify': {'value': B / dv, 'unit': 'verifies/s', 'cores': cores, 'single_thread_s_per_verify': v1},
+            'note': 'native Montgomery code on 64-bit limbs: several times faster than V8 BigInt would be, so GPU/CPU ratios '
+                    'against it are conservative; the Python-int oracle (oracle/*.py) needs ~3 s per proof per core'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    B, N = WORKLOADS[args.workload]
-    for _ in range(args.warmup and 1):
-        cpu_baseline(N, 1)
-    t = time.time()
-    tot = 0
-    info = None
-    for _ in range(args.steps):
-        info = cpu_baseline(N, 1)
-        tot += info['cores']
-    wall = time.time() - t
-    v = tot / wall
+    wname = args.workload or ('config2' if args.gpus == 1 else 'config3')
+    B, N = WORKLOADS[wname]
+    cores = usable_cores()
+    port = CpuPort(N, cores)
+    for _ in range(min(args.warmup, 2)):
+        port.prove(port.sample(cores, 3000))
+    tot_s = 0.0
+    tot_n = 0
+    for k in range(args.steps):
+        smp = port.sample(cores, 4000 + k)      # building the sample (keygen, signatures) is not timed
+        tot_s += port.prove(smp)
+        tot_n += cores
+    v = tot_n / tot_s
     line = {
         'impl': 'reference', 'metric': 'ZKAttest proofs/sec', 'value': v, 'unit': 'proofs/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u256 (Python int)',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_s / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u256/u258 (64-bit limbs, Montgomery, C++)',
         'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: ring N={N}, SecLevel {SEC_LEVEL}; each step = a bounded sample of '
-                               f'{info["cores"]} proofs (one per host core) of the batch-{B} workload'},
-        'cpu_baseline': {'value': v, 'unit': 'proofs/s', 'cores': info['cores'], 'kind': 'port',
-                         'sample': info['sample'] + '; the TypeScript reference itself cannot run here (no node)'},
+        'config': {'workload': f'{wname}: ring N={N}, SecLevel {SEC_LEVEL}; each step = a bounded sample of '
+                               f'{cores} proofs (one per host thread) of the batch-{B} workload'},
+        'cpu_baseline': {'value': v, 'unit': 'proofs/s', 'cores': cores, 'kind': 'port-c++',
+                         'sample': f'{tot_n} proofs in {tot_s:.1f} s on {cores} threads of oracle/cpu (C++ restatement of the '
+                                   'reference algorithms); the TypeScript reference itself cannot run here (no node)'},
         'e2e': {'value': v, 'unit': 'proofs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -243,33 +290,66 @@ def measured_int_peak(device_index: int):
         return 9000.0, 'fallback 9.0e12/s (31 IMAD.WIDE/clk/SM x 148 SM x 1.965 GHz)'
 
 
+def executed_mac_model(cfg, n_ring_bits, g_w=20, h_w=20):
+    """EXECUTED 32x32+64 multiply-accumulates per work item of the kernels that hold the arithmetic
+    (DESIGN.md 5).  Kernels not listed (hashing, byte assembly, layout, key dedup, the doubling chains of the
+    few distinct keys) are counted as ZERO, so the whole-step figure is a lower bound of the utilisation."""
+    T, P, Nn = MAC_PER_TOM_MODMUL, MAC_PER_P256_MODMUL, MAC_PER_N256_MODMUL
+    nwin = cfg['tom_nwin']
+    p256_madd = 13        # RCB15 Alg. 5: 11 M + 2 multiplications by b
+    p256_add, p256_dbl = 14, 13
+    pa_lookups = -(-256 // g_w) + -(-256 // h_w) + 52 * 31 / 32     # G table + h table + signed 5-bit pk table
+    return {
+        'TomCommitHTask': nwin * MODMUL_PER_MADD * T,
+        'TomCommitGTask': nwin * MODMUL_PER_MADD * T,
+        'TomCommitTask': 2 * nwin * MODMUL_PER_MADD * T,
+        'PhaseAAndRPointTask': 5 * Nn + pa_lookups * p256_madd * P,
+        'TomNormTask': 11 * T,              # per point; the chunk's binary inversion is ALU work + 4 products
+        'P256NormTask': 7 * P,
+        'ItemScalarsTask': 55 * P,
+        'PhaseBP256Task': p256_madd * P,
+        'DerivedTask': 6 * (9 + 1) * T,     # six complete additions + from_affine products
+        # verifier
+        'MsmP256WindowTask': (21 * 15 / 16 * p256_madd + 30 * p256_add) * P,
+        'VSampleP256Task': 52 * 31 / 32 * p256_madd * P,
+        'VParseEntriesTask': 9 * T,
+        'VDerivedTask': (6 * 10 + 4 * 7) * T,
+    }
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from zkp_ecdsa_b200 import api, sharding, synth
+    from zkp_ecdsa_b200 import verify_tape as VT
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the one JSON line (NCCL prints its version otherwise)
+        # NCCL's INFO log (rank/topology/NVLS lines the driver greps) goes to stderr: fd 1 is already routed
+        # there by quiet_stdout(), so nothing has to be silenced to keep stdout to the one JSON line
+        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    B, N = WORKLOADS[args.workload]
+    wname = args.workload or ('config2' if world == 1 else 'config3')
+    B, N = WORKLOADS[wname]
     if args.batch:
         B = args.batch
     if args.ring:
         N = args.ring
+    nbits = max(1, (N - 1).bit_length())
 
     eng = api.Engine(device=local)
     L = eng.lib
     params = eng.generate_params_list(SEC_LEVEL, rnd=synth.params_rnd(0))
     wl = synth.Workload(B, N, seed=100 + rank)
     ts = L.prove_tape_len(N, SEC_LEVEL)
-    ps = L.proof_max_len(N, SEC_LEVEL)
+    ps = (L.proof_max_len(N, SEC_LEVEL) + 15) & ~15     # 16-byte aligned rows (zka_proofs_pack moves uint4)
     tape_h = torch.from_numpy(synth.random_tape(B, ts, seed=200 + rank)).pin_memory()
 
     def pin(a):
@@ -278,22 +358,32 @@ def run_ours(args):
          'ring': pin(wl.ring)}
     d = {k: v.to(dev) for k, v in h.items()}
     tape_d = tape_h.to(dev)
-    proofs_d = torch.empty((B, ps), dtype=torch.uint8, device=dev)
+    proofs_d = torch.zeros((B, ps), dtype=torch.uint8, device=dev)
     plen_d = torch.zeros(B, dtype=torch.int32, device=dev)
     stat_d = torch.zeros(B, dtype=torch.int32, device=dev)
-    proofs_h = torch.empty((B, ps), dtype=torch.uint8).pin_memory()
+    proofs_h = torch.zeros((B, ps), dtype=torch.uint8).pin_memory()
     plen_h = torch.zeros(B, dtype=torch.int32).pin_memory()
     stat_h = torch.zeros(B, dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     lib_stream = torch.cuda.ExternalStream(L.stream_ptr(), device=dev)
+    gather = sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, groups=args.gather_groups) if world > 1 else None
+
+    def prove_dev(b0, b1):
+        L.prove_batch(params.handle, b1 - b0, d['msg'][b0:].data_ptr(), d['sig'][b0:].data_ptr(), d['pk'][b0:].data_ptr(),
+                      d['which'][4 * b0:].data_ptr(), d['ring'].data_ptr(), N, tape_d[b0:].data_ptr(), ts,
+                      proofs_d[b0:].data_ptr(), ps, plen_d[b0:].data_ptr(), stat_d[b0:].data_ptr())
 
     def step_device():
-        L.prove_batch(params.handle, B, d['msg'].data_ptr(), d['sig'].data_ptr(), d['pk'].data_ptr(),
-                      d['which'].data_ptr(), d['ring'].data_ptr(), N, tape_d.data_ptr(), ts,
-                      proofs_d.data_ptr(), ps, plen_d.data_ptr(), stat_d.data_ptr())
-        if world > 1:
-            # one all-gather of the proof rows (trimmed to the longest proof of the job) + their lengths
-            sharding.all_gather_proofs(proofs_d, plen_d, world, rank, B, trim=True)
+        if world == 1:
+            prove_dev(0, B)
+            return
+        # N > 1: the rank's batch is proved group by group; the NCCL all-gather of a finished group's packed
+        # proof bytes runs on the communication stream while the next group is being proved
+        gather.begin()
+        for (b0, b1) in gather.ranges:
+            prove_dev(b0, b1)
+            gather.submit(proofs_d, plen_d, b0, b1)
+        gather.finish()
 
     def step_host():
         L.prove_batch(params.handle, B, h['msg'].data_ptr(), h['sig'].data_ptr(), h['pk'].data_ptr(),
@@ -335,84 +425,89 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    L.profile_reset()
-    L.set_profiling(True)
     l0 = L.launch_count()
     ms_total = timed(step_device, args.steps)
     launches = L.launch_count() - l0
-    L.set_profiling(False)
-    prof = L.profile()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
+    gather_info = gather.check(proofs_d, plen_d) if gather else None
 
-    # end-to-end through the C ABI with host buffers (H2D + D2H inside)
+    # per-kernel CUDA-event pairs on the launching streams: a separate, un-timed pass (the event pairs
+    # serialise the lanes of a call, so they are kept out of the timed region)
+    psteps = max(1, min(args.steps, 3))
+    L.profile_reset()
+    L.set_profiling(True)
+    for _ in range(psteps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        prove_dev(0, B)
+    L.set_profiling(False)
+    prof = L.profile()
+    ms_prof_step = sum(e['ms'] for e in prof.values()) / psteps
+
+    # ---- end to end through the C ABI with host buffers (H2D + D2H inside)
     for _ in range(2):
         step_host()
-    e2e_ms = timed(step_host, max(1, min(args.steps, 3))) / max(1, min(args.steps, 3))
+    esteps = max(1, min(args.steps, 5))
+    e2e_ms = timed(step_host, esteps) / esteps
     assert int((stat_h != 0).sum().item()) == 0
     h2d = sum(int(v.numel()) for v in h.values()) + int(tape_h.numel())
     # the library copies back, per row, only the bytes up to the longest proof of the chunk
     d2h = int(plen_h.max().item()) * B + 8 * B
-    # the two arms must agree bit for bit
-    # (compare the valid prefix of every row; bytes past proof_len are padding)
+    # the two arms must agree bit for bit (valid prefix of every row; bytes past proof_len are padding)
     col = torch.arange(ps, device=dev).unsqueeze(0)
     valid = col < plen_d.unsqueeze(1)
     same = bool(torch.equal(plen_h.to(dev), plen_d)) and bool(((proofs_h.to(dev) == proofs_d) | ~valid).all().item())
+    del col, valid
+    # cost of producing the randomness itself (outside the timed regions: the C ABI takes the tape as an input)
+    t0 = time.perf_counter()
+    api.synth_os_tape(64, ts, SEC_LEVEL)
+    tape_gen_s_per_proof = (time.perf_counter() - t0) / 64
 
-    # ---- the same host-buffer call issued by TWO caller threads, each with its own context (own streams,
-    # workspace and tables): the copies of one caller overlap the kernels of the other, which is how a
-    # service with more than one request in flight keeps the device busy.  Reported beside e2e, not as e2e.
-    two = None
-    if world == 1 and not args.no_two_callers:
-        import threading
-        eng2 = api.Engine(device=local)
-        params2 = eng2.load_params(params.h_nist, params.h_proof, SEC_LEVEL)
-        outs2 = (torch.empty((B, ps), dtype=torch.uint8).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory(),
-                 torch.zeros(B, dtype=torch.int32).pin_memory())
-
-        def caller(lib, ph, outs, n):
-            for _ in range(n):
-                lib.prove_batch(ph, B, h['msg'].data_ptr(), h['sig'].data_ptr(), h['pk'].data_ptr(),
-                                h['which'].data_ptr(), h['ring'].data_ptr(), N, tape_h.data_ptr(), ts,
-                                outs[0].data_ptr(), ps, outs[1].data_ptr(), outs[2].data_ptr())
-        caller(eng2.lib, params2.handle, outs2, 2)          # warm-up of the second context
-        nsteps = max(2, min(args.steps, 4))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=caller, args=(L, params.handle, (proofs_h, plen_h, stat_h), nsteps)),
-              threading.Thread(target=caller, args=(eng2.lib, params2.handle, outs2, nsteps))]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        assert int((outs2[2] != 0).sum().item()) == 0 and bool(torch.equal(outs2[1], plen_h))
-        two = {'value': 2 * nsteps * B / wall, 'unit': 'proofs/s', 'callers': 2, 'steps_per_caller': nsteps,
-               'note': 'two host threads, one zka context each, same host buffers in / separate pinned buffers out'}
-        params2.close()
-        eng2.close()
-
-    # ---- verifySignatureList over the proofs just produced (device resident), verifies/s
-    from zkp_ecdsa_b200 import verify_tape as VT
+    # ---- verifySignatureList over the proofs just produced: device resident and end to end
     vts = L.verify_tape_len(N, SEC_LEVEL)
-    vt_d = torch.from_numpy(VT.random_verify_tape(B, vts, N, SEC_LEVEL, seed=300 + rank)).to(dev)
+    vt_h = torch.from_numpy(VT.random_verify_tape(B, vts, N, SEC_LEVEL, seed=300 + rank)).pin_memory()
+    vt_d = vt_h.to(dev)
     ok_d = torch.zeros(B, dtype=torch.uint8, device=dev)
     vst_d = torch.zeros(B, dtype=torch.int32, device=dev)
+    ok_h = torch.zeros(B, dtype=torch.uint8).pin_memory()
+    vst_h = torch.zeros(B, dtype=torch.int32).pin_memory()
+    ok_all = torch.zeros(world * B, dtype=torch.uint8, device=dev)
 
-    def step_verify():
+    def verify_dev():
         L.verify_batch(params.handle, B, d['msg'].data_ptr(), d['ring'].data_ptr(), N, proofs_d.data_ptr(), ps,
                        plen_d.data_ptr(), vt_d.data_ptr(), vts, ok_d.data_ptr(), vst_d.data_ptr())
+        if world > 1:   # configs[4]: the verdicts of all ranks on every rank
+            dist.all_gather_into_tensor(ok_all, ok_d)
+
+    def verify_host():
+        L.verify_batch(params.handle, B, h['msg'].data_ptr(), h['ring'].data_ptr(), N, proofs_h.data_ptr(), ps,
+                       plen_h.data_ptr(), vt_h.data_ptr(), vts, ok_h.data_ptr(), vst_h.data_ptr())
     for _ in range(2):
-        step_verify()
-    vsteps = max(1, min(args.steps, 3))
+        verify_dev()
+    vsteps = max(1, min(args.steps, 5))
+    lv0 = L.launch_count()
+    v_ms = timed(verify_dev, vsteps) / vsteps
+    vlaunches = (L.launch_count() - lv0) // vsteps
+    all_ok = bool((ok_d == 1).all().item()) and bool((vst_d == 0).all().item())
+    if world > 1:
+        all_ok = all_ok and bool((ok_all == 1).all().item())
     L.profile_reset()
     L.set_profiling(True)
-    v_ms = timed(step_verify, vsteps) / vsteps
+    for _ in range(2):
+        flush.zero_()
+        torch.cuda.synchronize()
+        L.verify_batch(params.handle, B, d['msg'].data_ptr(), d['ring'].data_ptr(), N, proofs_d.data_ptr(), ps,
+                       plen_d.data_ptr(), vt_d.data_ptr(), vts, ok_d.data_ptr(), vst_d.data_ptr())
     L.set_profiling(False)
     vprof = L.profile()
-    all_ok = bool((ok_d == 1).all().item()) and bool((vst_d == 0).all().item())
+    ms_vprof_step = sum(e['ms'] for e in vprof.values()) / 2
+    verify_host()
+    ve2e_ms = timed(verify_host, vsteps) / vsteps
+    v_e2e_ok = bool((ok_h == 1).all().item()) and bool((vst_h == 0).all().item())
+    v_h2d = int(plen_h.sum().item()) if False else B * ps + B * (32 + 4 + vts) + N * 32
+    zero_bits = ((plen_h.to(torch.int64) - (264 + 80 * 330 + 1 + 4 * nbits * 67 + (3 * nbits + 1) * 33)) // (3596 - 330)).float().mean().item()
 
     if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -423,87 +518,114 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel, from the CUDA-event pairs recorded during the timed steps
+    # ---- rooflines: executed multiply-accumulates against the measured IMAD.WIDE peak of this GPU
     cfg = L.config()
-    # dominant kernel = the split commitment kernel TomCommitHTask (C = K + r*h, 16 table lookups per
-    # commitment); its sibling TomCommitGTask (K = v*g) and the unsplit TomCommitTask run the same
-    # inner loop, so the three are also reported together.
-    lookups = {'TomCommitHTask': cfg['tom_nwin'], 'TomCommitGTask': cfg['tom_nwin'], 'TomCommitTask': 2 * cfg['tom_nwin']}
+    model = executed_mac_model(cfg, nbits)
+    peak_gmac, how = measured_int_peak(local)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
 
-    def commit_stats(names):
-        ms = macs = items = launches = 0.0
-        for k, e in prof.items():
-            short = k.replace('zk::', '')
-            if short in names:
-                ms += e['ms']
-                items += e['items']
-                launches += e['launches']
-                macs += e['items'] * lookups[short] * MODMUL_PER_MADD * MAC_PER_TOM_MODMUL
-        return ms, macs, items, launches
-    roof = None
-    ms_h, macs_h, items_h, launches_h = commit_stats({'TomCommitHTask'})
-    if launches_h:
-        ms_all, macs_all, items_all, _ = commit_stats(set(lookups))
-        peak_gmac, how = measured_int_peak(local)
-        avg_ms = ms_h / launches_h
-        per_launch = items_h / launches_h
-        ach = macs_h / (ms_h * 1e-3) / 1e9
-        alg_bytes = per_launch * (32 + 144 + 108)      # blinder + extended g-part in, projective point out
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
-        hbm_peak = peaks.get('hbm_gbs', 6650.0)
-        roof = {
-            'kernel': 'zk_task_kernel<TomCommitHTask> (fixed-base Pedersen commitments C = v*g + r*h, 258-bit field, '
-                      f"a=-1 image curve: {lookups['TomCommitHTask']} lookups x 7 modmul x 126 MAC per launch item)",
-            'bound': 'int32-multiplier pipe (IMAD.WIDE.U32) — not hbm/tensor: ~30 modmul per HBM byte',
-            'achieved': ach, 'peak': peak_gmac, 'unit': 'G(32x32+64 MAC)/s', 'frac': ach / peak_gmac,
-            'peak_source': how,
-            'avg_launch_ms': avg_ms, 'launches': launches_h, 'commitments_per_launch': per_launch,
-            'modmul_per_launch': per_launch * lookups['TomCommitHTask'] * MODMUL_PER_MADD,
-            'share_of_step': ms_h / ms_total,
-            'all_commit_kernels': {'share_of_step': ms_all / ms_total, 'achieved': macs_all / (ms_all * 1e-3) / 1e9,
-                                   'frac': macs_all / (ms_all * 1e-3) / 1e9 / peak_gmac},
-            'hbm': {'achieved': alg_bytes / (avg_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak,
-                    'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6.65 TB/s'},
-            # dram__bytes_read.sum + dram__bytes_write.sum from the `ncu --set full` capture of the commitment
-            # kernel (profiles/ncu_tomcommit_r1d_w16_noinline.md: 3.72 GB for 1 392 640 commitments x 32 lookups
-            # = 78 B of table traffic per lookup on top of the algorithmic bytes), scaled to this launch
-            'traffic': (per_launch * (284.0 + NCU_DRAM_BYTES_PER_LOOKUP[cfg['tom_w']] * lookups['TomCommitHTask'])
-                        if cfg['tom_w'] in NCU_DRAM_BYTES_PER_LOOKUP else None),
-            'traffic_unit': 'bytes/launch',
-            'traffic_note': 'algorithmic bytes are 284 B/commitment; the rest is the random 128-byte table lookups '
-                            f"({cfg['tom_nwin'] * (1 << cfg['tom_w']) * 128 / 1e6:.0f} MB table per base) — HBM stays < 10 % busy",
-        }
-    kernels = {k.replace('zk::', ''): {'ms_per_step': v['ms'] / args.steps, 'launches_per_step': v['launches'] / args.steps}
-               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
-    cpu = cpu_baseline(N, 1) if world == 1 and not args.no_cpu else None
+    def short(k):
+        return k.replace('zk::', '')
+
+    def kernel_roofline(pr, name, nsteps, macs_per_item, alg_bytes_per_item, what):
+        e = next((v for k, v in pr.items() if short(k) == name), None)
+        if not e or not e['launches']:
+            return None
+        avg_ms = e['ms'] / e['launches']
+        per_launch = e['items'] / e['launches']
+        ach = e['items'] * macs_per_item / (e['ms'] * 1e-3) / 1e9
+        return {'kernel': f'zk_task_kernel<{name}> ({what})',
+                'bound': 'int32-multiplier pipe (IMAD.WIDE.U32, fmaheavy) — not hbm/tensor: ~30 modmul per HBM byte',
+                'achieved': ach, 'peak': peak_gmac, 'unit': 'G(32x32+64 MAC)/s', 'frac': ach / peak_gmac,
+                'peak_source': how, 'mac_count': 'executed (117 IMAD.WIDE per 258-bit product)',
+                'avg_launch_ms': avg_ms, 'launches_per_step': e['launches'] / nsteps, 'items_per_launch': per_launch,
+                'hbm': {'achieved': per_launch * alg_bytes_per_item / (avg_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                        'frac': per_launch * alg_bytes_per_item / (avg_ms * 1e-3) / 1e9 / hbm_peak,
+                        'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6.65 TB/s'}}
+
+    def whole_step(pr, nsteps, step_ms, extra=None):
+        macs = 0.0
+        for k, e in pr.items():
+            m = (extra or {}).get(short(k), model.get(short(k), 0.0))
+            macs += e['items'] * m
+        macs /= nsteps
+        return {'executed_gmac_per_step': macs / 1e9, 'achieved': macs / (step_ms * 1e-3) / 1e9, 'peak': peak_gmac,
+                'frac': macs / (step_ms * 1e-3) / 1e9 / peak_gmac, 'unit': 'G(32x32+64 MAC)/s',
+                'note': 'sum over the modelled kernels of items x executed MACs per item (bench.py executed_mac_model; '
+                        'unlisted kernels count as zero) / ms_per_step of the timed region / measured peak'}
+
+    roof = kernel_roofline(prof, 'TomCommitHTask', psteps, model['TomCommitHTask'], 32 + 144 + 108,
+                           f"fixed-base Pedersen commitments C = K + r*h, 258-bit field, a=-1 image curve: {cfg['tom_nwin']} "
+                           'lookups x 7 modmul x 117 MAC per item')
+    if roof:
+        ms_c = sum(e['ms'] for k, e in prof.items() if short(k) in ('TomCommitHTask', 'TomCommitGTask', 'TomCommitTask'))
+        mac_c = sum(e['items'] * model[short(k)] for k, e in prof.items() if short(k) in ('TomCommitHTask', 'TomCommitGTask', 'TomCommitTask'))
+        roof['share_of_step'] = next(e['ms'] for k, e in prof.items() if short(k) == 'TomCommitHTask') / (ms_prof_step * psteps)
+        roof['all_commit_kernels'] = {'share_of_step': ms_c / (ms_prof_step * psteps), 'achieved': mac_c / (ms_c * 1e-3) / 1e9,
+                                      'frac': mac_c / (ms_c * 1e-3) / 1e9 / peak_gmac}
+        roof['whole_step'] = whole_step(prof, psteps, ms_step)
+        per_lookup = NCU_DRAM_BYTES_PER_LOOKUP.get(cfg['tom_w'])
+        roof['traffic'] = roof['items_per_launch'] * (284.0 + per_lookup * cfg['tom_nwin']) if per_lookup else None
+        roof['traffic_unit'] = 'bytes/launch'
+        roof['traffic_note'] = ('algorithmic bytes are 284 B/commitment; the rest is the random 128-byte table lookups '
+                                f"({cfg['tom_nwin'] * (1 << cfg['tom_w']) * 128 / 1e6:.0f} MB table per base, ncu capture in profiles/) — HBM stays < 15 % busy")
+    # verifier: the Pippenger window kernel (one thread per (proof, window); multiW + GK instances in one grid)
+    ent_w = 2 + 20 * (2 + 32 * zero_bits / 80.0)      # expected variable points of multiW for this batch
+    ent_g = 4 * nbits + 1
+    msm_macs = ((ent_w + ent_g) * 63 / 64 * 8 + 2 * 64 * 9) * MAC_PER_TOM_MODMUL      # per (proof, window): both instances
+    vextra = {'MsmTomWindowBothTask': msm_macs / 2,       # items counts both instances' threads
+              'MsmCombineAllTask': ((258 * 8 + 43 * 9) * 2 * MAC_PER_TOM_MODMUL + (256 * 13 + 64 * 14) * MAC_PER_P256_MODMUL) / 3,
+              'VValidateTask': (2 + 32 * zero_bits / 80.0) * 7 * MAC_PER_TOM_MODMUL}
+    vroof = kernel_roofline(vprof, 'MsmTomWindowBothTask', 2, msm_macs / 2, (ent_w + ent_g) / 2 * (128 + 32) / 43 + 144,
+                            f'sorted-bucket Pippenger, signed 6-bit windows: ~{ent_w:.0f} + {ent_g} points per proof, '
+                            '8 modmul per bucket addition + 2 x 32 x 9 for the running sums, x 117 MAC')
+    if vroof:
+        vroof['share_of_step'] = next(e['ms'] for k, e in vprof.items() if short(k) == 'MsmTomWindowBothTask') / (ms_vprof_step * 2)
+        vroof['whole_step'] = whole_step(vprof, 2, v_ms, vextra)
+
+    def kern(pr, nsteps):
+        return {short(k): {'ms_per_step': round(v['ms'] / nsteps, 4), 'launches_per_step': v['launches'] / nsteps}
+                for k, v in sorted(pr.items(), key=lambda kv: -kv[1]['ms'])}
+    cpu = cpu_baseline(N) if world == 1 and not args.no_cpu else None
     line = {
         'metric': 'ZKAttest proofs/sec', 'value': value, 'unit': 'proofs/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u256/u258 (32-bit limbs, Montgomery)', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: batch {B} proofs per GPU, ring N={N}, SecLevel {SEC_LEVEL}, '
-                               f'P-256 + tomEdwards256 (BASELINE.json configs)',
-                   'l2': 'working set per step > L2 (tape+proofs ~0.4 GB) and a 256 MiB buffer is rewritten between steps',
-                   'tom_window_bits': cfg['tom_w'], 'chunk': cfg['chunk'],
-                   'collective': 'none' if world == 1 else 'one NCCL all-gather of the proof rows (trimmed to the longest proof) + one of their lengths per step'},
+        'config': {'workload': f'{wname}: batch {B} proofs per GPU, ring N={N}, SecLevel {SEC_LEVEL}, '
+                               f'P-256 + tomEdwards256 (BASELINE.json configs[{ {"config1": 1, "config2": 2, "config3": 3}.get(wname, "-") }]'
+                               + ('; verify leg = configs[4])' if wname == 'config3' else ')'),
+                   'l2': 'working set per step > L2 (tape + proofs ~2.6 GB at 8192 proofs) and a 256 MiB buffer is rewritten between steps',
+                   'tom_window_bits': cfg['tom_w'], 'chunk': cfg['chunk'], 'lanes': cfg.get('lanes'),
+                   'collective': 'none' if world == 1 else gather.describe()},
         'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'proofs/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms, 'bit_identical_to_device_arm': same,
-                'two_callers': two},
+                'tape_generation': {'s_per_proof': tape_gen_s_per_proof, 'bytes_per_proof': ts,
+                                    'note': 'os.urandom + rnd() rejection (api.synth_os_tape), one host thread; NOT inside the timed '
+                                            'region — the C ABI takes the randomness tape as an input buffer'}},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roof,
         'cpu_baseline': cpu,
         'ref_equiv_modmul_per_s': value * W_PROVE_REF.get(N, 6.9e6),
-        'verify': {'value': world * B / (v_ms * 1e-3), 'unit': 'verifies/s', 'ms_per_step': v_ms, 'all_accepted': all_ok,
-                   'note': 'zka_verify_batch over the proofs of the last prove step, device resident, secparam 20 (zkpAttestList.ts:177)',
-                   'kernels': {k.replace('zk::', ''): round(v['ms'] / vsteps, 3)
-                               for k, v in sorted(vprof.items(), key=lambda kv: -kv[1]['ms'])[:10]}},
-        'kernels': kernels,
+        'verify': {'metric': 'ZKAttest verifies/sec', 'value': world * B / (v_ms * 1e-3), 'unit': 'verifies/s', 'ms_per_step': v_ms,
+                   'all_accepted': all_ok, 'gpu_launches_per_step': vlaunches,
+                   'collective': 'none' if world == 1 else 'one NCCL all-gather of ok[] (1 byte per proof) per step',
+                   'e2e': {'value': world * B / (ve2e_ms * 1e-3), 'unit': 'verifies/s', 'ms_per_step': ve2e_ms,
+                           'h2d_bytes_per_step': v_h2d, 'd2h_bytes_per_step': 5 * B, 'all_accepted': v_e2e_ok,
+                           'note': 'host proofs, messages, ring and verifier tape in; ok[] and status[] out'},
+                   'note': 'zka_verify_batch over the proofs of the last prove step, secparam 20 (zkpAttestList.ts:177)',
+                   'roofline': vroof, 'kernels': kern(vprof, 2)},
+        'kernels': kern(prof, psteps),
+        'kernels_note': 'per-kernel CUDA-event pairs from a separate un-timed pass (sum '
+                        f'{ms_prof_step:.2f} ms/step prove, {ms_vprof_step:.2f} ms/step verify; the timed steps overlap lanes)',
     }
+    if gather_info:
+        line['gather'] = gather_info
     emit_json(line)
     if world > 1:
         dist.destroy_process_group()
@@ -535,11 +657,12 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='config1', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
+                    help='default: config2 on one GPU, config3 (8192 per GPU x ring 1024) under torchrun')
+    ap.add_argument('--gather-groups', type=int, default=4, help='N>1: groups per rank whose all-gather overlaps the next group')
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--ring', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--no-two-callers', action='store_true', help='skip the two-caller host-buffer leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
