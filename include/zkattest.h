@@ -136,8 +136,29 @@ size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap);
  *   ZKA_P256_HW     window bits of the P-256 G / NistGroup.h tables, 8..24, default 20 (872 MB per base)
  *   ZKA_CHUNK       proofs per pipeline pass when all buffers are device memory, default 8192
  *   ZKA_HOST_CHUNK  proofs per pass when buffers are host memory (copies of one pass overlap the
- *                   kernels of the next), default 4096 */
+ *                   kernels of the next), default 4096
+ *   ZKA_LANES       concurrent pipelines inside one prove / verify call, 1..8, default 2: the batch is cut
+ *                   into chunks dealt round-robin to the lanes; every lane has its own streams and workspace
+ *                   and (beyond the first) its own host thread for the duration of the call, so the
+ *                   latency-bound stages and the host<->device copies of one chunk overlap the
+ *                   multiplier-bound kernels of another */
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk);
+int zka_lanes(const zka_ctx* ctx);
+/* change a knob between calls: key in {"lanes", "chunk", "host_chunk"}, value >= 1 */
+int zka_set_option(zka_ctx* ctx, const char* key, long value);
+
+/* ---- multi-GPU helpers: a rank's proofs as ONE contiguous block for the NCCL all-gather.
+ * Proof b starts at offsets[b] = sum_{i<b} align16(proof_len[i]); offsets[B] is the block length (the caller
+ * checks offsets[B] <= cap; pieces that would cross `cap` are not written).  Device pointers only.  With a
+ * non-NULL `stream` (a cudaStream_t) the two kernels are enqueued there and the call returns without waiting;
+ * with NULL they run on the library's stream and the call waits for them.
+ * 16-byte aligned rows (proof_stride % 16 == 0, aligned base pointers) are moved with 16-byte accesses. */
+int zka_proofs_pack(zka_ctx* ctx, uint32_t B, const uint8_t* proofs /* B x proof_stride */, size_t proof_stride,
+                    const uint32_t* proof_len /* B */, uint8_t* packed, size_t cap, uint64_t* offsets /* B + 1 */,
+                    void* stream);
+int zka_proofs_unpack(zka_ctx* ctx, uint32_t B, const uint8_t* packed, size_t cap, const uint32_t* proof_len /* B */,
+                      uint8_t* proofs /* B x proof_stride */, size_t proof_stride, uint64_t* offsets /* B + 1 */,
+                      void* stream);
 
 /* ---- layer-wise entry points (parity tests of the arithmetic underneath) ---- */
 /* Pedersen commit in the proof group: out[i] = v[i]*g + r[i]*h  (pedersen.ts:53-58 with r given) */

@@ -136,6 +136,16 @@ def test_multi_chunk_batches_equal_single_chunk():
     assert (outs[0][1] == outs[1][1]).all()
     for b in range(5):
         assert outs[0][0][b, :outs[0][1][b]].tobytes() == outs[1][0][b, :outs[1][1][b]].tobytes()
+    # the same three chunks dealt to two lanes (lane 1 runs on its own host thread): same bytes again
+    small.set_option('lanes', 2)
+    assert small.config()['lanes'] == 2
+    P, _ = common.make_params(small, 61, 20)
+    tape = synth.random_tape(5, small.prove_tape_len(4, 20), seed=62)
+    proofs, plen, status = common.run_prove(small, P, wl, tape, 20)
+    assert (status == 0).all() and (plen == outs[0][1]).all() and (proofs == outs[0][0]).all()
+    vt = VT.random_verify_tape(5, small.verify_tape_len(4, 20), 4, 20, seed=63)
+    ok, st = common.run_verify(small, P, wl.msg_hash, wl.ring, proofs, plen, vt)
+    assert (ok == 1).all() and (st == 0).all()
 
 
 def test_ragged_table_windows_bit_exact():

@@ -131,3 +131,129 @@ def test_alternate_code_paths_on_gpu():
         common.check_verify_parity(eng.lib, N=2100, sec_level=20, seed=43, tampers=4)
     finally:
         eng.close()
+
+
+# ---------------------------------------------------------------------------------- round 2
+def _cpu_port():
+    """oracle/cpu (C++ restatement of the reference algorithms): the fast checker for big shapes."""
+    import __graft_entry__ as g
+    from zkp_ecdsa_b200.capi import ZkaLib
+    assert __import__('os').path.exists(g.ORACLE_CPU), 'oracle/_ref/libzkattest_cpu.so missing: run build()'
+    return ZkaLib(g.ORACLE_CPU)
+
+
+def _spot_check(cpu, po_rnd, wl, tape, proofs, plen, spots, sec=80, python_spot=None):
+    """proofs[b] == oracle proof for b in spots (C++ port; one of them also against the Python oracle)."""
+    from oracle import flat
+    hn, hp = cpu.params_generate(po_rnd)
+    Pc = cpu.params_create(hn, hp, sec)
+    idx = np.array(spots)
+    sub = synth.Workload.__new__(synth.Workload)
+    sub.B, sub.N = len(spots), wl.N
+    sub.msg_hash, sub.sig, sub.pk, sub.which, sub.ring = (np.ascontiguousarray(wl.msg_hash[idx]), np.ascontiguousarray(wl.sig[idx]),
+                                                            np.ascontiguousarray(wl.pk[idx]), np.ascontiguousarray(wl.which[idx]), wl.ring)
+    ref, rlen, rst = common.run_prove(cpu, Pc, sub, np.ascontiguousarray(tape[idx]), sec)
+    assert not rst.any()
+    for k, b in enumerate(spots):
+        assert plen[b] == rlen[k] and proofs[b, :plen[b]].tobytes() == ref[k, :rlen[k]].tobytes(), f'proof {b} differs from oracle/cpu'
+    if python_spot is not None:
+        from oracle import zkattest as OZ
+        from oracle.big import Tape
+        po = OZ.generate_params_list(Tape(po_rnd), sec)
+        pr, _ = common.oracle_proof(po, wl, tape, python_spot)
+        assert proofs[python_spot, :plen[python_spot]].tobytes() == flat.ser_proof(pr)
+    cpu.params_destroy(Pc)
+
+
+def test_config3_shape_spot_proofs_bit_exact(gpu_engine):
+    """BASELINE configs[3] shape per GPU: 8192 proofs, ring N = 1024, SecLevel 80.  Three spot proofs are compared
+    byte for byte with the oracle (C++ port; proof 0 also with the Python oracle), all lengths with the layout law."""
+    from oracle import flat
+    L = gpu_engine.lib
+    rnd = synth.params_rnd(51)
+    P, _ = common.make_params(L, seed=51)
+    B, N = 8192, 1024
+    wl = synth.Workload(B=B, N=N, seed=51)
+    tape = synth.random_tape(B, L.prove_tape_len(N), seed=52)
+    proofs, plen, status = common.run_prove(L, P, wl, tape)
+    assert (status == 0).all()
+    zs = (plen.astype(np.int64) - flat.proof_len(0, 10)) // (flat.REP0_LEN - flat.REP1_LEN)
+    assert (plen == [flat.proof_len(int(z), 10) for z in zs]).all() and 38 < zs.mean() < 42
+    _spot_check(_cpu_port(), rnd, wl, tape, proofs, plen, [0, 4097, 8191], python_spot=0)
+    L.params_destroy(P)
+
+
+def test_host_pipeline_chunks_and_lanes_bit_exact(gpu_engine):
+    """B = 1024 with host buffers through >= 4 chunks of the three-stream pipeline, on 1, 2 and 3 lanes, must equal
+    the single-chunk device-pointer result and the oracle; the same for the verifier."""
+    import torch
+    from zkp_ecdsa_b200 import verify_tape as VT
+    L = gpu_engine.lib
+    rnd = synth.params_rnd(61)
+    P, _ = common.make_params(L, seed=61)
+    B, N = 1024, 8
+    wl = synth.Workload(B=B, N=N, seed=61)
+    ts, ps, vts = L.prove_tape_len(N), L.proof_max_len(N), L.verify_tape_len(N)
+    tape = synth.random_tape(B, ts, seed=62)
+    vt = VT.random_verify_tape(B, vts, N, 80, seed=63)
+    cfg0 = L.config()
+    dev = torch.device('cuda', 0)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)   # noqa: E731
+    d = [t(wl.msg_hash), t(wl.sig), t(wl.pk), t(wl.which.view(np.uint8)), t(wl.ring), t(tape), t(vt)]
+    pd = torch.zeros((B, ps), dtype=torch.uint8, device=dev)
+    ld = torch.zeros(B, dtype=torch.int32, device=dev)
+    sd = torch.zeros(B, dtype=torch.int32, device=dev)
+    okd = torch.zeros(B, dtype=torch.uint8, device=dev)
+    try:
+        L.set_option('lanes', 1)
+        L.set_option('chunk', 8192)
+        L.prove_batch(P, B, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(), N, d[5].data_ptr(),
+                      ts, pd.data_ptr(), ps, ld.data_ptr(), sd.data_ptr())
+        ref_p, ref_l = pd.cpu().numpy(), ld.cpu().numpy().astype(np.uint32)
+        assert not sd.cpu().numpy().any()
+        _spot_check(_cpu_port(), rnd, wl, tape, ref_p, ref_l, [0, 300, 1023])
+        L.set_option('host_chunk', 256)
+        for lanes in (1, 2, 3):
+            L.set_option('lanes', lanes)
+            proofs, plen, status = common.run_prove(L, P, wl, tape)
+            assert not status.any() and (plen == ref_l).all(), lanes
+            for b in range(B):
+                assert (proofs[b, :plen[b]] == ref_p[b, :plen[b]]).all(), (lanes, b)
+            # verifier: host buffers, 256-proof chunks, `lanes` lanes; then one tampered message
+            L.set_option('chunk', 256)
+            ok, st = common.run_verify(L, P, wl.msg_hash, wl.ring, proofs, plen, vt)
+            assert (ok == 1).all() and not st.any(), lanes
+            msg = wl.msg_hash.copy()
+            msg[777, 3] ^= 8
+            ok, st = common.run_verify(L, P, msg, wl.ring, proofs, plen, vt)
+            assert list(np.nonzero(ok == 0)[0]) == [777] and not st.any()
+            L.set_option('chunk', 8192)
+        # device-pointer verification of the device-resident proofs
+        L.verify_batch(P, B, d[0].data_ptr(), d[4].data_ptr(), N, pd.data_ptr(), ps, ld.data_ptr(), d[6].data_ptr(), vts,
+                       okd.data_ptr(), sd.data_ptr())
+        assert bool((okd == 1).all().item()) and not sd.cpu().numpy().any()
+    finally:
+        L.set_option('lanes', cfg0['lanes'])
+        L.set_option('chunk', cfg0['chunk'])
+        L.set_option('host_chunk', 4096)
+    L.params_destroy(P)
+
+
+def test_wild_index_and_error_rows_on_gpu(gpu_engine):
+    """`which` = 0xFFFFFFFF must not fault (the GK tasks read a clamped copy) and failed proofs leave as zero rows."""
+    L = gpu_engine.lib
+    P, po = common.make_params(L, seed=71)
+    wl = synth.Workload(B=4, N=8, seed=71)
+    wl.which[1] = 0xFFFFFFFF
+    wl.which[3] = 1 << 20
+    wl.pk[2, 10] ^= 4
+    tape = synth.random_tape(4, L.prove_tape_len(8), seed=72)
+    proofs, plen, status = common.run_prove(L, P, wl, tape)
+    assert list(status) == [0, 6, 1, 6]
+    assert plen[0] > 0 and not plen[1:].any() and not proofs[1:].any()
+    from oracle import flat
+    pr, _ = common.oracle_proof(po, wl, tape, 0)
+    assert proofs[0, :plen[0]].tobytes() == flat.ser_proof(pr)
+    # the context is still healthy
+    common.check_prove_parity(L, B=1, N=6, seed=73, sec_level=16)
+    L.params_destroy(P)

@@ -66,6 +66,23 @@ def _worker(rank, world, port, q):
     w = trimmed.shape[1]
     assert w <= stride and w >= int(alll.max()) and w - int(alll.max()) < 16
     assert torch.equal(trimmed, allp[:, :w]) and torch.equal(tlen, alll)
+    # overlapped, compacted gather (bench.py's N > 1 path): two groups per rank, pack -> all-gather -> unpack
+    stride16 = (stride + 15) & ~15
+    lp16 = torch.zeros((per, stride16), dtype=torch.uint8)
+    lp16[:, :stride] = lp
+    pg = sharding.ProofGather(lib, world, rank, per, stride16, N, SEC, torch.device('cpu'), groups=2)
+    pg.begin()
+    for (b0, b1) in pg.ranges:
+        pg.submit(lp16, ll, b0, b1)
+    pg.finish()
+    info = pg.check(lp16, ll)
+    assert info['checksums_match_all_ranks'] and info['own_rows_roundtrip'] and info['max_fill'] <= 1.0
+    for gi, (b0, b1) in enumerate(pg.ranges):
+        for r in range(world):
+            rows, lens = pg.unpack(gi, r)
+            for k in range(b1 - b0):
+                j = r * per + b0 + k
+                assert int(lens[k]) == int(alll[j]) and torch.equal(rows[k, :int(lens[k])], allp[j, :int(lens[k])])
     if rank == 0:
         q.put((allp.numpy(), alll.numpy()))
     dist.barrier()

@@ -25,6 +25,7 @@ SYMBOLS = [
     'zka_prove_batch', 'zka_verify_batch',
     'zka_tom_commit_batch', 'zka_p256_mul_batch', 'zka_field_op_batch', 'zka_hash80_batch',
     'zka_get_stream', 'zka_set_profiling', 'zka_profile_reset', 'zka_profile_json', 'zka_config',
+    'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack',
 ]
 
 STATUS_MESSAGES = {
@@ -101,6 +102,13 @@ class ZkaLib:
         L.zka_profile_json.restype = C.c_size_t
         L.zka_profile_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.zka_config.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        if hasattr(L, 'zka_set_option'):      # (oracle/cpu exports the core ABI only)
+            L.zka_lanes.argtypes = [C.c_void_p]
+            L.zka_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+            L.zka_proofs_pack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p, C.c_void_p]
+            L.zka_proofs_unpack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p, C.c_void_p]
         ctx = C.c_void_p()
         rc = L.zka_init(device, C.byref(ctx))
         if rc != 0 or not ctx:
@@ -141,7 +149,11 @@ class ZkaLib:
     def config(self) -> dict:
         w, nw, ch = C.c_int(), C.c_int(), C.c_int()
         self._check(self.lib.zka_config(self.ctx, C.byref(w), C.byref(nw), C.byref(ch)), 'zka_config')
-        return {'tom_w': w.value, 'tom_nwin': nw.value, 'chunk': ch.value}
+        lanes = int(self.lib.zka_lanes(self.ctx)) if hasattr(self.lib, 'zka_lanes') else 1
+        return {'tom_w': w.value, 'tom_nwin': nw.value, 'chunk': ch.value, 'lanes': lanes}
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.zka_set_option(self.ctx, key.encode(), int(value)), f'zka_set_option({key})')
 
     def proof_max_len(self, ring_size, sec_level=80): return int(self.lib.zka_proof_max_len(ring_size, sec_level))
     def prove_tape_len(self, ring_size, sec_level=80): return int(self.lib.zka_prove_tape_len(ring_size, sec_level))
@@ -183,6 +195,15 @@ class ZkaLib:
         self._check(self.lib.zka_verify_batch(self.ctx, params, B, _ptr(msg_hash), _ptr(ring), N, _ptr(proofs),
                                               proof_stride, _ptr(proof_len), _ptr(tape), tape_stride, _ptr(ok),
                                               _ptr(status)), 'zka_verify_batch')
+
+    # ------------------------------------------------------------------ multi-GPU helpers
+    def proofs_pack(self, B, proofs, stride, proof_len, packed, cap, offsets, stream=0):
+        self._check(self.lib.zka_proofs_pack(self.ctx, B, _ptr(proofs), stride, _ptr(proof_len), _ptr(packed), cap, _ptr(offsets),
+                                             C.c_void_p(stream or 0)), 'zka_proofs_pack')
+
+    def proofs_unpack(self, B, packed, cap, proof_len, proofs, stride, offsets, stream=0):
+        self._check(self.lib.zka_proofs_unpack(self.ctx, B, _ptr(packed), cap, _ptr(proof_len), _ptr(proofs), stride, _ptr(offsets),
+                                               C.c_void_p(stream or 0)), 'zka_proofs_unpack')
 
     # ------------------------------------------------------------------ layer-wise ops
     def tom_commit_batch(self, params, v: np.ndarray, r: np.ndarray) -> np.ndarray:

@@ -10,6 +10,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -207,6 +208,60 @@ struct KeyToIntTask {
   }
 };
 
+// ---- multi-GPU helpers: proofs leave a rank as ONE contiguous block (zka_proofs_pack / zka_proofs_unpack)
+ZK_HD uint64_t pack_align16(uint32_t len) { return ((uint64_t)len + 15u) & ~(uint64_t)15u; }
+struct PackScanTask {   // off[b] = sum_{i<b} align16(len[i]); one thread (B <= a few thousand per group)
+  const uint32_t* len;
+  uint64_t* off;        // [B + 1]
+  int B;
+  ZK_HD void operator()(int) const {
+    uint64_t acc = 0;
+    for (int b = 0; b < B; b++) { off[b] = acc; acc += pack_align16(len[b]); }
+    off[B] = acc;
+  }
+};
+struct PackCopyTask {   // one thread per (proof, 16-byte piece); dir 0: rows -> packed, 1: packed -> rows
+  uint8_t* rows;
+  size_t stride;
+  const uint32_t* len;
+  const uint64_t* off;
+  uint8_t* packed;
+  size_t cap;
+  int pieces;           // ceil(stride / 16)
+  int dir;
+  ZK_HD void operator()(int t) const {
+    const int b = t / pieces, j = t % pieces;
+    const size_t o = (size_t)16 * j;
+    if (o >= len[b]) return;
+    const size_t po = (size_t)off[b] + o;
+    if (po + 16 > cap) return;   // the caller checks off[B] <= cap
+    uint8_t* r = rows + (size_t)b * stride + o;
+    uint8_t* q = packed + po;
+    if (dir == 0) { for (int i = 0; i < 16; i++) q[i] = o + i < stride ? r[i] : 0; }
+    else { for (int i = 0; i < 16; i++) if (o + i < stride) r[i] = q[i]; }
+  }
+};
+struct PackCopy16Task {   // same, both sides 16-byte aligned: one uint4 per thread
+  uint8_t* rows;
+  size_t stride;
+  const uint32_t* len;
+  const uint64_t* off;
+  uint8_t* packed;
+  size_t cap;
+  int pieces;
+  int dir;
+  ZK_HD void operator()(int t) const {
+    const int b = t / pieces, j = t % pieces;
+    const size_t o = (size_t)16 * j;
+    if (o >= len[b]) return;
+    const size_t po = (size_t)off[b] + o;
+    if (po + 16 > cap) return;
+    U4* r = reinterpret_cast<U4*>(rows + (size_t)b * stride + o);
+    U4* q = reinterpret_cast<U4*>(packed + po);
+    if (dir == 0) *q = *r; else *r = *q;
+  }
+};
+
 }  // namespace zk
 
 using namespace zk;
@@ -220,17 +275,33 @@ struct FixedTable {   // positional table of one base point
 
 }  // namespace
 
-struct zka_ctx {
-  int device = 0;
+// A lane = one compute stream + two copy streams + its own grow-only workspace.  A prove / verify call cuts
+// the batch into chunks and deals them round-robin to the lanes; every lane beyond the first is driven by
+// its own host thread for the duration of the call, so the mid-pipeline host synchronisation of one lane
+// (the item count after the Fiat-Shamir scan) never stalls the others, the latency-bound stages of one
+// chunk (doubling chains, 16 KB hashes, scans) overlap the multiplier-bound kernels of another, and
+// host<->device copies of one lane overlap the kernels of the others.
+struct Lane {
   Stream st;
+  // copy streams + events of the host-buffer pipeline; slot = (lane-local chunk index) & 1
+  Stream cs_in, cs_out;
+  Event ev_small[2], ev_tape[2], ev_done[2], ev_out[2];
+  // workspace (grow-only)
+  DevBuf w[64];
+  DevBuf in[16], out[8];
   std::string err;
+};
+
+struct zka_ctx : Lane {
+  int device = 0;
+  std::vector<Lane*> extra;   // lanes 1 .. nlanes-1 (lane 0 is the context itself)
+  int nlanes = 2;             // ZKA_LANES
+  DevBuf ring_in, ring_m;     // the ring of the current call (shared by all lanes, read-only while they run)
+  Lane& lane(int i) { return i == 0 ? *this : *extra[i - 1]; }
   int tom_w = 22, tom_nwin = 12;   // per base: 12 windows x 2^22 entries x 128 B = 6.4 GB of HBM (ZKA_TOM_W)
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 8192;
   int host_chunk = 4096;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
-  // copy streams + events of the host-buffer pipeline (zka_prove_batch); slot = chunk index & 1
-  Stream cs_in, cs_out;
-  Event ev_small[2], ev_tape[2], ev_done[2], ev_out[2];
   int p256_hw = 20;       // window bits of the P-256 G table and of the per-params NistGroup.h table
                           // (13 windows x 2^20 entries x 64 B = 872 MB each; 16 -> 20 -> 22: PhaseA 13.4 -> 12.9 -> 12.6 ms)
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
@@ -239,9 +310,6 @@ struct zka_ctx {
   DevBuf tg_bytes;        // 67-byte encoding of g
   DevBuf lag;             // GK Lagrange matrix cache
   int lag_n = -1;
-  // workspace (grow-only)
-  DevBuf w[64];
-  DevBuf in[16], out[8];
 };
 
 struct zka_params {
@@ -374,6 +442,30 @@ const T* stage_in(zka_ctx* ctx, DevBuf& buf, const T* p, size_t count) {
   return stage_in(ctx->st, buf, p, count);
 }
 
+// Run fn(lane index) for lanes 0..used-1: lane 0 on the calling thread, the others on their own host threads
+// (each binds the context's device).  The first exception of any lane is rethrown on the caller.
+template <class Fn>
+void run_lanes(zka_ctx* ctx, int used, Fn fn) {
+  if (used <= 1) { fn(0); return; }
+  std::vector<std::thread> th;
+  std::vector<std::string> errs((size_t)used);
+  for (int li = 1; li < used; li++)
+    th.emplace_back([&, li] {
+      try {
+#if !defined(ZKA_HOSTSIM)
+        ZK_CUDA_CHECK(cudaSetDevice(ctx->device));
+#endif
+        fn(li);
+      } catch (const std::exception& e) {
+        errs[(size_t)li] = e.what()[0] ? e.what() : "lane failed";
+      }
+    });
+  try { fn(0); } catch (const std::exception& e) { errs[0] = e.what()[0] ? e.what() : "lane failed"; }
+  for (auto& t : th) t.join();
+  for (auto& e : errs)
+    if (!e.empty()) throw std::runtime_error(e);
+}
+
 }  // namespace
 
 // =============================================================================== C ABI
@@ -383,7 +475,12 @@ int zka_version(void) { return 1; }
 
 const char* zka_last_error(const zka_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-uint64_t zka_launch_count(const zka_ctx* ctx) { return ctx ? ctx->st.launches : 0; }
+uint64_t zka_launch_count(const zka_ctx* ctx) {
+  if (!ctx) return 0;
+  uint64_t n = ctx->st.launches;
+  for (const Lane* l : ctx->extra) n += l->st.launches;
+  return n;
+}
 
 void* zka_get_stream(zka_ctx* ctx) {
 #if !defined(ZKA_HOSTSIM)
@@ -394,22 +491,61 @@ void* zka_get_stream(zka_ctx* ctx) {
 }
 int zka_set_profiling(zka_ctx* ctx, int enable) {
   if (!ctx) return ZKA_E_ARG;
-  try { sync(ctx->st); } catch (...) { return ZKA_E_CUDA; }
-  ctx->st.profiling = enable != 0;
+  try {
+    for (int i = 0; i < 1 + (int)ctx->extra.size(); i++) { sync(ctx->lane(i).st); ctx->lane(i).st.profiling = enable != 0; }
+  } catch (...) { return ZKA_E_CUDA; }
   return 0;
 }
 int zka_profile_reset(zka_ctx* ctx) {
   if (!ctx) return ZKA_E_ARG;
-  try { sync(ctx->st); } catch (...) { return ZKA_E_CUDA; }
-  ctx->st.prof.clear();
+  try {
+    for (int i = 0; i < 1 + (int)ctx->extra.size(); i++) { sync(ctx->lane(i).st); ctx->lane(i).st.prof.clear(); }
+  } catch (...) { return ZKA_E_CUDA; }
+  return 0;
+}
+// knobs that may change between calls (tests, sweeps): "lanes", "chunk", "host_chunk"
+int zka_set_option(zka_ctx* ctx, const char* key, long value) {
+  if (!ctx || !key || value < 1) return ZKA_E_ARG;
+  const std::string k(key);
+  try {
+    if (k == "lanes") {
+      if (value > 8) return ZKA_E_ARG;
+      while ((int)ctx->extra.size() + 1 < value) {
+        Lane* l = new Lane();
+        stream_create(l->st);
+        stream_create(l->cs_in);
+        stream_create(l->cs_out);
+        l->st.profiling = ctx->st.profiling;
+        ctx->extra.push_back(l);
+      }
+      ctx->nlanes = (int)value;
+    } else if (k == "chunk") {
+      ctx->chunk = (int)value;
+    } else if (k == "host_chunk") {
+      ctx->host_chunk = (int)value;
+    } else {
+      return ZKA_E_ARG;
+    }
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
   return 0;
 }
 size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap) {
   if (!ctx) return 0;
-  try { sync(ctx->st); } catch (...) { return 0; }
+  std::map<std::string, ProfEntry> all;
+  try {
+    for (int i = 0; i < 1 + (int)ctx->extra.size(); i++) {
+      sync(ctx->lane(i).st);
+      for (auto& kv : ctx->lane(i).st.prof) {
+        ProfEntry& e = all[kv.first];
+        e.launches += kv.second.launches; e.ms += kv.second.ms; e.items += kv.second.items;
+      }
+    }
+  } catch (...) { return 0; }
   std::string j = "{";
   bool first = true;
-  for (auto& kv : ctx->st.prof) {
+  for (auto& kv : all) {
     char tmp[512];
     snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"items\": %llu}", first ? "" : ", ",
              kv.first.c_str(), (unsigned long long)kv.second.launches, kv.second.ms,
@@ -425,6 +561,7 @@ size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap) {
   }
   return j.size() + 1;
 }
+int zka_lanes(const zka_ctx* ctx) { return ctx ? ctx->nlanes : 0; }
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk) {
   if (!ctx) return ZKA_E_ARG;
   if (tom_w) *tom_w = ctx->tom_w;
@@ -472,6 +609,16 @@ int zka_init(int device, zka_ctx** out) {
     }
     stream_create(ctx->cs_in);
     stream_create(ctx->cs_out);
+    {
+      int lanes = 2;
+#if defined(ZKA_HOSTSIM)
+      lanes = 1;
+#endif
+      if (const char* e = getenv("ZKA_LANES")) lanes = atoi(e);
+      if (lanes < 1) lanes = 1;
+      if (lanes > 8) lanes = 8;
+      if (zka_set_option(ctx, "lanes", lanes) != 0) throw std::runtime_error("lanes");
+    }
     if (const char* e = getenv("ZKA_P256_HW")) {   // window bits of the P-256 G / NistGroup.h tables: 8..24
       int w = atoi(e);
       if (w >= 8 && w <= 24) ctx->p256_hw = w;
@@ -512,14 +659,23 @@ void zka_shutdown(zka_ctx* ctx) {
   for (auto& b : ctx->w) b.release();
   for (auto& b : ctx->in) b.release();
   for (auto& b : ctx->out) b.release();
-  for (int i = 0; i < 2; i++) {
-    ev_destroy(ctx->ev_small[i]); ev_destroy(ctx->ev_tape[i]); ev_destroy(ctx->ev_done[i]); ev_destroy(ctx->ev_out[i]);
+  ctx->ring_in.release();
+  ctx->ring_m.release();
+  for (int li = 0; li < 1 + (int)ctx->extra.size(); li++) {
+    Lane& l = ctx->lane(li);
+    if (li > 0) {
+      for (auto& b : l.w) b.release();
+      for (auto& b : l.in) b.release();
+      for (auto& b : l.out) b.release();
+    }
+    for (int i = 0; i < 2; i++) {
+      ev_destroy(l.ev_small[i]); ev_destroy(l.ev_tape[i]); ev_destroy(l.ev_done[i]); ev_destroy(l.ev_out[i]);
+    }
+    stream_destroy(l.cs_in);
+    stream_destroy(l.cs_out);
+    stream_destroy(l.st);
   }
-  stream_destroy(ctx->cs_in);
-  stream_destroy(ctx->cs_out);
-#if !defined(ZKA_HOSTSIM)
-  if (ctx->st.s) cudaStreamDestroy(ctx->st.s);
-#endif
+  for (Lane* l : ctx->extra) delete l;
   delete ctx;
 }
 
@@ -759,217 +915,229 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
   if (proof_stride < zka_proof_max_len(N, S)) return fail(ctx, ZKA_E_ARG, "proof_stride < zka_proof_max_len");
   if (tape_stride < (size_t)32 * prove_draws(0, n, S)) return fail(ctx, ZKA_E_ARG, "tape_stride too small");
   try {
-    Stream& st = ctx->st;
-    DevBuf* W = ctx->w;
-    // ring: once per call
-    const uint8_t* d_ring = stage_in(ctx, ctx->in[10], ring, (size_t)N * 32);
-    uint32_t* ring_m = W[40].get<uint32_t>(((size_t)1 << n) * 8);
-    launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
-    // Lagrange matrix for nodes 0..n-1: depends only on n, cached per context
-    if (ctx->lag_n != n) {
-      uint32_t* l = ctx->lag.get<uint32_t>((size_t)n * n * 8);
-      launch(st, 1, GkLagrangeTask{l, n});
-      ctx->lag_n = n;
+    // ring + Lagrange matrix: once per call, on lane 0, finished before the lanes start
+    {
+      Stream& st0 = ctx->st;
+      const uint8_t* d_ring = stage_in(st0, ctx->ring_in, ring, (size_t)N * 32);
+      uint32_t* rm = ctx->ring_m.get<uint32_t>(((size_t)1 << n) * 8);
+      launch(st0, 1ll << n, RingPrepTask{d_ring, rm, (int)N});
+      if (ctx->lag_n != n) {   // depends only on n, cached per context
+        uint32_t* l = ctx->lag.get<uint32_t>((size_t)n * n * 8);
+        launch(st0, 1, GkLagrangeTask{l, n});
+        ctx->lag_n = n;
+      }
+      sync(st0);
     }
+    const uint32_t* ring_m = (const uint32_t*)ctx->ring_m.p;
     uint32_t* lag = (uint32_t*)ctx->lag.p;
-
-    // Chunks are software-pipelined over three streams when buffers live in host memory: the inputs of
-    // chunk k+1 travel on cs_in and the proofs of chunk k-1 on cs_out while chunk k computes on st
-    // (staging buffers double-buffered by slot = k & 1).  Inside a chunk the tape (97 % of the input
-    // bytes) is only awaited by phase A, so it also overlaps the latency-bound statement stage.
     const bool out_dev = is_device_ptr(proofs);
     const bool len_dev = is_device_ptr(proof_len_out), st_dev = is_device_ptr(status);
-    const uint32_t chunk = (uint32_t)((out_dev && is_device_ptr(tape)) ? ctx->chunk : std::min(ctx->chunk, ctx->host_chunk));
-    const uint32_t nchunks = (B + chunk - 1) / chunk;
-    struct ChunkIn { const uint8_t *msg_hash, *sig, *pk, *tape; const uint32_t* which; } cin[2];
-    auto issue_inputs = [&](uint32_t k) {
-      const int slot = (int)(k & 1);
-      const uint32_t b0 = k * chunk;
-      const size_t Bc = std::min<uint32_t>(chunk, B - b0);
-      Stream& ci = ctx->cs_in;
-      DevBuf* in = ctx->in + 5 * slot;
-      ev_wait(ci, ctx->ev_done[slot]);   // chunk k-2 has finished reading these staging buffers
-      cin[slot].msg_hash = stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32);
-      cin[slot].sig = stage_in(ci, in[1], sig + (size_t)b0 * 64, Bc * 64);
-      cin[slot].pk = stage_in(ci, in[2], pk + (size_t)b0 * 65, Bc * 65);
-      cin[slot].which = stage_in(ci, in[3], which + b0, Bc);
-      ev_record(ctx->ev_small[slot], ci);
-      cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
-      ev_record(ctx->ev_tape[slot], ci);
-    };
-    ev_record(ctx->ev_done[0], st);      // the ring / Lagrange launches above precede every copy stream
-    ev_wait(ctx->cs_in, ctx->ev_done[0]);
-    ev_wait(ctx->cs_out, ctx->ev_done[0]);
-    issue_inputs(0);
-    for (uint32_t k = 0; k < nchunks; k++) {
-      const uint32_t b0 = k * chunk;
-      const int slot = (int)(k & 1);
-      const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
-      if (k + 1 < nchunks) issue_inputs(k + 1);
-      ev_wait(st, ctx->ev_small[slot]);
-      ev_wait(st, ctx->ev_out[slot]);    // the proofs of chunk k-2 have left the output staging buffers
-      ProveCtx c;
-      memset(&c, 0, sizeof(c));
-      c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.M = 0;
-      c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
-      c.msg_hash = cin[slot].msg_hash;
-      c.sig = cin[slot].sig;
-      c.pk = cin[slot].pk;
-      c.which = cin[slot].which;
-      c.tape = cin[slot].tape;
-      c.tape_stride = tape_stride;
-      c.tape_draws = (uint32_t)(tape_stride / 32);
-      c.ring_m = ring_m;
-      c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
-      c.g_tabw = ctx->gw.tab; c.g_w = ctx->p256_hw;
-      c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
-      c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
-      const size_t S1 = (size_t)S + 1;
-      const size_t nA = (size_t)Bc * S1;
-      const size_t n1 = (size_t)Bc * (2 + 2 * S);
-      c.s1 = W[0].get<uint32_t>((size_t)Bc * 8);
-      c.pk_aff = W[1].get<uint32_t>((size_t)Bc * 16);
-      c.q_aff = W[2].get<uint32_t>((size_t)Bc * 16);
-      c.q_inf = W[3].get<uint8_t>(Bc);
-      c.r_aff = W[4].get<uint32_t>((size_t)Bc * 16);
-      c.r_bytes = W[5].get<uint8_t>((size_t)Bc * BSTRIDE);
-      c.rpows = W[6].get<uint32_t>((size_t)Bc * RT_NWIN * P256_PROJ_WORDS);
-      c.rrows = W[7].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_PROJ_WORDS);
-      c.rtab = W[8].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_AFF_WORDS);
-      c.pa_T = W[9].get<uint32_t>(nA * P256_PROJ_WORDS);
-      c.pa_A = W[10].get<uint32_t>(nA * P256_PROJ_WORDS);
-      c.pa_T_aff = W[11].get<uint32_t>(nA * 16);
-      c.pa_T_inf = W[12].get<uint8_t>(nA);
-      c.pa_A_aff = W[13].get<uint32_t>(nA * 16);
-      c.pa_A_bytes = W[14].get<uint8_t>(nA * BSTRIDE);
-      c.pa_A_inf = W[15].get<uint8_t>(nA);
-      c.s1_jv = W[16].get<uint32_t>(n1 * 8);
-      c.s1_jr = W[17].get<uint32_t>(n1 * 8);
-      c.s1_proj = W[18].get<uint32_t>(n1 * TOM_PROJ_WORDS);
-      c.s1_aff = W[19].get<uint32_t>(n1 * TOM_AFF_WORDS);
-      c.s1_bytes = W[20].get<uint8_t>(n1 * BSTRIDE);
-      c.chal = W[21].get<uint32_t>((size_t)Bc * 3);
-      c.zcount = W[22].get<uint32_t>(Bc);
-      c.item_base = W[23].get<uint32_t>(Bc);
-      c.item_total = W[24].get<uint32_t>(2);
-      c.rep_off = W[25].get<uint32_t>((size_t)Bc * S);
-      c.gk_off = W[26].get<uint32_t>(Bc);
-      c.gk_dv = W[27].get<uint32_t>((size_t)Bc * n * 8);
-      c.gk_lag = lag;
-      c.gk_x = W[28].get<uint32_t>((size_t)Bc * 3);
-      c.u12 = W[46].get<uint32_t>((size_t)Bc * 16);
-      c.tab_of = W[48].get<uint32_t>(Bc);
-      c.tab_rep = W[49].get<uint32_t>((size_t)Bc * 2);
-      c.tab_count = W[50].get<uint32_t>(1);
-      c.which_s = W[52].get<uint32_t>(Bc);
-      c.proof_stride = proof_stride;
-      DevBuf* ob = ctx->out + 3 * slot;
-      c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ob[0].get<uint8_t>((size_t)Bc * proof_stride);
-      c.proof_len = len_dev ? proof_len_out + b0 : ob[1].get<uint32_t>(Bc);
-      c.status = st_dev ? status + b0 : ob[2].get<int32_t>(Bc);
-
-      // --- statement + per-proof tables of pk, then R = u1*G + u2*pk on the tables
-      launch(st, Bc, PreKeyTask{c});
-      // one table per DISTINCT key of the chunk (grids are sized for Bc tables, surplus threads return)
-      launch(st, Bc, KeyDedupTask{c});
-      launch(st, Bc, KeyRankTask{c});
-      launch(st, Bc, KeyAssignTask{c});
-      {
-        const int Bp = (Bc + 31) & ~31;
-        launch(st, (long long)Bp + Bc,
-               PowsAndPreTask{P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count}, PreTask{c}, Bp});
-      }
-      launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows, c.tab_count});
-      {
-        const long long np = (long long)Bc * RT_ENTRIES;
-        const int ch = norm_chunk_for(np, 5);
-        launch(st, (np + ch - 1) / ch, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np, ch, c.tab_count, RT_ENTRIES});
-      }
-      // --- phase A (first consumer of the tape) and R = u1*G + u2*pk side by side
-      ev_wait(st, ctx->ev_tape[slot]);
-      {
-        const int nAp = (int)((nA + 31) & ~(size_t)31);
-        launch(st, (long long)nAp + Bc, PhaseAAndRPointTask{PhaseAP256Task{c}, RPointTask{c}, (int)nA, nAp});
-      }
-      launch_p256_norm(st, c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (long long)(nA));
-      launch_p256_norm(st, c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (long long)(nA));
-      launch(st, (long long)n1, JobsATask{c});
-      launch(st, (long long)n1, TomCommitTask{c.s1_jv, c.s1_jr, c.tg_tab, c.th_tab, c.s1_proj, c.tom_w, c.tom_nwin});
-      launch_tom_norm(st, c.s1_proj, c.s1_aff, c.s1_bytes, (long long)(n1), 1);
-      // --- challenge, layout
-      launch(st, Bc, ExpChallengeTask{c});
-      launch(st, 1, ScanTask{c});
-      uint32_t tot2[2] = {0, 0};
-      copy_d2h(st, tot2, c.item_total, 8);
-      sync(st);
-      const uint32_t M = tot2[0];
-      const size_t max_len = (size_t)proof_len((int)tot2[1], n, S);
-      c.M = (int)M;
-      c.item_b = W[29].get<uint32_t>(M);
-      c.item_i = W[30].get<uint32_t>(M);
-      c.item_k = W[31].get<uint32_t>(M);
-      c.pb_T1 = W[32].get<uint32_t>((size_t)M * P256_PROJ_WORDS);
-      c.pb_T1_aff = W[33].get<uint32_t>((size_t)M * 16);
-      c.pb_T1_inf = W[34].get<uint8_t>(M);
-      const size_t n2 = c.s2_count();
-      c.s2_jv = W[35].get<uint32_t>(n2 * 8);
-      c.s2_jr = W[36].get<uint32_t>(n2 * 8);
-      c.s2_proj = W[37].get<uint32_t>(n2 * TOM_PROJ_WORDS);
-      c.s2_aff = W[38].get<uint32_t>(n2 * TOM_AFF_WORDS);
-      c.s2_bytes = W[39].get<uint8_t>(n2 * BSTRIDE);
-      c.secrets = W[42].get<uint32_t>((size_t)M * SECRETS_PER_ITEM * 8);
-      c.item_inv = W[47].get<uint32_t>((size_t)M * 8);
-      c.item_chal = W[43].get<uint32_t>((size_t)M * HASHES_PER_ITEM * 3);
-      launch(st, Bc, ItemsTask{c});
-      // --- phase B
-      launch(st, M, PhaseBP256Task{c});
-      launch_p256_norm(st, c.pb_T1, c.pb_T1_aff, nullptr, c.pb_T1_inf, (long long)(M));
-      launch(st, ((long long)M + ITEM_INV_CHUNK - 1) / ITEM_INV_CHUNK, ItemInvTask{c});
-      launch(st, M, ItemScalarsTask{c});
-      launch(st, (long long)Bc * n, GkJobsTask{c});
-      {
-        const int nblk = 1 << (n - gk_block_bits(n));
-        c.gk_part = nblk > 1 ? W[51].get<uint32_t>((size_t)Bc * n * nblk * 8) : nullptr;
-        launch(st, (long long)Bc * n * nblk, GkPolyTask{c});
-        if (nblk > 1) launch(st, (long long)Bc * n, GkPolyReduceTask{c});
-      }
-      launch(st, (long long)Bc * n, GkCdJobsTask{c});
-      {
-        const size_t nj = (size_t)M * JOBS_PER_ITEM, nd = (size_t)M * DERS_PER_ITEM, ng = (size_t)Bc * 4 * n;
-        const size_t g0 = nj + nd;
-        // item jobs: g-parts once per distinct committed value, then r*h on top (TomCommitG/HTask)
-        uint32_t* gext = W[45].get<uint32_t>((size_t)M * GJOBS_PER_ITEM * TOM_EXT_WORDS);
-        launch(st, (long long)M * GJOBS_PER_ITEM, TomCommitGTask{c.s2_jv, c.tg_tab, gext, c.tom_w, c.tom_nwin});
-        launch(st, (long long)nj, TomCommitHTask{c.s2_jr, c.th_tab, gext, c.s2_proj, c.tom_w, c.tom_nwin});
-        launch(st, (long long)ng, TomCommitTask{c.s2_jv + g0 * 8, c.s2_jr + g0 * 8, c.tg_tab, c.th_tab,
-                                                 c.s2_proj + g0 * TOM_PROJ_WORDS, c.tom_w, c.tom_nwin});
-        // only T1x, T1y (jobs 0, 1 of each item) are needed again as points (DerivedTask)
-        launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)(nj), 1, JOBS_PER_ITEM, 2);
-        launch(st, M, DerivedTask{c});
-        // derived points come from complete E1 additions, the GK commitments from the commit kernel (E2)
-        launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, nullptr, c.s2_bytes + nj * BSTRIDE, (long long)nd, 0);
-        launch_tom_norm(st, c.s2_proj + g0 * TOM_PROJ_WORDS, nullptr, c.s2_bytes + g0 * BSTRIDE, (long long)ng, 1);
-      }
-      launch(st, (long long)M * HASHES_PER_ITEM, ItemHashTask{c});
-      launch(st, (long long)M * 7, ItemEmitTask{c});
-      launch(st, (long long)nA, RepEmitTask{c});
-      launch(st, Bc, GkEmitTask{c});
-      launch(st, (long long)Bc * FIN_PARTS, FinalizeTask{c});
-      // --- results: on the output stream, behind this chunk's last kernel
-      ev_record(ctx->ev_done[slot], st);
-      if (!out_dev || !len_dev || !st_dev) {
-        Stream& co = ctx->cs_out;
-        ev_wait(co, ctx->ev_done[slot]);
-        // only the bytes up to the longest proof of the chunk are copied back (rows are stride-padded)
-        if (!out_dev) copy_d2h_2d(co, proofs + (size_t)b0 * proof_stride, proof_stride, c.proofs, proof_stride, max_len, Bc);
-        if (!len_dev) copy_d2h(co, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
-        if (!st_dev) copy_d2h(co, status + b0, c.status, (size_t)Bc * 4);
-        ev_record(ctx->ev_out[slot], co);
-      }
+    // chunk size: the configured one, but never so large that a lane stays idle (at least `lanes` chunks when
+    // the batch allows chunks of >= 256 proofs); rounded up to a multiple of 32
+    const int lanes = ctx->nlanes;
+    uint32_t chunk = (uint32_t)((out_dev && is_device_ptr(tape)) ? ctx->chunk : std::min(ctx->chunk, ctx->host_chunk));
+    if (lanes > 1) {
+      uint32_t per = (B + (uint32_t)lanes - 1) / (uint32_t)lanes;
+      per = std::max<uint32_t>((per + 31) & ~31u, 256);
+      chunk = std::min(chunk, per);
     }
-    sync(ctx->cs_in);
-    sync(ctx->cs_out);
-    sync(st);
+    const uint32_t nchunks = (B + chunk - 1) / chunk;
+    const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
+    // lane `li` processes chunks li, li + used, li + 2 used, ...  Within a lane, chunks are software-pipelined over
+    // three streams when buffers live in host memory (staging buffers double-buffered by slot).
+    auto run_lane = [&](int li) {
+      Lane& ln = ctx->lane(li);
+      Stream& st = ln.st;
+      DevBuf* W = ln.w;
+      struct ChunkIn { const uint8_t *msg_hash, *sig, *pk, *tape; const uint32_t* which; } cin[2];
+      auto slot_of = [&](uint32_t k) { return (int)(((k - (uint32_t)li) / (uint32_t)used) & 1u); };
+      auto issue_inputs = [&](uint32_t k) {
+        const int slot = slot_of(k);
+        const uint32_t b0 = k * chunk;
+        const size_t Bc = std::min<uint32_t>(chunk, B - b0);
+        Stream& ci = ln.cs_in;
+        DevBuf* in = ln.in + 5 * slot;
+        ev_wait(ci, ln.ev_done[slot]);   // the chunk that used these staging buffers before has finished reading them
+        cin[slot].msg_hash = stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32);
+        cin[slot].sig = stage_in(ci, in[1], sig + (size_t)b0 * 64, Bc * 64);
+        cin[slot].pk = stage_in(ci, in[2], pk + (size_t)b0 * 65, Bc * 65);
+        cin[slot].which = stage_in(ci, in[3], which + b0, Bc);
+        ev_record(ln.ev_small[slot], ci);
+        cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
+        ev_record(ln.ev_tape[slot], ci);
+      };
+      issue_inputs((uint32_t)li);
+      for (uint32_t k = (uint32_t)li; k < nchunks; k += (uint32_t)used) {
+        const uint32_t b0 = k * chunk;
+        const int slot = slot_of(k);
+        const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
+        if (k + (uint32_t)used < nchunks) issue_inputs(k + (uint32_t)used);
+        ev_wait(st, ln.ev_small[slot]);
+        ev_wait(st, ln.ev_out[slot]);    // the proofs of chunk k-2 have left the output staging buffers
+        ProveCtx c;
+        memset(&c, 0, sizeof(c));
+        c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.M = 0;
+        c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
+        c.msg_hash = cin[slot].msg_hash;
+        c.sig = cin[slot].sig;
+        c.pk = cin[slot].pk;
+        c.which = cin[slot].which;
+        c.tape = cin[slot].tape;
+        c.tape_stride = tape_stride;
+        c.tape_draws = (uint32_t)(tape_stride / 32);
+        c.ring_m = ring_m;
+        c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
+        c.g_tabw = ctx->gw.tab; c.g_w = ctx->p256_hw;
+        c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
+        c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
+        const size_t S1 = (size_t)S + 1;
+        const size_t nA = (size_t)Bc * S1;
+        const size_t n1 = (size_t)Bc * (2 + 2 * S);
+        c.s1 = W[0].get<uint32_t>((size_t)Bc * 8);
+        c.pk_aff = W[1].get<uint32_t>((size_t)Bc * 16);
+        c.q_aff = W[2].get<uint32_t>((size_t)Bc * 16);
+        c.q_inf = W[3].get<uint8_t>(Bc);
+        c.r_aff = W[4].get<uint32_t>((size_t)Bc * 16);
+        c.r_bytes = W[5].get<uint8_t>((size_t)Bc * BSTRIDE);
+        c.rpows = W[6].get<uint32_t>((size_t)Bc * RT_NWIN * P256_PROJ_WORDS);
+        c.rrows = W[7].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_PROJ_WORDS);
+        c.rtab = W[8].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_AFF_WORDS);
+        c.pa_T = W[9].get<uint32_t>(nA * P256_PROJ_WORDS);
+        c.pa_A = W[10].get<uint32_t>(nA * P256_PROJ_WORDS);
+        c.pa_T_aff = W[11].get<uint32_t>(nA * 16);
+        c.pa_T_inf = W[12].get<uint8_t>(nA);
+        c.pa_A_aff = W[13].get<uint32_t>(nA * 16);
+        c.pa_A_bytes = W[14].get<uint8_t>(nA * BSTRIDE);
+        c.pa_A_inf = W[15].get<uint8_t>(nA);
+        c.s1_jv = W[16].get<uint32_t>(n1 * 8);
+        c.s1_jr = W[17].get<uint32_t>(n1 * 8);
+        c.s1_proj = W[18].get<uint32_t>(n1 * TOM_PROJ_WORDS);
+        c.s1_aff = W[19].get<uint32_t>(n1 * TOM_AFF_WORDS);
+        c.s1_bytes = W[20].get<uint8_t>(n1 * BSTRIDE);
+        c.chal = W[21].get<uint32_t>((size_t)Bc * 3);
+        c.zcount = W[22].get<uint32_t>(Bc);
+        c.item_base = W[23].get<uint32_t>(Bc);
+        c.item_total = W[24].get<uint32_t>(2);
+        c.rep_off = W[25].get<uint32_t>((size_t)Bc * S);
+        c.gk_off = W[26].get<uint32_t>(Bc);
+        c.gk_dv = W[27].get<uint32_t>((size_t)Bc * n * 8);
+        c.gk_lag = lag;
+        c.gk_x = W[28].get<uint32_t>((size_t)Bc * 3);
+        c.u12 = W[46].get<uint32_t>((size_t)Bc * 16);
+        c.tab_of = W[48].get<uint32_t>(Bc);
+        c.tab_rep = W[49].get<uint32_t>((size_t)Bc * 2);
+        c.tab_count = W[50].get<uint32_t>(1);
+        c.which_s = W[52].get<uint32_t>(Bc);
+        c.proof_stride = proof_stride;
+        DevBuf* ob = ln.out + 3 * slot;
+        c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ob[0].get<uint8_t>((size_t)Bc * proof_stride);
+        c.proof_len = len_dev ? proof_len_out + b0 : ob[1].get<uint32_t>(Bc);
+        c.status = st_dev ? status + b0 : ob[2].get<int32_t>(Bc);
+  
+        // --- statement + per-proof tables of pk, then R = u1*G + u2*pk on the tables
+        launch(st, Bc, PreKeyTask{c});
+        // one table per DISTINCT key of the chunk (grids are sized for Bc tables, surplus threads return)
+        launch(st, Bc, KeyDedupTask{c});
+        launch(st, Bc, KeyRankTask{c});
+        launch(st, Bc, KeyAssignTask{c});
+        {
+          const int Bp = (Bc + 31) & ~31;
+          launch(st, (long long)Bp + Bc,
+                 PowsAndPreTask{P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count}, PreTask{c}, Bp});
+        }
+        launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows, c.tab_count});
+        {
+          const long long np = (long long)Bc * RT_ENTRIES;
+          const int ch = norm_chunk_for(np, 5);
+          launch(st, (np + ch - 1) / ch, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np, ch, c.tab_count, RT_ENTRIES});
+        }
+        // --- phase A (first consumer of the tape) and R = u1*G + u2*pk side by side
+        ev_wait(st, ln.ev_tape[slot]);
+        {
+          const int nAp = (int)((nA + 31) & ~(size_t)31);
+          launch(st, (long long)nAp + Bc, PhaseAAndRPointTask{PhaseAP256Task{c}, RPointTask{c}, (int)nA, nAp});
+        }
+        launch_p256_norm(st, c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (long long)(nA));
+        launch_p256_norm(st, c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (long long)(nA));
+        launch(st, (long long)n1, JobsATask{c});
+        launch(st, (long long)n1, TomCommitTask{c.s1_jv, c.s1_jr, c.tg_tab, c.th_tab, c.s1_proj, c.tom_w, c.tom_nwin});
+        launch_tom_norm(st, c.s1_proj, c.s1_aff, c.s1_bytes, (long long)(n1), 1);
+        // --- challenge, layout
+        launch(st, Bc, ExpChallengeTask{c});
+        launch(st, 1, ScanTask{c});
+        uint32_t tot2[2] = {0, 0};
+        copy_d2h(st, tot2, c.item_total, 8);
+        sync(st);
+        const uint32_t M = tot2[0];
+        const size_t max_len = (size_t)proof_len((int)tot2[1], n, S);
+        c.M = (int)M;
+        c.item_b = W[29].get<uint32_t>(M);
+        c.item_i = W[30].get<uint32_t>(M);
+        c.item_k = W[31].get<uint32_t>(M);
+        c.pb_T1 = W[32].get<uint32_t>((size_t)M * P256_PROJ_WORDS);
+        c.pb_T1_aff = W[33].get<uint32_t>((size_t)M * 16);
+        c.pb_T1_inf = W[34].get<uint8_t>(M);
+        const size_t n2 = c.s2_count();
+        c.s2_jv = W[35].get<uint32_t>(n2 * 8);
+        c.s2_jr = W[36].get<uint32_t>(n2 * 8);
+        c.s2_proj = W[37].get<uint32_t>(n2 * TOM_PROJ_WORDS);
+        c.s2_aff = W[38].get<uint32_t>(n2 * TOM_AFF_WORDS);
+        c.s2_bytes = W[39].get<uint8_t>(n2 * BSTRIDE);
+        c.secrets = W[42].get<uint32_t>((size_t)M * SECRETS_PER_ITEM * 8);
+        c.item_inv = W[47].get<uint32_t>((size_t)M * 8);
+        c.item_chal = W[43].get<uint32_t>((size_t)M * HASHES_PER_ITEM * 3);
+        launch(st, Bc, ItemsTask{c});
+        // --- phase B
+        launch(st, M, PhaseBP256Task{c});
+        launch_p256_norm(st, c.pb_T1, c.pb_T1_aff, nullptr, c.pb_T1_inf, (long long)(M));
+        launch(st, ((long long)M + ITEM_INV_CHUNK - 1) / ITEM_INV_CHUNK, ItemInvTask{c});
+        launch(st, M, ItemScalarsTask{c});
+        launch(st, (long long)Bc * n, GkJobsTask{c});
+        {
+          const int nblk = 1 << (n - gk_block_bits(n));
+          c.gk_part = nblk > 1 ? W[51].get<uint32_t>((size_t)Bc * n * nblk * 8) : nullptr;
+          launch(st, (long long)Bc * n * nblk, GkPolyTask{c});
+          if (nblk > 1) launch(st, (long long)Bc * n, GkPolyReduceTask{c});
+        }
+        launch(st, (long long)Bc * n, GkCdJobsTask{c});
+        {
+          const size_t nj = (size_t)M * JOBS_PER_ITEM, nd = (size_t)M * DERS_PER_ITEM, ng = (size_t)Bc * 4 * n;
+          const size_t g0 = nj + nd;
+          // item jobs: g-parts once per distinct committed value, then r*h on top (TomCommitG/HTask)
+          uint32_t* gext = W[45].get<uint32_t>((size_t)M * GJOBS_PER_ITEM * TOM_EXT_WORDS);
+          launch(st, (long long)M * GJOBS_PER_ITEM, TomCommitGTask{c.s2_jv, c.tg_tab, gext, c.tom_w, c.tom_nwin});
+          launch(st, (long long)nj, TomCommitHTask{c.s2_jr, c.th_tab, gext, c.s2_proj, c.tom_w, c.tom_nwin});
+          launch(st, (long long)ng, TomCommitTask{c.s2_jv + g0 * 8, c.s2_jr + g0 * 8, c.tg_tab, c.th_tab,
+                                                   c.s2_proj + g0 * TOM_PROJ_WORDS, c.tom_w, c.tom_nwin});
+          // only T1x, T1y (jobs 0, 1 of each item) are needed again as points (DerivedTask)
+          launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)(nj), 1, JOBS_PER_ITEM, 2);
+          launch(st, M, DerivedTask{c});
+          // derived points come from complete E1 additions, the GK commitments from the commit kernel (E2)
+          launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, nullptr, c.s2_bytes + nj * BSTRIDE, (long long)nd, 0);
+          launch_tom_norm(st, c.s2_proj + g0 * TOM_PROJ_WORDS, nullptr, c.s2_bytes + g0 * BSTRIDE, (long long)ng, 1);
+        }
+        launch(st, (long long)M * HASHES_PER_ITEM, ItemHashTask{c});
+        launch(st, (long long)M * 7, ItemEmitTask{c});
+        launch(st, (long long)nA, RepEmitTask{c});
+        launch(st, Bc, GkEmitTask{c});
+        launch(st, (long long)Bc * FIN_PARTS, FinalizeTask{c});
+        // --- results: on the output stream, behind this chunk's last kernel
+        ev_record(ln.ev_done[slot], st);
+        if (!out_dev || !len_dev || !st_dev) {
+          Stream& co = ln.cs_out;
+          ev_wait(co, ln.ev_done[slot]);
+          // only the bytes up to the longest proof of the chunk are copied back (rows are stride-padded)
+          if (!out_dev) copy_d2h_2d(co, proofs + (size_t)b0 * proof_stride, proof_stride, c.proofs, proof_stride, max_len, Bc);
+          if (!len_dev) copy_d2h(co, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
+          if (!st_dev) copy_d2h(co, status + b0, c.status, (size_t)Bc * 4);
+          ev_record(ln.ev_out[slot], co);
+        }
+      }
+      sync(ln.cs_in);
+      sync(ln.cs_out);
+      sync(st);
+    };
+    run_lanes(ctx, used, run_lane);
     return 0;
   } catch (const std::exception& e) {
     return fail(ctx, ZKA_E_CUDA, e.what());
@@ -988,23 +1156,41 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
   const int n = ceil_log2(N);
   if (tape_stride < verify_tape_len(n, S)) return fail(ctx, ZKA_E_ARG, "tape_stride < zka_verify_tape_len");
   try {
-    Stream& st = ctx->st;
-    DevBuf* W = ctx->w;
-    const uint8_t* d_ring = stage_in(ctx, ctx->in[10], ring, (size_t)N * 32);
-    uint32_t* ring_m = W[40].get<uint32_t>(((size_t)1 << n) * 8);
-    launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
-    const int vchunk = std::min(ctx->chunk, 4096);
-    for (uint32_t b0 = 0; b0 < B; b0 += (uint32_t)vchunk) {
+    {
+      Stream& st0 = ctx->st;
+      const uint8_t* d_ring = stage_in(st0, ctx->ring_in, ring, (size_t)N * 32);
+      uint32_t* rm = ctx->ring_m.get<uint32_t>(((size_t)1 << n) * 8);
+      launch(st0, 1ll << n, RingPrepTask{d_ring, rm, (int)N});
+      sync(st0);
+    }
+    const uint32_t* ring_m = (const uint32_t*)ctx->ring_m.p;
+    const int lanes = ctx->nlanes;
+    uint32_t vchunk = (uint32_t)std::min(ctx->chunk, 4096);
+    if (lanes > 1) {
+      uint32_t per = (B + (uint32_t)lanes - 1) / (uint32_t)lanes;
+      per = std::max<uint32_t>((per + 31) & ~31u, 256);
+      vchunk = std::min(vchunk, per);
+    }
+    const uint32_t nchunks = (B + vchunk - 1) / vchunk;
+    const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
+    // lane li verifies chunks li, li + used, ...: copy-in, kernels and copy-out of a chunk are sequential on the
+    // lane's stream; the copies of one lane overlap the kernels of the others
+    auto run_lane = [&](int li) {
+      Lane& ln = ctx->lane(li);
+      Stream& st = ln.st;
+      DevBuf* W = ln.w;
+      for (uint32_t k = (uint32_t)li; k < nchunks; k += (uint32_t)used) {
+      const uint32_t b0 = k * vchunk;
       const int Bc = (int)std::min<uint32_t>((uint32_t)vchunk, B - b0);
       VerifyCtx c;
       memset(&c, 0, sizeof(c));
       c.B = Bc; c.S = S; c.N = (int)N; c.n = n;
       c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
-      c.msg_hash = stage_in(ctx, ctx->in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
-      c.proofs = stage_in(ctx, ctx->in[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
+      c.msg_hash = stage_in(st, ln.in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
+      c.proofs = stage_in(st, ln.in[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
       c.proof_stride = proof_stride;
-      c.proof_len = stage_in(ctx, ctx->in[2], proof_len + b0, (size_t)Bc);
-      c.tape = stage_in(ctx, ctx->in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      c.proof_len = stage_in(st, ln.in[2], proof_len + b0, (size_t)Bc);
+      c.tape = stage_in(st, ln.in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
       c.tape_stride = tape_stride;
       c.ring_m = ring_m;
       c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
@@ -1055,8 +1241,8 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.win_g = W[42].get<uint32_t>((size_t)Bc * MSM_NWIN * 36);
       c.win_n = W[43].get<uint32_t>((size_t)Bc * MSM_NWIN_N * P256_PROJ_WORDS);
       c.id_flags = W[44].get<uint8_t>((size_t)Bc * 3);
-      c.ok = is_device_ptr(ok) ? ok + b0 : ctx->out[0].get<uint8_t>(Bc);
-      c.status = is_device_ptr(status) ? status + b0 : ctx->out[1].get<int32_t>(Bc);
+      c.ok = is_device_ptr(ok) ? ok + b0 : ln.out[0].get<uint8_t>(Bc);
+      c.status = is_device_ptr(status) ? status + b0 : ln.out[1].get<int32_t>(Bc);
 
       launch(st, Bc, VLayoutTask{c});
       launch(st, (long long)Bc * (S + 1), VValidateTask{c});
@@ -1106,10 +1292,50 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
       sync(st);
     }
+    };
+    run_lanes(ctx, used, run_lane);
     return 0;
   } catch (const std::exception& e) {
     return fail(ctx, ZKA_E_CUDA, e.what());
   }
+}
+
+// ---------------------------------------------------------------------------- multi-GPU helpers
+namespace {
+int pack_common(zka_ctx* ctx, uint32_t B, uint8_t* rows, size_t stride, const uint32_t* len, uint8_t* packed, size_t cap,
+                uint64_t* offsets, void* stream, int dir) {
+  if (!ctx || !rows || !len || !packed || !offsets || stride == 0) return ZKA_E_ARG;
+  if (B == 0) return 0;
+#if !defined(ZKA_HOSTSIM)
+  if (!is_device_ptr(rows) || !is_device_ptr(len) || !is_device_ptr(packed) || !is_device_ptr(offsets))
+    return fail(ctx, ZKA_E_ARG, "zka_proofs_pack/unpack take device pointers");
+#endif
+  try {
+    Stream tmp;          // borrowed stream (not owned, never destroyed here); launch counters go to lane 0
+    Stream* st = &ctx->st;
+#if !defined(ZKA_HOSTSIM)
+    if (stream) { tmp.s = (cudaStream_t)stream; st = &tmp; }
+#endif
+    const int pieces = (int)((stride + 15) / 16);
+    launch(*st, 1, PackScanTask{len, offsets, (int)B});
+    const bool al = (stride % 16 == 0) && (((size_t)rows | (size_t)packed) % 16 == 0);
+    if (al) launch(*st, (long long)B * pieces, PackCopy16Task{rows, stride, len, offsets, packed, cap, pieces, dir});
+    else launch(*st, (long long)B * pieces, PackCopyTask{rows, stride, len, offsets, packed, cap, pieces, dir});
+    if (st == &tmp) ctx->st.launches += tmp.launches; else sync(*st);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+}  // namespace
+
+int zka_proofs_pack(zka_ctx* ctx, uint32_t B, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
+                    uint8_t* packed, size_t cap, uint64_t* offsets, void* stream) {
+  return pack_common(ctx, B, const_cast<uint8_t*>(proofs), proof_stride, proof_len, packed, cap, offsets, stream, 0);
+}
+int zka_proofs_unpack(zka_ctx* ctx, uint32_t B, const uint8_t* packed, size_t cap, const uint32_t* proof_len, uint8_t* proofs,
+                      size_t proof_stride, uint64_t* offsets, void* stream) {
+  return pack_common(ctx, B, proofs, proof_stride, proof_len, const_cast<uint8_t*>(packed), cap, offsets, stream, 1);
 }
 
 }  // extern "C"

@@ -44,3 +44,152 @@ def all_gather_proofs(local_proofs, local_len, world: int, rank: int, per_rank: 
         return out, lens
     dist.all_gather_into_tensor(out, send.contiguous())
     return out, lens
+
+
+# ----------------------------------------------------------------------------------------------------
+# Overlapped, compacted all-gather (round 2).  A rank's batch is proved in `groups` sub-batches; as soon as
+# one is finished its proofs are packed to their true lengths (zka_proofs_pack, 16-byte aligned starts) and
+# their all-gather is queued on a communication stream, so the transfer of group g overlaps the proving of
+# group g + 1.  No host synchronisation sizes anything: every group's send block has a fixed capacity
+# (rows x the length of a proof with `Z_BOUND` zero challenge bits — the mean is SecLevel / 2 — or the worst
+# case for small groups); the true block lengths travel in offsets[] and are checked after the step.
+Z_BOUND_SIGMAS = 12
+
+
+def _proof_len(z: int, n: int, reps: int) -> int:
+    gk = 1 + 4 * n * 67 + (3 * n + 1) * 33
+    return 264 + z * 3596 + (reps - z) * 330 + gk
+
+
+def group_capacity(rows: int, ring_size: int, sec_level: int) -> int:
+    """Bytes reserved for the packed proofs of `rows` proofs: mean + 12 sigma of the sum of their lengths
+    (zero bits are Binomial(sec_level, 1/2) per proof), never more than the worst case; 256-byte aligned."""
+    n = max(1, (ring_size - 1).bit_length())
+    worst = rows * ((_proof_len(sec_level, n, sec_level) + 15) & ~15)
+    mean = rows * (_proof_len(0, n, sec_level) + 15) + rows * (sec_level / 2) * (3596 - 330)
+    sigma = (rows * sec_level / 4) ** 0.5 * (3596 - 330)
+    return (min(worst, int(mean + Z_BOUND_SIGMAS * sigma) + 4096) + 255) & ~255
+
+
+class ProofGather:
+    def __init__(self, lib, world: int, rank: int, B: int, stride: int, ring_size: int, sec_level: int, device, groups: int = 4):
+        import torch
+        self.lib, self.world, self.rank, self.B, self.stride = lib, world, rank, B, stride
+        groups = max(1, min(groups, B))
+        per = -(-B // groups)
+        self.ranges = [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
+        self.rows = per
+        self.cap = group_capacity(per, ring_size, sec_level)
+        G = len(self.ranges)
+        self.dev = device
+        self.send = [torch.zeros(self.cap, dtype=torch.uint8, device=device) for _ in range(G)]
+        self.recv = [torch.zeros(world * self.cap, dtype=torch.uint8, device=device) for _ in range(G)]
+        self.lens = [torch.zeros(per, dtype=torch.int32, device=device) for _ in range(G)]
+        self.lens_all = [torch.zeros(world * per, dtype=torch.int32, device=device) for _ in range(G)]
+        self.offs = [torch.zeros(per + 1, dtype=torch.int64, device=device) for _ in range(G)]
+        self.cuda = device.type == 'cuda'
+        self.comm = torch.cuda.Stream(device=device) if self.cuda else None
+        self.works = []
+        self.g = 0
+        self.exposed_ms = []
+
+    def describe(self) -> str:
+        return (f'{len(self.ranges)} groups per rank; per group one NCCL all-gather of the proofs packed to their true lengths '
+                f'(capacity {self.cap} B per rank per group) + one of their lengths, queued on a communication stream while the '
+                'next group is proved; no host synchronisation sizes the transfer')
+
+    def begin(self):
+        self.works = []
+        self.g = 0
+
+    def submit(self, proofs, plen, b0: int, b1: int):
+        """Queue the all-gather of rows [b0, b1) (already complete on the device)."""
+        import torch
+        import torch.distributed as dist
+        g = self.g
+        self.g += 1
+        rows = b1 - b0
+        ctx = torch.cuda.stream(self.comm) if self.cuda else _Null()
+        with ctx:
+            self.lens[g].zero_()
+            self.lens[g][:rows].copy_(plen[b0:b1])
+            self.lib.proofs_pack(self.rows, proofs[b0:].data_ptr(), self.stride, self.lens[g].data_ptr(), self.send[g].data_ptr(),
+                                 self.cap, self.offs[g].data_ptr(), self.comm.cuda_stream if self.cuda else 0)
+            if self.world > 1:
+                self.works.append(dist.all_gather_into_tensor(self.lens_all[g], self.lens[g], async_op=True))
+                self.works.append(dist.all_gather_into_tensor(self.recv[g], self.send[g], async_op=True))
+            else:
+                self.lens_all[g].copy_(self.lens[g])
+                self.recv[g].copy_(self.send[g])
+
+    def finish(self):
+        import time
+        import torch
+        t0 = time.perf_counter()
+        for w in self.works:
+            w.wait()
+        if self.cuda:
+            self.comm.synchronize()
+            torch.cuda.current_stream().synchronize()
+        self.exposed_ms.append((time.perf_counter() - t0) * 1e3)
+
+    def totals(self, g: int):
+        """Packed block length of every rank for group g (from the gathered lengths)."""
+        import torch
+        l = self.lens_all[g].view(self.world, self.rows).to(torch.int64)
+        return ((l + 15) & ~15).sum(dim=1)
+
+    def unpack(self, g: int, r: int):
+        """Rows [rows, stride] of rank r's group g from the gathered block (zka_proofs_unpack)."""
+        import torch
+        out = torch.zeros((self.rows, self.stride), dtype=torch.uint8, device=self.dev)
+        offs = torch.zeros(self.rows + 1, dtype=torch.int64, device=self.dev)
+        lens = self.lens_all[g][r * self.rows:(r + 1) * self.rows].contiguous()
+        self.lib.proofs_unpack(self.rows, self.recv[g][r * self.cap:].data_ptr(), self.cap, lens.data_ptr(), out.data_ptr(),
+                               self.stride, offs.data_ptr(), 0)
+        return out, lens
+
+    def check(self, proofs, plen):
+        """After a step: no block overflowed its capacity, every rank's block arrived intact on this rank
+        (checksum exchange), and this rank's own rows survive pack -> gather -> unpack bit for bit."""
+        import torch
+        import torch.distributed as dist
+        G = len(self.ranges)
+        info = {'groups': G, 'capacity_bytes': self.cap, 'exposed_ms_per_step': sum(self.exposed_ms) / max(1, len(self.exposed_ms))}
+        local = torch.zeros(G, dtype=torch.int64, device=self.dev)
+        seen = torch.zeros((G, self.world), dtype=torch.int64, device=self.dev)
+        maxfill = 0.0
+        for g in range(G):
+            tot = self.totals(g)
+            assert int(tot.max().item()) <= self.cap, 'packed block exceeded its capacity'
+            maxfill = max(maxfill, float(tot.max().item()) / self.cap)
+            for r in range(self.world):
+                n = int(tot[r].item())
+                blk = self.recv[g][r * self.cap:r * self.cap + n]
+                seen[g, r] = torch.sum(blk.view(torch.int32), dtype=torch.int64) if n else 0
+            n = int(tot[self.rank].item())
+            local[g] = torch.sum(self.send[g][:n].view(torch.int32), dtype=torch.int64) if n else 0
+        allc = torch.zeros(self.world * G, dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            dist.all_gather_into_tensor(allc, local)
+        else:
+            allc.copy_(local)
+        ok = bool(torch.equal(allc.view(self.world, G).t().contiguous(), seen))
+        # own rows back from the gathered block
+        same = True
+        for g, (b0, b1) in enumerate(self.ranges):
+            rows, lens = self.unpack(g, self.rank)
+            k = b1 - b0
+            col = torch.arange(self.stride, device=self.dev).unsqueeze(0)
+            valid = col < plen[b0:b1].unsqueeze(1)
+            same = same and bool(torch.equal(lens[:k], plen[b0:b1])) and bool(((rows[:k] == proofs[b0:b1]) | ~valid).all().item())
+            del col, valid, rows
+        info.update({'checksums_match_all_ranks': ok, 'own_rows_roundtrip': same, 'max_fill': maxfill,
+                     'bytes_received_per_step': int(sum(int(self.totals(g).sum().item()) for g in range(G)))})
+        assert ok and same, info
+        return info
+
+
+class _Null:
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
