@@ -277,9 +277,31 @@ enum { TOM_SQRTA = 0, TOM_INVSQRTA = 1, TOM_D1 = 2, TOM_GX1 = 3, TOM_GY = 4, TOM
 // Used ONLY by the prover's fixed-base commitment kernel (all its points lie in the prime-order
 // subgroup generated by g, where the a = -1 formulas have no exceptional cases; gen_consts.py).
 // Table entry: (v - w, v + w, 2 d2 w v).  Mixed addition "madd-2008-hwcd-3": 7M.
-template <bool kNeedT>
+// Field with the 258-bit multiplier INLINED at every use (no call, no argument marshalling): for loop bodies
+// that contain one mixed addition (7-8 products, ~40 KB of code) and are not unrolled.
+struct TompInl : Tomp {
+  ZK_HD static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__) && !defined(ZKA_NO_PTX_MUL)
+    ptx::tom_mul_body(r, a, b);
+#else
+    Tomp::mul(r, a, b);
+#endif
+  }
+  ZK_HD static void sqr(uint32_t* r, const uint32_t* a) { mul(r, a, a); }
+};
+#if defined(ZKA_COMMIT_INLINE)
+using TompCommit = TompInl;
+#else
+using TompCommit = Tomp;
+#endif
+#if defined(ZKA_MSM_INLINE)
+using TompMsm = TompInl;
+#else
+using TompMsm = Tomp;
+#endif
+
+template <bool kNeedT, class F = Tomp>
 ZK_HD void tom2_madd(TomPt& r, const TomPt& p, const TomPre& q) {   // q.x = v-w, q.y = v+w, q.k = 2 d2 w v
-  using F = Tomp;
   uint32_t A[9], B[9], C[9], D[9], E[9], Fv[9], G[9], H[9];
   F::sub(A, p.y, p.x);
   F::mul(A, A, q.x);
@@ -328,7 +350,17 @@ ZK_HD bool tom_on_curve(const uint32_t* x1, const uint32_t* y) {
   F::mul(r, r, d1);
   F::set_one(one);
   F::add(r, r, one);
-  return F::eq(l, r);
+  // l == r  <=>  (l - r) * 1 / R is 0 or p: one Montgomery product (output < 2p) and two compares instead of
+  // two 14-step canonical-reduction ladders (this test runs once per point of every proof in VValidateTask)
+  uint32_t d[9], o[9];
+  F::sub(d, l, r);               // l + 8p - r, r < 3p
+  zero_n<9>(o);
+  o[0] = 1;
+  F::mul(d, d, o);
+  uint32_t nz = 0, np = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) { nz |= d[i]; np |= d[i] ^ FpTom::p(i); }
+  return nz == 0 || np == 0;
 }
 
 // Hisil et al. 2008 section 3.1 unified addition with a = 1 (edwards.ts:161-183): 9M
@@ -355,9 +387,8 @@ ZK_HD void tom_add(TomPt& r, const TomPt& p, const TomPt& q) {
   F::mul(r.z, Fv, G);
 }
 // mixed addition with a precomputed entry (Z2 = 1, k = d' x2 y2): 7M (+1M for T3)
-template <bool kNeedT>
+template <bool kNeedT, class F = Tomp>
 ZK_HD void tom_madd(TomPt& r, const TomPt& p, const TomPre& q) {
-  using F = Tomp;
   uint32_t A[9], B[9], C[9], E[9], Fv[9], G[9], H[9];
   F::mul(A, p.x, q.x);
   F::mul(B, p.y, q.y);

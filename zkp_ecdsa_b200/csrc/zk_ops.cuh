@@ -654,11 +654,12 @@ struct TomCommitGTask {   // one thread per (item, g-part): K = v*g as an extend
     TomPt acc;
     tom_set_identity(acc);
     const size_t ne = (size_t)1 << w;
+#pragma unroll 1
     for (int j = 0; j < nwin; j++) {
       TomPre q;
       int width = (256 - j * w) < w ? (256 - j * w) : w;
       tom_ld_pre(q, gtab + ((size_t)j * ne + digit_w(v, j * w, width)) * TOM_PRE_WORDS);
-      tom2_madd<true>(acc, acc, q);
+      tom2_madd<true, TompCommit>(acc, acc, q);
     }
     uint32_t* o = ext + (size_t)t * TOM_EXT_WORDS;
     st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.t); st<9>(o + 27, acc.z);
@@ -678,11 +679,12 @@ struct TomCommitHTask {   // one thread per job: C = K + r*h
     const uint32_t* s = ext + ((size_t)item * GJOBS_PER_ITEM + item_gpart_of_job(jb)) * TOM_EXT_WORDS;
     ld<9>(acc.x, s); ld<9>(acc.y, s + 9); ld<9>(acc.t, s + 18); ld<9>(acc.z, s + 27);
     const size_t ne = (size_t)1 << w;
+#pragma unroll 1
     for (int j = 0; j < nwin; j++) {
       TomPre q;
       int width = (256 - j * w) < w ? (256 - j * w) : w;
       tom_ld_pre(q, htab + ((size_t)j * ne + digit_w(r, j * w, width)) * TOM_PRE_WORDS);
-      tom2_madd<true>(acc, acc, q);
+      tom2_madd<true, TompCommit>(acc, acc, q);
     }
     tom_st_xyz(proj + (size_t)t * TOM_PROJ_WORDS, acc.x, acc.y, acc.z);
   }

@@ -969,7 +969,7 @@ struct MsmTomWindowTask {
         Tomp::neg(pt.x, pt.x);
         Tomp::neg(pt.k, pt.k);
       }
-      tom_madd<true>(acc, acc, pt);
+      tom_madd<true, TompMsm>(acc, acc, pt);
     }
     bk_store(S[curd], acc);
     present |= 1ull << curd;

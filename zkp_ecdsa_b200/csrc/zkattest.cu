@@ -1187,7 +1187,18 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.B = Bc; c.S = S; c.N = (int)N; c.n = n;
       c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
       c.msg_hash = stage_in(st, ln.in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
-      c.proofs = stage_in(st, ln.in[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
+      if (is_device_ptr(proofs) || is_device_ptr(proof_len)) {
+        c.proofs = stage_in(st, ln.in[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
+      } else {
+        // host rows: only the bytes up to the longest proof of the chunk cross PCIe (rows are stride-padded;
+        // a length above the stride is rejected by VLayoutTask without reading the row)
+        size_t w = 0;
+        for (int i = 0; i < Bc; i++) w = std::max<size_t>(w, proof_len[b0 + i]);
+        w = std::min(proof_stride, (w + 15) & ~(size_t)15);
+        uint8_t* dp = ln.in[1].get<uint8_t>((size_t)Bc * proof_stride);
+        copy_d2h_2d(st, dp, proof_stride, proofs + (size_t)b0 * proof_stride, proof_stride, w, (size_t)Bc);
+        c.proofs = dp;
+      }
       c.proof_stride = proof_stride;
       c.proof_len = stage_in(st, ln.in[2], proof_len + b0, (size_t)Bc);
       c.tape = stage_in(st, ln.in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
