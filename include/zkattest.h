@@ -122,6 +122,15 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* params, uint32_t B,
                      const uint8_t* tape /* B x tape_stride */, size_t tape_stride,
                      uint8_t* ok /* B */, int32_t* status /* B */);
 
+/* The same with verifyExp's `secparam` (exp.ts:233-262) as a parameter: `samples` of the sec_level repetitions are
+ * checked (verifySignatureList passes the literal 20, zkpAttestList.ts:177; the reference's own exp test passes
+ * 80 on both sides).  The tape then holds 25 * samples packed exp drains: zka_verify_tape_len_ex. */
+size_t zka_verify_tape_len_ex(uint32_t ring_size, uint32_t sec_level, uint32_t samples);
+int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* params, uint32_t B,
+                        const uint8_t* msg_hash, const uint8_t* ring, uint32_t N,
+                        const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
+                        const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status, uint32_t samples);
+
 /* ---- measurement hooks (bench.py) ----
  * zka_get_stream: the cudaStream_t every kernel of this context is launched on (so callers can
  * record CUDA events on the launching stream).  zka_set_profiling(1) brackets every launch with a

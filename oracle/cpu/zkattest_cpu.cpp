@@ -1112,7 +1112,7 @@ int prove_one(const zka_params* P, const uint8_t* msg_hash, const uint8_t* sig, 
 
 // verifySignatureList (zkpAttestList.ts:147-184); verifier tape layout of include/zkattest.h / zk_verify.cuh
 int verify_one(const zka_params* P, const uint8_t* msg_hash, const std::vector<Fe>& keys, const uint8_t* proof, size_t len,
-               const uint8_t* tape, size_t tape_len, uint8_t* ok) {
+               const uint8_t* tape, size_t tape_len, uint8_t* ok, int samples) {
   *ok = 0;
   const int S = (int)P->sec_level;
   const int n = ceil_log2((uint32_t)keys.size());
@@ -1158,7 +1158,7 @@ int verify_one(const zka_params* P, const uint8_t* msg_hash, const std::vector<F
     Tape tg{tape, gbytes, 0};
     if (!verify_membership(W, kx, keys, gk, tg)) return ZKA_OK;   // false before verifyExp can throw
     Tape te{tape + gbytes + 96, tape_len - gbytes - 96, 0};
-    const bool okv = verify_exp(sigexp, W, comS1, kx, ky, reps, 20, tape + gbytes, te, &Q);
+    const bool okv = verify_exp(sigexp, W, comS1, kx, ky, reps, samples, tape + gbytes, te, &Q);
     *ok = okv ? 1 : 0;
     return ZKA_OK;
   } catch (const ZkErr& e) {
@@ -1264,7 +1264,10 @@ size_t zka_proof_max_len(uint32_t ring_size, uint32_t sec_level) { return proof_
 size_t zka_prove_tape_len(uint32_t ring_size, uint32_t sec_level) {
   return (size_t)32 * (3 + 4 * sec_level + 40 * sec_level + 5 * ceil_log2(ring_size));
 }
-size_t zka_verify_tape_len(uint32_t ring_size, uint32_t) { return (size_t)32 * (2 * ceil_log2(ring_size) + 1) + 96 + (size_t)32 * 25 * 20; }
+size_t zka_verify_tape_len_ex(uint32_t ring_size, uint32_t, uint32_t samples) {
+  return (size_t)32 * (2 * ceil_log2(ring_size) + 1) + 96 + (size_t)32 * 25 * samples;
+}
+size_t zka_verify_tape_len(uint32_t ring_size, uint32_t sec) { return zka_verify_tape_len_ex(ring_size, sec, 20); }
 
 int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* sig, const uint8_t* pk,
                     const uint32_t* which, const uint8_t* ring, uint32_t N, const uint8_t* tape, size_t tape_stride,
@@ -1284,23 +1287,30 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
   return 0;
 }
 
-int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring, uint32_t N,
-                     const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len_in, const uint8_t* tape, size_t tape_stride,
-                     uint8_t* ok, int32_t* status) {
+int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring, uint32_t N,
+                        const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len_in, const uint8_t* tape, size_t tape_stride,
+                        uint8_t* ok, int32_t* status, uint32_t samples) {
   if (!ctx || !P || !msg_hash || !ring || !proofs || !proof_len_in || !tape || !ok || !status) return ZKA_E_ARG;
   if (B == 0) return 0;
   if (N < 2 || N > (1u << 20)) { ctx->err = "ring size must be in [2, 2^20]"; return ZKA_E_ARG; }
-  if (P->sec_level < 20) { ctx->err = "security level not achieved"; return ZKA_E_ARG; }   // exp.ts:243-245
-  if (tape_stride < zka_verify_tape_len(N, P->sec_level)) { ctx->err = "tape_stride < zka_verify_tape_len"; return ZKA_E_ARG; }
+  if (samples < 1) { ctx->err = "samples must be >= 1"; return ZKA_E_ARG; }
+  if (P->sec_level < samples) { ctx->err = "security level not achieved"; return ZKA_E_ARG; }   // exp.ts:243-245
+  if (tape_stride < zka_verify_tape_len_ex(N, P->sec_level, samples)) { ctx->err = "tape_stride < zka_verify_tape_len"; return ZKA_E_ARG; }
   const std::vector<Fe> keys = ring_scalars(ring, N);
   parallel_for(ctx->threads, B, [&](uint32_t b) {
     const size_t len = std::min<size_t>(proof_len_in[b], proof_stride);
     status[b] = proof_len_in[b] > proof_stride ? ZKA_ERR_MALFORMED
                                                : verify_one(P, msg_hash + (size_t)b * 32, keys, proofs + (size_t)b * proof_stride, len,
-                                                            tape + (size_t)b * tape_stride, tape_stride, ok + b);
+                                                            tape + (size_t)b * tape_stride, tape_stride, ok + b, (int)samples);
     if (status[b] != ZKA_OK) ok[b] = 0;
   });
   return 0;
+}
+
+int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring, uint32_t N,
+                     const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len_in, const uint8_t* tape, size_t tape_stride,
+                     uint8_t* ok, int32_t* status) {
+  return zka_verify_batch_ex(ctx, P, B, msg_hash, ring, N, proofs, proof_stride, proof_len_in, tape, tape_stride, ok, status, 20);
 }
 
 // ---- layer-wise entry points

@@ -97,8 +97,9 @@ def prove_signature_list(params, msg_hash: bytes, sig_bytes: bytes, pk_bytes: by
     return SignatureProofList(R, comS1.p, pkX.p, pkY.p, sig_proof, membership)
 
 
-def verify_signature_list(params, msg_hash: bytes, keys, proof: SignatureProofList, tape) -> bool:
-    # zkpAttestList.ts:147-184 (note the literal secparam = 20 at :177)
+def verify_signature_list(params, msg_hash: bytes, keys, proof: SignatureProofList, tape, secparam: int = 20) -> bool:
+    # zkpAttestList.ts:147-184 (the reference passes the literal secparam = 20 at :177; other values exercise
+    # verifyExp's own parameter, exp.ts:233-245, as test/exp/exp.test.ts does with 80)
     ec = p256
     n = ec.order
     z = truncate_to_n(from_bytes(msg_hash), n)
@@ -113,6 +114,6 @@ def verify_signature_list(params, msg_hash: bytes, keys, proof: SignatureProofLi
     if not verify_membership(params.ProofGroup, proof.keyXcom, keys, proof.membershipProof, tape):
         return False
     if not verify_exp(params_sig_exp, params.ProofGroup, proof.comS1, proof.keyXcom, proof.keyYcom,
-                      proof.expProof, 20, tape, Q):
+                      proof.expProof, secparam, tape, Q):
         return False
     return True

@@ -179,3 +179,59 @@ def check_verify_parity(L, N=6, seed=3, tampers=24, sec_level=80):
         agree += 1
     L.params_destroy(P)
     return agree
+
+
+def check_verify_samples(L, K, N=5, seed=5, sec_level=80, B=2, tampers=4, oracle='python'):
+    """zka_verify_batch_ex with `K` sampled repetitions (verifyExp's secparam, exp.ts:233-262) against the oracle's
+    verdicts on valid and tampered proofs under identical randomness.  oracle = 'python' or a ZkaLib of oracle/cpu."""
+    from zkp_ecdsa_b200 import verify_tape as VT
+    P, po = make_params(L, seed, sec_level)
+    wl = synth.Workload(B=B, N=N, seed=seed)
+    tape = synth.random_tape(B, L.prove_tape_len(N, sec_level), seed=seed + 100)
+    proofs, plen, status = run_prove(L, P, wl, tape, sec_level)
+    assert (status == 0).all()
+    vts = L.verify_tape_len_ex(N, sec_level, K)
+    assert vts == VT.verify_tape_len(N, K)
+    rng = np.random.default_rng(seed)
+    cases = [(proofs[b, :plen[b]].copy(), wl.msg_hash[b].copy()) for b in range(B)]
+    good = proofs[0, :plen[0]]
+    for k in range(tampers):
+        p, msg = good.copy(), wl.msg_hash[0].copy()
+        if k % 2 == 0:
+            p[int(rng.integers(264, len(p) - 1200))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            msg[int(rng.integers(0, 32))] ^= 1
+        cases.append((p, msg))
+    T = len(cases)
+    vt = VT.random_verify_tape(T, vts, N, sec_level, seed=seed + 9)
+    ps = L.proof_max_len(N, sec_level)
+    arr = np.zeros((T, ps), np.uint8)
+    lens = np.zeros(T, np.uint32)
+    msgs = np.zeros((T, 32), np.uint8)
+    for i, (p, m) in enumerate(cases):
+        arr[i, :len(p)] = p
+        lens[i] = len(p)
+        msgs[i] = m
+    ok = np.zeros(T, np.uint8)
+    st = np.zeros(T, np.int32)
+    L.verify_batch_ex(P, T, msgs, wl.ring, N, arr, ps, lens, vt, vts, ok, st, K)
+    assert list(ok[:B]) == [1] * B and not st[:B].any(), (ok[:B], st[:B])
+    if oracle == 'python':
+        ring_ints = wl.ring_ints()
+        for i, (p, m) in enumerate(cases):
+            try:
+                prf = flat.de_proof(p.tobytes(), sec_level)
+                exp = OZ.verify_signature_list(po, m.tobytes(), ring_ints, prf, Tape(VT.oracle_stream(vt[i].tobytes(), N, sec_level)), K)
+            except ValueError:
+                exp = 'err'
+            got = 'err' if st[i] else bool(ok[i])
+            assert got == exp, (K, i, got, int(st[i]), exp)
+    else:
+        hn, hp = oracle.params_generate(synth.params_rnd(seed))
+        Pc = oracle.params_create(hn, hp, sec_level)
+        ok2 = np.zeros(T, np.uint8)
+        st2 = np.zeros(T, np.int32)
+        oracle.verify_batch_ex(Pc, T, msgs, wl.ring, N, arr, ps, lens, vt, vts, ok2, st2, K)
+        assert (ok == ok2).all() and ((st != 0) == (st2 != 0)).all(), (K, ok, ok2, st, st2)
+        oracle.params_destroy(Pc)
+    L.params_destroy(P)

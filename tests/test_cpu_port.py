@@ -65,3 +65,9 @@ def test_threads_give_identical_results(cpu_port, monkeypatch):
     a = common.run_prove(cpu_port, P1, wl, tape, 16)
     b = common.run_prove(L4, P4, wl, tape, 16)
     assert (a[1] == b[1]).all() and (a[0] == b[0]).all() and not a[2].any()
+
+
+@pytest.mark.parametrize('K', [5, 33])
+def test_verify_sample_count_cpu_port_vs_python(cpu_port, K):
+    """verifyExp's secparam as a parameter: the C++ port against the Python oracle."""
+    common.check_verify_samples(cpu_port, K, N=5, seed=15, sec_level=40, tampers=2, oracle='python')

@@ -36,3 +36,15 @@ def test_prove_bit_exact_sec_level_16(hostsim):
 
 def test_verify_decisions_match_oracle(hostsim):
     common.check_verify_parity(hostsim, N=6, seed=3, tampers=16)
+
+
+def test_verify_sample_count_is_a_parameter(hostsim):
+    """zka_verify_batch_ex: 5, 33 and all 80 sampled repetitions (80 = four MSM segments), verdicts incl. tampered
+    proofs equal the oracle's (C++ port of the reference algorithms) under identical randomness."""
+    import __graft_entry__ as g
+    from zkp_ecdsa_b200.capi import ZkaLib
+    g.build_oracle_cpu()
+    cpu = ZkaLib(g.ORACLE_CPU)
+    for K in (5, 33, 80):
+        common.check_verify_samples(hostsim, K, N=5, seed=25, sec_level=80, tampers=4, oracle=cpu)
+    common.check_verify_samples(hostsim, 7, N=4, seed=26, sec_level=20, tampers=2, oracle='python')

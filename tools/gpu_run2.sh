@@ -14,7 +14,4 @@ done
 ZKA_LIB=zkp_ecdsa_b200/libzkattest_inl.so ZKA_LANES=2 ZKA_CHUNK=4096 ZKA_HOST_CHUNK=4096 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_c2_r2b_inl_l2_c4096.json 2>> gpurun_out/bench_r2b.err
 ZKA_LIB=zkp_ecdsa_b200/libzkattest_inl.so ZKA_LANES=1 ZKA_CHUNK=8192 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_c2_r2b_inl_l1_c8192.json 2>> gpurun_out/bench_r2b.err
 tail -5 gpurun_out/bench_r2b.err
-for k in MsmTomWindowBoth PhaseAAndRPoint TomCommitH TomNormTask; do
-  ZKA_LANES=1 timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:$k -c 1 -f -o gpurun_out/ncu_r2b_$k python tools/profile_step.py 2>&1 | tail -2
-done
 ls -la gpurun_out | tail -20

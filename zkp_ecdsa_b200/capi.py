@@ -25,7 +25,7 @@ SYMBOLS = [
     'zka_prove_batch', 'zka_verify_batch',
     'zka_tom_commit_batch', 'zka_p256_mul_batch', 'zka_field_op_batch', 'zka_hash80_batch',
     'zka_get_stream', 'zka_set_profiling', 'zka_profile_reset', 'zka_profile_json', 'zka_config',
-    'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack',
+    'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack', 'zka_verify_batch_ex', 'zka_verify_tape_len_ex',
 ]
 
 STATUS_MESSAGES = {
@@ -102,8 +102,17 @@ class ZkaLib:
         L.zka_profile_json.restype = C.c_size_t
         L.zka_profile_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.zka_config.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        if hasattr(L, 'zka_verify_batch_ex') and not hasattr(L, 'zka_set_option'):
+            L.zka_verify_tape_len_ex.restype = C.c_size_t
+            L.zka_verify_tape_len_ex.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+            L.zka_verify_batch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                              C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32]
         if hasattr(L, 'zka_set_option'):      # (oracle/cpu exports the core ABI only)
             L.zka_lanes.argtypes = [C.c_void_p]
+            L.zka_verify_tape_len_ex.restype = C.c_size_t
+            L.zka_verify_tape_len_ex.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+            L.zka_verify_batch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                              C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32]
             L.zka_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
             L.zka_proofs_pack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.c_void_p]
@@ -195,6 +204,14 @@ class ZkaLib:
         self._check(self.lib.zka_verify_batch(self.ctx, params, B, _ptr(msg_hash), _ptr(ring), N, _ptr(proofs),
                                               proof_stride, _ptr(proof_len), _ptr(tape), tape_stride, _ptr(ok),
                                               _ptr(status)), 'zka_verify_batch')
+
+    def verify_tape_len_ex(self, ring_size, sec_level, samples):
+        return int(self.lib.zka_verify_tape_len_ex(ring_size, sec_level, samples))
+
+    def verify_batch_ex(self, params, B, msg_hash, ring, N, proofs, proof_stride, proof_len, tape, tape_stride, ok, status, samples):
+        self._check(self.lib.zka_verify_batch_ex(self.ctx, params, B, _ptr(msg_hash), _ptr(ring), N, _ptr(proofs), proof_stride,
+                                                 _ptr(proof_len), _ptr(tape), tape_stride, _ptr(ok), _ptr(status), samples),
+                    'zka_verify_batch_ex')
 
     # ------------------------------------------------------------------ multi-GPU helpers
     def proofs_pack(self, B, proofs, stride, proof_len, packed, cap, offsets, stream=0):

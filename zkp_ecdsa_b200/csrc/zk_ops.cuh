@@ -100,6 +100,18 @@ ZK_HD void tom_ld_xyz(uint32_t* x, uint32_t* y, uint32_t* z, const uint32_t* m) 
   for (int i = 0; i < 9; i++) { x[i] = w[i]; y[i] = w[9 + i]; z[i] = w[18 + i]; }
 }
 
+// negate a table entry of the a = -1 image curve: -(w, v) = (-w, v) swaps v - w and v + w and negates 2 d2 w v
+ZK_HD void tom2_pre_neg(TomPre& q, bool neg) {
+  uint32_t nk[9];
+  Tomp::neg(nk, q.k);
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    const uint32_t a = q.x[i], b = q.y[i];
+    q.x[i] = neg ? b : a;
+    q.y[i] = neg ? a : b;
+    q.k[i] = neg ? nk[i] : q.k[i];
+  }
+}
 ZK_HD void tom_ld_pre(TomPre& q, const uint32_t* m) {
 #if defined(__CUDA_ARCH__)
   // one 128-byte line, eight 16-byte loads (entries are 128-byte aligned)
@@ -142,12 +154,29 @@ ZK_HD void store_point_words(uint8_t* o, uint32_t tag, const uint32_t* x, const 
 // digit j of width w (w in {4, 8}) of a canonical 256-bit scalar
 ZK_HD uint32_t digit4(const uint32_t* k, int j) { return (k[j >> 3] >> (4 * (j & 7))) & 15u; }
 ZK_HD uint32_t digit8(const uint32_t* k, int j) { return (k[j >> 2] >> (8 * (j & 3))) & 255u; }
-// generic: bits [pos, pos+w) of a 256-bit scalar, w <= 16
+// generic: bits [pos, pos+w) of a 256-bit scalar, w <= 24
 ZK_HD uint32_t digit_w(const uint32_t* k, int pos, int w) {
   int wi = pos >> 5, sh = pos & 31;
   uint64_t v = k[wi];
   if (wi + 1 < 8) v |= (uint64_t)k[wi + 1] << 32;
   return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+}
+
+// Fixed-base tables hold SIGNED digits: k = sum_j d_j 2^(w j), d_j in [-2^(w-1), 2^(w-1)], so a window stores the
+// multiples 0 .. 2^(w-1) only (half the memory of unsigned digits at the same number of lookups); a negative
+// digit negates the entry on the fly.  ceil(257 / w) windows: the carry out of the top data window needs one
+// more window only when w divides 256.
+ZK_HD int fb_entries(int w) { return (1 << (w - 1)) + 1; }
+ZK_HD int fb_windows(int w) { return (256 + w) / w; }
+// digit j of k in signed form: returns |d_j| and its sign; `carry` is the running carry (start with 0)
+ZK_HD uint32_t signed_digit(const uint32_t* k, int j, int w, uint32_t& carry, bool& neg) {
+  const int pos = j * w;
+  uint32_t d = carry;
+  if (pos < 256) d += digit_w(k, pos, (256 - pos) < w ? (256 - pos) : w);
+  const uint32_t half = 1u << (w - 1);
+  neg = d > half;
+  carry = neg ? 1u : 0u;
+  return neg ? (1u << w) - d : d;
 }
 
 // read a 32-byte big-endian tape draw into 8 limbs
@@ -187,16 +216,16 @@ struct P256PowsTask {
     }
   }
 };
-// rows[(b*nwin + j)*(2^w) + d] = d * pows[b][j], d = 1..2^w-1  (entry 0 left untouched)
+// rows[(b*nwin + j)*E + d] = d * pows[b][j], d = 1..2^(w-1), E = fb_entries(w)  (entry 0 is never read)
 struct P256RowsTask {
   const uint32_t* pows;  // [nbase*nwin][24]
-  uint32_t* rows;        // [nbase*nwin][2^w][24]
+  uint32_t* rows;        // [nbase*nwin][E][24]
   int w;
   ZK_HD void operator()(int t) const {
     P256Pt p, acc;
     p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
     acc = p;
-    const int ne = 1 << w;
+    const int ne = fb_entries(w);
     uint32_t* out = rows + (size_t)t * ne * P256_PROJ_WORDS;
     // entry 0: store the base itself so the normaliser never sees garbage (it is never read)
     p256_st_proj(out, p);
@@ -230,32 +259,34 @@ struct P256RowsSignedTask {
 // Two-level rows for a wide fixed-base table (w > 8), same idea as TomRowsHi/LoTask
 struct P256RowsHiTask {
   const uint32_t* pows;   // [nwin][24]
-  uint32_t* hi;           // [nwin][2^(w-8)][24]
+  uint32_t* hi;           // [nwin][2^(w-9)][24]
+  uint32_t* rows;         // the top entry 2^(w-1) * pows of every window is written here directly
   int w;
   ZK_HD void operator()(int t) const {
     P256Pt p, acc;
     p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
     for (int k = 0; k < 8; k++) p256_dbl(p, p);
     p256_set_identity(acc);
-    const int nh = 1 << (w - 8);
+    const int nh = 1 << (w - 9);
     for (int m = 0; m < nh; m++) {
       p256_st_proj(hi + ((size_t)t * nh + m) * P256_PROJ_WORDS, acc);
       p256_add(acc, acc, p);
     }
+    p256_st_proj(rows + ((size_t)t * fb_entries(w) + ((size_t)1 << (w - 1))) * P256_PROJ_WORDS, acc);
   }
 };
 struct P256RowsLoTask {
   const uint32_t* pows;
   const uint32_t* hi;
-  uint32_t* rows;         // [nwin][2^w][24]  (entry 0 of each window is the identity: never read)
+  uint32_t* rows;         // [nwin][E][24]  (entry 0 of each window is the identity: never read)
   int w;
   ZK_HD void operator()(int t) const {
-    const int nh = 1 << (w - 8);
+    const int nh = 1 << (w - 9);
     const int j = t / nh, m = t % nh;
     P256Pt p, acc;
     p256_ld_proj(p, pows + (size_t)j * P256_PROJ_WORDS);
     p256_ld_proj(acc, hi + (size_t)t * P256_PROJ_WORDS);
-    uint32_t* out = rows + (((size_t)j << w) + ((size_t)m << 8)) * P256_PROJ_WORDS;
+    uint32_t* out = rows + ((size_t)j * fb_entries(w) + ((size_t)m << 8)) * P256_PROJ_WORDS;
     for (int d = 0; d < 256; d++) {
       p256_st_proj(out + (size_t)d * P256_PROJ_WORDS, acc);
       p256_add(acc, acc, p);
@@ -324,25 +355,18 @@ struct P256NormTask {
   }
 };
 
-// acc += sum_j T[j][digit_j(k)] for a w=8 fixed table [32][256] of affine entries
-ZK_HD void p256_accum_fixed8(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
-  for (int j = 0; j < 32; j++) {
-    uint32_t d = digit8(k, j);
-    if (d) {
-      P256Aff q;
-      p256_ld_aff(q, tab + ((size_t)j * 256 + d) * P256_AFF_WORDS);
-      p256_madd(acc, acc, q);
-    }
-  }
-}
-// acc += sum_j T[j][digit_j(k)] for a fixed table [ceil(256/w)][2^w] of affine entries
+// acc += k * base on a fixed table [fb_windows(w)][fb_entries(w)] of affine entries (signed digits)
 ZK_HD void p256_accum_fixed(P256Pt& acc, const uint32_t* tab, const uint32_t* k, int w) {
-  const int nwin = (256 + w - 1) / w;
+  const int nwin = fb_windows(w);
+  const size_t E = (size_t)fb_entries(w);
+  uint32_t carry = 0;
   for (int j = 0; j < nwin; j++) {
-    const uint32_t d = digit_w(k, j * w, (256 - j * w) < w ? (256 - j * w) : w);
+    bool neg;
+    const uint32_t d = signed_digit(k, j, w, carry, neg);
     if (d) {
       P256Aff q;
-      p256_ld_aff(q, tab + (((size_t)j << w) + d) * P256_AFF_WORDS);
+      p256_ld_aff(q, tab + ((size_t)j * E + d) * P256_AFF_WORDS);
+      if (neg) P256p::neg(q.y, q.y);
       p256_madd(acc, acc, q);
     }
   }
@@ -392,7 +416,7 @@ struct TomRowsTask {
     const uint32_t* s = pows + (size_t)t * 36;
     ld<9>(p.x, s); ld<9>(p.y, s + 9); ld<9>(p.t, s + 18); ld<9>(p.z, s + 27);
     tom_set_identity(acc);
-    const int ne = 1 << w;
+    const int ne = fb_entries(w);
     uint32_t* out = rows + (size_t)t * ne * TOM_PROJ_WORDS;
     for (int d = 0; d < ne; d++) {
       uint32_t* o = out + (size_t)d * TOM_PROJ_WORDS;
@@ -406,7 +430,8 @@ struct TomRowsTask {
 // 256 entries below it.  2^(w-8) + 256 sequential additions instead of 2^w.
 struct TomRowsHiTask {
   const uint32_t* pows;   // [nwin][36]
-  uint32_t* hi;           // [nwin][2^(w-8)][36]
+  uint32_t* hi;           // [nwin][2^(w-9)][36]
+  uint32_t* rows;         // the top entry 2^(w-1) * pows of every window is written here directly
   int w;
   ZK_HD void operator()(int t) const {
     TomPt p, acc;
@@ -414,28 +439,29 @@ struct TomRowsHiTask {
     ld<9>(p.x, s); ld<9>(p.y, s + 9); ld<9>(p.t, s + 18); ld<9>(p.z, s + 27);
     for (int k = 0; k < 8; k++) tom_dbl(p, p);
     tom_set_identity(acc);
-    const int nh = 1 << (w - 8);
+    const int nh = 1 << (w - 9);
     for (int m = 0; m < nh; m++) {
       uint32_t* o = hi + ((size_t)t * nh + m) * 36;
       st<9>(o, acc.x); st<9>(o + 9, acc.y); st<9>(o + 18, acc.t); st<9>(o + 27, acc.z);
       tom_add(acc, acc, p);
     }
+    tom_st_xyz(rows + ((size_t)t * fb_entries(w) + ((size_t)1 << (w - 1))) * TOM_PROJ_WORDS, acc.x, acc.y, acc.z);
   }
 };
 struct TomRowsLoTask {
   const uint32_t* pows;   // [nwin][36]
-  const uint32_t* hi;     // [nwin][2^(w-8)][36]
-  uint32_t* rows;         // [nwin][2^w][27]
+  const uint32_t* hi;     // [nwin][2^(w-9)][36]
+  uint32_t* rows;         // [nwin][E][27]
   int w;
   ZK_HD void operator()(int t) const {
-    const int nh = 1 << (w - 8);
+    const int nh = 1 << (w - 9);
     const int j = t / nh, m = t % nh;
     TomPt p, acc;
     const uint32_t* s = pows + (size_t)j * 36;
     ld<9>(p.x, s); ld<9>(p.y, s + 9); ld<9>(p.t, s + 18); ld<9>(p.z, s + 27);
     const uint32_t* h = hi + (size_t)t * 36;
     ld<9>(acc.x, h); ld<9>(acc.y, h + 9); ld<9>(acc.t, h + 18); ld<9>(acc.z, h + 27);
-    uint32_t* out = rows + (((size_t)j << w) + ((size_t)m << 8)) * TOM_PROJ_WORDS;
+    uint32_t* out = rows + ((size_t)j * fb_entries(w) + ((size_t)m << 8)) * TOM_PROJ_WORDS;
     for (int d = 0; d < 256; d++) {
       uint32_t* o = out + (size_t)d * TOM_PROJ_WORDS;
       tom_st_xyz(o, acc.x, acc.y, acc.z);
@@ -603,14 +629,17 @@ struct TomCommitTask {
     ld<8>(r, jr + (size_t)t * 8);
     TomPt acc;
     tom_set_identity(acc);
-    const size_t ne = (size_t)1 << w;
+    const size_t ne = (size_t)fb_entries(w);
+    uint32_t cv = 0, cr = 0;
     for (int j = 0; j < nwin; j++) {
       TomPre q;
-      int width = (256 - j * w) < w ? (256 - j * w) : w;
-      uint32_t dv = digit_w(v, j * w, width), dr = digit_w(r, j * w, width);
+      bool nv, nr;
+      const uint32_t dv = signed_digit(v, j, w, cv, nv), dr = signed_digit(r, j, w, cr, nr);
       tom_ld_pre(q, gtab + ((size_t)j * ne + dv) * TOM_PRE_WORDS);
+      tom2_pre_neg(q, nv);
       tom2_madd<true>(acc, acc, q);     // a = -1 image curve E2: 7M per lookup
       tom_ld_pre(q, htab + ((size_t)j * ne + dr) * TOM_PRE_WORDS);
+      tom2_pre_neg(q, nr);
       tom2_madd<true>(acc, acc, q);
     }
     uint32_t* o = proj + (size_t)t * TOM_PROJ_WORDS;
@@ -653,12 +682,15 @@ struct TomCommitGTask {   // one thread per (item, g-part): K = v*g as an extend
     ld<8>(v, jv + ((size_t)item * JOBS_PER_ITEM + item_job_of_gpart(g)) * 8);
     TomPt acc;
     tom_set_identity(acc);
-    const size_t ne = (size_t)1 << w;
+    const size_t ne = (size_t)fb_entries(w);
+    uint32_t carry = 0;
 #pragma unroll 1
     for (int j = 0; j < nwin; j++) {
       TomPre q;
-      int width = (256 - j * w) < w ? (256 - j * w) : w;
-      tom_ld_pre(q, gtab + ((size_t)j * ne + digit_w(v, j * w, width)) * TOM_PRE_WORDS);
+      bool neg;
+      const uint32_t d = signed_digit(v, j, w, carry, neg);
+      tom_ld_pre(q, gtab + ((size_t)j * ne + d) * TOM_PRE_WORDS);
+      tom2_pre_neg(q, neg);
       tom2_madd<true, TompCommit>(acc, acc, q);
     }
     uint32_t* o = ext + (size_t)t * TOM_EXT_WORDS;
@@ -678,12 +710,15 @@ struct TomCommitHTask {   // one thread per job: C = K + r*h
     TomPt acc;
     const uint32_t* s = ext + ((size_t)item * GJOBS_PER_ITEM + item_gpart_of_job(jb)) * TOM_EXT_WORDS;
     ld<9>(acc.x, s); ld<9>(acc.y, s + 9); ld<9>(acc.t, s + 18); ld<9>(acc.z, s + 27);
-    const size_t ne = (size_t)1 << w;
+    const size_t ne = (size_t)fb_entries(w);
+    uint32_t carry = 0;
 #pragma unroll 1
     for (int j = 0; j < nwin; j++) {
       TomPre q;
-      int width = (256 - j * w) < w ? (256 - j * w) : w;
-      tom_ld_pre(q, htab + ((size_t)j * ne + digit_w(r, j * w, width)) * TOM_PRE_WORDS);
+      bool neg;
+      const uint32_t d = signed_digit(r, j, w, carry, neg);
+      tom_ld_pre(q, htab + ((size_t)j * ne + d) * TOM_PRE_WORDS);
+      tom2_pre_neg(q, neg);
       tom2_madd<true, TompCommit>(acc, acc, q);
     }
     tom_st_xyz(proj + (size_t)t * TOM_PROJ_WORDS, acc.x, acc.y, acc.z);

@@ -32,10 +32,10 @@
 namespace zk {
 
 enum : int {
-  V_SAMPLES = 20,              // zkpAttestList.ts:177
+  V_SAMPLES = 20,              // default number of sampled repetitions: the literal secparam of zkpAttestList.ts:177
   V_ENT_PER_SAMPLE = 34,       // variable tomEdwards256 points of one sampled 0-bit repetition
-  V_ENT_TOM = V_SAMPLES * V_ENT_PER_SAMPLE + 2,   // + keyXcom, keyYcom
-  V_ENT_NIST = V_SAMPLES + 1,  // A_j + comS1
+  V_SEG = 20,                  // sampled repetitions per MSM segment (one window thread walks <= V_ENT_SEG entries)
+  V_ENT_SEG = V_SEG * V_ENT_PER_SAMPLE + 2,       // 682 (+ keyXcom, keyYcom ride with segment 0)
   V_IDX_PAD = 96,
   V_PART_WORDS = 7 * 8,        // per-sample partial sums: gW hW pkX pkY | sR shN sCom
   MSM_C = 6,                   // SIGNED 6-bit bucket windows (tom): digits in [-32, 31], 32 buckets,
@@ -44,12 +44,14 @@ enum : int {
   MSM_NWIN_N = 64,
 };
 
-ZK_LAYOUT_FN size_t verify_tape_len(int n, int /*reps*/) {
-  return (size_t)32 * (2 * n + 1) + V_IDX_PAD + (size_t)32 * 25 * V_SAMPLES;
+// K = number of sampled repetitions (verifyExp's secparam, exp.ts:233-262): 20 in verifySignatureList
+ZK_LAYOUT_FN size_t verify_tape_len(int n, int /*reps*/, int K = V_SAMPLES) {
+  return (size_t)32 * (2 * n + 1) + V_IDX_PAD + (size_t)32 * 25 * K;
 }
 
 struct VerifyCtx {
   int B, S, N, n;
+  int K;                       // sampled repetitions (<= S)
   int tom_w, tom_nwin;
   const uint8_t* msg_hash;     // [B][32]
   const uint8_t* proofs;       // [B][proof_stride]
@@ -112,6 +114,9 @@ struct VerifyCtx {
   uint8_t* ok;          // [B]
   int32_t* status;      // [B]
 
+  ZK_HD int ent_tom() const { return K * V_ENT_PER_SAMPLE + 2; }   // variable tomEdwards256 points per proof (+ keyXcom, keyYcom)
+  ZK_HD int ent_nist() const { return K + 1; }                     // A_j + comS1
+  ZK_HD int segs() const { return (K + V_SEG - 1) / V_SEG; }
   ZK_HD const uint8_t* proof_of(int b) const { return proofs + (size_t)b * proof_stride; }
   ZK_HD const uint8_t* tape_of(int b) const { return tape + (size_t)b * tape_stride; }
   ZK_HD size_t gk_tape_bytes() const { return (size_t)32 * (2 * n + 1); }
@@ -333,13 +338,13 @@ struct VChallengeTask {
     uint32_t tg[3];
     ld<3>(tg, c.tagbits + (size_t)b * 3);
     uint32_t draw = 0;
-    for (int j = 0; j < V_SAMPLES; j++) {
+    for (int j = 0; j < c.K; j++) {
       const int i = perm[j];
       const uint32_t bit = (c3[i >> 5] >> (i & 31)) & 1u;
       const uint32_t tag = (tg[i >> 5] >> (i & 31)) & 1u;
       if (bit != tag) ZK_SET_STATUS(c.status + b, ZKA_ERR_PARAMS_NOT_FOUND);   // exp.ts:269-271,301-303
-      c.samp_idx[(size_t)b * V_SAMPLES + j] = (uint32_t)i;
-      c.samp_draw[(size_t)b * V_SAMPLES + j] = draw;
+      c.samp_idx[(size_t)b * c.K + j] = (uint32_t)i;
+      c.samp_draw[(size_t)b * c.K + j] = draw;
       draw += bit ? 3 : 25;
     }
   }
@@ -349,7 +354,7 @@ struct VChallengeTask {
 struct VSampleP256Task {
   VerifyCtx c;
   ZK_HD void operator()(int t) const {
-    const int b = t / V_SAMPLES;
+    const int b = t / c.K;
     const int i = c.samp_idx[t];
     const uint8_t* rep = c.proof_of(b) + c.rep_off[(size_t)b * c.S + i];
     uint32_t s[8];
@@ -372,7 +377,7 @@ struct VSampleP256Task {
 struct VSampleJobsTask {
   VerifyCtx c;
   ZK_HD void operator()(int t) const {
-    const int b = t / V_SAMPLES;
+    const int b = t / c.K;
     const int i = c.samp_idx[t];
     const uint8_t* rep = c.proof_of(b) + c.rep_off[(size_t)b * c.S + i];
     uint32_t v[8], r[8];
@@ -403,7 +408,7 @@ struct VDerivedTask {
     tom_st_xyz(o, p.x, p.y, p.z);
   }
   ZK_HD void operator()(int t) const {
-    const int b = t / V_SAMPLES;
+    const int b = t / c.K;
     const int i = c.samp_idx[t];
     const uint8_t* pr = c.proof_of(b);
     const uint8_t* rep = pr + c.rep_off[(size_t)b * c.S + i];
@@ -431,7 +436,7 @@ struct VItemHashTask {
   VerifyCtx c;
   ZK_HD void operator()(int t) const {
     const int sample = t / HASHES_PER_ITEM, h = t % HASHES_PER_ITEM;
-    const int b = sample / V_SAMPLES;
+    const int b = sample / c.K;
     const int i = c.samp_idx[sample];
     const uint8_t* rep = c.proof_of(b) + c.rep_off[(size_t)b * c.S + i];
     uint32_t c3[3] = {0, 0, 0};
@@ -471,14 +476,14 @@ struct VRelationsTask {
   ZK_HD void ent(int b, int j, int e, const uint32_t* s_mont, uint32_t off) const {
     uint32_t v[8];
     Tomq::from_mont(v, s_mont);
-    const size_t idx = (size_t)b * V_ENT_TOM + (size_t)j * V_ENT_PER_SAMPLE + e;
+    const size_t idx = (size_t)b * c.ent_tom() + (size_t)j * V_ENT_PER_SAMPLE + e;
     st<8>(c.ent_scalar + idx * 8, v);
     c.ent_off[idx] = off;
   }
   ZK_HD void operator()(int t) const {
     using F = Tomq;
     using Fn = P256n;
-    const int b = t / V_SAMPLES, j = t % V_SAMPLES;
+    const int b = t / c.K, j = t % c.K;
     const int i = c.samp_idx[t];
     const uint8_t* pr = c.proof_of(b);
     const uint32_t roff = c.rep_off[(size_t)b * c.S + i];
@@ -504,7 +509,7 @@ struct VRelationsTask {
       uint32_t neg[8], z[8];
       zero_n<8>(z);
       Fn::sub(neg, z, rho);            // -rho mod n, canonical
-      st<8>(c.nent_scalar + ((size_t)b * V_ENT_NIST + j) * 8, neg);
+      st<8>(c.nent_scalar + ((size_t)b * c.ent_nist() + j) * 8, neg);
     }
     // coordinates of T / T1 as proof-group scalars
     uint32_t sx[8], sy[8];
@@ -649,8 +654,8 @@ struct VRelationsTask {
     P256Aff A;
     bool inf;
     p256_parse(A, inf, rep + 1);
-    p256_st_aff(c.nent_aff + ((size_t)b * V_ENT_NIST + j) * 16, A);
-    c.nent_skip[(size_t)b * V_ENT_NIST + j] = inf ? 1 : 0;
+    p256_st_aff(c.nent_aff + ((size_t)b * c.ent_nist() + j) * 16, A);
+    c.nent_skip[(size_t)b * c.ent_nist() + j] = inf ? 1 : 0;
   }
 };
 
@@ -663,8 +668,8 @@ struct VReduceTask {
     using Fn = P256n;
     uint32_t gW[8], hW[8], pX[8], pY[8], sR[8], sH[8], sC[8];
     zero_n<8>(gW); zero_n<8>(hW); zero_n<8>(pX); zero_n<8>(pY); zero_n<8>(sR); zero_n<8>(sH); zero_n<8>(sC);
-    for (int j = 0; j < V_SAMPLES; j++) {
-      const uint32_t* p = c.part + ((size_t)b * V_SAMPLES + j) * V_PART_WORDS;
+    for (int j = 0; j < c.K; j++) {
+      const uint32_t* p = c.part + ((size_t)b * c.K + j) * V_PART_WORDS;
       uint32_t t[8];
       ld<8>(t, p); F::add(gW, gW, t);
       ld<8>(t, p + 8); F::add(hW, hW, t);
@@ -679,17 +684,17 @@ struct VReduceTask {
     F::from_mont(v, gW); st<8>(c.fx_jv + ((size_t)b * 2 + 1) * 8, v);
     F::from_mont(v, hW); st<8>(c.fx_jr + ((size_t)b * 2 + 1) * 8, v);
     // keyXcom / keyYcom entries
-    size_t idx = (size_t)b * V_ENT_TOM + V_SAMPLES * V_ENT_PER_SAMPLE;
+    size_t idx = (size_t)b * c.ent_tom() + (size_t)c.K * V_ENT_PER_SAMPLE;
     F::from_mont(v, pX); st<8>(c.ent_scalar + idx * 8, v); c.ent_off[idx] = 2 * NP;
     F::from_mont(v, pY); st<8>(c.ent_scalar + (idx + 1) * 8, v); c.ent_off[idx + 1] = 2 * NP + WP;
     // multiN: comS1 entry and the fixed part
     Fn::from_mont(v, sC);
-    st<8>(c.nent_scalar + ((size_t)b * V_ENT_NIST + V_SAMPLES) * 8, v);
+    st<8>(c.nent_scalar + ((size_t)b * c.ent_nist() + c.K) * 8, v);
     P256Aff cs;
     bool inf;
     p256_parse(cs, inf, c.proof_of(b) + NP);
-    p256_st_aff(c.nent_aff + ((size_t)b * V_ENT_NIST + V_SAMPLES) * 16, cs);
-    c.nent_skip[(size_t)b * V_ENT_NIST + V_SAMPLES] = inf ? 1 : 0;
+    p256_st_aff(c.nent_aff + ((size_t)b * c.ent_nist() + c.K) * 16, cs);
+    c.nent_skip[(size_t)b * c.ent_nist() + c.K] = inf ? 1 : 0;
     uint32_t kR[8], kH[8];
     Fn::from_mont(kR, sR);
     Fn::from_mont(kH, sH);
@@ -911,20 +916,31 @@ struct MsmTomWindowTask {
   const uint32_t* scalar;   // [inst][stride][8]
   const uint32_t* pre;      // [inst][stride][32]
   const uint32_t* cnt;      // [inst][groups] entries used per group (or null: all `group_len` used)
-  int stride, groups, group_len, tail;   // entries = groups*group_len (+ tail always used)
-  uint32_t* win;            // [inst][MSM_NWIN][36]
+  int stride, groups, group_len, tail;   // entries of an instance = groups*group_len, then `tail` always-used ones
+  int seg_groups, segs;     // the groups are walked in `segs` segments of <= seg_groups groups (one thread per segment
+                            // and window: <= V_ENT_SEG entries each); the tail rides with segment 0
+  uint32_t* win;            // [inst][segs][MSM_NWIN][36]
   ZK_HD void operator()(int t) const {
-    const int inst = t / MSM_NWIN, w = t % MSM_NWIN;
+    const int is = t / MSM_NWIN, w = t % MSM_NWIN;
+    const int inst = is / segs, seg = is % segs;
     constexpr int NB = 33;          // bucket 0 (skipped) .. 32
     const uint32_t* sc = scalar + (size_t)inst * stride * 8;
     const uint32_t* pp = pre + (size_t)inst * stride * TOM_PRE_WORDS;
-    uint16_t order[V_ENT_TOM];     // sign << 15 | (bucket - 1) << 10 | entry index, sorted by bucket
+    const int g0 = seg * seg_groups;
+    int ng = groups - g0;
+    if (ng > seg_groups) ng = seg_groups;
+    if (ng < 0) ng = 0;
+    const int tl = seg == 0 ? tail : 0;
+    const int gbase = g0 * group_len;           // first entry of this segment's groups
+    const int tbase = groups * group_len;       // first tail entry
+    const int nloc = ng * group_len;            // local indices [0, nloc) are group entries, [nloc, nloc + tl) the tail
+    uint16_t order[V_ENT_SEG];     // sign << 15 | (bucket - 1) << 10 | LOCAL entry index, sorted by bucket
     uint16_t start[NB + 1];
     for (int d = 0; d <= NB; d++) start[d] = 0;
     // pass 1: histogram of buckets
-    for (int gidx = 0; gidx <= groups; gidx++) {
-      const int base = gidx * group_len;
-      const int m = gidx < groups ? (cnt ? (int)cnt[(size_t)inst * groups + gidx] : group_len) : tail;
+    for (int gidx = 0; gidx <= ng; gidx++) {
+      const int m = gidx < ng ? (cnt ? (int)cnt[(size_t)inst * groups + g0 + gidx] : group_len) : tl;
+      const int base = gidx < ng ? gbase + gidx * group_len : tbase;
       for (int e = 0; e < m; e++) {
         bool neg;
         const uint32_t bk = msm_digit6(sc + (size_t)(base + e) * 8, w, neg);
@@ -935,13 +951,14 @@ struct MsmTomWindowTask {
     uint16_t fillp[NB];
     for (int d = 0; d < NB; d++) fillp[d] = start[d];
     // pass 2: scatter
-    for (int gidx = 0; gidx <= groups; gidx++) {
-      const int base = gidx * group_len;
-      const int m = gidx < groups ? (cnt ? (int)cnt[(size_t)inst * groups + gidx] : group_len) : tail;
+    for (int gidx = 0; gidx <= ng; gidx++) {
+      const int m = gidx < ng ? (cnt ? (int)cnt[(size_t)inst * groups + g0 + gidx] : group_len) : tl;
+      const int base = gidx < ng ? gbase + gidx * group_len : tbase;
+      const int lbase = gidx < ng ? gidx * group_len : nloc;
       for (int e = 0; e < m; e++) {
         bool neg;
         const uint32_t bk = msm_digit6(sc + (size_t)(base + e) * 8, w, neg);
-        const uint32_t enc = bk ? (((neg ? 1u : 0u) << 15) | ((bk - 1) << 10) | (uint32_t)(base + e)) : (uint32_t)(base + e);
+        const uint32_t enc = bk ? (((neg ? 1u : 0u) << 15) | ((bk - 1) << 10) | (uint32_t)(lbase + e)) : (uint32_t)(lbase + e);
         order[fillp[bk]++] = (uint16_t)enc;
       }
     }
@@ -964,7 +981,8 @@ struct MsmTomWindowTask {
         curd = d;
       }
       TomPre pt;
-      tom_ld_pre(pt, pp + (size_t)(oe & 1023u) * TOM_PRE_WORDS);
+      const int loc = (int)(oe & 1023u);
+      tom_ld_pre(pt, pp + (size_t)(loc < nloc ? gbase + loc : tbase + (loc - nloc)) * TOM_PRE_WORDS);
       if (oe & 0x8000u) {            // negative digit: -(x, y) = (-x, y), k = d x y changes sign too
         Tomp::neg(pt.x, pt.x);
         Tomp::neg(pt.k, pt.k);
@@ -990,18 +1008,21 @@ struct MsmTomWindowTask {
 };
 // Horner over the windows + the fixed-base part; verdict = identity?  One thread per instance.
 struct MsmTomCombineTask {
-  const uint32_t* win;      // [inst][MSM_NWIN][36]
+  const uint32_t* win;      // [inst][segs][MSM_NWIN][36]
   const uint32_t* fixed;    // fixed-base commitment of instance i at fixed[(i*fix_stride + fix_off)*27]
   uint8_t* flag;            // verdict of instance i at flag[i*3 + flag_off]
   int fix_stride, fix_off, flag_off;
+  int segs = 1;
   ZK_HD void operator()(int inst) const {
     TomPt acc, wsum;
     tom_set_identity(acc);
     for (int w = MSM_NWIN - 1; w >= 0; w--) {
       for (int k = 0; k < MSM_C; k++) tom_dbl(acc, acc);
-      const uint32_t* s = win + ((size_t)inst * MSM_NWIN + w) * 36;
-      ld<9>(wsum.x, s); ld<9>(wsum.y, s + 9); ld<9>(wsum.t, s + 18); ld<9>(wsum.z, s + 27);
-      tom_add(acc, acc, wsum);
+      for (int sg = 0; sg < segs; sg++) {
+        const uint32_t* s = win + (((size_t)inst * segs + sg) * MSM_NWIN + w) * 36;
+        ld<9>(wsum.x, s); ld<9>(wsum.y, s + 9); ld<9>(wsum.t, s + 18); ld<9>(wsum.z, s + 27);
+        tom_add(acc, acc, wsum);
+      }
     }
     TomPt f;
     const uint32_t* fp = fixed + ((size_t)inst * fix_stride + fix_off) * TOM_PROJ_WORDS;
@@ -1030,18 +1051,19 @@ struct MsmP256WindowTask {
   const uint32_t* aff;      // [B][21][16]
   const uint8_t* skip;      // [B][21]
   uint32_t* win;            // [B][RT_NWIN][24]
+  int nent = V_SAMPLES + 1; // entries per proof: K sampled A_j + comS1
   ZK_HD void operator()(int t) const {
     const int b = t / MSM_NWIN_N, w = t % MSM_NWIN_N;
     P256Pt bucket[15];
     for (int d = 0; d < 15; d++) p256_set_identity(bucket[d]);
-    for (int e = 0; e < V_ENT_NIST; e++) {
-      if (skip[(size_t)b * V_ENT_NIST + e]) continue;
+    for (int e = 0; e < nent; e++) {
+      if (skip[(size_t)b * nent + e]) continue;
       uint32_t k[8];
-      ld<8>(k, scalar + ((size_t)b * V_ENT_NIST + e) * 8);
+      ld<8>(k, scalar + ((size_t)b * nent + e) * 8);
       const uint32_t dgt = digit4(k, w);
       if (dgt) {
         P256Aff q;
-        p256_ld_aff(q, aff + ((size_t)b * V_ENT_NIST + e) * 16);
+        p256_ld_aff(q, aff + ((size_t)b * nent + e) * 16);
         p256_madd(bucket[dgt - 1], bucket[dgt - 1], q);
       }
     }
@@ -1078,11 +1100,12 @@ struct MsmP256CombineTask {
 // short GK threads fill the SMs the long multiW threads leave idle (one 1024-proof batch is 0.8 of a wave).
 struct MsmTomWindowBothTask {
   MsmTomWindowTask w, gk;
-  int nW, nWp;   // multiW threads, rounded up to a warp multiple
+  int nW, nWp;   // multiW threads (proofs x segments x windows), rounded up to a warp multiple
+  int nG;        // GK threads (proofs x windows)
   ZK_HD void operator()(int t) const {
     if (t < nWp) {
       if (t < nW) w(t);
-    } else if (t - nWp < nW) {
+    } else if (t - nWp < nG) {
       gk(t - nWp);
     }
   }

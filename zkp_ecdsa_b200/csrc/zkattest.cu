@@ -298,7 +298,7 @@ struct zka_ctx : Lane {
   int nlanes = 2;             // ZKA_LANES
   DevBuf ring_in, ring_m;     // the ring of the current call (shared by all lanes, read-only while they run)
   Lane& lane(int i) { return i == 0 ? *this : *extra[i - 1]; }
-  int tom_w = 22, tom_nwin = 12;   // per base: 12 windows x 2^22 entries x 128 B = 6.4 GB of HBM (ZKA_TOM_W)
+  int tom_w = 22, tom_nwin = 12;   // per base: 12 windows x (2^21 + 1) signed-digit entries x 128 B = 3.2 GB of HBM (ZKA_TOM_W)
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 8192;
   int host_chunk = 4096;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
@@ -374,21 +374,22 @@ inline void launch_tom_norm(Stream& st, const uint32_t* proj, uint32_t* aff, uin
 }
 
 // ---- table construction -------------------------------------------------------------------
-// P-256 w=8 positional table from one affine Montgomery base (device pointer, 16 words)
+// P-256 positional table (signed digits, fb_entries(w) multiples per window) from one affine Montgomery base
+// (device pointer, 16 words)
 void build_p256_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out, int w) {
   Stream& st = ctx->st;
-  const int nwin = (256 + w - 1) / w;
-  const size_t count = (size_t)nwin << w;
+  const int nwin = fb_windows(w);
+  const size_t E = (size_t)fb_entries(w), count = (size_t)nwin * E;
   DevBuf pows, rows;
   uint32_t* d_pows = pows.get<uint32_t>((size_t)nwin * P256_PROJ_WORDS);
   uint32_t* d_rows = rows.get<uint32_t>(count * P256_PROJ_WORDS);
   out.tab = out.buf.get<uint32_t>(count * P256_AFF_WORDS);
   launch(st, 1, P256PowsTask{base_aff_dev, nullptr, d_pows, 1, nwin, w});
-  if (w > 8) {
+  if (w > 9) {
     DevBuf hi;
-    const int nh = 1 << (w - 8);
+    const int nh = 1 << (w - 9);
     uint32_t* d_hi = hi.get<uint32_t>((size_t)nwin * nh * P256_PROJ_WORDS);
-    launch(st, nwin, P256RowsHiTask{d_pows, d_hi, w});
+    launch(st, nwin, P256RowsHiTask{d_pows, d_hi, d_rows, w});
     launch(st, (long long)nwin * nh, P256RowsLoTask{d_pows, d_hi, d_rows, w});
     sync(st);
     hi.release();
@@ -400,21 +401,21 @@ void build_p256_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out,
   pows.release();
   rows.release();
 }
-// tomEdwards256 positional table [nwin][2^w] from one image-curve affine base (18 words, device)
+// tomEdwards256 positional table [nwin][fb_entries(w)] from one image-curve affine base (18 words, device)
 void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) {
   Stream& st = ctx->st;
   const int w = ctx->tom_w, nwin = ctx->tom_nwin;
-  const size_t ne = (size_t)1 << w, count = (size_t)nwin * ne;
+  const size_t ne = (size_t)fb_entries(w), count = (size_t)nwin * ne;
   DevBuf pows, rows;
   uint32_t* d_pows = pows.get<uint32_t>((size_t)nwin * 36);
   uint32_t* d_rows = rows.get<uint32_t>(count * TOM_PROJ_WORDS);
   out.tab = out.buf.get<uint32_t>(count * TOM_PRE_WORDS);
   launch(st, 1, TomPowsTask{base_aff_dev, d_pows, 1, nwin, w});
-  if (w > 8) {
+  if (w > 9) {
     DevBuf hi;
-    const int nh = 1 << (w - 8);
+    const int nh = 1 << (w - 9);
     uint32_t* d_hi = hi.get<uint32_t>((size_t)nwin * nh * 36);
-    launch(st, nwin, TomRowsHiTask{d_pows, d_hi, w});
+    launch(st, nwin, TomRowsHiTask{d_pows, d_hi, d_rows, w});
     launch(st, (long long)nwin * nh, TomRowsLoTask{d_pows, d_hi, d_rows, w});
     sync(st);
     hi.release();
@@ -591,7 +592,7 @@ int zka_init(int device, zka_ctx** out) {
       int w = atoi(e);
       if (w >= 2 && w <= 24) ctx->tom_w = w;
     }
-    ctx->tom_nwin = (256 + ctx->tom_w - 1) / ctx->tom_w;
+    ctx->tom_nwin = fb_windows(ctx->tom_w);
     if (const char* e = getenv("ZKA_CHUNK")) {
       int c = atoi(e);
       if (c >= 1) ctx->chunk = c;
@@ -1144,17 +1145,30 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
   }
 }
 
+size_t zka_verify_tape_len_ex(uint32_t ring_size, uint32_t sec_level, uint32_t samples) {
+  return verify_tape_len(ceil_log2(ring_size), (int)sec_level, (int)samples);
+}
+
 int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring,
                      uint32_t N, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
                      const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status) {
+  // verifySignatureList hard-codes secparam = 20 (zkpAttestList.ts:177)
+  return zka_verify_batch_ex(ctx, P, B, msg_hash, ring, N, proofs, proof_stride, proof_len, tape, tape_stride, ok, status, V_SAMPLES);
+}
+
+int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring,
+                        uint32_t N, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
+                        const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status, uint32_t samples) {
   if (!ctx || !P || !msg_hash || !ring || !proofs || !proof_len || !tape || !ok || !status) return ZKA_E_ARG;
   if (B == 0) return 0;
   if (N < 2 || N > (1u << 20)) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
   const int S = (int)P->sec_level;
-  // verifyExp throws 'security level not achieved' when 20 > pi.length (exp.ts:243-245)
-  if (S < V_SAMPLES) return fail(ctx, ZKA_E_ARG, "security level not achieved");
+  const int K = (int)samples;
+  if (K < 1) return fail(ctx, ZKA_E_ARG, "samples must be >= 1");
+  // verifyExp throws 'security level not achieved' when secparam > pi.length (exp.ts:243-245)
+  if (S < K) return fail(ctx, ZKA_E_ARG, "security level not achieved");
   const int n = ceil_log2(N);
-  if (tape_stride < verify_tape_len(n, S)) return fail(ctx, ZKA_E_ARG, "tape_stride < zka_verify_tape_len");
+  if (tape_stride < verify_tape_len(n, S, K)) return fail(ctx, ZKA_E_ARG, "tape_stride < zka_verify_tape_len");
   try {
     {
       Stream& st0 = ctx->st;
@@ -1184,7 +1198,7 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       const int Bc = (int)std::min<uint32_t>((uint32_t)vchunk, B - b0);
       VerifyCtx c;
       memset(&c, 0, sizeof(c));
-      c.B = Bc; c.S = S; c.N = (int)N; c.n = n;
+      c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.K = K;
       c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
       c.msg_hash = stage_in(st, ln.in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
       if (is_device_ptr(proofs) || is_device_ptr(proof_len)) {
@@ -1207,7 +1221,8 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
       c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
       c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
-      const size_t ns = (size_t)Bc * V_SAMPLES;
+      const size_t ns = (size_t)Bc * K;
+      const int ET = c.ent_tom(), EN = c.ent_nist(), SG = c.segs();
       const int ngk = 4 * n + 1;
       c.rep_off = W[0].get<uint32_t>((size_t)Bc * S);
       c.gk_off = W[1].get<uint32_t>(Bc);
@@ -1233,14 +1248,14 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.td_aff = W[21].get<uint32_t>(ns * DERS_PER_ITEM * TOM_AFF_WORDS);
       c.td_bytes = W[22].get<uint8_t>(ns * DERS_PER_ITEM * BSTRIDE);
       c.item_chal = W[23].get<uint32_t>(ns * HASHES_PER_ITEM * 3);
-      c.ent_scalar = W[24].get<uint32_t>((size_t)Bc * V_ENT_TOM * 8);
-      c.ent_off = W[25].get<uint32_t>((size_t)Bc * V_ENT_TOM);
-      c.ent_pre = W[26].get<uint32_t>((size_t)Bc * V_ENT_TOM * TOM_PRE_WORDS);
+      c.ent_scalar = W[24].get<uint32_t>((size_t)Bc * ET * 8);
+      c.ent_off = W[25].get<uint32_t>((size_t)Bc * ET);
+      c.ent_pre = W[26].get<uint32_t>((size_t)Bc * ET * TOM_PRE_WORDS);
       c.ent_cnt = W[27].get<uint32_t>(ns);
       c.part = W[28].get<uint32_t>(ns * V_PART_WORDS);
-      c.nent_scalar = W[29].get<uint32_t>((size_t)Bc * V_ENT_NIST * 8);
-      c.nent_aff = W[30].get<uint32_t>((size_t)Bc * V_ENT_NIST * 16);
-      c.nent_skip = W[31].get<uint8_t>((size_t)Bc * V_ENT_NIST);
+      c.nent_scalar = W[29].get<uint32_t>((size_t)Bc * EN * 8);
+      c.nent_aff = W[30].get<uint32_t>((size_t)Bc * EN * 16);
+      c.nent_skip = W[31].get<uint8_t>((size_t)Bc * EN);
       c.gk_scalar = W[32].get<uint32_t>((size_t)Bc * ngk * 8);
       c.gk_pre = W[33].get<uint32_t>((size_t)Bc * ngk * TOM_PRE_WORDS);
       uint32_t* gk_offs = W[34].get<uint32_t>((size_t)Bc * ngk);
@@ -1248,7 +1263,7 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       c.fx_jr = W[36].get<uint32_t>((size_t)Bc * 2 * 8);
       c.fx_proj = W[37].get<uint32_t>((size_t)Bc * 2 * TOM_PROJ_WORDS);
       c.nfix = W[38].get<uint32_t>((size_t)Bc * P256_PROJ_WORDS);
-      c.win_w = W[39].get<uint32_t>((size_t)Bc * MSM_NWIN * 36);
+      c.win_w = W[39].get<uint32_t>((size_t)Bc * SG * MSM_NWIN * 36);
       c.win_g = W[42].get<uint32_t>((size_t)Bc * MSM_NWIN * 36);
       c.win_n = W[43].get<uint32_t>((size_t)Bc * MSM_NWIN_N * P256_PROJ_WORDS);
       c.id_flags = W[44].get<uint8_t>((size_t)Bc * 3);
@@ -1272,7 +1287,7 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch(st, (long long)ns, VDerivedTask{c});
       launch_tom_norm(st, c.td_proj, nullptr, c.td_bytes, (long long)(ns * DERS_PER_ITEM), 0);
       launch(st, (long long)ns * HASHES_PER_ITEM, VItemHashTask{c});
-      dev_memset(st, c.ent_off, 0, (size_t)Bc * V_ENT_TOM * 4);
+      dev_memset(st, c.ent_off, 0, (size_t)Bc * ET * 4);
       launch(st, (long long)ns, VRelationsTask{c});
       {
         const int nblk = 1 << (n - gk_block_bits(n));
@@ -1282,20 +1297,20 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
       launch(st, Bc, VGkTask{c});
       launch(st, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
       launch(st, Bc, VReduceTask{c});
-      launch(st, (long long)Bc * V_ENT_TOM, VParseEntriesTask{c.proofs, proof_stride, c.ent_off, c.ent_pre, V_ENT_TOM});
+      launch(st, (long long)Bc * ET, VParseEntriesTask{c.proofs, proof_stride, c.ent_off, c.ent_pre, ET});
       launch(st, (long long)Bc * ngk, VParseEntriesTask{c.proofs, proof_stride, gk_offs, c.gk_pre, ngk});
       launch(st, (long long)Bc * 2, TomCommitTask{c.fx_jv, c.fx_jr, c.tg_tab, c.th_tab, c.fx_proj, c.tom_w, c.tom_nwin});
       {
-        const int nW = Bc * MSM_NWIN, nWp = (nW + 31) & ~31;
-        launch(st, (long long)nWp + nW,
-               MsmTomWindowBothTask{MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, V_ENT_TOM, V_SAMPLES, V_ENT_PER_SAMPLE, 2, c.win_w},
-                                    MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, c.win_g}, nW, nWp});
+        const int nW = Bc * SG * MSM_NWIN, nWp = (nW + 31) & ~31, nG = Bc * MSM_NWIN;
+        launch(st, (long long)nWp + nG,
+               MsmTomWindowBothTask{MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, ET, K, V_ENT_PER_SAMPLE, 2, V_SEG, SG, c.win_w},
+                                    MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, V_SEG, 1, c.win_g}, nW, nWp, nG});
       }
-      launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n});
+      launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n, EN});
       {
         const int Bp = (Bc + 31) & ~31;
         launch(st, 3ll * Bp, MsmCombineAllTask{MsmTomCombineTask{c.win_g, c.fx_proj, c.id_flags, 2, 0, 0},
-                                               MsmTomCombineTask{c.win_w, c.fx_proj, c.id_flags, 2, 1, 1},
+                                               MsmTomCombineTask{c.win_w, c.fx_proj, c.id_flags, 2, 1, 1, SG},
                                                MsmP256CombineTask{c.win_n, c.nfix, c.id_flags}, Bc, Bp});
       }
       launch(st, Bc, VFinalTask{c});

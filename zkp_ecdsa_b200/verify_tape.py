@@ -14,8 +14,8 @@ def ceil_log2(v: int) -> int:
     return n
 
 
-def verify_tape_len(ring_size: int) -> int:
-    return 32 * (2 * ceil_log2(ring_size) + 1) + IDX_PAD + 32 * 25 * V_SAMPLES
+def verify_tape_len(ring_size: int, samples: int = V_SAMPLES) -> int:
+    return 32 * (2 * ceil_log2(ring_size) + 1) + IDX_PAD + 32 * 25 * samples
 
 
 def random_verify_tape(rows: int, stride: int, ring_size: int, sec_level: int = 80, seed: int = 0) -> np.ndarray:
@@ -23,7 +23,7 @@ def random_verify_tape(rows: int, stride: int, ring_size: int, sec_level: int = 
     0xffffffff00000000... so they are valid for both moduli (see synth.random_tape)."""
     from .synth import random_tape
     n = ceil_log2(ring_size)
-    assert stride >= verify_tape_len(ring_size) and stride % 32 == 0
+    assert stride >= 32 * (2 * n + 1) + IDX_PAD + 32 and stride % 32 == 0
     t = random_tape(rows, stride, seed)
     g = 32 * (2 * n + 1)
     rng = np.random.Generator(np.random.PCG64(seed + 12345))
