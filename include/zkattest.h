@@ -131,6 +131,40 @@ int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* params, uint32_t B,
                         const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
                         const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status, uint32_t samples);
 
+/* ---- stand-alone sub-proof verifiers: the surface of the reference's own unit tests and benches ----
+ * verifyExp(paramsNIST, paramsWario, Clambda, Px, Py, pi, secparam, Q?)   /root/reference/src/exp/exp.ts:233-349
+ *   paramsNIST = (p256, g = base[i], h = NistGroup.h of `params`), paramsWario = ProofGroup of `params`;
+ *   pi = the sec_level repetitions of `params` in the flat layout above (rep*), `samples` = secparam, q = NULL when
+ *   the statement has no Q (test/exp/exp.test.ts:37-40) else B x 65 (65 zero bytes = identity).
+ *   tape per statement: the sec_level-2 generateIndices bytes (exp.ts:101-106), zero-padded to 96 bytes, then the
+ *   25 * samples packed Relation.drain scalars in consumption order (as in zka_verify_batch). */
+int zka_verify_exp_batch(zka_ctx* ctx, const zka_params* params, uint32_t B,
+                         const uint8_t* base /* B x 65 */, const uint8_t* com /* B x 65: Clambda */,
+                         const uint8_t* px /* B x 67 */, const uint8_t* py /* B x 67 */, const uint8_t* q /* B x 65 or NULL */,
+                         const uint8_t* proofs /* B x proof_stride */, size_t proof_stride, const uint32_t* proof_len /* B */,
+                         const uint8_t* tape /* B x tape_stride */, size_t tape_stride, uint32_t samples,
+                         uint8_t* ok /* B */, int32_t* status /* B */);
+/* verifyMembership(params = ProofGroup, com, ring, proof)                /root/reference/src/proofGK/gk.ts:197-262
+ *   proofs: GK blocks in the flat layout above; tape per statement: the 2n+1 Relation.drain scalars in call order
+ *   (rel0_0, rel1_0, ..., relFinal), n = ceil(log2 N). */
+int zka_verify_membership_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* com /* B x 67 */,
+                                const uint8_t* ring /* N x 32 */, uint32_t N,
+                                const uint8_t* proofs /* B x proof_stride */, size_t proof_stride, const uint32_t* proof_len /* B */,
+                                const uint8_t* tape /* B x tape_stride */, size_t tape_stride,
+                                uint8_t* ok /* B */, int32_t* status /* B */);
+
+/* verifyEquality(params, C1, C2, pi)            /root/reference/src/commit/equality.ts:80-116   points: B x 2 x 67
+ * verifyMult(params, Cx, Cy, Cz, pi)             /root/reference/src/commit/mult.ts:133-175      points: B x 3 x 67
+ * verifyPointAdd(params, PX,PY,QX,QY,RX,RY, pi)  /root/reference/src/exp/pointAdd.ts:181-259     points: B x 6 x 67
+ * over params = ProofGroup; proofs: B x 233 / 633 / 3266 bytes in the flat layout above; tape per statement: the 2 / 5 /
+ * 24 Relation.drain scalars (mod tomEdwards256.order) in call order. */
+int zka_verify_equality_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* points, const uint8_t* proofs,
+                              const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status);
+int zka_verify_mult_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* points, const uint8_t* proofs,
+                          const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status);
+int zka_verify_pointadd_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* points, const uint8_t* proofs,
+                              const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status);
+
 /* ---- measurement hooks (bench.py) ----
  * zka_get_stream: the cudaStream_t every kernel of this context is launched on (so callers can
  * record CUDA events on the launching stream).  zka_set_profiling(1) brackets every launch with a
@@ -143,10 +177,11 @@ size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap);
  *   ZKA_TOM_W       window bits of the tomEdwards256 fixed-base tables, 2..24, default 22
  *                   (ceil(256/w) windows x 2^w entries x 128 B per base: 6.4 GB at 22, 134 MB at 16)
  *   ZKA_P256_HW     window bits of the P-256 G / NistGroup.h tables, 8..24, default 20 (872 MB per base)
- *   ZKA_CHUNK       proofs per pipeline pass when all buffers are device memory, default 8192
- *   ZKA_HOST_CHUNK  proofs per pass when buffers are host memory (copies of one pass overlap the
- *                   kernels of the next), default 4096
- *   ZKA_LANES       concurrent pipelines inside one prove / verify call, 1..8, default 2: the batch is cut
+ *   ZKA_CHUNK       largest chunk (proofs per pipeline pass) when all buffers are device memory, default 4096
+ *   ZKA_HOST_CHUNK  largest chunk when buffers are host memory, default 2048; the schedule is tapered
+ *                   (quarter, half, full ..., half, quarter chunks) so that little copy time is exposed before
+ *                   the first and after the last kernel
+ *   ZKA_LANES       concurrent pipelines inside one prove / verify call, 1..8, default 3: the batch is cut
  *                   into chunks dealt round-robin to the lanes; every lane has its own streams and workspace
  *                   and (beyond the first) its own host thread for the duration of the call, so the
  *                   latency-bound stages and the host<->device copies of one chunk overlap the

@@ -257,3 +257,12 @@ def test_wild_index_and_error_rows_on_gpu(gpu_engine):
     # the context is still healthy
     common.check_prove_parity(L, B=1, N=6, seed=73, sec_level=16)
     L.params_destroy(P)
+
+
+def test_verify_sample_count_on_gpu(gpu_engine):
+    """zka_verify_batch_ex: 5, 33 and all 80 repetitions sampled (80 = four MSM segments per proof); verdicts on valid
+    and tampered proofs equal oracle/cpu's under identical randomness."""
+    cpu = _cpu_port()
+    for K in (5, 33, 80):
+        common.check_verify_samples(gpu_engine.lib, K, N=5, seed=25, sec_level=80, tampers=6, oracle=cpu)
+    common.check_verify_samples(gpu_engine.lib, 7, N=4, seed=26, sec_level=20, tampers=2, oracle='python')

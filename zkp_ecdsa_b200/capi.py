@@ -26,6 +26,8 @@ SYMBOLS = [
     'zka_tom_commit_batch', 'zka_p256_mul_batch', 'zka_field_op_batch', 'zka_hash80_batch',
     'zka_get_stream', 'zka_set_profiling', 'zka_profile_reset', 'zka_profile_json', 'zka_config',
     'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack', 'zka_verify_batch_ex', 'zka_verify_tape_len_ex',
+    'zka_verify_exp_batch', 'zka_verify_membership_batch', 'zka_verify_equality_batch', 'zka_verify_mult_batch',
+    'zka_verify_pointadd_batch',
 ]
 
 STATUS_MESSAGES = {
@@ -114,6 +116,13 @@ class ZkaLib:
             L.zka_verify_batch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                               C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32]
             L.zka_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+            L.zka_verify_exp_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_size_t, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
+            L.zka_verify_membership_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                      C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+            for f in ('zka_verify_equality_batch', 'zka_verify_mult_batch', 'zka_verify_pointadd_batch'):
+                getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p, C.c_void_p]
             L.zka_proofs_pack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.c_void_p]
             L.zka_proofs_unpack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -212,6 +221,35 @@ class ZkaLib:
         self._check(self.lib.zka_verify_batch_ex(self.ctx, params, B, _ptr(msg_hash), _ptr(ring), N, _ptr(proofs), proof_stride,
                                                  _ptr(proof_len), _ptr(tape), tape_stride, _ptr(ok), _ptr(status), samples),
                     'zka_verify_batch_ex')
+
+    # ------------------------------------------------------------------ stand-alone sub-proof verifiers
+    def verify_exp_batch(self, params, base, com, px, py, q, proofs, proof_len, tape, samples):
+        B = base.shape[0]
+        ok = np.zeros(B, np.uint8)
+        st = np.zeros(B, np.int32)
+        self._check(self.lib.zka_verify_exp_batch(self.ctx, params, B, _ptr(base), _ptr(com), _ptr(px), _ptr(py), _ptr(q), _ptr(proofs),
+                                                  proofs.shape[1], _ptr(proof_len), _ptr(tape), tape.shape[1], samples, _ptr(ok), _ptr(st)),
+                    'zka_verify_exp_batch')
+        return ok, st
+
+    def verify_membership_batch(self, params, com, ring, proofs, proof_len, tape):
+        B = com.shape[0]
+        ok = np.zeros(B, np.uint8)
+        st = np.zeros(B, np.int32)
+        self._check(self.lib.zka_verify_membership_batch(self.ctx, params, B, _ptr(com), _ptr(ring), ring.shape[0], _ptr(proofs),
+                                                         proofs.shape[1], _ptr(proof_len), _ptr(tape), tape.shape[1], _ptr(ok), _ptr(st)),
+                    'zka_verify_membership_batch')
+        return ok, st
+
+    def verify_sub_batch(self, kind: str, params, points, proofs, tape):
+        """kind in {'equality', 'mult', 'pointadd'}; points [B, k*67], proofs [B, 233|633|3266], tape [B, >= 32*draws]"""
+        B = points.shape[0]
+        ok = np.zeros(B, np.uint8)
+        st = np.zeros(B, np.int32)
+        fn = getattr(self.lib, f'zka_verify_{kind}_batch')
+        self._check(fn(self.ctx, params, B, _ptr(points), _ptr(proofs), _ptr(tape), tape.shape[1], _ptr(ok), _ptr(st)),
+                    f'zka_verify_{kind}_batch')
+        return ok, st
 
     # ------------------------------------------------------------------ multi-GPU helpers
     def proofs_pack(self, B, proofs, stride, proof_len, packed, cap, offsets, stream=0):

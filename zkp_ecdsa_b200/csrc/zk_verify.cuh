@@ -52,6 +52,9 @@ ZK_LAYOUT_FN size_t verify_tape_len(int n, int /*reps*/, int K = V_SAMPLES) {
 struct VerifyCtx {
   int B, S, N, n;
   int K;                       // sampled repetitions (<= S)
+  int mode;                    // 0: verifySignatureList; 1: verifyExp alone (exp.ts:233, no GK block, Q given or absent);
+                               // 2: verifyMembership alone (gk.ts:197)
+  const uint8_t* q_ext;        // mode 1: [B][65] Q points (all-zero = identity) or null (no Q: T1 = g*z)
   int tom_w, tom_nwin;
   const uint8_t* msg_hash;     // [B][32]
   const uint8_t* proofs;       // [B][proof_stride]
@@ -119,7 +122,7 @@ struct VerifyCtx {
   ZK_HD int segs() const { return (K + V_SEG - 1) / V_SEG; }
   ZK_HD const uint8_t* proof_of(int b) const { return proofs + (size_t)b * proof_stride; }
   ZK_HD const uint8_t* tape_of(int b) const { return tape + (size_t)b * tape_stride; }
-  ZK_HD size_t gk_tape_bytes() const { return (size_t)32 * (2 * n + 1); }
+  ZK_HD size_t gk_tape_bytes() const { return mode == 1 ? 0 : (size_t)32 * (2 * n + 1); }
   ZK_HD const uint8_t* exp_tape(int b) const { return tape_of(b) + gk_tape_bytes() + V_IDX_PAD; }
   ZK_HD size_t ta_pt(size_t sample, int j) const { return sample * 2 + j; }   // 0 T1x, 1 T1y
   ZK_HD size_t td_pt(size_t sample, int j) const { return sample * DERS_PER_ITEM + j; }
@@ -190,7 +193,13 @@ struct VLayoutTask {
       if (off > len) bad = true;
     }
     int ngk = 0;
-    if (!bad) {
+    if (!bad && c.mode == 1) {           // verifyExp alone: the row ends with the last repetition
+      if (off != len) bad = true;
+      uint32_t z[8];
+      zero_n<8>(z);                      // no GK instance: its fixed-base job is 0*g + 0*h
+      st<8>(c.fx_jv + (size_t)b * 2 * 8, z);
+      st<8>(c.fx_jr + (size_t)b * 2 * 8, z);
+    } else if (!bad) {
       if (off + 1 > len) bad = true;
       else {
         ngk = pr[off];
@@ -199,7 +208,7 @@ struct VLayoutTask {
     }
     st<3>(c.tagbits + (size_t)b * 3, tg);
     c.gk_off[b] = off;
-    c.gk_ok_len[b] = (!bad && ngk == c.n) ? 1 : 0;
+    c.gk_ok_len[b] = (!bad && (c.mode == 1 || ngk == c.n)) ? 1 : 0;
     if (bad) {
       ZK_SET_STATUS(c.status + b, ZKA_ERR_MALFORMED);
       // park the offsets on the header so later stages read in-bounds garbage
@@ -214,6 +223,16 @@ struct VLayoutTask {
     if (!okR) { ZK_SET_STATUS(c.status + b, ZKA_ERR_MALFORMED); p256_set_generator(R); }
     if (rinf) ZK_SET_STATUS(c.status + b, ZKA_ERR_R_INFINITY);   // zkpAttestList.ts:158-160
     p256_st_aff(c.r_aff + (size_t)b * 16, R);
+    if (c.mode == 1) {   // Q is an input (or absent): no statement to derive it from
+      P256Aff Qa;
+      bool qinf = true, okq = true;
+      if (c.q_ext) okq = p256_parse(Qa, qinf, c.q_ext + (size_t)b * NP);
+      if (!okq) ZK_SET_STATUS(c.status + b, ZKA_ERR_MALFORMED);
+      if (qinf || !okq) p256_set_generator(Qa);
+      p256_st_aff(c.q_aff + (size_t)b * 16, Qa);
+      c.q_inf[b] = (qinf || !okq) ? 1 : 0;
+      return;
+    }
     uint32_t z[8], rx[8], zm[8], rm[8], rinv[8], t[8], z1[8];
     limbs_from_be<8>(z, c.msg_hash + (size_t)b * 32, 32);
     reduce_once<FnP256>(z);
@@ -275,10 +294,12 @@ struct VValidateTask {
     if (slot == c.S) {
       ok = p256_parse(a, inf, pr + NP) && ok;             // comS1 (R is checked in VLayoutTask)
       ok = wpts(pr + 2 * NP, 2) && ok;                    // keyXcom keyYcom
-      const uint8_t* g = pr + c.gk_off[b];
-      const int n = g[0];
-      ok = wpts(g + 1, 4 * n) && ok;
-      ok = wscs(g + 1 + (size_t)4 * n * WP, 3 * n + 1) && ok;
+      if (c.mode != 1) {
+        const uint8_t* g = pr + c.gk_off[b];
+        const int n = g[0];
+        ok = wpts(g + 1, 4 * n) && ok;
+        ok = wscs(g + 1 + (size_t)4 * n * WP, 3 * n + 1) && ok;
+      }
     } else {
       const uint8_t* rep = pr + c.rep_off[(size_t)b * c.S + slot];
       ok = p256_parse(a, inf, rep + 1) && ok;
@@ -1126,6 +1147,324 @@ struct MsmCombineAllTask {
   }
 };
 
+
+// ---- stand-alone sub-proof verifiers (the reference's unit-test / bench surface) -------------------------------
+// Rows for the shared tasks are assembled on the device: a 264-byte header followed by the caller's proof bytes.
+//   verifyExp        (exp.ts:233):  header = paramsNIST.g | Clambda | Px | Py, body = the repetitions
+//   verifyMembership (gk.ts:197):   header = 0 | 0 | com | 0,              body = the GK block
+struct VAssembleTask {
+  const uint8_t *h0, *h1, *h2, *h3;   // [B][65] [B][65] [B][67] [B][67]; null = zero bytes
+  const uint8_t* body;                // [B][body_stride]
+  size_t body_stride;
+  const uint32_t* body_len;           // [B]
+  uint8_t* rows;                      // [B][row_stride]
+  size_t row_stride;
+  uint32_t* row_len;                  // [B]  = HEAD_LEN + body_len (clamped to the stride)
+  int pieces;                         // 64-byte pieces per row
+  ZK_HD void operator()(int t) const {
+    const int b = t / pieces, j = t % pieces;
+    uint32_t bl = body_len[b];
+    if ((size_t)bl > body_stride) bl = (uint32_t)body_stride + 1;   // stays "too long" -> MALFORMED
+    if (j == 0) row_len[b] = HEAD_LEN + bl;
+    uint8_t* row = rows + (size_t)b * row_stride;
+    const size_t lo = (size_t)64 * j, hi = lo + 64;
+    for (size_t o = lo; o < hi && o < row_stride; o++) {
+      uint8_t v = 0;
+      if (o < NP) v = h0 ? h0[(size_t)b * NP + o] : 0;
+      else if (o < 2 * NP) v = h1 ? h1[(size_t)b * NP + (o - NP)] : 0;
+      else if (o < 2 * NP + WP) v = h2 ? h2[(size_t)b * WP + (o - 2 * NP)] : 0;
+      else if (o < HEAD_LEN) v = h3 ? h3[(size_t)b * WP + (o - 2 * NP - WP)] : 0;
+      else if (o - HEAD_LEN < bl && o - HEAD_LEN < body_stride) v = body[(size_t)b * body_stride + (o - HEAD_LEN)];
+      row[o] = v;
+    }
+  }
+};
+// verifyMembership alone: layout + deserialisation checks of com and the GK block.  One thread per proof.
+struct VGkOnlyLayoutTask {
+  VerifyCtx c;
+  ZK_HD void operator()(int b) const {
+    c.status[b] = ZKA_OK;
+    c.ok[b] = 0;
+    const uint8_t* pr = c.proof_of(b);
+    const uint32_t len = c.proof_len[b];
+    bool bad = len < HEAD_LEN + 1 || len > c.proof_stride;
+    int ngk = 0;
+    if (!bad) {
+      ngk = pr[HEAD_LEN];
+      if (HEAD_LEN + (uint32_t)gk_len(ngk) != len) bad = true;
+    }
+    c.gk_off[b] = bad ? 0 : HEAD_LEN;
+    bool okp = true;
+    if (!bad) {
+      uint32_t x[9], y[9], r[8];
+      okp = tom_parse(x, y, pr + 2 * NP);
+      const uint8_t* g = pr + HEAD_LEN;
+      for (int i = 0; i < 4 * ngk; i++) okp = tom_parse(x, y, g + 1 + (size_t)i * WP) && okp;
+      for (int i = 0; i < 3 * ngk + 1; i++) okp = wscalar_parse(r, g + 1 + (size_t)4 * ngk * WP + (size_t)i * WS) && okp;
+    }
+    if (bad || !okp) ZK_SET_STATUS(c.status + b, ZKA_ERR_MALFORMED);
+    c.gk_ok_len[b] = (!bad && okp && ngk == c.n) ? 1 : 0;
+  }
+};
+struct VGkOnlyFinalTask {
+  VerifyCtx c;
+  ZK_HD void operator()(int b) const {
+    const int st = c.status[b];
+    c.ok[b] = (st == ZKA_OK && c.gk_ok_len[b] && c.id_flags[(size_t)b * 3]) ? 1 : 0;
+  }
+};
+
+// ---- verifyEquality / verifyMult / verifyPointAdd alone (equality.ts:80-116, mult.ts:133-175, pointAdd.ts:181-259)
+// Row = the statement's commitments (2 / 3 / 6 x 67 bytes, in the reference's argument order) followed by the proof
+// (233 / 633 / 3266 bytes).  One thread per statement folds all relations under the tape's randomizers into
+//   * scalars of the variable points (inputs and proof points)  -> entries of ONE Pippenger instance,
+//   * the coefficients of g and h                                -> one fixed-base commitment,
+// exactly like the batched verifier does for a sampled repetition; derived commitments (C7, C9, C12, Cint) are
+// expanded onto the inputs they are sums of.
+enum : int { SUB_EQ = 0, SUB_MULT = 1, SUB_PADD = 2, SUB_ENT_MAX = 38 };
+ZK_LAYOUT_FN int sub_points(int kind) { return kind == SUB_EQ ? 2 : kind == SUB_MULT ? 3 : 6; }
+ZK_LAYOUT_FN int sub_proof_len(int kind) { return kind == SUB_EQ ? EQ_LEN : kind == SUB_MULT ? MULT_LEN : PA_LEN; }
+ZK_LAYOUT_FN int sub_draws(int kind) { return kind == SUB_EQ ? 2 : kind == SUB_MULT ? 5 : 24; }
+ZK_LAYOUT_FN int sub_entries(int kind) { return kind == SUB_EQ ? 4 : kind == SUB_MULT ? 9 : SUB_ENT_MAX; }
+
+// encoding (67 bytes in a 68-byte slot) of an E1 affine point given as Montgomery (x', y)
+ZK_HD void tom_encode_affine(uint8_t* out, const uint32_t* x1m, const uint32_t* ym) {
+  uint32_t isa[9], cx[9], cy[9];
+  tom_const(isa, TOM_INVSQRTA);
+  Tomp::mul(cx, x1m, isa);
+  Tomp::from_mont(cx, cx);
+  Tomp::from_mont(cy, ym);
+  store_point_words<9, 33>(out, 0x04u, cx, cy);
+}
+ZK_HD void tom_encode_proj(uint8_t* out, const TomPt& p) {   // one inversion: low-volume paths only
+  uint32_t zi[9], x[9], y[9];
+  Tomp::inv(zi, p.z);
+  Tomp::mul(x, p.x, zi);
+  Tomp::mul(y, p.y, zi);
+  tom_encode_affine(out, x, y);
+}
+
+struct VSubProofTask {
+  int kind;
+  const uint8_t* rows;     // [B][stride]
+  size_t stride;
+  const uint8_t* tape;     // [B][tape_stride] drains (mod tom.order) in Relation.drain call order
+  size_t tape_stride;
+  const uint8_t* tg_bytes; // encoding of ProofGroup.g (C_14 of pi_8, pointAdd.ts:220)
+  uint32_t* ent_scalar;    // [B][SUB_ENT_MAX][8] canonical
+  uint32_t* ent_off;       // [B][SUB_ENT_MAX] byte offset of the point in the row
+  uint32_t *fx_jv, *fx_jr; // [B][2][8]: job 1 = (coefficient of g, coefficient of h); job 0 = 0
+  int32_t* status;         // [B]
+  uint8_t* ok;             // [B]
+
+  struct Fold {            // running state of one statement
+    uint32_t gW[8], hW[8];
+    bool tape_ok;
+  };
+  ZK_HD static void acc_add(uint32_t* a, const uint32_t* v) { Tomq::add(a, a, v); }
+  // aggregateMult (mult.ts:148-175).  bx/by/bz: 67-byte encodings; mp: MultProof bytes; dr: 5 drains.
+  // cx/cy/cz: Montgomery coefficient accumulators of Cx, Cy, Cz; es: canonical scalars of C4 Ax Ay Az A41 A42.
+  ZK_HD static void mult(Fold& f, const uint8_t* bx, const uint8_t* by, const uint8_t* bz, const uint8_t* mp, const uint8_t* dr,
+                         uint32_t* cx, uint32_t* cy, uint32_t* cz, uint32_t (*es)[8]) {
+    using F = Tomq;
+    Sha256 h;
+    h.init();
+    h.update(bx, WP); h.update(by, WP); h.update(bz, WP); h.update(mp, 6 * WP);
+    uint32_t c3[3], cc[8], cm[8];
+    h.final80(c3);
+    challenge_to_limbs(cc, c3);
+    F::to_mont(cm, cc);
+    uint32_t ts[7][8], rr[5][8], rho[8], t0[8], coef[8], neg[8], z[8];
+    zero_n<8>(z);
+    for (int q = 0; q < 7; q++) { wscalar_parse(ts[q], mp + 6 * WP + q * WS); F::to_mont(ts[q], ts[q]); }
+    for (int q = 0; q < 5; q++) { f.tape_ok = vdraw(rho, dr + 32 * q, false) && f.tape_ok; F::to_mont(rr[q], rho); }
+    // rho1: t_x g + t_rx h + c Cx - A_x
+    F::mul(t0, rr[0], ts[0]); acc_add(f.gW, t0);
+    F::mul(t0, rr[0], ts[3]); acc_add(f.hW, t0);
+    F::mul(coef, rr[0], cm); acc_add(cx, coef);
+    F::sub(neg, z, rr[0]); F::from_mont(es[1], neg);
+    // rho2: t_y g + t_ry h + c Cy - A_y ; rho5: t_x Cy + c C_4 - A_4_2
+    F::mul(t0, rr[1], ts[1]); acc_add(f.gW, t0);
+    F::mul(t0, rr[1], ts[4]); acc_add(f.hW, t0);
+    F::mul(coef, rr[1], cm);
+    F::mul(t0, rr[4], ts[0]); F::add(coef, coef, t0);
+    acc_add(cy, coef);
+    F::sub(neg, z, rr[1]); F::from_mont(es[2], neg);
+    // rho3: t_z g + t_rz h + c Cz - A_z
+    F::mul(t0, rr[2], ts[2]); acc_add(f.gW, t0);
+    F::mul(t0, rr[2], ts[5]); acc_add(f.hW, t0);
+    F::mul(coef, rr[2], cm); acc_add(cz, coef);
+    F::sub(neg, z, rr[2]); F::from_mont(es[3], neg);
+    // rho4: t_z g + t_r4 h + c C_4 - A_4_1
+    F::mul(t0, rr[3], ts[2]); acc_add(f.gW, t0);
+    F::mul(t0, rr[3], ts[6]); acc_add(f.hW, t0);
+    F::add(coef, rr[3], rr[4]); F::mul(coef, coef, cm); F::from_mont(es[0], coef);   // C_4: (rho4 + rho5) c
+    F::sub(neg, z, rr[3]); F::from_mont(es[4], neg);
+    F::sub(neg, z, rr[4]); F::from_mont(es[5], neg);
+  }
+  // aggregateEquality (equality.ts:94-116): es = canonical scalars of A1, A2
+  ZK_HD static void equality(Fold& f, const uint8_t* b1, const uint8_t* b2, const uint8_t* ep, const uint8_t* dr, uint32_t* c1,
+                             uint32_t* c2, uint32_t (*es)[8]) {
+    using F = Tomq;
+    Sha256 h;
+    h.init();
+    h.update(b1, WP); h.update(b2, WP); h.update(ep, 2 * WP);
+    uint32_t c3[3], cc[8], cm[8];
+    h.final80(c3);
+    challenge_to_limbs(cc, c3);
+    F::to_mont(cm, cc);
+    uint32_t tx[8], tr1[8], tr2[8], ra[8], rb[8], rho[8], t0[8], t1[8], coef[8], neg[8], z[8];
+    zero_n<8>(z);
+    wscalar_parse(tx, ep + 2 * WP); F::to_mont(tx, tx);
+    wscalar_parse(tr1, ep + 2 * WP + WS); F::to_mont(tr1, tr1);
+    wscalar_parse(tr2, ep + 2 * WP + 2 * WS); F::to_mont(tr2, tr2);
+    f.tape_ok = vdraw(rho, dr, false) && f.tape_ok; F::to_mont(ra, rho);
+    f.tape_ok = vdraw(rho, dr + 32, false) && f.tape_ok; F::to_mont(rb, rho);
+    F::add(t1, ra, rb); F::mul(t0, t1, tx); acc_add(f.gW, t0);
+    F::mul(t0, ra, tr1); acc_add(f.hW, t0);
+    F::mul(t0, rb, tr2); acc_add(f.hW, t0);
+    F::mul(coef, ra, cm); acc_add(c1, coef);
+    F::mul(coef, rb, cm); acc_add(c2, coef);
+    F::sub(neg, z, ra); F::from_mont(es[0], neg);
+    F::sub(neg, z, rb); F::from_mont(es[1], neg);
+  }
+  ZK_HD void emit(int b, int e, const uint32_t* canon, uint32_t off) const {
+    st<8>(ent_scalar + ((size_t)b * SUB_ENT_MAX + e) * 8, canon);
+    ent_off[(size_t)b * SUB_ENT_MAX + e] = off;
+  }
+  ZK_HD void emit_m(int b, int e, const uint32_t* mont, uint32_t off) const {
+    uint32_t v[8];
+    Tomq::from_mont(v, mont);
+    emit(b, e, v, off);
+  }
+  ZK_HD void operator()(int b) const {
+    using F = Tomq;
+    const uint8_t* row = rows + (size_t)b * stride;
+    const uint8_t* dr = tape + (size_t)b * tape_stride;
+    const int np = sub_points(kind);
+    const uint8_t* proof = row + (size_t)np * WP;
+    const uint32_t poff = (uint32_t)(np * WP);
+    status[b] = ZKA_OK;
+    ok[b] = 0;
+    // deserialisation checks of every point and scalar (deserializePoint / deserializeScalar would throw)
+    bool good = true;
+    {
+      uint32_t x[9], y[9], r[8];
+      for (int i = 0; i < np; i++) good = tom_parse(x, y, row + (size_t)i * WP) && good;
+      if (kind == SUB_EQ) {
+        for (int i = 0; i < 2; i++) good = tom_parse(x, y, proof + (size_t)i * WP) && good;
+        for (int i = 0; i < 3; i++) good = wscalar_parse(r, proof + 2 * WP + (size_t)i * WS) && good;
+      } else {
+        const int nm = kind == SUB_MULT ? 1 : 4;
+        const uint8_t* m0 = kind == SUB_MULT ? proof : proof + 4 * WP;
+        if (kind == SUB_PADD) for (int i = 0; i < 4; i++) good = tom_parse(x, y, proof + (size_t)i * WP) && good;
+        for (int m = 0; m < nm; m++) {
+          for (int i = 0; i < 6; i++) good = tom_parse(x, y, m0 + (size_t)m * MULT_LEN + (size_t)i * WP) && good;
+          for (int i = 0; i < 7; i++) good = wscalar_parse(r, m0 + (size_t)m * MULT_LEN + 6 * WP + (size_t)i * WS) && good;
+        }
+        if (kind == SUB_PADD)
+          for (int e = 0; e < 2; e++) {
+            const uint8_t* ep = proof + 4 * WP + 4 * MULT_LEN + (size_t)e * EQ_LEN;
+            for (int i = 0; i < 2; i++) good = tom_parse(x, y, ep + (size_t)i * WP) && good;
+            for (int i = 0; i < 3; i++) good = wscalar_parse(r, ep + 2 * WP + (size_t)i * WS) && good;
+          }
+      }
+    }
+    Fold f;
+    zero_n<8>(f.gW); zero_n<8>(f.hW);
+    f.tape_ok = true;
+    uint32_t zero[8];
+    zero_n<8>(zero);
+    for (int e = 0; e < SUB_ENT_MAX; e++) emit(b, e, zero, 0);   // unused entries: scalar 0 on the first input point
+    if (!good) {
+      ZK_SET_STATUS(status + b, ZKA_ERR_MALFORMED);
+    } else if (kind == SUB_EQ) {
+      uint32_t c1[8], c2[8], es[2][8];
+      zero_n<8>(c1); zero_n<8>(c2);
+      equality(f, row, row + WP, proof, dr, c1, c2, es);
+      emit_m(b, 0, c1, 0); emit_m(b, 1, c2, WP);
+      emit(b, 2, es[0], poff); emit(b, 3, es[1], poff + WP);
+    } else if (kind == SUB_MULT) {
+      uint32_t cx[8], cy[8], cz[8], es[6][8];
+      zero_n<8>(cx); zero_n<8>(cy); zero_n<8>(cz);
+      mult(f, row, row + WP, row + 2 * WP, proof, dr, cx, cy, cz, es);
+      emit_m(b, 0, cx, 0); emit_m(b, 1, cy, WP); emit_m(b, 2, cz, 2 * WP);
+      for (int i = 0; i < 6; i++) emit(b, 3 + i, es[i], poff + (uint32_t)i * WP);
+    } else {
+      // aggregatePointAdd (pointAdd.ts:199-259): C1..C6 = PX QX RX PY QY RY
+      const uint8_t *PX = row, *PY = row + WP, *QX = row + 2 * WP, *QY = row + 3 * WP, *RX = row + 4 * WP, *RY = row + 5 * WP;
+      TomPt p1, p2, p3, p4, p5, p6, n, r;
+      uint32_t x[9], y[9];
+      tom_parse(x, y, PX); tom_from_affine(p1, x, y);
+      tom_parse(x, y, QX); tom_from_affine(p2, x, y);
+      tom_parse(x, y, RX); tom_from_affine(p3, x, y);
+      tom_parse(x, y, PY); tom_from_affine(p4, x, y);
+      tom_parse(x, y, QY); tom_from_affine(p5, x, y);
+      tom_parse(x, y, RY); tom_from_affine(p6, x, y);
+      uint8_t d7[BSTRIDE], d9[BSTRIDE], d12[BSTRIDE], dix[BSTRIDE], diy[BSTRIDE];
+      tom_neg(n, p1); tom_add(r, p2, n); tom_encode_proj(d7, r);        // C7 = C2 - C1
+      tom_neg(n, p4); tom_add(r, p5, n); tom_encode_proj(d9, r);        // C9 = C5 - C4
+      tom_neg(n, p3); tom_add(r, p1, n); tom_encode_proj(d12, r);       // C12 = C1 - C3
+      tom_add(r, p3, p1); tom_add(r, r, p2); tom_encode_proj(dix, r);   // Cint = C3 + C1 + C2
+      tom_add(r, p4, p6); tom_encode_proj(diy, r);                      // Cint = C4 + C6
+      const uint8_t *C8 = proof, *C10 = proof + WP, *C11 = proof + 2 * WP, *C13 = proof + 3 * WP;
+      const uint8_t* mp = proof + 4 * WP;
+      const uint8_t* ep = mp + 4 * MULT_LEN;
+      uint32_t a7[8], a8[8], a9[8], a10[8], a11[8], a12[8], a13[8], aix[8], aiy[8], ag[8];
+      zero_n<8>(a7); zero_n<8>(a8); zero_n<8>(a9); zero_n<8>(a10); zero_n<8>(a11); zero_n<8>(a12); zero_n<8>(a13);
+      zero_n<8>(aix); zero_n<8>(aiy); zero_n<8>(ag);
+      uint32_t es[6][8], ee[2][8];
+      const uint32_t om = poff + 4 * WP, oe = om + 4 * MULT_LEN;
+      mult(f, d7, C8, tg_bytes, mp, dr, a7, a8, ag, es);                                  // pi_8
+      for (int i = 0; i < 6; i++) emit(b, 10 + i, es[i], om + (uint32_t)i * WP);
+      mult(f, C8, d9, C10, mp + MULT_LEN, dr + 32 * 5, a8, a9, a10, es);                  // pi_10
+      for (int i = 0; i < 6; i++) emit(b, 16 + i, es[i], om + MULT_LEN + (uint32_t)i * WP);
+      mult(f, C10, C10, C11, mp + 2 * MULT_LEN, dr + 32 * 10, a10, a10, a11, es);         // pi_11
+      for (int i = 0; i < 6; i++) emit(b, 22 + i, es[i], om + 2 * MULT_LEN + (uint32_t)i * WP);
+      equality(f, C11, dix, ep, dr + 32 * 15, a11, aix, ee);                              // pi_x
+      emit(b, 34, ee[0], oe); emit(b, 35, ee[1], oe + WP);
+      mult(f, C10, d12, C13, mp + 3 * MULT_LEN, dr + 32 * 17, a10, a12, a13, es);         // pi_13
+      for (int i = 0; i < 6; i++) emit(b, 28 + i, es[i], om + 3 * MULT_LEN + (uint32_t)i * WP);
+      equality(f, C13, diy, ep + EQ_LEN, dr + 32 * 22, a13, aiy, ee);                     // pi_y
+      emit(b, 36, ee[0], oe + EQ_LEN); emit(b, 37, ee[1], oe + EQ_LEN + WP);
+      acc_add(f.gW, ag);                                                                  // C_14 = g
+      // derived commitments expanded onto the inputs
+      uint32_t cPX[8], cPY[8], cQX[8], cQY[8], cRX[8], cRY[8];
+      F::sub(cPX, a12, a7); F::add(cPX, cPX, aix);       // -C7 +C12 +Cint
+      F::add(cQX, a7, aix);
+      F::sub(cRX, aix, a12);
+      F::sub(cPY, aiy, a9);
+      copy_n<8>(cQY, a9);
+      copy_n<8>(cRY, aiy);
+      emit_m(b, 0, cPX, 0); emit_m(b, 1, cPY, WP); emit_m(b, 2, cQX, 2 * WP); emit_m(b, 3, cQY, 3 * WP);
+      emit_m(b, 4, cRX, 4 * WP); emit_m(b, 5, cRY, 5 * WP);
+      emit_m(b, 6, a8, poff); emit_m(b, 7, a10, poff + WP); emit_m(b, 8, a11, poff + 2 * WP); emit_m(b, 9, a13, poff + 3 * WP);
+    }
+    if (good && !f.tape_ok) ZK_SET_STATUS(status + b, ZKA_ERR_TAPE_RANGE);
+    uint32_t v[8];
+    zero_n<8>(v);
+    st<8>(fx_jv + (size_t)b * 16, v); st<8>(fx_jr + (size_t)b * 16, v);
+    F::from_mont(v, f.gW); st<8>(fx_jv + (size_t)b * 16 + 8, v);
+    F::from_mont(v, f.hW); st<8>(fx_jr + (size_t)b * 16 + 8, v);
+  }
+};
+struct VSubFinalTask {
+  int32_t* status;
+  const uint8_t* id_flags;   // [B][3], verdict at [b][1]
+  uint8_t* ok;
+  ZK_HD void operator()(int b) const { ok[b] = (status[b] == ZKA_OK && id_flags[(size_t)b * 3 + 1]) ? 1 : 0; }
+};
+struct VConcatTask {   // rows[b] = a[b] (la bytes) || c[b] (lc bytes)
+  const uint8_t *a, *c;
+  int la, lc;
+  uint8_t* rows;
+  size_t stride;
+  ZK_HD void operator()(int t) const {
+    const int per = la + lc;
+    const int b = t / per, o = t % per;
+    rows[(size_t)b * stride + o] = o < la ? a[(size_t)b * la + o] : c[(size_t)b * lc + (o - la)];
+  }
+};
 
 // final verdict (zkpAttestList.ts:165-183): GK first, then exp
 struct VFinalTask {

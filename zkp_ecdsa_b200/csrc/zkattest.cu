@@ -10,6 +10,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <string>
 #include <vector>
@@ -295,13 +296,13 @@ struct Lane {
 struct zka_ctx : Lane {
   int device = 0;
   std::vector<Lane*> extra;   // lanes 1 .. nlanes-1 (lane 0 is the context itself)
-  int nlanes = 2;             // ZKA_LANES
+  int nlanes = 3;             // ZKA_LANES
   DevBuf ring_in, ring_m;     // the ring of the current call (shared by all lanes, read-only while they run)
   Lane& lane(int i) { return i == 0 ? *this : *extra[i - 1]; }
   int tom_w = 22, tom_nwin = 12;   // per base: 12 windows x (2^21 + 1) signed-digit entries x 128 B = 3.2 GB of HBM (ZKA_TOM_W)
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
-  int chunk = 8192;
-  int host_chunk = 4096;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
+  int chunk = 4096;       // largest chunk of a call whose buffers are all device memory (ZKA_CHUNK)
+  int host_chunk = 2048;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
   int p256_hw = 20;       // window bits of the P-256 G table and of the per-params NistGroup.h table
                           // (13 windows x 2^20 entries x 64 B = 872 MB each; 16 -> 20 -> 22: PhaseA 13.4 -> 12.9 -> 12.6 ms)
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
@@ -441,6 +442,40 @@ const T* stage_in(Stream& st, DevBuf& buf, const T* p, size_t count) {
 template <class T>
 const T* stage_in(zka_ctx* ctx, DevBuf& buf, const T* p, size_t count) {
   return stage_in(ctx->st, buf, p, count);
+}
+
+// Chunk schedule of a call: boundaries off[0..nchunks] of the batch.  `cmax` = largest chunk, `lanes` = lanes that
+// will run.  Plain: near-equal chunks, at least one per lane when chunks of >= 256 proofs allow it.  Tapered (used
+// when a buffer lives in host memory): the first chunks are small so that the kernels start after a short input
+// copy, the last ones small so that little output copy is left exposed after the last kernel, and lanes that
+// claim chunks dynamically drift out of phase (one copies while another computes):
+//   cmax/4, cmax/2, [full chunks], cmax/2, cmax/4.
+std::vector<uint32_t> chunk_schedule(uint32_t B, uint32_t cmax, int lanes, bool taper) {
+  std::vector<uint32_t> off{0};
+  auto r32 = [](uint32_t v) { return v < 32 ? std::max<uint32_t>(v, 1) : ((v + 31) & ~31u); };
+  if (lanes > 1) {
+    uint32_t per = r32((B + (uint32_t)lanes - 1) / (uint32_t)lanes);
+    cmax = std::min(cmax, std::max<uint32_t>(per, 256));
+  }
+  uint32_t done = 0;
+  auto push = [&](uint32_t n) { n = std::min(n, B - done); if (n) { done += n; off.push_back(done); } };
+  if (taper && cmax >= 1024 && B >= 3 * cmax) {
+    const uint32_t q = r32(cmax / 4), h = r32(cmax / 2);
+    push(q);
+    push(h);
+    const uint32_t mid = B - done - (h + q);
+    const uint32_t nm = (mid + cmax - 1) / cmax;
+    const uint32_t each = r32((mid + nm - 1) / nm);
+    for (uint32_t i = 0; i + 1 < nm; i++) push(each);
+    push(B - done - (h + q));
+    push(h);
+    push(q);
+  } else {
+    const uint32_t nk = (B + cmax - 1) / cmax;
+    const uint32_t each = r32((B + nk - 1) / nk);
+    while (done < B) push(each);
+  }
+  return off;
 }
 
 // Run fn(lane index) for lanes 0..used-1: lane 0 on the calling thread, the others on their own host threads
@@ -611,7 +646,7 @@ int zka_init(int device, zka_ctx** out) {
     stream_create(ctx->cs_in);
     stream_create(ctx->cs_out);
     {
-      int lanes = 2;
+      int lanes = 3;
 #if defined(ZKA_HOSTSIM)
       lanes = 1;
 #endif
@@ -933,29 +968,23 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
     uint32_t* lag = (uint32_t*)ctx->lag.p;
     const bool out_dev = is_device_ptr(proofs);
     const bool len_dev = is_device_ptr(proof_len_out), st_dev = is_device_ptr(status);
-    // chunk size: the configured one, but never so large that a lane stays idle (at least `lanes` chunks when
-    // the batch allows chunks of >= 256 proofs); rounded up to a multiple of 32
     const int lanes = ctx->nlanes;
-    uint32_t chunk = (uint32_t)((out_dev && is_device_ptr(tape)) ? ctx->chunk : std::min(ctx->chunk, ctx->host_chunk));
-    if (lanes > 1) {
-      uint32_t per = (B + (uint32_t)lanes - 1) / (uint32_t)lanes;
-      per = std::max<uint32_t>((per + 31) & ~31u, 256);
-      chunk = std::min(chunk, per);
-    }
-    const uint32_t nchunks = (B + chunk - 1) / chunk;
+    const bool all_dev = out_dev && is_device_ptr(tape);
+    const std::vector<uint32_t> off = chunk_schedule(B, (uint32_t)(all_dev ? ctx->chunk : std::min(ctx->chunk, ctx->host_chunk)), lanes, !all_dev);
+    const uint32_t nchunks = (uint32_t)off.size() - 1;
     const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
-    // lane `li` processes chunks li, li + used, li + 2 used, ...  Within a lane, chunks are software-pipelined over
-    // three streams when buffers live in host memory (staging buffers double-buffered by slot).
+    std::atomic<uint32_t> next_chunk(0);
+    // Every lane claims chunks from a shared counter (one ahead of the one it is computing, so that its inputs are
+    // already on their way).  Within a lane, chunks are software-pipelined over three streams when buffers live in
+    // host memory (staging buffers double-buffered by slot).
     auto run_lane = [&](int li) {
       Lane& ln = ctx->lane(li);
       Stream& st = ln.st;
       DevBuf* W = ln.w;
       struct ChunkIn { const uint8_t *msg_hash, *sig, *pk, *tape; const uint32_t* which; } cin[2];
-      auto slot_of = [&](uint32_t k) { return (int)(((k - (uint32_t)li) / (uint32_t)used) & 1u); };
-      auto issue_inputs = [&](uint32_t k) {
-        const int slot = slot_of(k);
-        const uint32_t b0 = k * chunk;
-        const size_t Bc = std::min<uint32_t>(chunk, B - b0);
+      auto issue_inputs = [&](uint32_t k, int slot) {
+        const uint32_t b0 = off[k];
+        const size_t Bc = off[k + 1] - b0;
         Stream& ci = ln.cs_in;
         DevBuf* in = ln.in + 5 * slot;
         ev_wait(ci, ln.ev_done[slot]);   // the chunk that used these staging buffers before has finished reading them
@@ -967,12 +996,15 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
         ev_record(ln.ev_tape[slot], ci);
       };
-      issue_inputs((uint32_t)li);
-      for (uint32_t k = (uint32_t)li; k < nchunks; k += (uint32_t)used) {
-        const uint32_t b0 = k * chunk;
-        const int slot = slot_of(k);
-        const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
-        if (k + (uint32_t)used < nchunks) issue_inputs(k + (uint32_t)used);
+      uint32_t k = next_chunk.fetch_add(1);
+      int slot = 0;
+      if (k < nchunks) issue_inputs(k, slot);
+      for (; k < nchunks; slot ^= 1) {
+        const uint32_t b0 = off[k];
+        const int Bc = (int)(off[k + 1] - b0);
+        const uint32_t kn = next_chunk.fetch_add(1);
+        if (kn < nchunks) issue_inputs(kn, slot ^ 1);
+        k = kn;
         ev_wait(st, ln.ev_small[slot]);
         ev_wait(st, ln.ev_out[slot]);    // the proofs of chunk k-2 have left the output staging buffers
         ProveCtx c;
@@ -1156,10 +1188,24 @@ int zka_verify_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_
   return zka_verify_batch_ex(ctx, P, B, msg_hash, ring, N, proofs, proof_stride, proof_len, tape, tape_stride, ok, status, V_SAMPLES);
 }
 
+static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring,
+                       uint32_t N, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
+                       const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status, uint32_t samples, int mode,
+                       const uint8_t* q_ext);
+
 int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring,
                         uint32_t N, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
                         const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status, uint32_t samples) {
-  if (!ctx || !P || !msg_hash || !ring || !proofs || !proof_len || !tape || !ok || !status) return ZKA_E_ARG;
+  if (!msg_hash || !ring) return ZKA_E_ARG;
+  return verify_impl(ctx, P, B, msg_hash, ring, N, proofs, proof_stride, proof_len, tape, tape_stride, ok, status, samples, 0, nullptr);
+}
+
+// mode 0: verifySignatureList; mode 1: verifyExp alone on assembled rows (msg_hash / ring unused, Q from q_ext)
+static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* ring,
+                       uint32_t N, const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len,
+                       const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status, uint32_t samples, int mode,
+                       const uint8_t* q_ext) {
+  if (!ctx || !P || !proofs || !proof_len || !tape || !ok || !status) return ZKA_E_ARG;
   if (B == 0) return 0;
   if (N < 2 || N > (1u << 20)) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
   const int S = (int)P->sec_level;
@@ -1168,9 +1214,10 @@ int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* P, uint32_t B, const uin
   // verifyExp throws 'security level not achieved' when secparam > pi.length (exp.ts:243-245)
   if (S < K) return fail(ctx, ZKA_E_ARG, "security level not achieved");
   const int n = ceil_log2(N);
-  if (tape_stride < verify_tape_len(n, S, K)) return fail(ctx, ZKA_E_ARG, "tape_stride < zka_verify_tape_len");
+  if (tape_stride < (mode == 1 ? (size_t)V_IDX_PAD + (size_t)32 * 25 * K : verify_tape_len(n, S, K)))
+    return fail(ctx, ZKA_E_ARG, "tape_stride < zka_verify_tape_len");
   try {
-    {
+    if (mode == 0) {
       Stream& st0 = ctx->st;
       const uint8_t* d_ring = stage_in(st0, ctx->ring_in, ring, (size_t)N * 32);
       uint32_t* rm = ctx->ring_m.get<uint32_t>(((size_t)1 << n) * 8);
@@ -1179,28 +1226,26 @@ int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* P, uint32_t B, const uin
     }
     const uint32_t* ring_m = (const uint32_t*)ctx->ring_m.p;
     const int lanes = ctx->nlanes;
-    uint32_t vchunk = (uint32_t)std::min(ctx->chunk, 4096);
-    if (lanes > 1) {
-      uint32_t per = (B + (uint32_t)lanes - 1) / (uint32_t)lanes;
-      per = std::max<uint32_t>((per + 31) & ~31u, 256);
-      vchunk = std::min(vchunk, per);
-    }
-    const uint32_t nchunks = (B + vchunk - 1) / vchunk;
+    const bool all_dev = is_device_ptr(proofs) && is_device_ptr(tape);
+    const std::vector<uint32_t> off = chunk_schedule(B, (uint32_t)std::min(ctx->chunk, all_dev ? 4096 : std::min(4096, ctx->host_chunk)), lanes, !all_dev);
+    const uint32_t nchunks = (uint32_t)off.size() - 1;
     const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
-    // lane li verifies chunks li, li + used, ...: copy-in, kernels and copy-out of a chunk are sequential on the
+    std::atomic<uint32_t> next_chunk(0);
+    // every lane claims chunks from a shared counter: copy-in, kernels and copy-out of a chunk are sequential on the
     // lane's stream; the copies of one lane overlap the kernels of the others
     auto run_lane = [&](int li) {
       Lane& ln = ctx->lane(li);
       Stream& st = ln.st;
       DevBuf* W = ln.w;
-      for (uint32_t k = (uint32_t)li; k < nchunks; k += (uint32_t)used) {
-      const uint32_t b0 = k * vchunk;
-      const int Bc = (int)std::min<uint32_t>((uint32_t)vchunk, B - b0);
+      for (uint32_t k = next_chunk.fetch_add(1); k < nchunks; k = next_chunk.fetch_add(1)) {
+      const uint32_t b0 = off[k];
+      const int Bc = (int)(off[k + 1] - b0);
       VerifyCtx c;
       memset(&c, 0, sizeof(c));
-      c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.K = K;
+      c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.K = K; c.mode = mode;
+      c.q_ext = q_ext ? q_ext + (size_t)b0 * NP : nullptr;
       c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
-      c.msg_hash = stage_in(st, ln.in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32);
+      c.msg_hash = msg_hash ? stage_in(st, ln.in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32) : nullptr;
       if (is_device_ptr(proofs) || is_device_ptr(proof_len)) {
         c.proofs = stage_in(st, ln.in[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
       } else {
@@ -1289,22 +1334,22 @@ int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* P, uint32_t B, const uin
       launch(st, (long long)ns * HASHES_PER_ITEM, VItemHashTask{c});
       dev_memset(st, c.ent_off, 0, (size_t)Bc * ET * 4);
       launch(st, (long long)ns, VRelationsTask{c});
-      {
+      if (mode == 0) {
         const int nblk = 1 << (n - gk_block_bits(n));
         c.gk_part = nblk > 1 ? W[51].get<uint32_t>((size_t)Bc * nblk * 8) : nullptr;
         if (nblk > 1) launch(st, (long long)Bc * nblk, VGkSumTask{c});
+        launch(st, Bc, VGkTask{c});
+        launch(st, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
       }
-      launch(st, Bc, VGkTask{c});
-      launch(st, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
       launch(st, Bc, VReduceTask{c});
       launch(st, (long long)Bc * ET, VParseEntriesTask{c.proofs, proof_stride, c.ent_off, c.ent_pre, ET});
-      launch(st, (long long)Bc * ngk, VParseEntriesTask{c.proofs, proof_stride, gk_offs, c.gk_pre, ngk});
+      if (mode == 0) launch(st, (long long)Bc * ngk, VParseEntriesTask{c.proofs, proof_stride, gk_offs, c.gk_pre, ngk});
       launch(st, (long long)Bc * 2, TomCommitTask{c.fx_jv, c.fx_jr, c.tg_tab, c.th_tab, c.fx_proj, c.tom_w, c.tom_nwin});
       {
         const int nW = Bc * SG * MSM_NWIN, nWp = (nW + 31) & ~31, nG = Bc * MSM_NWIN;
         launch(st, (long long)nWp + nG,
                MsmTomWindowBothTask{MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, ET, K, V_ENT_PER_SAMPLE, 2, V_SEG, SG, c.win_w},
-                                    MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, V_SEG, 1, c.win_g}, nW, nWp, nG});
+                                    MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, mode == 0 ? ngk : 0, V_SEG, 1, c.win_g}, nW, nWp, nG});
       }
       launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n, EN});
       {
@@ -1324,6 +1369,177 @@ int zka_verify_batch_ex(zka_ctx* ctx, const zka_params* P, uint32_t B, const uin
   } catch (const std::exception& e) {
     return fail(ctx, ZKA_E_CUDA, e.what());
   }
+}
+
+// ------------------------------------------------------------------ stand-alone sub-proof verifiers
+// verifyExp(paramsNIST = (p256, base, NistGroup.h), paramsWario = ProofGroup, Clambda, Px, Py, pi, secparam, Q?)
+// (exp.ts:233-349) for B independent statements.  The repetitions arrive in the flat layout of include/zkattest.h.
+int zka_verify_exp_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* base, const uint8_t* com,
+                         const uint8_t* px, const uint8_t* py, const uint8_t* q, const uint8_t* proofs, size_t proof_stride,
+                         const uint32_t* proof_len, const uint8_t* tape, size_t tape_stride, uint32_t samples, uint8_t* ok,
+                         int32_t* status) {
+  if (!ctx || !P || !base || !com || !px || !py || !proofs || !proof_len || !tape || !ok || !status || proof_stride == 0) return ZKA_E_ARG;
+  if (B == 0) return 0;
+  try {
+    Stream& st = ctx->st;
+    DevBuf bufs[8];
+    const uint8_t* d_base = stage_in(st, bufs[0], base, (size_t)B * NP);
+    const uint8_t* d_com = stage_in(st, bufs[1], com, (size_t)B * NP);
+    const uint8_t* d_px = stage_in(st, bufs[2], px, (size_t)B * WP);
+    const uint8_t* d_py = stage_in(st, bufs[3], py, (size_t)B * WP);
+    const uint8_t* d_q = q ? stage_in(st, bufs[4], q, (size_t)B * NP) : nullptr;
+    const uint8_t* d_body = stage_in(st, bufs[5], proofs, (size_t)B * proof_stride);
+    const uint32_t* d_len = stage_in(st, bufs[6], proof_len, (size_t)B);
+    const uint8_t* d_tape = stage_in(st, bufs[7], tape, (size_t)B * tape_stride);
+    const size_t row_stride = (HEAD_LEN + proof_stride + 15) & ~(size_t)15;
+    DevBuf rows, rlen;
+    uint8_t* d_rows = rows.get<uint8_t>((size_t)B * row_stride);
+    uint32_t* d_rlen = rlen.get<uint32_t>(B);
+    const int pieces = (int)((row_stride + 63) / 64);
+    launch(st, (long long)B * pieces, VAssembleTask{d_base, d_com, d_px, d_py, d_body, proof_stride, d_len, d_rows, row_stride, d_rlen, pieces});
+    sync(st);
+    const int rc = verify_impl(ctx, P, B, nullptr, nullptr, 2, d_rows, row_stride, d_rlen, d_tape, tape_stride, ok, status, samples, 1, d_q);
+    for (auto& b : bufs) b.release();
+    rows.release();
+    rlen.release();
+    return rc;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+// verifyMembership(ProofGroup params, com, ring, proof) (gk.ts:197-262) for B commitments over one ring.
+// tape: the 2n+1 Relation.drain scalars per proof, in call order.
+int zka_verify_membership_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* com, const uint8_t* ring, uint32_t N,
+                                const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_len, const uint8_t* tape,
+                                size_t tape_stride, uint8_t* ok, int32_t* status) {
+  if (!ctx || !P || !com || !ring || !proofs || !proof_len || !tape || !ok || !status || proof_stride == 0) return ZKA_E_ARG;
+  if (B == 0) return 0;
+  if (N < 2 || N > (1u << 20)) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
+  const int n = ceil_log2(N);
+  if (tape_stride < (size_t)32 * (2 * n + 1)) return fail(ctx, ZKA_E_ARG, "tape_stride < 32 * (2n + 1)");
+  try {
+    Stream& st = ctx->st;
+    DevBuf* W = ctx->w;
+    DevBuf bufs[4];
+    const uint8_t* d_ring = stage_in(st, ctx->ring_in, ring, (size_t)N * 32);
+    uint32_t* ring_m = ctx->ring_m.get<uint32_t>(((size_t)1 << n) * 8);
+    launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
+    const size_t row_stride = (HEAD_LEN + proof_stride + 15) & ~(size_t)15;
+    const int pieces = (int)((row_stride + 63) / 64);
+    const int ngk = 4 * n + 1;
+    const uint32_t chunk = 4096;
+    for (uint32_t b0 = 0; b0 < B; b0 += chunk) {
+      const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
+      const uint8_t* d_com = stage_in(st, bufs[0], com + (size_t)b0 * WP, (size_t)Bc * WP);
+      const uint8_t* d_body = stage_in(st, bufs[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
+      const uint32_t* d_len = stage_in(st, bufs[2], proof_len + b0, (size_t)Bc);
+      VerifyCtx c;
+      memset(&c, 0, sizeof(c));
+      c.B = Bc; c.S = (int)P->sec_level; c.N = (int)N; c.n = n; c.K = 1; c.mode = 2;
+      c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
+      c.tape = stage_in(st, bufs[3], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      c.tape_stride = tape_stride;
+      c.ring_m = ring_m;
+      c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
+      uint8_t* d_rows = W[0].get<uint8_t>((size_t)Bc * row_stride);
+      uint32_t* d_rlen = W[1].get<uint32_t>(Bc);
+      c.proofs = d_rows; c.proof_stride = row_stride; c.proof_len = d_rlen;
+      c.gk_off = W[2].get<uint32_t>(Bc);
+      c.gk_ok_len = W[3].get<uint8_t>(Bc);
+      c.gk_scalar = W[4].get<uint32_t>((size_t)Bc * ngk * 8);
+      c.gk_pre = W[5].get<uint32_t>((size_t)Bc * ngk * TOM_PRE_WORDS);
+      uint32_t* gk_offs = W[6].get<uint32_t>((size_t)Bc * ngk);
+      c.fx_jv = W[7].get<uint32_t>((size_t)Bc * 2 * 8);
+      c.fx_jr = W[8].get<uint32_t>((size_t)Bc * 2 * 8);
+      c.fx_proj = W[9].get<uint32_t>((size_t)Bc * 2 * TOM_PROJ_WORDS);
+      c.win_g = W[10].get<uint32_t>((size_t)Bc * MSM_NWIN * 36);
+      c.id_flags = W[11].get<uint8_t>((size_t)Bc * 3);
+      c.ok = is_device_ptr(ok) ? ok + b0 : ctx->out[0].get<uint8_t>(Bc);
+      c.status = is_device_ptr(status) ? status + b0 : ctx->out[1].get<int32_t>(Bc);
+      launch(st, (long long)Bc * pieces, VAssembleTask{nullptr, nullptr, d_com, nullptr, d_body, proof_stride, d_len, d_rows, row_stride, d_rlen, pieces});
+      launch(st, Bc, VGkOnlyLayoutTask{c});
+      dev_memset(st, c.fx_jv, 0, (size_t)Bc * 2 * 8 * 4);
+      dev_memset(st, c.fx_jr, 0, (size_t)Bc * 2 * 8 * 4);
+      {
+        const int nblk = 1 << (n - gk_block_bits(n));
+        c.gk_part = nblk > 1 ? W[12].get<uint32_t>((size_t)Bc * nblk * 8) : nullptr;
+        if (nblk > 1) launch(st, (long long)Bc * nblk, VGkSumTask{c});
+      }
+      launch(st, Bc, VGkTask{c});
+      launch(st, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
+      launch(st, (long long)Bc * ngk, VParseEntriesTask{c.proofs, row_stride, gk_offs, c.gk_pre, ngk});
+      launch(st, (long long)Bc * 2, TomCommitTask{c.fx_jv, c.fx_jr, c.tg_tab, c.th_tab, c.fx_proj, c.tom_w, c.tom_nwin});
+      launch(st, (long long)Bc * MSM_NWIN, MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, ngk, V_SEG, 1, c.win_g});
+      launch(st, Bc, MsmTomCombineTask{c.win_g, c.fx_proj, c.id_flags, 2, 0, 0});
+      launch(st, Bc, VGkOnlyFinalTask{c});
+      if (!is_device_ptr(ok)) copy_d2h(st, ok + b0, c.ok, (size_t)Bc);
+      if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
+      sync(st);
+    }
+    for (auto& b : bufs) b.release();
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+// verifyEquality / verifyMult / verifyPointAdd alone (kind = 0 / 1 / 2): fixed-size inputs and proofs
+static int verify_sub(zka_ctx* ctx, const zka_params* P, int kind, uint32_t B, const uint8_t* points, const uint8_t* proofs,
+                      const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status) {
+  if (!ctx || !P || !points || !proofs || !tape || !ok || !status) return ZKA_E_ARG;
+  if (B == 0) return 0;
+  if (tape_stride < (size_t)32 * sub_draws(kind)) return fail(ctx, ZKA_E_ARG, "tape_stride too small for this sub-proof");
+  try {
+    Stream& st = ctx->st;
+    DevBuf* W = ctx->w;
+    const int la = sub_points(kind) * WP, lc = sub_proof_len(kind), ne = sub_entries(kind);
+    const size_t stride = (size_t)(la + lc + 15) & ~(size_t)15;
+    const uint32_t chunk = 8192;
+    for (uint32_t b0 = 0; b0 < B; b0 += chunk) {
+      const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
+      const uint8_t* d_pts = stage_in(st, ctx->in[0], points + (size_t)b0 * la, (size_t)Bc * la);
+      const uint8_t* d_prf = stage_in(st, ctx->in[1], proofs + (size_t)b0 * lc, (size_t)Bc * lc);
+      const uint8_t* d_tape = stage_in(st, ctx->in[2], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      uint8_t* rows = W[0].get<uint8_t>((size_t)Bc * stride);
+      uint32_t* ent_scalar = W[1].get<uint32_t>((size_t)Bc * SUB_ENT_MAX * 8);
+      uint32_t* ent_off = W[2].get<uint32_t>((size_t)Bc * SUB_ENT_MAX);
+      uint32_t* ent_pre = W[3].get<uint32_t>((size_t)Bc * SUB_ENT_MAX * TOM_PRE_WORDS);
+      uint32_t* fx_jv = W[4].get<uint32_t>((size_t)Bc * 2 * 8);
+      uint32_t* fx_jr = W[5].get<uint32_t>((size_t)Bc * 2 * 8);
+      uint32_t* fx_proj = W[6].get<uint32_t>((size_t)Bc * 2 * TOM_PROJ_WORDS);
+      uint32_t* win = W[7].get<uint32_t>((size_t)Bc * MSM_NWIN * 36);
+      uint8_t* flags = W[8].get<uint8_t>((size_t)Bc * 3);
+      uint8_t* d_ok = is_device_ptr(ok) ? ok + b0 : ctx->out[0].get<uint8_t>(Bc);
+      int32_t* d_st = is_device_ptr(status) ? status + b0 : ctx->out[1].get<int32_t>(Bc);
+      launch(st, (long long)Bc * (la + lc), VConcatTask{d_pts, d_prf, la, lc, rows, stride});
+      launch(st, Bc, VSubProofTask{kind, rows, stride, d_tape, tape_stride, (const uint8_t*)ctx->tg_bytes.p, ent_scalar, ent_off,
+                                   fx_jv, fx_jr, d_st, d_ok});
+      launch(st, (long long)Bc * SUB_ENT_MAX, VParseEntriesTask{rows, stride, ent_off, ent_pre, SUB_ENT_MAX});
+      launch(st, (long long)Bc * 2, TomCommitTask{fx_jv, fx_jr, ctx->tg.tab, P->th.tab, fx_proj, ctx->tom_w, ctx->tom_nwin});
+      launch(st, (long long)Bc * MSM_NWIN, MsmTomWindowTask{ent_scalar, ent_pre, nullptr, SUB_ENT_MAX, 0, 0, ne, V_SEG, 1, win});
+      launch(st, Bc, MsmTomCombineTask{win, fx_proj, flags, 2, 1, 1});
+      launch(st, Bc, VSubFinalTask{d_st, flags, d_ok});
+      if (!is_device_ptr(ok)) copy_d2h(st, ok + b0, d_ok, (size_t)Bc);
+      if (!is_device_ptr(status)) copy_d2h(st, status + b0, d_st, (size_t)Bc * 4);
+      sync(st);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+int zka_verify_equality_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* points, const uint8_t* proofs,
+                              const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status) {
+  return verify_sub(ctx, P, SUB_EQ, B, points, proofs, tape, tape_stride, ok, status);
+}
+int zka_verify_mult_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* points, const uint8_t* proofs,
+                          const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status) {
+  return verify_sub(ctx, P, SUB_MULT, B, points, proofs, tape, tape_stride, ok, status);
+}
+int zka_verify_pointadd_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* points, const uint8_t* proofs,
+                              const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status) {
+  return verify_sub(ctx, P, SUB_PADD, B, points, proofs, tape, tape_stride, ok, status);
 }
 
 // ---------------------------------------------------------------------------- multi-GPU helpers
