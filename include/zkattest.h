@@ -165,6 +165,26 @@ int zka_verify_mult_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, co
 int zka_verify_pointadd_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* points, const uint8_t* proofs,
                               const uint8_t* tape, size_t tape_stride, uint8_t* ok, int32_t* status);
 
+/* ---- stand-alone sub-proof provers ----
+ * proveExp(paramsNIST = (p256, base[i], NistGroup.h), paramsWario = ProofGroup, s, Cs, P = pk, Px, Py, sec_level, Q?)
+ *                                                                          /root/reference/src/exp/exp.ts:126-231
+ *   The statement is s*base - Q = pk (Q = NULL: s*base = pk, as in test/exp/exp.test.ts:26-38); it is checked and
+ *   ZKA_ERR_POINTS_DONT_ADD reported otherwise (pointAdd.ts:104).  Tape: the layout of zka_prove_batch — draws 0..2 are
+ *   the blinders of Cs, Px, Py (drawn when those commitments were made: Cs = s*base + r0*h, Px = commit(pk.x, r1),
+ *   Py = commit(pk.y, r2)), then 4 per repetition, then 40 per 0-bit repetition.  Rows: the repetitions only
+ *   (proof_stride >= sec_level * 3596), as consumed by zka_verify_exp_batch. */
+int zka_prove_exp_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* base /* B x 65 */,
+                        const uint8_t* s /* B x 32 */, const uint8_t* pk /* B x 65 */, const uint8_t* q /* B x 65 or NULL */,
+                        const uint8_t* tape, size_t tape_stride, uint8_t* proofs, size_t proof_stride,
+                        uint32_t* proof_len /* B */, int32_t* status /* B */);
+/* proveMembership(params = ProofGroup, com, index, ring)                    /root/reference/src/proofGK/gk.ts:94-195
+ *   com_r: blinder of com = commit(ring[index]); tape: the 5n draws r_i, a_i, s_i, t_i, rho_i per round (gk.ts:117-123).
+ *   Rows: the GK block (proof_stride >= 1 + 4n*67 + (3n+1)*33). */
+int zka_prove_membership_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* com_r /* B x 32 */,
+                               const uint32_t* index /* B */, const uint8_t* ring /* N x 32 */, uint32_t N,
+                               const uint8_t* tape, size_t tape_stride, uint8_t* proofs, size_t proof_stride,
+                               uint32_t* proof_len /* B */, int32_t* status /* B */);
+
 /* ---- measurement hooks (bench.py) ----
  * zka_get_stream: the cudaStream_t every kernel of this context is launched on (so callers can
  * record CUDA events on the launching stream).  zka_set_profiling(1) brackets every launch with a

@@ -226,3 +226,101 @@ def test_verify_small_subproofs(hostsim, kind):
 @pytest.mark.parametrize('kind', ['equality', 'mult', 'pointadd'])
 def test_verify_small_subproofs_on_gpu(gpu_engine, kind):
     check_verify_small(gpu_engine.lib, kind, seed=41, tampers=6)
+
+
+def check_prove_exp(L, sec=10, with_q=False, seed=51, B=2):
+    """zka_prove_exp_batch == oracle proveExp byte for byte (arbitrary base, optional Q), its output verifies with
+    zka_verify_exp_batch, and a false statement reports "Points don't add up!"."""
+    P, po = common.make_params(L, seed, sec)
+    d = synth.Drbg(seed, 'provexp')
+    n_ord, q = p256.order, tom.order
+    ndraw = 3 + 4 * sec + 40 * sec
+    tape = synth.random_tape(B + 1, 32 * ndraw, seed=seed + 1)
+    base_b, s_b, pk_b, q_b, want = [], [], [], [], []
+    for b in range(B + 1):
+        s = d.below(n_ord)
+        base = p256.generator().mul(p256.new_scalar(d.below(n_ord)))
+        Q = p256.generator().mul(p256.new_scalar(d.below(n_ord))) if with_q else None
+        pk = base.mul(p256.new_scalar(s))
+        if Q is not None:
+            pk = pk.sub(Q)
+        if b == B:                                  # false statement: another public key
+            pk = pk.add(p256.generator())
+        x, y = pk.to_affine()
+        tp = Tape(tape[b].tobytes())
+        nist = OC.PedersenParams(p256, base, po.NistGroup.h)
+        Cs = nist.commit(s, tp)                     # draw 0
+        Cx, Cy = po.ProofGroup.commit(x, tp), po.ProofGroup.commit(y, tp)   # draws 1, 2
+        try:
+            pi = OE.prove_exp(nist, po.ProofGroup, s, Cs, pk, Cx, Cy, sec, tp, Q)
+            want.append((b''.join(flat.ser_exp(e) for e in pi), nist, Cs, Cx, Cy, Q, base))
+        except ValueError as e:
+            assert "don't add up" in str(e)
+            want.append(None)
+        base_b.append(flat._pt(base, 65)); s_b.append(s.to_bytes(32, 'big')); pk_b.append(flat._pt(pk, 65))
+        q_b.append(flat._pt(Q, 65) if Q is not None else bytes(65))
+    arr = lambda rows: np.array([list(r) for r in rows], np.uint8)   # noqa: E731
+    proofs, plen, st = L.prove_exp_batch(P, arr(base_b), arr(s_b), arr(pk_b), arr(q_b) if with_q else None, tape, sec)
+    assert list(st[:B]) == [0] * B and st[B] == 4 and plen[B] == 0 and want[B] is None
+    for b in range(B):
+        assert proofs[b, :plen[b]].tobytes() == want[b][0], b
+    # round trip through the stand-alone verifier
+    K = sec
+    vt = synth.random_tape(B, 96 + 32 * 25 * K, seed=seed + 2)
+    rng = np.random.default_rng(seed)
+    for i in range(sec - 2):
+        vt[:, i] = rng.integers(0, sec - i, size=B, dtype=np.uint8)
+    vt[:, sec - 2:96] = 0
+    ok, vst = L.verify_exp_batch(P, arr(base_b[:B]), arr([flat._pt(w[2].p, 65) for w in want[:B]]), arr([w[3].p.to_bytes() for w in want[:B]]),
+                                 arr([w[4].p.to_bytes() for w in want[:B]]), arr(q_b[:B]) if with_q else None,
+                                 np.ascontiguousarray(proofs[:B]), plen[:B].copy(), vt, K)
+    assert (ok == 1).all() and not vst.any()
+    L.params_destroy(P)
+
+
+def check_prove_membership(L, ring_vals, indices, seed=61):
+    P, po = common.make_params(L, seed, 8)
+    params = po.ProofGroup
+    N = len(ring_vals)
+    n = len(bin(N - 1)) - 2
+    B = len(indices)
+    tape = synth.random_tape(B, 32 * 5 * n, seed=seed + 1)
+    rs = synth.random_tape(B, 32, seed=seed + 2)
+    want = []
+    for b, idx in enumerate(indices):
+        r = int.from_bytes(rs[b].tobytes(), 'big')
+        com = OC.Commitment(OG.gk_commit(params, ring_vals[idx] % tom.order, r), tom.new_scalar(r))
+        want.append((flat.ser_gk(OG.prove_membership(params, com, idx, ring_vals, Tape(tape[b].tobytes()))), com))
+    ring = np.array([list(int(v % tom.order).to_bytes(32, 'big')) for v in ring_vals], np.uint8)
+    idx_arr = np.array(list(indices) + [N + 5], np.uint32)          # one index outside the ring
+    proofs, plen, st = L.prove_membership_batch(P, np.concatenate([rs, rs[:1]]), idx_arr, ring, np.concatenate([tape, tape[:1]]))
+    assert list(st) == [0] * B + [6] and plen[B] == 0
+    for b in range(B):
+        assert proofs[b, :plen[b]].tobytes() == want[b][0], b
+    vt = synth.random_tape(B, 32 * (2 * n + 1), seed=seed + 3)
+    ok, vst = L.verify_membership_batch(P, np.array([list(w[1].p.to_bytes()) for w in want], np.uint8), ring,
+                                        np.ascontiguousarray(proofs[:B]), plen[:B].copy(), vt)
+    assert (ok == 1).all() and not vst.any()
+    L.params_destroy(P)
+
+
+def test_prove_exp_alone_without_q(hostsim):
+    check_prove_exp(hostsim, sec=10, with_q=False)
+
+
+def test_prove_exp_alone_with_q(hostsim):
+    check_prove_exp(hostsim, sec=9, with_q=True, seed=52, B=1)
+
+
+def test_prove_membership_alone(hostsim):
+    check_prove_membership(hostsim, [3, 5, 7, 11, 13], [3, 0, 4])       # test/proofGK/gk.test.ts shape
+    check_prove_membership(hostsim, [10 ** 30 + i for i in range(9)], [8], seed=62)
+
+
+@pytest.mark.gpu
+def test_subproof_provers_on_gpu(gpu_engine):
+    L = gpu_engine.lib
+    check_prove_exp(L, sec=20, with_q=False, seed=71, B=3)
+    check_prove_exp(L, sec=12, with_q=True, seed=72, B=2)
+    check_prove_membership(L, [3, 5, 7, 11, 13], [3, 0, 4], seed=73)
+    check_prove_membership(L, list(range(500, 500 + 300)), [0, 299, 150, 7], seed=74)

@@ -27,7 +27,7 @@ SYMBOLS = [
     'zka_get_stream', 'zka_set_profiling', 'zka_profile_reset', 'zka_profile_json', 'zka_config',
     'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack', 'zka_verify_batch_ex', 'zka_verify_tape_len_ex',
     'zka_verify_exp_batch', 'zka_verify_membership_batch', 'zka_verify_equality_batch', 'zka_verify_mult_batch',
-    'zka_verify_pointadd_batch',
+    'zka_verify_pointadd_batch', 'zka_prove_exp_batch', 'zka_prove_membership_batch',
 ]
 
 STATUS_MESSAGES = {
@@ -123,6 +123,10 @@ class ZkaLib:
             for f in ('zka_verify_equality_batch', 'zka_verify_mult_batch', 'zka_verify_pointadd_batch'):
                 getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.c_void_p]
+            L.zka_prove_exp_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p, C.c_size_t,
+                                              C.c_void_p, C.c_void_p]
+            L.zka_prove_membership_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
             L.zka_proofs_pack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.c_void_p]
             L.zka_proofs_unpack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -240,6 +244,28 @@ class ZkaLib:
                                                          proofs.shape[1], _ptr(proof_len), _ptr(tape), tape.shape[1], _ptr(ok), _ptr(st)),
                     'zka_verify_membership_batch')
         return ok, st
+
+    def prove_exp_batch(self, params, base, s, pk, q, tape, sec_level):
+        B = base.shape[0]
+        stride = sec_level * 3596
+        proofs = np.zeros((B, stride), np.uint8)
+        plen = np.zeros(B, np.uint32)
+        st = np.zeros(B, np.int32)
+        self._check(self.lib.zka_prove_exp_batch(self.ctx, params, B, _ptr(base), _ptr(s), _ptr(pk), _ptr(q), _ptr(tape), tape.shape[1],
+                                                 _ptr(proofs), stride, _ptr(plen), _ptr(st)), 'zka_prove_exp_batch')
+        return proofs, plen, st
+
+    def prove_membership_batch(self, params, com_r, index, ring, tape):
+        B, N = com_r.shape[0], ring.shape[0]
+        n = max(1, (N - 1).bit_length()) if N > 1 else 0
+        stride = 1 + 4 * n * 67 + (3 * n + 1) * 33
+        proofs = np.zeros((B, stride), np.uint8)
+        plen = np.zeros(B, np.uint32)
+        st = np.zeros(B, np.int32)
+        self._check(self.lib.zka_prove_membership_batch(self.ctx, params, B, _ptr(com_r), _ptr(index), _ptr(ring), N, _ptr(tape),
+                                                        tape.shape[1], _ptr(proofs), stride, _ptr(plen), _ptr(st)),
+                    'zka_prove_membership_batch')
+        return proofs, plen, st
 
     def verify_sub_batch(self, kind: str, params, points, proofs, tape):
         """kind in {'equality', 'mult', 'pointadd'}; points [B, k*67], proofs [B, 233|633|3266], tape [B, >= 32*draws]"""

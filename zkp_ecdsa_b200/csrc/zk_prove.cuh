@@ -30,6 +30,13 @@ struct ProveCtx {
   int n;        // ceil(log2 N)
   int M;        // total 0-bit repetitions (items) in the chunk (valid after the scan)
   int tom_w, tom_nwin;
+  int mode;                  // 0: proveSignatureList; 1: proveExp alone (exp.ts:126-231): R = `base`, s and Q are inputs,
+                             //    the row holds the repetitions only (no header, no GK block)
+  int head_len;              // bytes before the first repetition (HEAD_LEN, or 0 in mode 1)
+  const uint8_t* base;       // mode 1: [B][65] paramsNIST.g
+  const uint8_t* s_in;       // mode 1: [B][32] the committed exponent
+  const uint8_t* q_in;       // mode 1: [B][65] Q (65 zero bytes = identity) or null
+  uint32_t* base_aff;        // [B][16] base of the per-key tables: pk in mode 0, `base` in mode 1
   // inputs (device copies)
   const uint8_t* msg_hash;   // [B][32]
   const uint8_t* sig;        // [B][64]
@@ -168,6 +175,23 @@ struct PreKeyTask {   // validate and store the public key (everything the key t
       p256_set_generator(pk);
     }
     p256_st_aff(c.pk_aff + (size_t)b * 16, pk);
+    if (c.mode == 1) {   // the tables are built for paramsNIST.g, an input of its own
+      const uint8_t* bb = c.base + (size_t)b * 65;
+      limbs_from_be<8>(px, bb + 1, 32);
+      limbs_from_be<8>(py, bb + 33, 32);
+      reduce_once<FpP256>(px);
+      reduce_once<FpP256>(py);
+      P256Aff g;
+      Fp::to_mont(g.x, px);
+      Fp::to_mont(g.y, py);
+      if (!(bb[0] == 0x04 && p256_on_curve(g.x, g.y))) {
+        ZK_SET_STATUS(c.status + b, ZKA_ERR_INVALID_PK);
+        p256_set_generator(g);
+      }
+      p256_st_aff(c.base_aff + (size_t)b * 16, g);
+      c.which_s[b] = 0;
+      return;
+    }
     // an index outside the ring is flagged by RPointTask (ZKA_ERR_BAD_INDEX); the Groth-Kohlweiss tasks
     // must still stay inside ring_m[2^n], so they read this clamped copy
     const uint32_t w = c.which[b];
@@ -179,6 +203,34 @@ struct PreTask {      // the scalars of the statement and Q = z1*G
   ZK_HD void operator()(int b) const {
     using Fp = P256p;
     using Fn = P256n;
+    if (c.mode == 1) {   // alpha*R = 0*G + alpha*base; s and Q are given
+      uint32_t s1[8], u[8];
+      limbs_from_be<8>(s1, c.s_in + (size_t)b * 32, 32);
+      reduce_once<FnP256>(s1);
+      st<8>(c.s1 + (size_t)b * 8, s1);
+      zero_n<8>(u);
+      st<8>(c.u12 + (size_t)b * 16, u);
+      Fn::set_one(u);
+      st<8>(c.u12 + (size_t)b * 16 + 8, u);
+      P256Aff Qa;
+      bool qinf = true;
+      if (c.q_in) {
+        const uint8_t* qb = c.q_in + (size_t)b * 65;
+        uint32_t qx[8], qy[8];
+        limbs_from_be<8>(qx, qb + 1, 32);
+        limbs_from_be<8>(qy, qb + 33, 32);
+        qinf = (qb[0] == 0) && is_zero_n<8>(qx) && is_zero_n<8>(qy);
+        reduce_once<FpP256>(qx);
+        reduce_once<FpP256>(qy);
+        Fp::to_mont(Qa.x, qx);
+        Fp::to_mont(Qa.y, qy);
+        if (!qinf && !(qb[0] == 0x04 && p256_on_curve(Qa.x, Qa.y))) { ZK_SET_STATUS(c.status + b, ZKA_ERR_INVALID_PK); qinf = true; }
+      }
+      if (qinf) p256_set_generator(Qa);
+      p256_st_aff(c.q_aff + (size_t)b * 16, Qa);
+      c.q_inf[b] = qinf ? 1 : 0;
+      return;
+    }
     uint32_t z[8], r[8], s[8];
     limbs_from_be<8>(z, c.msg_hash + (size_t)b * 32, 32);   // truncateToN is the identity for 32 bytes
     limbs_from_be<8>(r, c.sig + (size_t)b * 64, 32);
@@ -226,10 +278,10 @@ struct KeyDedupTask {
   ProveCtx c;
   ZK_HD void operator()(int b) const {
     uint32_t mine[16];
-    ld<16>(mine, c.pk_aff + (size_t)b * 16);
+    ld<16>(mine, c.base_aff + (size_t)b * 16);
     int rep = b;
     for (int o = 0; o < b; o++) {
-      const uint32_t* q = c.pk_aff + (size_t)o * 16;
+      const uint32_t* q = c.base_aff + (size_t)o * 16;
       if (q[0] != mine[0]) continue;
       bool same = true;
       for (int i = 1; i < 16; i++) same = same && (q[i] == mine[i]);
@@ -297,17 +349,19 @@ struct RPointTask {
       Fp::mul(Ra.x, R.x, zi);
       Fp::mul(Ra.y, R.y, zi);
     }
-    uint32_t r[8];
-    limbs_from_be<8>(r, c.sig + (size_t)b * 64, 32);
-    reduce_once<FnP256>(r);
-    if (is_zero_n<8>(r)) ZK_SET_STATUS_OVER(c.status + b, ZKA_ERR_POINTS_DONT_ADD, ZKA_ERR_TAPE_RANGE);  // rinv = 0: T1 + pk != T (pointAdd.ts:105)
+    if (c.mode == 0) {
+      uint32_t r[8];
+      limbs_from_be<8>(r, c.sig + (size_t)b * 64, 32);
+      reduce_once<FnP256>(r);
+      if (is_zero_n<8>(r)) ZK_SET_STATUS_OVER(c.status + b, ZKA_ERR_POINTS_DONT_ADD, ZKA_ERR_TAPE_RANGE);  // rinv = 0: T1 + pk != T (pointAdd.ts:105)
+    }
     p256_st_aff(c.r_aff + (size_t)b * 16, Ra);
     uint8_t* rb = c.r_bytes + (size_t)b * BSTRIDE;
     uint32_t cv[8];
     rb[0] = 0x04;
     Fp::from_mont(cv, Ra.x); limbs_to_be<8>(rb + 1, cv, 32);
     Fp::from_mont(cv, Ra.y); limbs_to_be<8>(rb + 33, cv, 32);
-    if (c.which[b] >= (uint32_t)c.N) ZK_SET_STATUS_OVER(c.status + b, ZKA_ERR_BAD_INDEX, ZKA_ERR_TAPE_RANGE);
+    if (c.mode == 0 && c.which[b] >= (uint32_t)c.N) ZK_SET_STATUS_OVER(c.status + b, ZKA_ERR_BAD_INDEX, ZKA_ERR_TAPE_RANGE);
   }
 };
 
@@ -413,7 +467,7 @@ struct ExpChallengeTask {
     Src src{&c, b};
     hash_points80(c3, src, 2 + 3 * c.S);
     st<3>(c.chal + (size_t)b * 3, c3);
-    uint32_t off = HEAD_LEN, z = 0;
+    uint32_t off = (uint32_t)c.head_len, z = 0;
     for (int i = 0; i < c.S; i++) {
       const uint32_t bit = (c3[i >> 5] >> (i & 31)) & 1u;   // LSB first (exp.ts:169,228)
       c.rep_off[(size_t)b * c.S + i] = off;
@@ -422,7 +476,7 @@ struct ExpChallengeTask {
     }
     c.zcount[b] = z;
     c.gk_off[b] = off;
-    c.proof_len[b] = off + gk_len(c.n);
+    c.proof_len[b] = c.mode == 1 ? off : off + gk_len(c.n);
   }
 };
 // single-thread exclusive scan of zcount (B <= a few thousand per chunk)
@@ -806,6 +860,7 @@ struct RepEmitTask {
     const int b = t / S1, i = t % S1;
     uint8_t* proof = c.proofs + (size_t)b * c.proof_stride;
     if (i == c.S) {
+      if (c.mode == 1) return;   // proveExp alone: the row holds the repetitions only
       cp(proof, c.r_bytes + (size_t)b * BSTRIDE, NP);
       cp(proof + NP, c.pa_A_bytes + ((size_t)b * S1 + c.S) * BSTRIDE, NP);
       cp(proof + 2 * NP, c.s1_bytes + c.s1_pt(b, 0) * BSTRIDE, WP);
@@ -1057,6 +1112,56 @@ struct GkEmitTask {
     F::mul(t, rpk, xp);           // pkX.r * x^n
     F::add(zd, zd, t);
     put_scalar<WS>(ozd, zd);
+  }
+};
+
+// proveExp alone: the statement  s*g - Q = P  is an input here, not something the pipeline constructed.  Phase B
+// evaluates T1 = T_i - P, which equals the reference's g*z + Q exactly when the statement holds; otherwise the
+// reference throws "Points don't add up!" in provePointAdd (pointAdd.ts:104-106).  Slot S of phase A is s*g.
+struct ExpStatementTask {
+  ProveCtx c;
+  ZK_HD void operator()(int b) const {
+    using F = P256p;
+    const size_t slot = (size_t)b * (c.S + 1) + c.S;
+    P256Aff sg, q, pk;
+    p256_ld_aff(sg, c.pa_T_aff + slot * 16);
+    p256_ld_aff(pk, c.pk_aff + (size_t)b * 16);
+    P256Pt acc;
+    if (c.pa_T_inf[slot]) p256_set_identity(acc); else p256_from_affine(acc, sg);
+    if (!c.q_inf[b]) {
+      p256_ld_aff(q, c.q_aff + (size_t)b * 16);
+      F::neg(q.y, q.y);
+      p256_madd(acc, acc, q);
+    }
+    F::neg(pk.y, pk.y);
+    p256_madd(acc, acc, pk);          // s*g - Q - P
+    if (!p256_is_identity(acc)) ZK_SET_STATUS(c.status + b, ZKA_ERR_POINTS_DONT_ADD);
+  }
+};
+
+// proveMembership alone: per-proof setup of the pieces the GK tasks expect from the full pipeline.  The internal
+// tape row is [0, com.r, 0] followed by the caller's 5n draws (with S = 0 the GK draws start at index 3).
+struct GkAloneSetupTask {
+  ProveCtx c;
+  const uint8_t* com_r;    // [B][32]
+  const uint8_t* tape;     // [B][tape_stride]
+  size_t tape_stride;
+  uint8_t* itape;          // [B][96 + tape_stride]
+  ZK_HD void operator()(int b) const {
+    c.status[b] = ZKA_OK;
+    c.zcount[b] = 0;
+    c.gk_off[b] = 0;
+    c.proof_len[b] = (uint32_t)gk_len(c.n);
+    const uint32_t w = c.which[b];
+    c.which_s[b] = w < (uint32_t)c.N ? w : 0u;
+    if (w >= (uint32_t)c.N) ZK_SET_STATUS(c.status + b, ZKA_ERR_BAD_INDEX);
+    uint8_t* row = itape + (size_t)b * c.tape_stride;
+    for (int i = 0; i < 96; i++) row[i] = (i >= 32 && i < 64) ? com_r[(size_t)b * 32 + (i - 32)] : 0;
+    const size_t need = (size_t)32 * 5 * c.n;
+    for (size_t i = 0; i < need; i++) row[96 + i] = tape[(size_t)b * tape_stride + i];
+    uint32_t r[8];
+    tape_draw(r, row, DRAW_PKX_R);
+    if (!lt_p<FpP256>(r)) ZK_SET_STATUS(c.status + b, ZKA_ERR_TAPE_RANGE);
   }
 };
 

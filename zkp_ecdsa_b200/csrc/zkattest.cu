@@ -937,22 +937,25 @@ int zka_key_to_int(zka_ctx* ctx, uint32_t count, const uint8_t* pk, uint8_t* x_o
 }
 
 // ------------------------------------------------------------------------------- prove
-int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* sig,
-                    const uint8_t* pk, const uint32_t* which, const uint8_t* ring, uint32_t N, const uint8_t* tape,
-                    size_t tape_stride, uint8_t* proofs, size_t proof_stride, uint32_t* proof_len_out,
-                    int32_t* status) {
-  if (!ctx || !P || !msg_hash || !sig || !pk || !which || !ring || !tape || !proofs || !proof_len_out || !status)
-    return ZKA_E_ARG;
+// mode 0: proveSignatureList.  mode 1: proveExp alone (exp.ts:126-231) — base / s_in / q_in are the statement,
+// msg_hash / sig / which / ring are unused, the rows hold the repetitions only.
+static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* sig,
+                      const uint8_t* pk, const uint32_t* which, const uint8_t* ring, uint32_t N, const uint8_t* tape,
+                      size_t tape_stride, uint8_t* proofs, size_t proof_stride, uint32_t* proof_len_out,
+                      int32_t* status, int mode, const uint8_t* base, const uint8_t* s_in, const uint8_t* q_in) {
+  if (!ctx || !P || !pk || !tape || !proofs || !proof_len_out || !status) return ZKA_E_ARG;
+  if (mode == 0 && (!msg_hash || !sig || !which || !ring)) return ZKA_E_ARG;
+  if (mode == 1 && (!base || !s_in)) return ZKA_E_ARG;
   if (B == 0) return 0;
   // N = 1 makes hashPoints([]) throw in the reference (group.ts:223 reduce of an empty array)
-  if (N < 2 || N > (1u << 20)) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
+  if (mode == 0 && (N < 2 || N > (1u << 20))) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
   const int S = (int)P->sec_level;
-  const int n = ceil_log2(N);
-  if (proof_stride < zka_proof_max_len(N, S)) return fail(ctx, ZKA_E_ARG, "proof_stride < zka_proof_max_len");
-  if (tape_stride < (size_t)32 * prove_draws(0, n, S)) return fail(ctx, ZKA_E_ARG, "tape_stride too small");
+  const int n = mode == 0 ? ceil_log2(N) : 0;
+  if (proof_stride < (mode == 0 ? zka_proof_max_len(N, S) : (size_t)S * REP0_LEN)) return fail(ctx, ZKA_E_ARG, "proof_stride < zka_proof_max_len");
+  if (tape_stride < (size_t)32 * (mode == 0 ? prove_draws(0, n, S) : draws_before_items(S))) return fail(ctx, ZKA_E_ARG, "tape_stride too small");
   try {
     // ring + Lagrange matrix: once per call, on lane 0, finished before the lanes start
-    {
+    if (mode == 0) {
       Stream& st0 = ctx->st;
       const uint8_t* d_ring = stage_in(st0, ctx->ring_in, ring, (size_t)N * 32);
       uint32_t* rm = ctx->ring_m.get<uint32_t>(((size_t)1 << n) * 8);
@@ -981,17 +984,21 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       Lane& ln = ctx->lane(li);
       Stream& st = ln.st;
       DevBuf* W = ln.w;
-      struct ChunkIn { const uint8_t *msg_hash, *sig, *pk, *tape; const uint32_t* which; } cin[2];
+      struct ChunkIn { const uint8_t *msg_hash, *sig, *pk, *tape, *base, *s_in, *q_in; const uint32_t* which; } cin[2];
       auto issue_inputs = [&](uint32_t k, int slot) {
         const uint32_t b0 = off[k];
         const size_t Bc = off[k + 1] - b0;
         Stream& ci = ln.cs_in;
         DevBuf* in = ln.in + 5 * slot;
         ev_wait(ci, ln.ev_done[slot]);   // the chunk that used these staging buffers before has finished reading them
-        cin[slot].msg_hash = stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32);
-        cin[slot].sig = stage_in(ci, in[1], sig + (size_t)b0 * 64, Bc * 64);
+        cin[slot].msg_hash = msg_hash ? stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32) : nullptr;
+        cin[slot].sig = sig ? stage_in(ci, in[1], sig + (size_t)b0 * 64, Bc * 64) : nullptr;
         cin[slot].pk = stage_in(ci, in[2], pk + (size_t)b0 * 65, Bc * 65);
-        cin[slot].which = stage_in(ci, in[3], which + b0, Bc);
+        cin[slot].which = which ? stage_in(ci, in[3], which + b0, Bc) : nullptr;
+        DevBuf* inx = ln.in + 10 + 3 * slot;
+        cin[slot].base = base ? stage_in(ci, inx[0], base + (size_t)b0 * 65, Bc * 65) : nullptr;
+        cin[slot].s_in = s_in ? stage_in(ci, inx[1], s_in + (size_t)b0 * 32, Bc * 32) : nullptr;
+        cin[slot].q_in = q_in ? stage_in(ci, inx[2], q_in + (size_t)b0 * 65, Bc * 65) : nullptr;
         ev_record(ln.ev_small[slot], ci);
         cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
         ev_record(ln.ev_tape[slot], ci);
@@ -1010,6 +1017,8 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         ProveCtx c;
         memset(&c, 0, sizeof(c));
         c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.M = 0;
+        c.mode = mode; c.head_len = mode == 0 ? HEAD_LEN : 0;
+        c.base = cin[slot].base; c.s_in = cin[slot].s_in; c.q_in = cin[slot].q_in;
         c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
         c.msg_hash = cin[slot].msg_hash;
         c.sig = cin[slot].sig;
@@ -1061,6 +1070,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         c.tab_rep = W[49].get<uint32_t>((size_t)Bc * 2);
         c.tab_count = W[50].get<uint32_t>(1);
         c.which_s = W[52].get<uint32_t>(Bc);
+        c.base_aff = mode == 0 ? c.pk_aff : W[53].get<uint32_t>((size_t)Bc * 16);
         c.proof_stride = proof_stride;
         DevBuf* ob = ln.out + 3 * slot;
         c.proofs = out_dev ? proofs + (size_t)b0 * proof_stride : ob[0].get<uint8_t>((size_t)Bc * proof_stride);
@@ -1076,7 +1086,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         {
           const int Bp = (Bc + 31) & ~31;
           launch(st, (long long)Bp + Bc,
-                 PowsAndPreTask{P256PowsTask{c.pk_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count}, PreTask{c}, Bp});
+                 PowsAndPreTask{P256PowsTask{c.base_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count}, PreTask{c}, Bp});
         }
         launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows, c.tab_count});
         {
@@ -1092,6 +1102,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         }
         launch_p256_norm(st, c.pa_T, c.pa_T_aff, nullptr, c.pa_T_inf, (long long)(nA));
         launch_p256_norm(st, c.pa_A, c.pa_A_aff, c.pa_A_bytes, c.pa_A_inf, (long long)(nA));
+        if (mode == 1) launch(st, Bc, ExpStatementTask{c});
         launch(st, (long long)n1, JobsATask{c});
         launch(st, (long long)n1, TomCommitTask{c.s1_jv, c.s1_jr, c.tg_tab, c.th_tab, c.s1_proj, c.tom_w, c.tom_nwin});
         launch_tom_norm(st, c.s1_proj, c.s1_aff, c.s1_bytes, (long long)(n1), 1);
@@ -1102,7 +1113,8 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         copy_d2h(st, tot2, c.item_total, 8);
         sync(st);
         const uint32_t M = tot2[0];
-        const size_t max_len = (size_t)proof_len((int)tot2[1], n, S);
+        const size_t max_len = mode == 0 ? (size_t)proof_len((int)tot2[1], n, S)
+                                         : (size_t)tot2[1] * REP0_LEN + (size_t)(S - (int)tot2[1]) * REP1_LEN;
         c.M = (int)M;
         c.item_b = W[29].get<uint32_t>(M);
         c.item_i = W[30].get<uint32_t>(M);
@@ -1152,7 +1164,7 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
         launch(st, (long long)M * HASHES_PER_ITEM, ItemHashTask{c});
         launch(st, (long long)M * 7, ItemEmitTask{c});
         launch(st, (long long)nA, RepEmitTask{c});
-        launch(st, Bc, GkEmitTask{c});
+        if (mode == 0) launch(st, Bc, GkEmitTask{c});
         launch(st, (long long)Bc * FIN_PARTS, FinalizeTask{c});
         // --- results: on the output stream, behind this chunk's last kernel
         ev_record(ln.ev_done[slot], st);
@@ -1171,6 +1183,102 @@ int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t
       sync(st);
     };
     run_lanes(ctx, used, run_lane);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
+int zka_prove_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* msg_hash, const uint8_t* sig,
+                    const uint8_t* pk, const uint32_t* which, const uint8_t* ring, uint32_t N, const uint8_t* tape,
+                    size_t tape_stride, uint8_t* proofs, size_t proof_stride, uint32_t* proof_len_out,
+                    int32_t* status) {
+  return prove_impl(ctx, P, B, msg_hash, sig, pk, which, ring, N, tape, tape_stride, proofs, proof_stride, proof_len_out, status, 0,
+                    nullptr, nullptr, nullptr);
+}
+
+// proveExp(paramsNIST = (p256, base, NistGroup.h), paramsWario = ProofGroup, s, Cs, P = pk, Px, Py, secparam = sec_level, Q?)
+// (exp.ts:126-231).  Tape layout = zka_prove_batch's: draws 0..2 are the blinders of Cs, Px, Py (drawn when those
+// commitments were made), then 4 per repetition, then 40 per 0-bit repetition.  Rows: the repetitions only.
+int zka_prove_exp_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* base, const uint8_t* s, const uint8_t* pk,
+                        const uint8_t* q, const uint8_t* tape, size_t tape_stride, uint8_t* proofs, size_t proof_stride,
+                        uint32_t* proof_len, int32_t* status) {
+  return prove_impl(ctx, P, B, nullptr, nullptr, pk, nullptr, nullptr, 2, tape, tape_stride, proofs, proof_stride, proof_len, status, 1,
+                    base, s, q);
+}
+
+// proveMembership(params = ProofGroup, com, index, ring) (gk.ts:94-195) for B commitments over one ring.
+// com_r: the blinder of com = commit(ring[index]) (B x 32); tape: the 5n draws (r_i, a_i, s_i, t_i, rho_i per round).
+// Rows: the GK block of the flat layout.
+int zka_prove_membership_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* com_r, const uint32_t* index,
+                               const uint8_t* ring, uint32_t N, const uint8_t* tape, size_t tape_stride, uint8_t* proofs,
+                               size_t proof_stride, uint32_t* proof_len, int32_t* status) {
+  if (!ctx || !P || !com_r || !index || !ring || !tape || !proofs || !proof_len || !status) return ZKA_E_ARG;
+  if (B == 0) return 0;
+  if (N < 2 || N > (1u << 20)) return fail(ctx, ZKA_E_ARG, "ring size must be in [2, 2^20]");
+  const int n = ceil_log2(N);
+  if (proof_stride < (size_t)gk_len(n)) return fail(ctx, ZKA_E_ARG, "proof_stride < GK block length");
+  if (tape_stride < (size_t)32 * 5 * n) return fail(ctx, ZKA_E_ARG, "tape_stride < 32 * 5n");
+  try {
+    Stream& st = ctx->st;
+    DevBuf* W = ctx->w;
+    const uint8_t* d_ring = stage_in(st, ctx->ring_in, ring, (size_t)N * 32);
+    uint32_t* ring_m = ctx->ring_m.get<uint32_t>(((size_t)1 << n) * 8);
+    launch(st, 1ll << n, RingPrepTask{d_ring, ring_m, (int)N});
+    if (ctx->lag_n != n) {
+      uint32_t* l = ctx->lag.get<uint32_t>((size_t)n * n * 8);
+      launch(st, 1, GkLagrangeTask{l, n});
+      ctx->lag_n = n;
+    }
+    const size_t it_stride = 96 + tape_stride;   // internal tape: [pad, com.r, pad] then the caller's draws (S = 0: GK draws start at 3)
+    const uint32_t chunk = 8192;
+    for (uint32_t b0 = 0; b0 < B; b0 += chunk) {
+      const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
+      const uint8_t* d_cr = stage_in(st, ctx->in[0], com_r + (size_t)b0 * 32, (size_t)Bc * 32);
+      const uint32_t* d_idx = stage_in(st, ctx->in[1], index + b0, (size_t)Bc);
+      const uint8_t* d_tape = stage_in(st, ctx->in[2], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      ProveCtx c;
+      memset(&c, 0, sizeof(c));
+      c.B = Bc; c.S = 0; c.N = (int)N; c.n = n; c.M = 0;
+      c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
+      c.which = d_idx;
+      c.ring_m = ring_m;
+      c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
+      uint8_t* itape = W[0].get<uint8_t>((size_t)Bc * it_stride);
+      c.tape = itape; c.tape_stride = it_stride; c.tape_draws = (uint32_t)(it_stride / 32);
+      c.which_s = W[1].get<uint32_t>(Bc);
+      c.zcount = W[2].get<uint32_t>(Bc);
+      c.gk_off = W[3].get<uint32_t>(Bc);
+      c.gk_dv = W[4].get<uint32_t>((size_t)Bc * n * 8);
+      c.gk_lag = (uint32_t*)ctx->lag.p;
+      c.gk_x = W[5].get<uint32_t>((size_t)Bc * 3);
+      const size_t ng = (size_t)Bc * 4 * n;
+      c.s2_jv = W[6].get<uint32_t>(ng * 8);
+      c.s2_jr = W[7].get<uint32_t>(ng * 8);
+      c.s2_proj = W[8].get<uint32_t>(ng * TOM_PROJ_WORDS);
+      c.s2_bytes = W[9].get<uint8_t>(ng * BSTRIDE);
+      c.proof_stride = proof_stride;
+      c.proofs = is_device_ptr(proofs) ? proofs + (size_t)b0 * proof_stride : ctx->out[0].get<uint8_t>((size_t)Bc * proof_stride);
+      c.proof_len = is_device_ptr(proof_len) ? proof_len + b0 : ctx->out[1].get<uint32_t>(Bc);
+      c.status = is_device_ptr(status) ? status + b0 : ctx->out[2].get<int32_t>(Bc);
+      launch(st, Bc, GkAloneSetupTask{c, d_cr, d_tape, tape_stride, itape});
+      launch(st, (long long)Bc * n, GkJobsTask{c});
+      {
+        const int nblk = 1 << (n - gk_block_bits(n));
+        c.gk_part = nblk > 1 ? W[10].get<uint32_t>((size_t)Bc * n * nblk * 8) : nullptr;
+        launch(st, (long long)Bc * n * nblk, GkPolyTask{c});
+        if (nblk > 1) launch(st, (long long)Bc * n, GkPolyReduceTask{c});
+      }
+      launch(st, (long long)Bc * n, GkCdJobsTask{c});
+      launch(st, (long long)ng, TomCommitTask{c.s2_jv, c.s2_jr, c.tg_tab, c.th_tab, c.s2_proj, c.tom_w, c.tom_nwin});
+      launch_tom_norm(st, c.s2_proj, nullptr, c.s2_bytes, (long long)ng, 1);
+      launch(st, Bc, GkEmitTask{c});
+      launch(st, (long long)Bc * FIN_PARTS, FinalizeTask{c});
+      if (!is_device_ptr(proofs)) copy_d2h_2d(st, proofs + (size_t)b0 * proof_stride, proof_stride, c.proofs, proof_stride, (size_t)gk_len(n), Bc);
+      if (!is_device_ptr(proof_len)) copy_d2h(st, proof_len + b0, c.proof_len, (size_t)Bc * 4);
+      if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
+      sync(st);
+    }
     return 0;
   } catch (const std::exception& e) {
     return fail(ctx, ZKA_E_CUDA, e.what());
