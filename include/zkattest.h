@@ -185,6 +185,22 @@ int zka_prove_membership_batch(zka_ctx* ctx, const zka_params* params, uint32_t 
                                const uint8_t* tape, size_t tape_stride, uint8_t* proofs, size_t proof_stride,
                                uint32_t* proof_len /* B */, int32_t* status /* B */);
 
+/* proveEquality(params, x, C1, C2)          /root/reference/src/commit/equality.ts:60-78
+ *   scalars: B x [x, C1.r, C2.r] (32 bytes each);  tape: k, A1.r, A2.r;  out: C1 C2 (B x 2 x 67), proofs B x 233
+ * proveMult(params, x, y, z, Cx, Cy, Cz)     /root/reference/src/commit/mult.ts:93-131
+ *   scalars: B x [x, y, z, Cx.r, Cy.r, Cz.r];      tape: k_x k_y k_z Ax.r Ay.r Az.r A4_1.r;  out: Cx Cy Cz, proofs B x 633
+ * provePointAdd(params, P, Q, R, PX, PY, QX, QY, RX, RY)   /root/reference/src/exp/pointAdd.ts:92-163
+ *   points: B x [P, Q, R] (65 bytes each, P + Q = R on P-256);  blinders: B x [PX.r PY.r QX.r QY.r RX.r RY.r];
+ *   tape: the 38 draws of SURVEY.md 3.1 (C8.r C10.r C11.r C13.r, pi8[7], pi10[7], pi11[7], pix[3], pi13[7], piy[3]);
+ *   out: the six coordinate commitments (B x 6 x 67), proofs B x 3266.
+ * The statement's commitments are given by their openings (the prover knows them); the library returns their points. */
+int zka_prove_equality_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* scalars, const uint8_t* tape,
+                             size_t tape_stride, uint8_t* commitments, uint8_t* proofs, int32_t* status);
+int zka_prove_mult_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* scalars, const uint8_t* tape,
+                         size_t tape_stride, uint8_t* commitments, uint8_t* proofs, int32_t* status);
+int zka_prove_pointadd_batch(zka_ctx* ctx, const zka_params* params, uint32_t B, const uint8_t* points, const uint8_t* blinders,
+                             const uint8_t* tape, size_t tape_stride, uint8_t* commitments, uint8_t* proofs, int32_t* status);
+
 /* ---- measurement hooks (bench.py) ----
  * zka_get_stream: the cudaStream_t every kernel of this context is launched on (so callers can
  * record CUDA events on the launching stream).  zka_set_profiling(1) brackets every launch with a

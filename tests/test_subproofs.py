@@ -324,3 +324,73 @@ def test_subproof_provers_on_gpu(gpu_engine):
     check_prove_exp(L, sec=12, with_q=True, seed=72, B=2)
     check_prove_membership(L, [3, 5, 7, 11, 13], [3, 0, 4], seed=73)
     check_prove_membership(L, list(range(500, 500 + 300)), [0, 299, 150, 7], seed=74)
+
+
+def check_prove_small(L, kind, seed=81, B=3):
+    """zka_prove_{equality,mult,pointadd}_batch == the oracle's proof bytes; outputs verify with the stand-alone verifier."""
+    P, po = common.make_params(L, seed, 8)
+    params = po.ProofGroup
+    q = tom.order
+    d = synth.Drbg(seed, 'prove' + kind)
+    nd = {'equality': 3, 'mult': 7, 'pointadd': 38}[kind]
+    tape = synth.random_tape(B, 32 * nd, seed=seed + 1)
+    bl = synth.random_tape(B, 32 * 6, seed=seed + 2)
+    rows, blind, want_pf, want_com = [], [], [], []
+    i32 = lambda v: int(v).to_bytes(32, 'big')   # noqa: E731
+    for b in range(B):
+        r = [int.from_bytes(bl[b, 32 * i:32 * i + 32].tobytes(), 'big') for i in range(6)]
+        tp = Tape(tape[b].tobytes())
+        mk = lambda v, rr: OC.Commitment(params.h.dblmul(tom.new_scalar(rr), params.g, tom.new_scalar(v)), tom.new_scalar(rr))   # noqa: E731
+        if kind == 'equality':
+            x = d.below(q)
+            C1, C2 = mk(x, r[0]), mk(x, r[1])
+            pi = OC.prove_equality(params, x, C1, C2, tp)
+            rows.append(i32(x) + i32(r[0]) + i32(r[1]))
+            want_pf.append(flat.ser_equality(pi)); want_com.append(C1.p.to_bytes() + C2.p.to_bytes())
+        elif kind == 'mult':
+            x, y = d.below(q), d.below(q)
+            z = x * y % q
+            Cx, Cy, Cz = mk(x, r[0]), mk(y, r[1]), mk(z, r[2])
+            pi = OC.prove_mult(params, x, y, z, Cx, Cy, Cz, tp)
+            rows.append(i32(x) + i32(y) + i32(z) + i32(r[0]) + i32(r[1]) + i32(r[2]))
+            want_pf.append(flat.ser_mult(pi)); want_com.append(Cx.p.to_bytes() + Cy.p.to_bytes() + Cz.p.to_bytes())
+        else:
+            Pp = p256.generator().mul(p256.new_scalar(d.below(p256.order)))
+            Qp = p256.generator().mul(p256.new_scalar(d.below(p256.order)))
+            Rp = Pp.add(Qp)
+            if b == B - 1:
+                Rp = Rp.add(p256.generator())          # false statement -> "Points don't add up!"
+            (x1, y1), (x2, y2), (x3, y3) = Pp.to_affine(), Qp.to_affine(), Rp.to_affine()
+            cs = [mk(v, rr) for v, rr in zip((x1, y1, x2, y2, x3, y3), r)]
+            rows.append(flat._pt(Pp, 65) + flat._pt(Qp, 65) + flat._pt(Rp, 65))
+            blind.append(b''.join(i32(v) for v in r))
+            try:
+                pi = OE.prove_point_add(params, Pp, Qp, Rp, *cs, tp)
+                want_pf.append(flat.ser_point_add(pi)); want_com.append(b''.join(c.p.to_bytes() for c in cs))
+            except ValueError:
+                want_pf.append(None); want_com.append(None)
+    arr = lambda rr: np.array([list(x) for x in rr], np.uint8)   # noqa: E731
+    com, proofs, st = L.prove_sub_batch(kind, P, arr(rows), tape, arr(blind) if kind == 'pointadd' else None)
+    good = []
+    for b in range(B):
+        if want_pf[b] is None:
+            assert st[b] == 4 and not proofs[b].any() and not com[b].any()
+        else:
+            assert st[b] == 0 and proofs[b].tobytes() == want_pf[b] and com[b].tobytes() == want_com[b], (kind, b)
+            good.append(b)
+    vdraws = {'equality': 2, 'mult': 5, 'pointadd': 24}[kind]
+    vt = synth.random_tape(len(good), 32 * vdraws, seed=seed + 3)
+    ok, vst = L.verify_sub_batch(kind, P, np.ascontiguousarray(com[good]), np.ascontiguousarray(proofs[good]), vt)
+    assert (ok == 1).all() and not vst.any()
+    L.params_destroy(P)
+
+
+@pytest.mark.parametrize('kind', ['equality', 'mult', 'pointadd'])
+def test_prove_small_subproofs(hostsim, kind):
+    check_prove_small(hostsim, kind)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind', ['equality', 'mult', 'pointadd'])
+def test_prove_small_subproofs_on_gpu(gpu_engine, kind):
+    check_prove_small(gpu_engine.lib, kind, seed=91, B=5)

@@ -28,6 +28,7 @@ SYMBOLS = [
     'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack', 'zka_verify_batch_ex', 'zka_verify_tape_len_ex',
     'zka_verify_exp_batch', 'zka_verify_membership_batch', 'zka_verify_equality_batch', 'zka_verify_mult_batch',
     'zka_verify_pointadd_batch', 'zka_prove_exp_batch', 'zka_prove_membership_batch',
+    'zka_prove_equality_batch', 'zka_prove_mult_batch', 'zka_prove_pointadd_batch',
 ]
 
 STATUS_MESSAGES = {
@@ -127,6 +128,11 @@ class ZkaLib:
                                               C.c_void_p, C.c_void_p]
             L.zka_prove_membership_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+            for f in ('zka_prove_equality_batch', 'zka_prove_mult_batch'):
+                getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+            L.zka_prove_pointadd_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]
             L.zka_proofs_pack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.c_void_p]
             L.zka_proofs_unpack.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -266,6 +272,22 @@ class ZkaLib:
                                                         tape.shape[1], _ptr(proofs), stride, _ptr(plen), _ptr(st)),
                     'zka_prove_membership_batch')
         return proofs, plen, st
+
+    def prove_sub_batch(self, kind: str, params, inputs, tape, blinders=None):
+        """kind 'equality' (inputs [B, 3*32]), 'mult' ([B, 6*32]) or 'pointadd' (inputs [B, 3*65] + blinders [B, 6*32])"""
+        B = inputs.shape[0]
+        nc, plen = {'equality': (2, 233), 'mult': (3, 633), 'pointadd': (6, 3266)}[kind]
+        com = np.zeros((B, nc * 67), np.uint8)
+        proofs = np.zeros((B, plen), np.uint8)
+        st = np.zeros(B, np.int32)
+        if kind == 'pointadd':
+            rc = self.lib.zka_prove_pointadd_batch(self.ctx, params, B, _ptr(inputs), _ptr(blinders), _ptr(tape), tape.shape[1], _ptr(com),
+                                                   _ptr(proofs), _ptr(st))
+        else:
+            rc = getattr(self.lib, f'zka_prove_{kind}_batch')(self.ctx, params, B, _ptr(inputs), _ptr(tape), tape.shape[1], _ptr(com),
+                                                              _ptr(proofs), _ptr(st))
+        self._check(rc, f'zka_prove_{kind}_batch')
+        return com, proofs, st
 
     def verify_sub_batch(self, kind: str, params, points, proofs, tape):
         """kind in {'equality', 'mult', 'pointadd'}; points [B, k*67], proofs [B, 233|633|3266], tape [B, >= 32*draws]"""

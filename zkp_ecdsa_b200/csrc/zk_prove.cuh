@@ -1165,6 +1165,188 @@ struct GkAloneSetupTask {
   }
 };
 
+// ---- proveEquality / proveMult alone (equality.ts:60-78, mult.ts:93-131) ---------------------------------------
+// The statement's commitments are given by their openings; every point of the proof is a commitment with a known
+// opening, so all of them are jobs of the fixed-base commitment kernel.
+//   equality: scalars = x r1 r2,       draws = k A1.r A2.r,                    jobs = C1 C2 A1 A2
+//   mult:     scalars = x y z rx ry rz, draws = k_x k_y k_z Ax.r Ay.r Az.r A4_1.r, jobs = Cx Cy Cz C4 Ax Ay Az A4_1 A4_2
+enum : int { SUBP_EQ_JOBS = 4, SUBP_MULT_JOBS = 9 };
+struct SubProveJobsTask {
+  int kind;                 // 0 equality, 1 mult
+  const uint8_t* scalars;   // [B][3|6][32]
+  const uint8_t* tape;      // [B][tape_stride]
+  size_t tape_stride;
+  uint32_t *jv, *jr;        // [B][4|9][8]
+  int32_t* status;
+  ZK_HD bool rd(uint32_t* r, const uint8_t* p) const {
+    limbs_from_be<8>(r, p, 32);
+    if (lt_p<FpP256>(r)) return true;
+    sub_p<FpP256>(r, r);
+    return false;
+  }
+  ZK_HD void operator()(int b) const {
+    using F = Tomq;
+    status[b] = ZKA_OK;
+    const uint8_t* sc = scalars + (size_t)b * (kind == 0 ? 3 : 6) * 32;
+    const uint8_t* dr = tape + (size_t)b * tape_stride;
+    const int J = kind == 0 ? SUBP_EQ_JOBS : SUBP_MULT_JOBS;
+    uint32_t* v = jv + (size_t)b * J * 8;
+    uint32_t* r = jr + (size_t)b * J * 8;
+    bool ok = true;
+    if (kind == 0) {
+      uint32_t x[8], r1[8], r2[8], k[8], ra[8], rb[8];
+      rd(x, sc); rd(r1, sc + 32); rd(r2, sc + 64);      // newScalar reduces the statement's values
+      ok = rd(k, dr) && ok; ok = rd(ra, dr + 32) && ok; ok = rd(rb, dr + 64) && ok;
+      st<8>(v, x); st<8>(r, r1); st<8>(v + 8, x); st<8>(r + 8, r2);
+      st<8>(v + 16, k); st<8>(r + 16, ra); st<8>(v + 24, k); st<8>(r + 24, rb);
+    } else {
+      uint32_t x[8], y[8], z[8], rx[8], ry[8], rz[8], kx[8], ky[8], kz[8], a1[8], a2[8], a3[8], a4[8];
+      rd(x, sc); rd(y, sc + 32); rd(z, sc + 64); rd(rx, sc + 96); rd(ry, sc + 128); rd(rz, sc + 160);
+      ok = rd(kx, dr) && ok; ok = rd(ky, dr + 32) && ok; ok = rd(kz, dr + 64) && ok;
+      ok = rd(a1, dr + 96) && ok; ok = rd(a2, dr + 128) && ok; ok = rd(a3, dr + 160) && ok; ok = rd(a4, dr + 192) && ok;
+      uint32_t xm[8], kxm[8], t[8], u[8];
+      F::to_mont(xm, x);
+      F::to_mont(kxm, kx);
+      st<8>(v, x); st<8>(r, rx); st<8>(v + 8, y); st<8>(r + 8, ry); st<8>(v + 16, z); st<8>(r + 16, rz);
+      F::mul(t, xm, y); F::mul(u, xm, ry);              // C4 = Cy*x = (x y) g + (x ry) h   (mult.ts:103-104)
+      st<8>(v + 24, t); st<8>(r + 24, u);
+      st<8>(v + 32, kx); st<8>(r + 32, a1); st<8>(v + 40, ky); st<8>(r + 40, a2);
+      st<8>(v + 48, kz); st<8>(r + 48, a3); st<8>(v + 56, kz); st<8>(r + 56, a4);
+      F::mul(t, kxm, y); F::mul(u, kxm, ry);            // A4_2 = Cy*k_x                    (mult.ts:114)
+      st<8>(v + 64, t); st<8>(r + 64, u);
+    }
+    if (!ok) ZK_SET_STATUS(status + b, ZKA_ERR_TAPE_RANGE);
+  }
+};
+struct SubProveEmitTask {
+  int kind;
+  const uint8_t* scalars;
+  const uint8_t* tape;
+  size_t tape_stride;
+  const uint32_t* jr;       // [B][J][8] (r4 = x*ry is job 3's blinder)
+  const uint8_t* bytes;     // [B][J][BSTRIDE] encodings of the jobs
+  uint8_t* commitments;     // [B][2|3][67]
+  uint8_t* proofs;          // [B][233|633]
+  int32_t* status;
+  ZK_HD void operator()(int b) const {
+    using F = Tomq;
+    const int J = kind == 0 ? SUBP_EQ_JOBS : SUBP_MULT_JOBS, nc = kind == 0 ? 2 : 3, plen = kind == 0 ? EQ_LEN : MULT_LEN;
+    uint8_t* out = proofs + (size_t)b * plen;
+    uint8_t* com = commitments + (size_t)b * nc * WP;
+    if (status[b] != ZKA_OK) {
+      for (int i = 0; i < plen; i++) out[i] = 0;
+      for (int i = 0; i < nc * WP; i++) com[i] = 0;
+      return;
+    }
+    const uint8_t* pb = bytes + (size_t)b * J * BSTRIDE;
+    const uint8_t* sc = scalars + (size_t)b * (kind == 0 ? 3 : 6) * 32;
+    const uint8_t* dr = tape + (size_t)b * tape_stride;
+    Sha256 h;
+    h.init();
+    for (int j = 0; j < J; j++) h.update(pb + (size_t)j * BSTRIDE, WP);
+    uint32_t c3[3], cc[8];
+    h.final80(c3);
+    challenge_to_limbs(cc, c3);
+    for (int j = 0; j < nc; j++) copy_point(com + (size_t)j * WP, pb + (size_t)j * BSTRIDE, WP);
+    for (int j = nc; j < J; j++) copy_point(out + (size_t)(j - nc) * WP, pb + (size_t)j * BSTRIDE, WP);
+    uint8_t* o = out + (size_t)(J - nc) * WP;
+    auto resp = [&](int q, const uint8_t* kbytes, const uint32_t* w_canon) {
+      uint32_t k[8], wm[8];
+      limbs_from_be<8>(k, kbytes, 32);
+      reduce_once<FpP256>(k);
+      F::to_mont(wm, w_canon);
+      response(o + (size_t)q * WS, k, cc, wm);
+    };
+    uint32_t w[8];
+    if (kind == 0) {   // t_x = k - c x, t_r1 = A1.r - c r1, t_r2 = A2.r - c r2
+      for (int q = 0; q < 3; q++) { limbs_from_be<8>(w, sc + 32 * q, 32); reduce_once<FpP256>(w); resp(q, dr + 32 * q, w); }
+    } else {           // t_x t_y t_z t_rx t_ry t_rz t_r4
+      for (int q = 0; q < 6; q++) { limbs_from_be<8>(w, sc + 32 * q, 32); reduce_once<FpP256>(w); resp(q, dr + 32 * q, w); }
+      ld<8>(w, jr + ((size_t)b * J + 3) * 8);
+      resp(6, dr + 32 * 6, w);
+    }
+  }
+};
+
+// ---- provePointAdd alone (pointAdd.ts:92-163): one statement = one "item" of the batched prover ------------------
+// The stage tasks of a 0-bit repetition are reused with S = 1: T1 := P, pk := Q, T_0 := R.  Internal tape row:
+//   [0, QX.r, QY.r, 0, 0, RX.r, RY.r, PX.r, PY.r, the caller's 38 draws].
+struct PaddSetupTask {
+  ProveCtx c;
+  const uint8_t* points;    // [B][3][65] P Q R
+  const uint8_t* blinders;  // [B][6][32] PX.r PY.r QX.r QY.r RX.r RY.r
+  const uint8_t* tape;      // [B][tape_stride] 38 draws
+  size_t tape_stride;
+  uint8_t* itape;           // [B][c.tape_stride]
+  ZK_HD bool parse(P256Aff& a, const uint8_t* pb) const {
+    uint32_t x[8], y[8];
+    limbs_from_be<8>(x, pb + 1, 32);
+    limbs_from_be<8>(y, pb + 33, 32);
+    reduce_once<FpP256>(x);
+    reduce_once<FpP256>(y);
+    P256p::to_mont(a.x, x);
+    P256p::to_mont(a.y, y);
+    return pb[0] == 0x04 && p256_on_curve(a.x, a.y);
+  }
+  ZK_HD void operator()(int b) const {
+    c.status[b] = ZKA_OK;
+    P256Aff P, Q, R;
+    const uint8_t* pb = points + (size_t)b * 3 * 65;
+    const bool okP = parse(P, pb), okQ = parse(Q, pb + 65), okR = parse(R, pb + 130);
+    if (!okP || !okQ || !okR) {     // not on the curve, or an identity encoding: 'P/Q/R is at infinity' (pointAdd.ts:113-124)
+      ZK_SET_STATUS(c.status + b, ZKA_ERR_INVALID_PK);
+      p256_set_generator(P); p256_set_generator(Q); p256_set_generator(R);
+    } else {
+      P256Pt s, nr;
+      p256_from_affine(s, P);
+      p256_madd(s, s, Q);
+      P256Aff n = R;
+      P256p::neg(n.y, n.y);
+      p256_madd(nr, s, n);
+      if (!p256_is_identity(nr)) ZK_SET_STATUS(c.status + b, ZKA_ERR_POINTS_DONT_ADD);   // pointAdd.ts:104-106
+    }
+    p256_st_aff(c.pb_T1_aff + (size_t)b * 16, P);
+    p256_st_aff(c.pk_aff + (size_t)b * 16, Q);
+    p256_st_aff(c.pa_T_aff + (size_t)b * 2 * 16, R);
+    c.pa_T_inf[(size_t)b * 2] = 0; c.pa_T_inf[(size_t)b * 2 + 1] = 0;
+    c.pa_A_inf[(size_t)b * 2] = 0; c.pa_A_inf[(size_t)b * 2 + 1] = 0;
+    c.pb_T1_inf[b] = 0;
+    c.chal[(size_t)b * 3] = 0; c.chal[(size_t)b * 3 + 1] = 0; c.chal[(size_t)b * 3 + 2] = 0;
+    c.zcount[b] = 1;
+    c.item_base[b] = (uint32_t)b;
+    c.item_b[b] = (uint32_t)b; c.item_i[b] = 0; c.item_k[b] = 0;
+    c.rep_off[b] = 0;
+    uint32_t z[8];
+    zero_n<8>(z);
+    st<8>(c.s1 + (size_t)b * 8, z);
+    uint8_t* row = itape + (size_t)b * c.tape_stride;
+    const uint8_t* bl = blinders + (size_t)b * 6 * 32;
+    const int src[9] = {-1, 2, 3, -1, -1, 4, 5, 0, 1};   // draw index -> blinder index
+    for (int d = 0; d < 9; d++)
+      for (int i = 0; i < 32; i++) row[32 * d + i] = src[d] < 0 ? 0 : bl[32 * src[d] + i];
+    for (int i = 0; i < 32 * 38; i++) row[32 * 9 + i] = tape[(size_t)b * tape_stride + i];
+  }
+};
+struct PaddExtractTask {
+  ProveCtx c;
+  uint8_t* commitments;     // [B][6][67] PX PY QX QY RX RY
+  uint8_t* proofs;          // [B][3266]
+  ZK_HD void operator()(int b) const {
+    uint8_t* out = proofs + (size_t)b * PA_LEN;
+    uint8_t* com = commitments + (size_t)b * 6 * WP;
+    if (c.status[b] != ZKA_OK) {
+      for (int i = 0; i < PA_LEN; i++) out[i] = 0;
+      for (int i = 0; i < 6 * WP; i++) com[i] = 0;
+      return;
+    }
+    const uint8_t* pa = c.proofs + (size_t)b * c.proof_stride + REP_HEAD + 2 * NS;
+    for (int i = 0; i < PA_LEN; i++) out[i] = pa[i];
+    copy_point(com, c.s2_bytes + c.s2_job(b, JOB_T1X) * BSTRIDE, WP);
+    copy_point(com + WP, c.s2_bytes + c.s2_job(b, JOB_T1Y) * BSTRIDE, WP);
+    for (int j = 0; j < 4; j++) copy_point(com + (size_t)(2 + j) * WP, c.s1_bytes + c.s1_pt(b, j) * BSTRIDE, WP);
+  }
+};
+
 // Last stage: a proof whose status is not ZKA_OK must not leave the library (its blinders may have been
 // replaced by zeros or reduced values, which would open the commitments): the row is zeroed and its
 // length set to 0.  FIN_PARTS threads per proof, each clears its share of the row with 16-byte stores.

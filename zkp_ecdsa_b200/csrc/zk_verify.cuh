@@ -40,8 +40,8 @@ enum : int {
   V_PART_WORDS = 7 * 8,        // per-sample partial sums: gW hW pkX pkY | sR shN sCom
   MSM_C = 6,                   // SIGNED 6-bit bucket windows (tom): digits in [-32, 31], 32 buckets,
   MSM_NWIN = 43,               // 43 windows cover the 258 bits of k + offset (msm_digit6)
-  MSM_C_N = 4,                 // P-256 MSM: 64 windows
-  MSM_NWIN_N = 64,
+  MSM_C_N = 4,                 // P-256 MSM: SIGNED 4-bit windows, digits in [-8, 7], 8 buckets,
+  MSM_NWIN_N = 65,             // 65 windows cover the 257 bits of k + offset (msm_digit4)
 };
 
 // K = number of sampled repetitions (verifyExp's secparam, exp.ts:233-262): 20 in verifySignatureList
@@ -1067,31 +1067,52 @@ struct MsmTomCombineTask {
 };
 
 // Bucket MSM over P-256 (multiN): 21 points, 4-bit windows.  One thread per (proof, window).
+// signed 4-bit digits without a carry chain (see msm_digit6): windows of k + sum_{j<64} 8 * 16^j, minus 8
+ZK_HD uint32_t msm_digit4(const uint32_t* k, int w, bool& neg) {
+  uint32_t kp[9];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)k[i] + 0x88888888u;
+    kp[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  kp[8] = (uint32_t)c;
+  uint32_t word = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    if (i == (w >> 3)) word = kp[i];
+  const int d = (int)((word >> (4 * (w & 7))) & 15u) - (w < 64 ? 8 : 0);
+  neg = d < 0;
+  return (uint32_t)(d < 0 ? -d : d);
+}
 struct MsmP256WindowTask {
-  const uint32_t* scalar;   // [B][21][8]
-  const uint32_t* aff;      // [B][21][16]
-  const uint8_t* skip;      // [B][21]
-  uint32_t* win;            // [B][RT_NWIN][24]
+  const uint32_t* scalar;   // [B][nent][8]
+  const uint32_t* aff;      // [B][nent][16]
+  const uint8_t* skip;      // [B][nent]
+  uint32_t* win;            // [B][MSM_NWIN_N][24]
   int nent = V_SAMPLES + 1; // entries per proof: K sampled A_j + comS1
   ZK_HD void operator()(int t) const {
     const int b = t / MSM_NWIN_N, w = t % MSM_NWIN_N;
-    P256Pt bucket[15];
-    for (int d = 0; d < 15; d++) p256_set_identity(bucket[d]);
+    P256Pt bucket[8];
+    for (int d = 0; d < 8; d++) p256_set_identity(bucket[d]);
     for (int e = 0; e < nent; e++) {
       if (skip[(size_t)b * nent + e]) continue;
       uint32_t k[8];
       ld<8>(k, scalar + ((size_t)b * nent + e) * 8);
-      const uint32_t dgt = digit4(k, w);
+      bool neg;
+      const uint32_t dgt = msm_digit4(k, w, neg);
       if (dgt) {
         P256Aff q;
         p256_ld_aff(q, aff + ((size_t)b * nent + e) * 16);
+        if (neg) P256p::neg(q.y, q.y);
         p256_madd(bucket[dgt - 1], bucket[dgt - 1], q);
       }
     }
     P256Pt run, tot;
     p256_set_identity(run);
     p256_set_identity(tot);
-    for (int d = 14; d >= 0; d--) {
+    for (int d = 7; d >= 0; d--) {
       p256_add(run, run, bucket[d]);
       p256_add(tot, tot, run);
     }
@@ -1131,6 +1152,10 @@ struct MsmTomWindowBothTask {
     }
   }
 };
+
+#if !defined(ZKA_HOSTSIM) && defined(ZKA_MSM_MINBLOCKS)
+template <> struct TaskMinBlocks<MsmTomWindowBothTask> { static constexpr int value = ZKA_MSM_MINBLOCKS; };
+#endif
 
 // The three Horner passes of a proof (GK, multiW, multiN) are 250-doubling latency chains run by one
 // thread each; launched as ONE grid they overlap instead of queueing (3 B threads are still few).

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <string>
 #include <vector>
@@ -976,7 +977,10 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
     const std::vector<uint32_t> off = chunk_schedule(B, (uint32_t)(all_dev ? ctx->chunk : std::min(ctx->chunk, ctx->host_chunk)), lanes, !all_dev);
     const uint32_t nchunks = (uint32_t)off.size() - 1;
     const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
-    std::atomic<uint32_t> next_chunk(0);
+    const bool trace = getenv("ZKA_TRACE") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
+    std::atomic<uint32_t> next_chunk((uint32_t)used);
     // Every lane claims chunks from a shared counter (one ahead of the one it is computing, so that its inputs are
     // already on their way).  Within a lane, chunks are software-pipelined over three streams when buffers live in
     // host memory (staging buffers double-buffered by slot).
@@ -1003,15 +1007,18 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
         ev_record(ln.ev_tape[slot], ci);
       };
-      uint32_t k = next_chunk.fetch_add(1);
+      // the first `used` chunks are dealt statically (lane threads start at slightly different times); later ones are
+      // claimed from the shared counter at the mid-pipeline synchronisation point of the current chunk, when about
+      // half of its kernels are queued: early enough for the next inputs to travel behind them, late enough that a
+      // lane that started first does not grab the chunks of lanes that are still starting
+      uint32_t k = (uint32_t)li;
       int slot = 0;
       if (k < nchunks) issue_inputs(k, slot);
       for (; k < nchunks; slot ^= 1) {
         const uint32_t b0 = off[k];
         const int Bc = (int)(off[k + 1] - b0);
-        const uint32_t kn = next_chunk.fetch_add(1);
-        if (kn < nchunks) issue_inputs(kn, slot ^ 1);
-        k = kn;
+        const uint32_t k_this = k;
+        const double t_begin = ms_now();
         ev_wait(st, ln.ev_small[slot]);
         ev_wait(st, ln.ev_out[slot]);    // the proofs of chunk k-2 have left the output staging buffers
         ProveCtx c;
@@ -1112,6 +1119,12 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         uint32_t tot2[2] = {0, 0};
         copy_d2h(st, tot2, c.item_total, 8);
         sync(st);
+        const double t_mid = ms_now();
+        {
+          const uint32_t kn = next_chunk.fetch_add(1);
+          if (kn < nchunks) issue_inputs(kn, slot ^ 1);
+          k = kn;
+        }
         const uint32_t M = tot2[0];
         const size_t max_len = mode == 0 ? (size_t)proof_len((int)tot2[1], n, S)
                                          : (size_t)tot2[1] * REP0_LEN + (size_t)(S - (int)tot2[1]) * REP1_LEN;
@@ -1176,6 +1189,14 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
           if (!len_dev) copy_d2h(co, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
           if (!st_dev) copy_d2h(co, status + b0, c.status, (size_t)Bc * 4);
           ev_record(ln.ev_out[slot], co);
+        }
+        if (trace) {
+          const double t_enq = ms_now();
+          sync(st);
+          const double t_comp = ms_now();
+          sync(ln.cs_out);
+          fprintf(stderr, "TRACE lane %d chunk %u rows %d begin %.2f mid %.2f enqueued %.2f computed %.2f copied %.2f\n", li, k_this, Bc,
+                  t_begin, t_mid, t_enq, t_comp, ms_now());
         }
       }
       sync(ln.cs_in);
@@ -1285,6 +1306,141 @@ int zka_prove_membership_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, co
   }
 }
 
+// proveEquality / proveMult alone (kind 0 / 1): see SubProveJobsTask
+static int prove_sub(zka_ctx* ctx, const zka_params* P, int kind, uint32_t B, const uint8_t* scalars, const uint8_t* tape,
+                     size_t tape_stride, uint8_t* commitments, uint8_t* proofs, int32_t* status) {
+  if (!ctx || !P || !scalars || !tape || !commitments || !proofs || !status) return ZKA_E_ARG;
+  if (B == 0) return 0;
+  const int ns = kind == 0 ? 3 : 6, nd = kind == 0 ? 3 : 7, J = kind == 0 ? SUBP_EQ_JOBS : SUBP_MULT_JOBS;
+  const int nc = kind == 0 ? 2 : 3, plen = kind == 0 ? EQ_LEN : MULT_LEN;
+  if (tape_stride < (size_t)32 * nd) return fail(ctx, ZKA_E_ARG, "tape_stride too small for this sub-proof");
+  try {
+    Stream& st = ctx->st;
+    DevBuf* W = ctx->w;
+    const uint32_t chunk = 16384;
+    for (uint32_t b0 = 0; b0 < B; b0 += chunk) {
+      const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
+      const uint8_t* d_sc = stage_in(st, ctx->in[0], scalars + (size_t)b0 * ns * 32, (size_t)Bc * ns * 32);
+      const uint8_t* d_tape = stage_in(st, ctx->in[1], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      const size_t nj = (size_t)Bc * J;
+      uint32_t* jv = W[0].get<uint32_t>(nj * 8);
+      uint32_t* jr = W[1].get<uint32_t>(nj * 8);
+      uint32_t* proj = W[2].get<uint32_t>(nj * TOM_PROJ_WORDS);
+      uint8_t* bytes = W[3].get<uint8_t>(nj * BSTRIDE);
+      const bool cd = is_device_ptr(commitments), pd = is_device_ptr(proofs), sd = is_device_ptr(status);
+      uint8_t* d_com = cd ? commitments + (size_t)b0 * nc * WP : ctx->out[0].get<uint8_t>((size_t)Bc * nc * WP);
+      uint8_t* d_prf = pd ? proofs + (size_t)b0 * plen : ctx->out[1].get<uint8_t>((size_t)Bc * plen);
+      int32_t* d_st = sd ? status + b0 : ctx->out[2].get<int32_t>(Bc);
+      launch(st, Bc, SubProveJobsTask{kind, d_sc, d_tape, tape_stride, jv, jr, d_st});
+      launch(st, (long long)nj, TomCommitTask{jv, jr, ctx->tg.tab, P->th.tab, proj, ctx->tom_w, ctx->tom_nwin});
+      launch_tom_norm(st, proj, nullptr, bytes, (long long)nj, 1);
+      launch(st, Bc, SubProveEmitTask{kind, d_sc, d_tape, tape_stride, jr, bytes, d_com, d_prf, d_st});
+      if (!cd) copy_d2h(st, commitments + (size_t)b0 * nc * WP, d_com, (size_t)Bc * nc * WP);
+      if (!pd) copy_d2h(st, proofs + (size_t)b0 * plen, d_prf, (size_t)Bc * plen);
+      if (!sd) copy_d2h(st, status + b0, d_st, (size_t)Bc * 4);
+      sync(st);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+int zka_prove_equality_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* scalars, const uint8_t* tape,
+                             size_t tape_stride, uint8_t* commitments, uint8_t* proofs, int32_t* status) {
+  return prove_sub(ctx, P, 0, B, scalars, tape, tape_stride, commitments, proofs, status);
+}
+int zka_prove_mult_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* scalars, const uint8_t* tape,
+                         size_t tape_stride, uint8_t* commitments, uint8_t* proofs, int32_t* status) {
+  return prove_sub(ctx, P, 1, B, scalars, tape, tape_stride, commitments, proofs, status);
+}
+
+// provePointAdd alone (pointAdd.ts:92-163): the item stages of the batched prover with S = 1 (see PaddSetupTask)
+int zka_prove_pointadd_batch(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8_t* points, const uint8_t* blinders,
+                             const uint8_t* tape, size_t tape_stride, uint8_t* commitments, uint8_t* proofs, int32_t* status) {
+  if (!ctx || !P || !points || !blinders || !tape || !commitments || !proofs || !status) return ZKA_E_ARG;
+  if (B == 0) return 0;
+  if (tape_stride < (size_t)32 * 38) return fail(ctx, ZKA_E_ARG, "tape_stride < 32 * 38");
+  try {
+    Stream& st = ctx->st;
+    DevBuf* W = ctx->w;
+    const size_t it_stride = (size_t)32 * (9 + 38);
+    const size_t row_stride = REP0_LEN;
+    const uint32_t chunk = 8192;
+    for (uint32_t b0 = 0; b0 < B; b0 += chunk) {
+      const int Bc = (int)std::min<uint32_t>(chunk, B - b0);
+      const uint8_t* d_pts = stage_in(st, ctx->in[0], points + (size_t)b0 * 195, (size_t)Bc * 195);
+      const uint8_t* d_bl = stage_in(st, ctx->in[1], blinders + (size_t)b0 * 192, (size_t)Bc * 192);
+      const uint8_t* d_tape = stage_in(st, ctx->in[2], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      ProveCtx c;
+      memset(&c, 0, sizeof(c));
+      c.B = Bc; c.S = 1; c.N = 2; c.n = 0; c.M = Bc; c.mode = 1; c.head_len = 0;
+      c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
+      c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
+      c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
+      uint8_t* itape = W[0].get<uint8_t>((size_t)Bc * it_stride);
+      c.tape = itape; c.tape_stride = it_stride; c.tape_draws = (uint32_t)(it_stride / 32);
+      const size_t n1 = (size_t)Bc * 4, n2 = (size_t)Bc * (JOBS_PER_ITEM + DERS_PER_ITEM);
+      c.s1 = W[1].get<uint32_t>((size_t)Bc * 8);
+      c.pk_aff = W[2].get<uint32_t>((size_t)Bc * 16);
+      c.pa_T_aff = W[3].get<uint32_t>((size_t)Bc * 2 * 16);
+      c.pa_T_inf = W[4].get<uint8_t>((size_t)Bc * 2);
+      c.pa_A_inf = W[5].get<uint8_t>((size_t)Bc * 2);
+      c.pb_T1_aff = W[6].get<uint32_t>((size_t)Bc * 16);
+      c.pb_T1_inf = W[7].get<uint8_t>(Bc);
+      c.chal = W[8].get<uint32_t>((size_t)Bc * 3);
+      c.zcount = W[9].get<uint32_t>(Bc);
+      c.item_base = W[10].get<uint32_t>(Bc);
+      c.item_b = W[11].get<uint32_t>(Bc);
+      c.item_i = W[12].get<uint32_t>(Bc);
+      c.item_k = W[13].get<uint32_t>(Bc);
+      c.rep_off = W[14].get<uint32_t>(Bc);
+      c.s1_jv = W[15].get<uint32_t>(n1 * 8);
+      c.s1_jr = W[16].get<uint32_t>(n1 * 8);
+      c.s1_proj = W[17].get<uint32_t>(n1 * TOM_PROJ_WORDS);
+      c.s1_aff = W[18].get<uint32_t>(n1 * TOM_AFF_WORDS);
+      c.s1_bytes = W[19].get<uint8_t>(n1 * BSTRIDE);
+      c.s2_jv = W[20].get<uint32_t>(n2 * 8);
+      c.s2_jr = W[21].get<uint32_t>(n2 * 8);
+      c.s2_proj = W[22].get<uint32_t>(n2 * TOM_PROJ_WORDS);
+      c.s2_aff = W[23].get<uint32_t>(n2 * TOM_AFF_WORDS);
+      c.s2_bytes = W[24].get<uint8_t>(n2 * BSTRIDE);
+      c.secrets = W[25].get<uint32_t>((size_t)Bc * SECRETS_PER_ITEM * 8);
+      c.item_inv = W[26].get<uint32_t>((size_t)Bc * 8);
+      c.item_chal = W[27].get<uint32_t>((size_t)Bc * HASHES_PER_ITEM * 3);
+      uint32_t* gext = W[28].get<uint32_t>((size_t)Bc * GJOBS_PER_ITEM * TOM_EXT_WORDS);
+      c.proof_stride = row_stride;
+      c.proofs = W[29].get<uint8_t>((size_t)Bc * row_stride);
+      c.proof_len = W[30].get<uint32_t>(Bc);
+      const bool cd = is_device_ptr(commitments), pd = is_device_ptr(proofs), sd = is_device_ptr(status);
+      c.status = sd ? status + b0 : ctx->out[2].get<int32_t>(Bc);
+      uint8_t* d_com = cd ? commitments + (size_t)b0 * 6 * WP : ctx->out[0].get<uint8_t>((size_t)Bc * 6 * WP);
+      uint8_t* d_prf = pd ? proofs + (size_t)b0 * PA_LEN : ctx->out[1].get<uint8_t>((size_t)Bc * PA_LEN);
+      launch(st, Bc, PaddSetupTask{c, d_pts, d_bl, d_tape, tape_stride, itape});
+      launch(st, (long long)n1, JobsATask{c});
+      launch(st, (long long)n1, TomCommitTask{c.s1_jv, c.s1_jr, c.tg_tab, c.th_tab, c.s1_proj, c.tom_w, c.tom_nwin});
+      launch_tom_norm(st, c.s1_proj, c.s1_aff, c.s1_bytes, (long long)n1, 1);
+      launch(st, ((long long)Bc + ITEM_INV_CHUNK - 1) / ITEM_INV_CHUNK, ItemInvTask{c});
+      launch(st, Bc, ItemScalarsTask{c});
+      const size_t nj = (size_t)Bc * JOBS_PER_ITEM, nd = (size_t)Bc * DERS_PER_ITEM;
+      launch(st, (long long)Bc * GJOBS_PER_ITEM, TomCommitGTask{c.s2_jv, c.tg_tab, gext, c.tom_w, c.tom_nwin});
+      launch(st, (long long)nj, TomCommitHTask{c.s2_jr, c.th_tab, gext, c.s2_proj, c.tom_w, c.tom_nwin});
+      launch_tom_norm(st, c.s2_proj, c.s2_aff, c.s2_bytes, (long long)nj, 1, JOBS_PER_ITEM, 2);
+      launch(st, Bc, DerivedTask{c});
+      launch_tom_norm(st, c.s2_proj + nj * TOM_PROJ_WORDS, nullptr, c.s2_bytes + nj * BSTRIDE, (long long)nd, 0);
+      launch(st, (long long)Bc * HASHES_PER_ITEM, ItemHashTask{c});
+      launch(st, (long long)Bc * 7, ItemEmitTask{c});
+      launch(st, Bc, PaddExtractTask{c, d_com, d_prf});
+      if (!cd) copy_d2h(st, commitments + (size_t)b0 * 6 * WP, d_com, (size_t)Bc * 6 * WP);
+      if (!pd) copy_d2h(st, proofs + (size_t)b0 * PA_LEN, d_prf, (size_t)Bc * PA_LEN);
+      if (!sd) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
+      sync(st);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(ctx, ZKA_E_CUDA, e.what());
+  }
+}
+
 size_t zka_verify_tape_len_ex(uint32_t ring_size, uint32_t sec_level, uint32_t samples) {
   return verify_tape_len(ceil_log2(ring_size), (int)sec_level, (int)samples);
 }
@@ -1338,14 +1494,14 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
     const std::vector<uint32_t> off = chunk_schedule(B, (uint32_t)std::min(ctx->chunk, all_dev ? 4096 : std::min(4096, ctx->host_chunk)), lanes, !all_dev);
     const uint32_t nchunks = (uint32_t)off.size() - 1;
     const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
-    std::atomic<uint32_t> next_chunk(0);
-    // every lane claims chunks from a shared counter: copy-in, kernels and copy-out of a chunk are sequential on the
+    std::atomic<uint32_t> next_chunk((uint32_t)used);
+    // every lane starts with chunk `li` and then claims chunks from a shared counter: copy-in, kernels and copy-out of a chunk are sequential on the
     // lane's stream; the copies of one lane overlap the kernels of the others
     auto run_lane = [&](int li) {
       Lane& ln = ctx->lane(li);
       Stream& st = ln.st;
       DevBuf* W = ln.w;
-      for (uint32_t k = next_chunk.fetch_add(1); k < nchunks; k = next_chunk.fetch_add(1)) {
+      for (uint32_t k = (uint32_t)li; k < nchunks; k = next_chunk.fetch_add(1)) {
       const uint32_t b0 = off[k];
       const int Bc = (int)(off[k + 1] - b0);
       VerifyCtx c;
