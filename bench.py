@@ -455,8 +455,13 @@ def run_ours(args):
     esteps = max(1, min(args.steps, 5))
     e2e_ms = timed(step_host, esteps) / esteps
     assert int((stat_h != 0).sum().item()) == 0
-    h2d = sum(int(v.numel()) for v in h.values()) + int(tape_h.numel())
-    # the library copies back, per row, only the bytes up to the longest proof of the chunk
+    # bytes that cross PCIe per step: the small inputs; the tape as the library uploads it (two strided copies: the
+    # 3 + 4S draws before the challenge, then the item / GK draws up to the longest proof — counted here with the
+    # longest proof of the whole batch; ZKA_TAPE_SPLIT=0: the full stride); every proof row up to the longest proof
+    # (rows are stride-padded; one 2-D copy per chunk), the lengths and statuses
+    zmax = int(((plen_h.max().item() - (264 + 80 * 330 + 1 + 4 * nbits * 67 + (3 * nbits + 1) * 33)) // (3596 - 330)))
+    tape_bytes = 32 * (3 + 4 * SEC_LEVEL + 40 * zmax + 5 * nbits) if os.environ.get('ZKA_TAPE_SPLIT', '1') != '0' else int(tape_h.shape[1])
+    h2d = sum(int(v.numel()) for v in h.values()) + B * tape_bytes
     d2h = int(plen_h.max().item()) * B + 8 * B
     # the two arms must agree bit for bit (valid prefix of every row; bytes past proof_len are padding)
     col = torch.arange(ps, device=dev).unsqueeze(0)
@@ -586,12 +591,36 @@ def run_ours(args):
     vextra = {'MsmTomWindowBothTask': msm_macs / 2,       # items counts both instances' threads
               'MsmCombineAllTask': ((258 * 8 + 43 * 9) * 2 * MAC_PER_TOM_MODMUL + (256 * 13 + 64 * 14) * MAC_PER_P256_MODMUL) / 3,
               'VValidateTask': (2 + 32 * zero_bits / 80.0) * 7 * MAC_PER_TOM_MODMUL}
-    vroof = kernel_roofline(vprof, 'MsmTomWindowBothTask', 2, msm_macs / 2, (ent_w + ent_g) / 2 * (128 + 32) / 43 + 144,
-                            f'sorted-bucket Pippenger, signed 6-bit windows: ~{ent_w:.0f} + {ent_g} points per proof, '
-                            '8 modmul per bucket addition + 2 x 32 x 9 for the running sums, x 117 MAC')
+    agg_c = L.stat('agg_c') if hasattr(L, 'stat') else 0
+    agg_name = 'AggBucketTask<AggTomSrc>'
+    agg_e = next((v for k, v in vprof.items() if short(k) == agg_name), None)
+    agg_on = bool(agg_e and agg_e['ms'] > 0 and agg_c > 0)
+    if agg_on:
+        # chunk-wide aggregate check: ONE wide-window MSM per chunk, one thread per (window, bucket); every entry costs
+        # one mixed addition (8 modmul) in every window; the bucket tree costs ~2.1 additions (9 modmul) per bucket
+        nwin = -(-258 // agg_c)
+        entries = B * (ent_w + ent_g)
+        vextra['AggBucketTask<AggTomSrc>'] = entries * nwin * 8 * MAC_PER_TOM_MODMUL / (agg_e['items'] / 2)
+        lv = next((v for k, v in vprof.items() if short(k) == 'AggLevelTask<AggTomSrc>'), None)
+        if lv and lv['items']:
+            vextra['AggLevelTask<AggTomSrc>'] = (agg_e['items'] / 2) * 2.1 * 9 * MAC_PER_TOM_MODMUL / (lv['items'] / 2)
+        vroof = kernel_roofline(vprof, agg_name, 2, vextra[agg_name], (128 + 4 + 32 / nwin) * entries * nwin / (agg_e['items'] / 2) + 144,
+                                f'aggregate check of a whole chunk: signed {agg_c}-bit windows x {nwin}, ~{ent_w + ent_g:.0f} points per '
+                                'proof, one thread per (window, bucket), 8 modmul per bucket addition x 117 MAC')
+    else:
+        vroof = kernel_roofline(vprof, 'MsmTomWindowBothTask', 2, msm_macs / 2, (ent_w + ent_g) / 2 * (128 + 32) / 43 + 144,
+                                f'sorted-bucket Pippenger, signed 6-bit windows: ~{ent_w:.0f} + {ent_g} points per proof, '
+                                '8 modmul per bucket addition + 2 x 32 x 9 for the running sums, x 117 MAC')
     if vroof:
-        vroof['share_of_step'] = next(e['ms'] for k, e in vprof.items() if short(k) == 'MsmTomWindowBothTask') / (ms_vprof_step * 2)
+        vroof['share_of_step'] = next(e['ms'] for k, e in vprof.items() if short(k) == (agg_name if agg_on else 'MsmTomWindowBothTask')) / (ms_vprof_step * 2)
+        if agg_on:
+            for k in ('MsmTomWindowBothTask', 'MsmCombineAllTask'):      # they return at once after an accepted aggregate
+                vextra[k] = 0.0
         vroof['whole_step'] = whole_step(vprof, 2, v_ms, vextra)
+        vroof['aggregate'] = {'window_bits': agg_c, 'chunks_accepted': L.stat('agg_pass'), 'chunks_per_proof_path': L.stat('agg_fail'),
+                              'note': 'zk_verify_agg.cuh: the sum over all proofs of a chunk of the three linear combinations '
+                                      '(every relation has its own random scalar, multimult.ts:147-174) is checked first; the '
+                                      'per-proof MSMs run only for a chunk whose sum is not the identity (ZKA_AGG=0: always)'} if agg_on else None
 
     def kern(pr, nsteps):
         return {short(k): {'ms_per_step': round(v['ms'] / nsteps, 4), 'launches_per_step': v['launches'] / nsteps}

@@ -224,8 +224,15 @@ size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap);
  *                   multiplier-bound kernels of another */
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk);
 int zka_lanes(const zka_ctx* ctx);
-/* change a knob between calls: key in {"lanes", "chunk", "host_chunk"}, value >= 1 */
+/* change a knob between calls: key in {"lanes", "chunk", "host_chunk", "agg" (1 = off, 2 = on), "agg_c" (4..16)}, value >= 1 */
 int zka_set_option(zka_ctx* ctx, const char* key, long value);
+/* counters since zka_init: "agg_pass" = verifier chunks accepted as a whole by the chunk-wide aggregate check (the
+ * sum over all proofs of the chunk of the reference's three linear combinations, multimult.ts:147-174, evaluated as one
+ * wide-window MSM; every relation carries its own random scalar, so the sum is the identity iff (w.h.p.) every
+ * per-proof combination is), "agg_fail" = chunks that went on to the per-proof evaluation (some proof invalid or
+ * already rejected by the parsers; verdicts and statuses are then exactly the per-proof ones).  -1: unknown key.
+ * ZKA_AGG=0 disables the aggregate check, ZKA_AGG_C=4..16 fixes its window bits. */
+long long zka_stat(zka_ctx* ctx, const char* key);
 
 /* ---- multi-GPU helpers: a rank's proofs as ONE contiguous block for the NCCL all-gather.
  * Proof b starts at offsets[b] = sum_{i<b} align16(proof_len[i]); offsets[B] is the block length (the caller

@@ -109,6 +109,20 @@ def check_prove_parity(L, B=2, N=6, seed=3, sec_level=80):
     return proofs, plen
 
 
+def check_prove_few_keys(L, B=10, N=5, signers=1, seed=41, sec_level=16, spots=(0, 3, 9)):
+    """Few distinct signers in a larger batch: the per-key tables of the prover get wider windows (chosen on the device
+    from the number of distinct keys, key_window_bits in zk_ops.cuh); the bytes stay the oracle's."""
+    P, po = make_params(L, seed, sec_level)
+    wl = synth.Workload(B=B, N=N, seed=seed, distinct_signers=signers)
+    tape = synth.random_tape(B, L.prove_tape_len(N, sec_level), seed=seed + 100)
+    proofs, plen, status = run_prove(L, P, wl, tape, sec_level)
+    assert (status == 0).all(), status
+    for b in spots:
+        pr, _ = oracle_proof(po, wl, tape, b)
+        assert proofs[b, :plen[b]].tobytes() == flat.ser_proof(pr), f'proof {b} differs'
+    L.params_destroy(P)
+
+
 # ------------------------------------------------------------------------------------- verify
 def run_verify(L, P, msg_hash, ring, proofs, plen, vtape):
     B = msg_hash.shape[0]

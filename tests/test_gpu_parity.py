@@ -266,3 +266,10 @@ def test_verify_sample_count_on_gpu(gpu_engine):
     for K in (5, 33, 80):
         common.check_verify_samples(gpu_engine.lib, K, N=5, seed=25, sec_level=80, tampers=6, oracle=cpu)
     common.check_verify_samples(gpu_engine.lib, 7, N=4, seed=26, sec_level=20, tampers=2, oracle='python')
+
+
+@pytest.mark.gpu
+def test_prove_few_distinct_keys_wide_key_tables_on_gpu(gpu_engine):
+    """256 proofs of 2 / 40 signers: the per-key tables use 8-bit / 7-bit windows (device-chosen) instead of 5."""
+    common.check_prove_few_keys(gpu_engine.lib, B=256, N=64, signers=2, seed=43, sec_level=80, spots=(0, 255))
+    common.check_prove_few_keys(gpu_engine.lib, B=256, N=64, signers=40, seed=44, sec_level=16, spots=(5, 130, 255))

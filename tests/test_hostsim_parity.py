@@ -34,6 +34,11 @@ def test_prove_bit_exact_sec_level_16(hostsim):
     common.check_prove_parity(hostsim, B=3, N=17, seed=4, sec_level=16)
 
 
+def test_prove_few_distinct_keys_wide_key_tables(hostsim):
+    common.check_prove_few_keys(hostsim, B=10, N=5, signers=1, seed=41, sec_level=16)     # one key: 6/7-bit windows
+    common.check_prove_few_keys(hostsim, B=12, N=5, signers=3, seed=42, sec_level=16, spots=(1, 11))
+
+
 def test_verify_decisions_match_oracle(hostsim):
     common.check_verify_parity(hostsim, N=6, seed=3, tampers=16)
 

@@ -28,7 +28,7 @@ SYMBOLS = [
     'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack', 'zka_verify_batch_ex', 'zka_verify_tape_len_ex',
     'zka_verify_exp_batch', 'zka_verify_membership_batch', 'zka_verify_equality_batch', 'zka_verify_mult_batch',
     'zka_verify_pointadd_batch', 'zka_prove_exp_batch', 'zka_prove_membership_batch',
-    'zka_prove_equality_batch', 'zka_prove_mult_batch', 'zka_prove_pointadd_batch',
+    'zka_prove_equality_batch', 'zka_prove_mult_batch', 'zka_prove_pointadd_batch', 'zka_stat',
 ]
 
 STATUS_MESSAGES = {
@@ -117,6 +117,8 @@ class ZkaLib:
             L.zka_verify_batch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                               C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32]
             L.zka_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+            L.zka_stat.restype = C.c_longlong
+            L.zka_stat.argtypes = [C.c_void_p, C.c_char_p]
             L.zka_verify_exp_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_size_t, C.c_void_p, C.c_void_p,
                                                C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
             L.zka_verify_membership_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
@@ -182,6 +184,11 @@ class ZkaLib:
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.zka_set_option(self.ctx, key.encode(), int(value)), f'zka_set_option({key})')
+
+    def stat(self, key: str) -> int:
+        """Counters since zka_init ('agg_pass', 'agg_fail': verifier chunks decided by the chunk-wide aggregate check /
+        sent on to the per-proof evaluation)."""
+        return int(self.lib.zka_stat(self.ctx, key.encode()))
 
     def proof_max_len(self, ring_size, sec_level=80): return int(self.lib.zka_proof_max_len(ring_size, sec_level))
     def prove_tape_len(self, ring_size, sec_level=80): return int(self.lib.zka_prove_tape_len(ring_size, sec_level))

@@ -198,8 +198,11 @@ struct P256PowsTask {
   int nbase, nwin, w;
   const uint32_t* index = nullptr;      // optional: base t is base_aff[index[t]]
   const uint32_t* count_dev = nullptr;  // optional: number of bases actually present (<= nbase)
+  const uint32_t* w_dev = nullptr;      // optional: window bits chosen on the device (key_window_bits); nwin follows
   ZK_HD void operator()(int t) const {
     if (count_dev && (uint32_t)t >= *count_dev) return;
+    const int w = w_dev ? (int)*w_dev : this->w;
+    const int nwin = w_dev ? fb_windows(w) : this->nwin;
     const size_t src = index ? index[t] : (size_t)t;
     P256Aff a;
     p256_ld_aff(a, base_aff + src * P256_AFF_WORDS);
@@ -221,7 +224,11 @@ struct P256RowsTask {
   const uint32_t* pows;  // [nbase*nwin][24]
   uint32_t* rows;        // [nbase*nwin][E][24]
   int w;
+  const uint32_t* count_dev = nullptr;   // optional: number of bases actually present
+  const uint32_t* w_dev = nullptr;       // optional: window bits chosen on the device (key_window_bits)
   ZK_HD void operator()(int t) const {
+    const int w = w_dev ? (int)*w_dev : this->w;
+    if (count_dev && (uint32_t)(t / fb_windows(w)) >= *count_dev) return;
     P256Pt p, acc;
     p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
     acc = p;
@@ -235,6 +242,25 @@ struct P256RowsTask {
     }
   }
 };
+// ---- per-KEY tables of the prover: the generic signed-digit format [fb_windows(w)][fb_entries(w)][16] with the window
+// bits chosen ON THE DEVICE from the number of distinct keys of the chunk (KeyRankTask).  Grids and buffers are sized
+// for the worst case (every proof its own key, w = 5: KEY_CAP entries per proof); fewer keys get wider windows inside
+// the same memory: 256 keys in a chunk of 4096 proofs -> w = 8, 33 instead of 52 lookups per alpha*pk.
+enum : int { KEY_W_MIN = 5, KEY_W_MAX = 8, KEY_CAP = 52 * 17 };
+ZK_HD int key_window_bits(uint32_t count, uint32_t B, uint32_t uses) {   // uses = products per proof (S + 2)
+  int best = KEY_W_MIN;
+  uint64_t best_cost = ~0ull;
+  for (int w = KEY_W_MIN; w <= KEY_W_MAX; w++) {
+    const uint64_t nwin = (uint64_t)fb_windows(w), ne = (uint64_t)fb_entries(w);
+    if (w > KEY_W_MIN && (uint64_t)count * nwin * ne > (uint64_t)B * KEY_CAP) break;
+    // building an entry = one addition + its share of a normalisation (~2 mixed additions), used `uses` times per proof
+    const uint64_t cost = nwin * ((uint64_t)count * (ne - 1) * 2 + (uint64_t)B * uses);
+    if (cost < best_cost) { best_cost = cost; best = w; }
+  }
+  return best;
+}
+ZK_HD size_t key_table_words(int w) { return (size_t)fb_windows(w) * fb_entries(w) * P256_AFF_WORDS; }
+
 // Per-base SIGNED 5-bit table (the per-proof table of R): k = sum_j d_j 32^j with d_j in [-16, 16],
 // 52 windows x 16 entries (1..16 multiples); a negative digit negates y of the affine entry.
 // 52 mixed additions per scalar multiplication instead of 64 with unsigned 4-bit windows, and the
@@ -304,10 +330,12 @@ struct P256NormTask {
   int chunk;             // points per thread (<= NORM_CHUNK_MAX)
   const uint32_t* groups_dev = nullptr;  // optional: only the first *groups_dev * group_size points exist
   int group_size = 0;
+  const uint32_t* w_dev = nullptr;       // optional: group_size = entries of a key table with *w_dev window bits
   ZK_HD void operator()(int t) const {
     using F = P256p;
     const int lo = t * chunk;
     int total = count;
+    const int group_size = w_dev ? fb_windows((int)*w_dev) * fb_entries((int)*w_dev) : this->group_size;
     if (groups_dev) {
       const long long present = (long long)*groups_dev * group_size;
       if (present < total) total = (int)present;

@@ -66,10 +66,10 @@ struct ProveCtx {
   uint32_t* u12;       // [B][16] u1 = z/s, u2 = r/s (Montgomery mod n): R = u1*G + u2*pk
   uint32_t* tab_of;    // [B]   table index of the proof's pk (equal keys of a batch share one table)
   uint32_t* tab_rep;   // [B]   proof index that owns table t; tab_count[0] = number of tables
-  uint32_t* tab_count; // [1]
-  uint32_t* rpows;     // [B][RT_NWIN][24]          per-KEY signed 5-bit table of pk:
-  uint32_t* rrows;     // [B][RT_NWIN][RT_ROW][24]    every alpha*R of the proof is evaluated as
-  uint32_t* rtab;      // [B][RT_NWIN][RT_ROW][16]    (alpha u1)*G + (alpha u2)*pk, so no table of R is needed
+  uint32_t* tab_count; // [2]   [0] number of tables, [1] their window bits (key_window_bits)
+  uint32_t* rpows;     // [B][52][24]               per-KEY signed-digit table of pk (window bits tab_count[1]):
+  uint32_t* rrows;     // [B * KEY_CAP][24]           every alpha*R of the proof is evaluated as
+  uint32_t* rtab;      // [B * KEY_CAP][16]           (alpha u1)*G + (alpha u2)*pk, so no table of R is needed
   // phase A (P-256): slot i in [0,S] per proof; slot S is comS1
   uint32_t* pa_T;      // [B][S+1][24]
   uint32_t* pa_A;      // [B][S+1][24]
@@ -303,6 +303,7 @@ struct KeyRankTask {
       uint32_t total = 0;
       for (uint32_t o = 0; o < (uint32_t)c.B; o++) total += (c.tab_of[o] == o) ? 1u : 0u;
       c.tab_count[0] = total;
+      c.tab_count[1] = (uint32_t)key_window_bits(total, (uint32_t)c.B, (uint32_t)c.S + 2);
     }
   }
 };
@@ -338,7 +339,8 @@ struct RPointTask {
     P256Pt R;
     p256_set_identity(R);
     p256_accum_fixed(R, c.g_tabw, u1, c.g_w);
-    p256_accum_rtab(R, c.rtab + (size_t)c.tab_of[b] * RT_ENTRIES * P256_AFF_WORDS, u2);
+    const int kw = (int)c.tab_count[1];
+    p256_accum_fixed(R, c.rtab + (size_t)c.tab_of[b] * key_table_words(kw), u2, kw);
     uint32_t zi[8];
     P256Aff Ra;
     if (p256_is_identity(R)) {
@@ -391,7 +393,8 @@ struct PhaseAP256Task {
     P256Pt T, A;
     p256_set_identity(T);
     p256_accum_fixed(T, c.g_tabw, a1, c.g_w);
-    p256_accum_rtab(T, c.rtab + (size_t)c.tab_of[b] * RT_ENTRIES * P256_AFF_WORDS, a2);
+    const int kw = (int)c.tab_count[1];
+    p256_accum_fixed(T, c.rtab + (size_t)c.tab_of[b] * key_table_words(kw), a2, kw);
     A = T;
     p256_accum_fixed(A, c.h_tab8, r, c.h_w);
     p256_st_proj(c.pa_T + (size_t)t * P256_PROJ_WORDS, T);

@@ -42,6 +42,11 @@ enum : int {
   MSM_NWIN = 43,               // 43 windows cover the 258 bits of k + offset (msm_digit6)
   MSM_C_N = 4,                 // P-256 MSM: SIGNED 4-bit windows, digits in [-8, 7], 8 buckets,
   MSM_NWIN_N = 65,             // 65 windows cover the 257 bits of k + offset (msm_digit4)
+  // control words of the chunk-wide aggregate check (zk_verify_agg.cuh)
+  AGG_SKIP = 0,                // != 0: some proof of the chunk is not eligible, the aggregate kernels return at once
+  AGG_TOM_PASS = 1,            // != 0: sum_b (GK_b + W_b) is the identity -> the per-proof tomEdwards256 MSMs are skipped
+  AGG_NIST_PASS = 2,           // != 0: sum_b N_b is the identity -> the per-proof P-256 MSMs are skipped
+  AGG_CTL_WORDS = 4,
 };
 
 // K = number of sampled repetitions (verifyExp's secparam, exp.ts:233-262): 20 in verifySignatureList
@@ -113,6 +118,7 @@ struct VerifyCtx {
   uint32_t* win_g;      // [B][MSM_NWIN][36]
   uint32_t* win_n;      // [B][MSM_NWIN_N][24]
   uint8_t* id_flags;    // [B][3]  gk, W, N identity
+  const uint32_t* agg_ctl;  // aggregate verdicts of the chunk (AGG_*), or null
   // outputs
   uint8_t* ok;          // [B]
   int32_t* status;      // [B]
@@ -1092,7 +1098,9 @@ struct MsmP256WindowTask {
   const uint8_t* skip;      // [B][nent]
   uint32_t* win;            // [B][MSM_NWIN_N][24]
   int nent = V_SAMPLES + 1; // entries per proof: K sampled A_j + comS1
+  const uint32_t* ctl = nullptr;
   ZK_HD void operator()(int t) const {
+    if (ctl && ctl[AGG_NIST_PASS]) return;
     const int b = t / MSM_NWIN_N, w = t % MSM_NWIN_N;
     P256Pt bucket[8];
     for (int d = 0; d < 8; d++) p256_set_identity(bucket[d]);
@@ -1144,7 +1152,9 @@ struct MsmTomWindowBothTask {
   MsmTomWindowTask w, gk;
   int nW, nWp;   // multiW threads (proofs x segments x windows), rounded up to a warp multiple
   int nG;        // GK threads (proofs x windows)
+  const uint32_t* ctl = nullptr;
   ZK_HD void operator()(int t) const {
+    if (ctl && ctl[AGG_TOM_PASS]) return;
     if (t < nWp) {
       if (t < nW) w(t);
     } else if (t - nWp < nG) {
@@ -1163,9 +1173,11 @@ struct MsmCombineAllTask {
   MsmTomCombineTask gk, w;
   MsmP256CombineTask n;
   int B, Bp;   // Bp = B rounded up to a warp multiple: the P-256 chain never shares a warp with a Tom chain
+  const uint32_t* ctl = nullptr;
   ZK_HD void operator()(int t) const {
     const int kind = t / Bp, i = t % Bp;
     if (i >= B) return;
+    if (ctl && ctl[kind == 2 ? AGG_NIST_PASS : AGG_TOM_PASS]) return;
     if (kind == 0) gk(i);
     else if (kind == 1) w(i);
     else n(i);
@@ -1495,7 +1507,10 @@ struct VConcatTask {   // rows[b] = a[b] (la bytes) || c[b] (lc bytes)
 struct VFinalTask {
   VerifyCtx c;
   ZK_HD void operator()(int b) const {
-    const uint8_t* f = c.id_flags + (size_t)b * 3;
+    const uint8_t* fl = c.id_flags + (size_t)b * 3;
+    // the aggregate check of the chunk stands for every per-proof identity test of its group (zk_verify_agg.cuh)
+    const bool tom_pass = c.agg_ctl && c.agg_ctl[AGG_TOM_PASS], nist_pass = c.agg_ctl && c.agg_ctl[AGG_NIST_PASS];
+    const bool f[3] = {tom_pass || fl[0], tom_pass || fl[1], nist_pass || fl[2]};
     const int st = c.status[b];
     const bool gk = c.gk_ok_len[b] && f[0];
     if (st == ZKA_ERR_MALFORMED || st == ZKA_ERR_R_INFINITY) { c.ok[b] = 0; return; }

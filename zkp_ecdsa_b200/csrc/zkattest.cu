@@ -11,6 +11,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
+#include <mutex>
 #include <chrono>
 #include <thread>
 #include <string>
@@ -18,7 +20,7 @@
 
 #include "zk_launch.cuh"
 #include "zk_prove.cuh"
-#include "zk_verify.cuh"
+#include "zk_verify_agg.cuh"
 
 namespace zk {
 // ---- small helper tasks of the C ABI layer (namespace scope: kernel template arguments) ----
@@ -291,6 +293,7 @@ struct Lane {
   // workspace (grow-only)
   DevBuf w[64];
   DevBuf in[16], out[8];
+  DevBuf agg[48];   // workspace of the verifier's chunk-wide aggregate check (zk_verify_agg.cuh)
   std::string err;
 };
 
@@ -304,6 +307,13 @@ struct zka_ctx : Lane {
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 4096;       // largest chunk of a call whose buffers are all device memory (ZKA_CHUNK)
   int host_chunk = 2048;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
+  int agg = 1;            // verifier: chunk-wide aggregate check before the per-proof MSMs (ZKA_AGG=0 disables it)
+  int agg_c = 0;          // window bits of the aggregate MSM (0: chosen from the chunk size; ZKA_AGG_C)
+  uint64_t agg_pass = 0, agg_fail = 0;   // chunks decided by the aggregate / sent to the per-proof path (zka_stat)
+  std::mutex stat_mu;
+  int agg_c_last = 0;
+  bool tape_split = true; // host tapes travel in two strided copies: the 3 + 4S draws before the challenge, then only the
+                          // item / GK draws up to the longest proof of the chunk (ZKA_TAPE_SPLIT=0: one full-stride copy)
   int p256_hw = 20;       // window bits of the P-256 G table and of the per-params NistGroup.h table
                           // (13 windows x 2^20 entries x 64 B = 872 MB each; 16 -> 20 -> 22: PhaseA 13.4 -> 12.9 -> 12.6 ms)
   FixedTable g8;          // P-256 generator, w=8 [32][256][16]
@@ -329,6 +339,75 @@ namespace {
 int fail(zka_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
+}
+
+// ---- chunk-wide aggregate check of the verifier (zk_verify_agg.cuh) ------------------------------------------------
+struct AggPlan {
+  AggDigits D;
+  int levels;
+  int lm[AGG_MAX_LEVELS];   // log2 fan-in of every level of the bucket reduction (sum = c - 1)
+};
+// window bits from a cost model: ceil(258/c) windows x (entries / warp efficiency + 2.3 x 2^(c-1) bucket additions); the
+// warp efficiency accounts for the spread of the bucket sizes inside a warp (Poisson: mean + ~2.2 sigma)
+AggPlan agg_plan(double entries, int c_forced) {
+  int best = 4;
+  double best_cost = 1e300;
+  for (int c = 4; c <= 16; c++) {
+    const double nb = (double)(1u << (c - 1)), load = entries / nb;
+    const double eff = load / (load + 2.2 * std::sqrt(load > 1.0 ? load : 1.0));
+    const double cost = std::ceil(258.0 / c) * (entries / (eff > 0.05 ? eff : 0.05) + 2.3 * nb);
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  const int c = c_forced ? c_forced : best;
+  AggPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.D.c = c;
+  pl.D.nwin = (258 + c - 1) / c;
+  pl.D.nb = 1 << (c - 1);
+  for (int j = 0; j < pl.D.nwin; j++) {   // offs = sum_j 2^(c-1) 2^(c j)
+    const int pos = c * j + c - 1;
+    pl.D.offs[pos >> 5] |= 1u << (pos & 31);
+  }
+  // top window: digits 0 .. top_max, spread over 2^top_shift sub-buckets each
+  const int tb = 256 - c * (pl.D.nwin - 1);
+  const int top_max = 1 << (tb > 0 ? tb : 0);
+  pl.D.top_shift = 0;
+  while (((top_max + 1) << (pl.D.top_shift + 1)) <= pl.D.nb) pl.D.top_shift++;
+  const int bits = c - 1;
+  pl.levels = (bits + AGG_FAN_BITS - 1) / AGG_FAN_BITS;
+  for (int i = 0; i < pl.levels; i++) pl.lm[i] = bits / pl.levels + (i < bits % pl.levels ? 1 : 0);
+  return pl;
+}
+// enqueue histogram, prefix sums, scatter, bucket sums and the reduction tree of one group; returns the root sums
+template <class Src>
+void agg_msm(Stream& st, DevBuf* A, const Src& src, const AggPlan& pl, const uint32_t* ctl, const uint32_t** rootA,
+             const uint32_t** rootB) {
+  const AggDigits& D = pl.D;
+  const int nwin = D.nwin, nb = D.nb, nseg = (nb + 1 + AGG_SEG - 1) / AGG_SEG;
+  const size_t cap = (size_t)src.slots();
+  uint32_t* hist = A[0].get<uint32_t>((size_t)nwin * (nb + 1));
+  uint32_t* bstart = A[1].get<uint32_t>((size_t)nwin * (nb + 2));
+  uint32_t* segtot = A[2].get<uint32_t>((size_t)nwin * nseg);
+  uint32_t* sorted = A[3].get<uint32_t>((size_t)nwin * cap);
+  uint32_t* bsum = A[4].get<uint32_t>((size_t)nwin * nb * Src::PTW);
+  dev_memset(st, hist, 0, (size_t)nwin * (nb + 1) * 4);
+  launch(st, (long long)cap, AggHistTask<Src>{src, D, ctl, hist});
+  launch(st, (long long)nwin * nseg, AggSegSumTask{ctl, hist, segtot, nb, nseg});
+  launch(st, nwin, AggSegScanTask{ctl, segtot, nseg});
+  launch(st, (long long)nwin * nseg, AggOffsetsTask{ctl, segtot, hist, bstart, nb, nseg});
+  launch(st, (long long)cap, AggScatterTask<Src>{src, D, ctl, hist, sorted, cap});
+  launch(st, (long long)nwin * nb, AggBucketTask<Src>{src, ctl, bstart, sorted, bsum, cap, nb});
+  const uint32_t *inA = bsum, *inB = nullptr;
+  int nin = nb, ll = 0;
+  for (int lv = 0; lv < pl.levels; lv++) {
+    const int nout = nin >> pl.lm[lv];
+    uint32_t* oA = A[5 + 2 * lv].get<uint32_t>((size_t)nwin * nout * Src::PTW);
+    uint32_t* oB = A[6 + 2 * lv].get<uint32_t>((size_t)nwin * nout * Src::PTW);
+    launch(st, (long long)nwin * nout, AggLevelTask<Src>{ctl, inA, inB, oA, oB, nin, pl.lm[lv], ll, nwin, D.top_shift});
+    inA = oA; inB = oB; nin = nout; ll += pl.lm[lv];
+  }
+  *rootA = inA;
+  *rootB = inB;
 }
 
 int ceil_log2(uint32_t v) {
@@ -560,6 +639,11 @@ int zka_set_option(zka_ctx* ctx, const char* key, long value) {
       ctx->chunk = (int)value;
     } else if (k == "host_chunk") {
       ctx->host_chunk = (int)value;
+    } else if (k == "agg") {          // 1: off, 2: on (values start at 1)
+      ctx->agg = (int)value - 1;
+    } else if (k == "agg_c") {
+      if (value < 4 || value > 16) return ZKA_E_ARG;
+      ctx->agg_c = (int)value;
     } else {
       return ZKA_E_ARG;
     }
@@ -567,6 +651,15 @@ int zka_set_option(zka_ctx* ctx, const char* key, long value) {
     return fail(ctx, ZKA_E_CUDA, e.what());
   }
   return 0;
+}
+long long zka_stat(zka_ctx* ctx, const char* key) {
+  if (!ctx || !key) return -1;
+  const std::string k(key);
+  std::lock_guard<std::mutex> g(ctx->stat_mu);
+  if (k == "agg_pass") return (long long)ctx->agg_pass;
+  if (k == "agg_fail") return (long long)ctx->agg_fail;
+  if (k == "agg_c") return (long long)ctx->agg_c_last;        // window bits of the last tomEdwards256 aggregate MSM
+  return -1;
 }
 size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap) {
   if (!ctx) return 0;
@@ -656,6 +749,12 @@ int zka_init(int device, zka_ctx** out) {
       if (lanes > 8) lanes = 8;
       if (zka_set_option(ctx, "lanes", lanes) != 0) throw std::runtime_error("lanes");
     }
+    if (const char* e = getenv("ZKA_TAPE_SPLIT")) ctx->tape_split = atoi(e) != 0;
+    if (const char* e = getenv("ZKA_AGG")) ctx->agg = atoi(e);
+    if (const char* e = getenv("ZKA_AGG_C")) {
+      int c = atoi(e);
+      if (c >= 4 && c <= 16) ctx->agg_c = c;
+    }
     if (const char* e = getenv("ZKA_P256_HW")) {   // window bits of the P-256 G / NistGroup.h tables: 8..24
       int w = atoi(e);
       if (w >= 8 && w <= 24) ctx->p256_hw = w;
@@ -696,6 +795,8 @@ void zka_shutdown(zka_ctx* ctx) {
   for (auto& b : ctx->w) b.release();
   for (auto& b : ctx->in) b.release();
   for (auto& b : ctx->out) b.release();
+  for (int li = 0; li < 1 + (int)ctx->extra.size(); li++)
+    for (auto& b : ctx->lane(li).agg) b.release();
   ctx->ring_in.release();
   ctx->ring_m.release();
   for (int li = 0; li < 1 + (int)ctx->extra.size(); li++) {
@@ -1004,7 +1105,18 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         cin[slot].s_in = s_in ? stage_in(ci, inx[1], s_in + (size_t)b0 * 32, Bc * 32) : nullptr;
         cin[slot].q_in = q_in ? stage_in(ci, inx[2], q_in + (size_t)b0 * 65, Bc * 65) : nullptr;
         ev_record(ln.ev_small[slot], ci);
-        cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
+        if (is_device_ptr(tape)) {
+          cin[slot].tape = tape + (size_t)b0 * tape_stride;
+        } else if (!ctx->tape_split) {
+          cin[slot].tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
+        } else {
+          // host tape: only the draws used before the challenge (3 + 4S of up to 3 + 44S + 5n) travel now; the
+          // item and GK draws of each proof follow after the challenge, when their number is known
+          uint8_t* dt = in[4].get<uint8_t>(Bc * tape_stride);
+          const size_t pre = std::min(tape_stride, (size_t)32 * draws_before_items(S));
+          copy_d2h_2d(ci, dt, tape_stride, tape + (size_t)b0 * tape_stride, tape_stride, pre, Bc);
+          cin[slot].tape = dt;
+        }
         ev_record(ln.ev_tape[slot], ci);
       };
       // the first `used` chunks are dealt statically (lane threads start at slightly different times); later ones are
@@ -1049,8 +1161,8 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         c.r_aff = W[4].get<uint32_t>((size_t)Bc * 16);
         c.r_bytes = W[5].get<uint8_t>((size_t)Bc * BSTRIDE);
         c.rpows = W[6].get<uint32_t>((size_t)Bc * RT_NWIN * P256_PROJ_WORDS);
-        c.rrows = W[7].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_PROJ_WORDS);
-        c.rtab = W[8].get<uint32_t>((size_t)Bc * RT_ENTRIES * P256_AFF_WORDS);
+        c.rrows = W[7].get<uint32_t>((size_t)Bc * KEY_CAP * P256_PROJ_WORDS);
+        c.rtab = W[8].get<uint32_t>((size_t)Bc * KEY_CAP * P256_AFF_WORDS);
         c.pa_T = W[9].get<uint32_t>(nA * P256_PROJ_WORDS);
         c.pa_A = W[10].get<uint32_t>(nA * P256_PROJ_WORDS);
         c.pa_T_aff = W[11].get<uint32_t>(nA * 16);
@@ -1075,7 +1187,7 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         c.u12 = W[46].get<uint32_t>((size_t)Bc * 16);
         c.tab_of = W[48].get<uint32_t>(Bc);
         c.tab_rep = W[49].get<uint32_t>((size_t)Bc * 2);
-        c.tab_count = W[50].get<uint32_t>(1);
+        c.tab_count = W[50].get<uint32_t>(2);
         c.which_s = W[52].get<uint32_t>(Bc);
         c.base_aff = mode == 0 ? c.pk_aff : W[53].get<uint32_t>((size_t)Bc * 16);
         c.proof_stride = proof_stride;
@@ -1093,13 +1205,19 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         {
           const int Bp = (Bc + 31) & ~31;
           launch(st, (long long)Bp + Bc,
-                 PowsAndPreTask{P256PowsTask{c.base_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count}, PreTask{c}, Bp});
+                 PowsAndPreTask{P256PowsTask{c.base_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W, c.tab_rep, c.tab_count, c.tab_count + 1}, PreTask{c}, Bp});
         }
-        launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows, c.tab_count});
+        // the window bits of these tables are chosen on the device from the number of distinct keys (tab_count[1]);
+        // grids are sized for the worst case, surplus threads return
+        launch(st, (long long)Bc * RT_NWIN, P256RowsTask{c.rpows, c.rrows, KEY_W_MIN, c.tab_count, c.tab_count + 1});
         {
-          const long long np = (long long)Bc * RT_ENTRIES;
-          const int ch = norm_chunk_for(np, 5);
-          launch(st, (np + ch - 1) / ch, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np, ch, c.tab_count, RT_ENTRIES});
+          const long long np = (long long)Bc * KEY_CAP;
+          // points per thread from the EXPECTED table volume (at most min(N, Bc) distinct keys when every key is a ring
+          // member); the grid still covers the worst case
+          const uint32_t kest = std::min<uint32_t>(N, (uint32_t)Bc);
+          const int west = key_window_bits(kest, (uint32_t)Bc, (uint32_t)S + 2);
+          const int ch = norm_chunk_for((long long)kest * fb_windows(west) * fb_entries(west), 5);
+          launch(st, (np + ch - 1) / ch, P256NormTask{c.rrows, c.rtab, nullptr, nullptr, (int)np, ch, c.tab_count, 0, c.tab_count + 1});
         }
         // --- phase A (first consumer of the tape) and R = u1*G + u2*pk side by side
         ev_wait(st, ln.ev_tape[slot]);
@@ -1118,7 +1236,16 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         launch(st, 1, ScanTask{c});
         uint32_t tot2[2] = {0, 0};
         copy_d2h(st, tot2, c.item_total, 8);
+        const bool tape_host = ctx->tape_split && !is_device_ptr(tape);
         sync(st);
+        if (tape_host) {
+          // second part of the tape: draws [3 + 4S, 3 + 4S + 40 zmax + 5n) of every row in one strided copy
+          // (zmax = the largest zero-bit count of the chunk)
+          const size_t o0 = (size_t)32 * draws_before_items(S);
+          const size_t o1 = std::min(tape_stride, (size_t)32 * prove_draws((int)tot2[1], n, S));
+          if (o1 > o0)
+            copy_d2h_2d(st, const_cast<uint8_t*>(c.tape) + o0, tape_stride, tape + (size_t)b0 * tape_stride + o0, tape_stride, o1 - o0, Bc);
+        }
         const double t_mid = ms_now();
         {
           const uint32_t kn = next_chunk.fetch_add(1);
@@ -1185,6 +1312,8 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
           Stream& co = ln.cs_out;
           ev_wait(co, ln.ev_done[slot]);
           // only the bytes up to the longest proof of the chunk are copied back (rows are stride-padded)
+          // (one cudaMemcpyAsync per row with its exact length was measured: 8192 driver calls per step cost more than
+          // the ~25 % of padding they save — config2 e2e 89.9k -> 38.5k proofs/s, gpurun_out/bench_c2_r2g.json)
           if (!out_dev) copy_d2h_2d(co, proofs + (size_t)b0 * proof_stride, proof_stride, c.proofs, proof_stride, max_len, Bc);
           if (!len_dev) copy_d2h(co, proof_len_out + b0, c.proof_len, (size_t)Bc * 4);
           if (!st_dev) copy_d2h(co, status + b0, c.status, (size_t)Bc * 4);
@@ -1609,23 +1738,61 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
       launch(st, (long long)Bc * ET, VParseEntriesTask{c.proofs, proof_stride, c.ent_off, c.ent_pre, ET});
       if (mode == 0) launch(st, (long long)Bc * ngk, VParseEntriesTask{c.proofs, proof_stride, gk_offs, c.gk_pre, ngk});
       launch(st, (long long)Bc * 2, TomCommitTask{c.fx_jv, c.fx_jr, c.tg_tab, c.th_tab, c.fx_proj, c.tom_w, c.tom_nwin});
+      // chunk-wide aggregate check (zk_verify_agg.cuh): the sum over all proofs of the chunk of the three linear
+      // combinations, as ONE wide-window MSM per group; when both sums are the identity the per-proof MSMs below
+      // return at once
+      uint32_t* ctl = nullptr;
+      if (ctx->agg && mode == 0) {
+        DevBuf* A = ln.agg;
+        ctl = A[0].get<uint32_t>(AGG_CTL_WORDS);
+        dev_memset(st, ctl, 0, AGG_CTL_WORDS * 4);
+        launch(st, Bc, AggGateTask{c, ctl});
+        const AggTomSrc tsrc{c.ent_scalar, c.ent_pre, c.ent_cnt, c.gk_scalar, c.gk_pre, Bc, ET, K, ngk};
+        const AggNistSrc nsrc{c.nent_scalar, c.nent_aff, c.nent_skip, Bc, EN};
+        const AggPlan tp = agg_plan((double)Bc * (0.5 * K * V_ENT_PER_SAMPLE + 2 + ngk), ctx->agg_c);
+        const AggPlan np = agg_plan((double)Bc * EN, 0);
+        ctx->agg_c_last = tp.D.c;
+        const uint32_t *tA, *tB, *nA, *nB;
+        agg_msm(st, A + 1, tsrc, tp, ctl, &tA, &tB);
+        agg_msm(st, A + 20, nsrc, np, ctl, &nA, &nB);
+        // fixed-base parts: one commitment for the summed tomEdwards256 scalars, a two-level sum of the P-256 points
+        const int fgroups = (Bc * 2 + 63) / 64, ngroups = (Bc + 31) / 32;
+        uint32_t* fpart = A[40].get<uint32_t>((size_t)fgroups * 16);
+        uint32_t* fjv = A[41].get<uint32_t>(8);
+        uint32_t* fjr = A[42].get<uint32_t>(8);
+        uint32_t* fproj = A[43].get<uint32_t>(TOM_PROJ_WORDS);
+        uint32_t* npart = A[44].get<uint32_t>((size_t)ngroups * P256_PROJ_WORDS);
+        launch(st, fgroups, AggFixPartTask{ctl, c.fx_jv, c.fx_jr, fpart, Bc});
+        launch(st, 1, AggFixSumTask{ctl, fpart, fjv, fjr, fgroups});
+        launch(st, 1, TomCommitTask{fjv, fjr, c.tg_tab, c.th_tab, fproj, c.tom_w, c.tom_nwin});
+        launch(st, ngroups, AggNistFixPartTask{ctl, c.nfix, npart, Bc});
+        launch(st, 33, AggFinalTask{ctl, tA, tB, fproj, tp.D.nwin, tp.D.c, nA, nB, npart, np.D.nwin, np.D.c, ngroups});
+        c.agg_ctl = ctl;
+      }
       {
         const int nW = Bc * SG * MSM_NWIN, nWp = (nW + 31) & ~31, nG = Bc * MSM_NWIN;
         launch(st, (long long)nWp + nG,
                MsmTomWindowBothTask{MsmTomWindowTask{c.ent_scalar, c.ent_pre, c.ent_cnt, ET, K, V_ENT_PER_SAMPLE, 2, V_SEG, SG, c.win_w},
-                                    MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, mode == 0 ? ngk : 0, V_SEG, 1, c.win_g}, nW, nWp, nG});
+                                    MsmTomWindowTask{c.gk_scalar, c.gk_pre, nullptr, ngk, 0, 0, mode == 0 ? ngk : 0, V_SEG, 1, c.win_g}, nW, nWp, nG, ctl});
       }
-      launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n, EN});
+      launch(st, (long long)Bc * MSM_NWIN_N, MsmP256WindowTask{c.nent_scalar, c.nent_aff, c.nent_skip, c.win_n, EN, ctl});
       {
         const int Bp = (Bc + 31) & ~31;
         launch(st, 3ll * Bp, MsmCombineAllTask{MsmTomCombineTask{c.win_g, c.fx_proj, c.id_flags, 2, 0, 0},
                                                MsmTomCombineTask{c.win_w, c.fx_proj, c.id_flags, 2, 1, 1, SG},
-                                               MsmP256CombineTask{c.win_n, c.nfix, c.id_flags}, Bc, Bp});
+                                               MsmP256CombineTask{c.win_n, c.nfix, c.id_flags}, Bc, Bp, ctl});
       }
       launch(st, Bc, VFinalTask{c});
       if (!is_device_ptr(ok)) copy_d2h(st, ok + b0, c.ok, (size_t)Bc);
       if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
+      uint32_t hctl[AGG_CTL_WORDS] = {0, 0, 0, 0};
+      if (ctl) copy_d2h(st, hctl, ctl, sizeof(hctl));
       sync(st);
+      if (ctl) {
+        std::lock_guard<std::mutex> g(ctx->stat_mu);
+        if (hctl[AGG_TOM_PASS] && hctl[AGG_NIST_PASS]) ctx->agg_pass++;
+        else ctx->agg_fail++;
+      }
     }
     };
     run_lanes(ctx, used, run_lane);
