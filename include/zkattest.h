@@ -86,6 +86,13 @@ uint64_t zka_launch_count(const zka_ctx* ctx);
 
 /* generateParamsList (zkpAttestList.ts:88-92, pedersen.ts:61-69): h_nist = G * rnd[0..32),
  * h_proof = g * rnd[32..64).  Draws must be < p256.n and < tom.order respectively. */
+/* Which ProofGroup this library was built for, and the byte sizes of its points / scalars in the flat layout:
+ *   libzkattest.so         "tomEdwards256"  67 / 33   (instances.ts:44-54, the default of generateParamsList)
+ *   libzkattest_war256.so  "war256"         65 / 32   (instances.ts:34-41; the other legal SystemParametersList.ProofGroup,
+ *                                                      zkpAttestList.ts:70) — same entry points, same grammar with these
+ *                                                      sizes: wherever this header says 67 read point_bytes, 33 scalar_bytes.
+ * A host picks the library by `params.ProofGroup.name`. */
+int zka_proof_group(char* name, size_t cap, int* point_bytes, int* scalar_bytes);
 int zka_params_generate(zka_ctx* ctx, const uint8_t rnd[64], uint8_t h_nist[65], uint8_t h_proof[67]);
 /* SystemParametersList{NistGroup.h, ProofGroup.h, SecLevel} (zkpAttestList.ts:65-78) as a device
  * handle holding the fixed-base tables of both h points.  g is the curve generator. */

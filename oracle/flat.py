@@ -35,6 +35,22 @@ PA_LEN = 4 * WP + 4 * MULT_LEN + 2 * EQ_LEN   # 3266
 REP1_LEN = 1 + NP + 2 * WP + 2 * NS + 2 * WS  # 330
 REP0_LEN = 1 + NP + 2 * WP + 2 * NS + PA_LEN + 2 * WS  # 3596
 HEAD_LEN = 2 * NP + 2 * WP          # 264
+PROOF_GROUP = tomEdwards256
+
+
+def set_proof_group(group):
+    """Select the ProofGroup of the flat layout: tomEdwards256 (default; 67-byte points, 33-byte scalars) or war256
+    (65 / 32).  The grammar is the same, only the primitive sizes change (group.ts:49-52 sizeFieldBytes)."""
+    global WP, WS, EQ_LEN, MULT_LEN, PA_LEN, REP1_LEN, REP0_LEN, HEAD_LEN, PROOF_GROUP
+    PROOF_GROUP = group
+    WS = group.size_field_bytes()
+    WP = 1 + 2 * WS
+    EQ_LEN = 2 * WP + 3 * WS
+    MULT_LEN = 6 * WP + 7 * WS
+    PA_LEN = 4 * WP + 4 * MULT_LEN + 2 * EQ_LEN
+    REP1_LEN = 1 + NP + 2 * WP + 2 * NS + 2 * WS
+    REP0_LEN = 1 + NP + 2 * WP + 2 * NS + PA_LEN + 2 * WS
+    HEAD_LEN = 2 * NP + 2 * WP
 
 
 def gk_len(n: int) -> int:
@@ -113,9 +129,9 @@ class _Rd:
         v = self.take(NP)
         return p256.identity() if v == bytes(NP) else p256.deserialize_point(v)
 
-    def wpt(self): return tomEdwards256.deserialize_point(self.take(WP))
+    def wpt(self): return PROOF_GROUP.deserialize_point(self.take(WP))
     def nsc(self): return p256.deserialize_scalar(self.take(NS))
-    def wsc(self): return tomEdwards256.deserialize_scalar(self.take(WS))
+    def wsc(self): return PROOF_GROUP.deserialize_scalar(self.take(WS))
 
 
 def _de_mult(r):

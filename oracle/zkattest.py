@@ -51,10 +51,12 @@ def truncate_to_n(msg: int, n: int) -> int:
     return msg
 
 
-def generate_params_list(tape, sec_level: int = 80) -> SystemParametersList:
-    # zkpAttestList.ts:88-92 (draw order: p256 scalar, then tomEdwards256 scalar)
+def generate_params_list(tape, sec_level: int = 80, proof_group=tomEdwards256) -> SystemParametersList:
+    # zkpAttestList.ts:88-92 (draw order: p256 scalar, then tomEdwards256 scalar).  `proof_group`: the reference
+    # hard-codes tomEdwards256 here, but SystemParametersList.ProofGroup (zkpAttestList.ts:70) is any group whose order
+    # is p256.p — war256 (instances.ts:34-41) is the other one the JSON initialiser accepts (instances.ts:58-69).
     nist = generate_pedersen_params(p256, tape)
-    proof = generate_pedersen_params(tomEdwards256, tape)
+    proof = generate_pedersen_params(proof_group, tape)
     return SystemParametersList(nist, proof, sec_level)
 
 

@@ -34,6 +34,27 @@ def hostsim():
 
 
 @pytest.fixture(scope='session')
+def hostsim_war():
+    """Host-simulator build with ProofGroup = war256 (-DZKA_PG_WAR256); tests only."""
+    import __graft_entry__ as g
+    g.build_hostsim(war=True)
+    from zkp_ecdsa_b200.capi import ZkaLib
+    old = os.environ.get('ZKA_TOM_W')
+    os.environ['ZKA_TOM_W'] = '9'
+    os.environ['ZKA_P256_HW'] = '8'
+    try:
+        L = ZkaLib(g.HOSTSIM_WAR)
+    finally:
+        if old is None:
+            os.environ.pop('ZKA_TOM_W', None)
+        else:
+            os.environ['ZKA_TOM_W'] = old
+        os.environ.pop('ZKA_P256_HW', None)
+    assert L.group == 'war256' and (L.wp, L.ws) == (65, 32)
+    return L
+
+
+@pytest.fixture(scope='session')
 def gpu_engine():
     """The product path: libzkattest.so on cuda:0.  Fails loudly without it."""
     from zkp_ecdsa_b200 import api

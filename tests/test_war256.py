@@ -1,0 +1,36 @@
+"""ProofGroup = war256 (/root/reference/src/curves/instances.ts:34-41): the war256 build of the library
+(libzkattest_war256.so, same sources with -DZKA_PG_WAR256, same C ABI with 65-byte points / 32-byte scalars) against the
+oracle run with that proof group — field, commitments, whole proofs byte for byte, verifier verdicts."""
+import numpy as np
+import pytest
+
+import common
+
+
+def test_war_field_ops(hostsim_war):
+    common.check_field_ops(hostsim_war, count=12)
+
+
+def test_war_params_and_commit(hostsim_war):
+    P, po = common.make_params(hostsim_war, seed=5, sec_level=16)
+    assert po.ProofGroup.g.group.name == 'war256'
+    common.check_tom_commit(hostsim_war, P, po)
+    hostsim_war.params_destroy(P)
+
+
+def test_war_prove_bit_exact(hostsim_war):
+    common.check_prove_parity(hostsim_war, B=2, N=5, seed=51, sec_level=16)
+
+
+def test_war_prove_bit_exact_sec_level_80(hostsim_war):
+    common.check_prove_parity(hostsim_war, B=1, N=8, seed=52, sec_level=80)
+
+
+def test_war_verify_decisions_match_oracle(hostsim_war):
+    common.check_verify_parity(hostsim_war, N=6, seed=53, tampers=16, sec_level=20)
+
+
+def test_war_prove_few_keys_and_aggregate(hostsim_war):
+    common.check_prove_few_keys(hostsim_war, B=8, N=5, signers=1, seed=54, sec_level=16, spots=(0, 7))
+    import test_verify_aggregate as tva
+    tva.check_aggregate(hostsim_war, B=4, N=6, seed=55, cs=(0, 7))

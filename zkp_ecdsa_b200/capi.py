@@ -28,7 +28,7 @@ SYMBOLS = [
     'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack', 'zka_verify_batch_ex', 'zka_verify_tape_len_ex',
     'zka_verify_exp_batch', 'zka_verify_membership_batch', 'zka_verify_equality_batch', 'zka_verify_mult_batch',
     'zka_verify_pointadd_batch', 'zka_prove_exp_batch', 'zka_prove_membership_batch',
-    'zka_prove_equality_batch', 'zka_prove_mult_batch', 'zka_prove_pointadd_batch', 'zka_stat',
+    'zka_prove_equality_batch', 'zka_prove_mult_batch', 'zka_prove_pointadd_batch', 'zka_stat', 'zka_proof_group',
 ]
 
 STATUS_MESSAGES = {
@@ -74,6 +74,18 @@ class ZkaLib:
         self.path = path
         self.lib = C.CDLL(path)
         L = self.lib
+        # ProofGroup of this build and its point / scalar sizes in the flat layout (oracle/cpu exports the core ABI only)
+        self.group, self.wp, self.ws = 'tomEdwards256', 67, 33
+        if hasattr(L, 'zka_proof_group'):
+            nm, pb, sb = C.create_string_buffer(32), C.c_int(), C.c_int()
+            L.zka_proof_group.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+            L.zka_proof_group(nm, 32, C.byref(pb), C.byref(sb))
+            self.group, self.wp, self.ws = nm.value.decode(), pb.value, sb.value
+        self.eq_len = 2 * self.wp + 3 * self.ws                                  # 233 for tomEdwards256
+        self.mult_len = 6 * self.wp + 7 * self.ws                                # 633
+        self.pa_len = 4 * self.wp + 4 * self.mult_len + 2 * self.eq_len          # 3266
+        self.rep0_len = 1 + 65 + 2 * self.wp + 64 + self.pa_len + 2 * self.ws    # 3596
+        self.rep1_len = 1 + 65 + 2 * self.wp + 64 + 2 * self.ws                  # 330
         L.zka_init.restype = C.c_int
         L.zka_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.zka_shutdown.argtypes = [C.c_void_p]
@@ -198,7 +210,7 @@ class ZkaLib:
     def params_generate(self, rnd: bytes):
         assert len(rnd) == 64
         hn = np.zeros(65, np.uint8)
-        hp = np.zeros(67, np.uint8)
+        hp = np.zeros(self.wp, np.uint8)
         self._check(self.lib.zka_params_generate(self.ctx, _ptr(rnd), _ptr(hn), _ptr(hp)), 'zka_params_generate')
         return hn.tobytes(), hp.tobytes()
 
@@ -260,7 +272,7 @@ class ZkaLib:
 
     def prove_exp_batch(self, params, base, s, pk, q, tape, sec_level):
         B = base.shape[0]
-        stride = sec_level * 3596
+        stride = sec_level * self.rep0_len
         proofs = np.zeros((B, stride), np.uint8)
         plen = np.zeros(B, np.uint32)
         st = np.zeros(B, np.int32)
@@ -271,7 +283,7 @@ class ZkaLib:
     def prove_membership_batch(self, params, com_r, index, ring, tape):
         B, N = com_r.shape[0], ring.shape[0]
         n = max(1, (N - 1).bit_length()) if N > 1 else 0
-        stride = 1 + 4 * n * 67 + (3 * n + 1) * 33
+        stride = 1 + 4 * n * self.wp + (3 * n + 1) * self.ws
         proofs = np.zeros((B, stride), np.uint8)
         plen = np.zeros(B, np.uint32)
         st = np.zeros(B, np.int32)
@@ -283,8 +295,8 @@ class ZkaLib:
     def prove_sub_batch(self, kind: str, params, inputs, tape, blinders=None):
         """kind 'equality' (inputs [B, 3*32]), 'mult' ([B, 6*32]) or 'pointadd' (inputs [B, 3*65] + blinders [B, 6*32])"""
         B = inputs.shape[0]
-        nc, plen = {'equality': (2, 233), 'mult': (3, 633), 'pointadd': (6, 3266)}[kind]
-        com = np.zeros((B, nc * 67), np.uint8)
+        nc, plen = {'equality': (2, self.eq_len), 'mult': (3, self.mult_len), 'pointadd': (6, self.pa_len)}[kind]
+        com = np.zeros((B, nc * self.wp), np.uint8)
         proofs = np.zeros((B, plen), np.uint8)
         st = np.zeros(B, np.int32)
         if kind == 'pointadd':
@@ -318,7 +330,7 @@ class ZkaLib:
     # ------------------------------------------------------------------ layer-wise ops
     def tom_commit_batch(self, params, v: np.ndarray, r: np.ndarray) -> np.ndarray:
         count = v.shape[0]
-        out = np.zeros((count, 67), np.uint8)
+        out = np.zeros((count, self.wp), np.uint8)
         self._check(self.lib.zka_tom_commit_batch(self.ctx, params, count, _ptr(v), _ptr(r), _ptr(out)),
                     'zka_tom_commit_batch')
         return out

@@ -15,236 +15,82 @@
 namespace zk {
 
 // ------------------------------------------------------------------------------------ P-256
-struct P256Pt {  // projective, Montgomery residues mod p256.p
-  uint32_t x[8], y[8], z[8];
-};
-struct P256Aff {  // affine Montgomery residues; inf != 0 marks the identity
-  uint32_t x[8], y[8];
-};
+#define WEI_PT P256Pt
+#define WEI_AFF P256Aff
+#define WEI_JAC P256Jac
+#define WEI_F P256p
+#define WEI_FN(n) p256_##n
+#define WEI_B_MONT ZK_P256_B_MONT
+#define WEI_GX_MONT ZK_P256_GX_MONT
+#define WEI_GY_MONT ZK_P256_GY_MONT
+#include "zk_weier.inc"
+#undef WEI_PT
+#undef WEI_AFF
+#undef WEI_JAC
+#undef WEI_F
+#undef WEI_FN
+#undef WEI_B_MONT
+#undef WEI_GX_MONT
+#undef WEI_GY_MONT
 
-ZK_HD void p256_const_b(uint32_t* r) {
-  constexpr uint32_t t[8] = ZK_P256_B_MONT;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r[i] = t[i];
-}
-ZK_HD void p256_set_identity(P256Pt& p) {
-  zero_n<8>(p.x);
-  P256p::set_one(p.y);
-  zero_n<8>(p.z);
-}
-ZK_HD void p256_set_generator(P256Aff& g) {
-  constexpr uint32_t gx[8] = ZK_P256_GX_MONT;
-  constexpr uint32_t gy[8] = ZK_P256_GY_MONT;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    g.x[i] = gx[i];
-    g.y[i] = gy[i];
-  }
-}
-ZK_HD void p256_from_affine(P256Pt& p, const P256Aff& a) {
-  copy_n<8>(p.x, a.x);
-  copy_n<8>(p.y, a.y);
-  P256p::set_one(p.z);
-}
-ZK_HD bool p256_is_identity(const P256Pt& p) { return is_zero_n<8>(p.z); }
+#if defined(ZKA_PG_WAR256)
+// ------------------------------------------------------------------------------------ war256
+// The war256 build of the library (-DZKA_PG_WAR256 -> libzkattest_war256.so): ProofGroup = war256
+// (/root/reference/src/curves/instances.ts:34-41; a legal SystemParametersList.ProofGroup, zkpAttestList.ts:70).
+// The curve is short Weierstrass with a = -3 like P-256, so the group law is the second inclusion of zk_weier.inc;
+// the stage tasks keep their names and are written against the small proof-group interface below (PGL limbs, PGp
+// field, TomPt / TomPre point types, tom_* operations), which the tomEdwards256 build implements with the Edwards
+// image curves and this build with the complete Renes-Costello-Batina formulas.
+#define WEI_PT WarPt
+#define WEI_AFF WarAff
+#define WEI_JAC WarJac
+#define WEI_F Warp
+#define WEI_FN(n) war_##n
+#define WEI_B_MONT ZK_WAR_B_MONT
+#define WEI_GX_MONT ZK_WAR_GX_MONT
+#define WEI_GY_MONT ZK_WAR_GY_MONT
+#include "zk_weier.inc"
+#undef WEI_PT
+#undef WEI_AFF
+#undef WEI_JAC
+#undef WEI_F
+#undef WEI_FN
+#undef WEI_B_MONT
+#undef WEI_GX_MONT
+#undef WEI_GY_MONT
 
-// y^2 == x^3 - 3x + b  (weier.ts:56-70 with z = 1), Montgomery residues
-ZK_HD bool p256_on_curve(const uint32_t* x, const uint32_t* y) {
-  using F = P256p;
-  uint32_t l[8], r[8], t[8], b[8];
-  F::sqr(l, y);
-  F::sqr(t, x);
-  F::mul(r, t, x);
-  F::add(t, x, x);
-  F::add(t, t, x);
-  F::sub(r, r, t);
-  p256_const_b(b);
-  F::add(r, r, b);
-  return eq_n<8>(l, r);
+enum : int { PGL = 8 };        // limbs of a proof-group coordinate
+using PGp = Warp;              // coordinate field of the proof group
+using FpPG = FpWar;
+using TomPt = WarPt;           // homogeneous projective (X : Y : Z)
+using TomPre = WarAff;         // affine point: table entry / parsed proof point
+using TompMsm = Warp;
+using TompCommit = Warp;
+ZK_HD void tom_set_identity(TomPt& p) { war_set_identity(p); }
+ZK_HD void tom_from_affine(TomPt& p, const uint32_t* x, const uint32_t* y) {
+  copy_n<8>(p.x, x);
+  copy_n<8>(p.y, y);
+  Warp::set_one(p.z);
 }
-
-// RCB15 Algorithm 6 (a = -3): 8M + 3S + 2m_b  (weier.ts:133-175)
-ZK_HD void p256_dbl(P256Pt& r, const P256Pt& p) {
-  using F = P256p;
-  uint32_t t0[8], t1[8], t2[8], t3[8], x3[8], y3[8], z3[8], b[8];
-  p256_const_b(b);
-  F::sqr(t0, p.x);
-  F::sqr(t1, p.y);
-  F::sqr(t2, p.z);
-  F::mul(t3, p.x, p.y);
-  F::add(t3, t3, t3);
-  F::mul(z3, p.x, p.z);
-  F::add(z3, z3, z3);
-  F::mul(y3, b, t2);
-  F::sub(y3, y3, z3);
-  F::add(x3, y3, y3);
-  F::add(y3, x3, y3);
-  F::sub(x3, t1, y3);
-  F::add(y3, t1, y3);
-  F::mul(y3, x3, y3);
-  F::mul(x3, x3, t3);
-  F::add(t3, t2, t2);
-  F::add(t2, t2, t3);
-  F::mul(z3, b, z3);
-  F::sub(z3, z3, t2);
-  F::sub(z3, z3, t0);
-  F::add(t3, z3, z3);
-  F::add(z3, z3, t3);
-  F::add(t3, t0, t0);
-  F::add(t0, t3, t0);
-  F::sub(t0, t0, t2);
-  F::mul(t0, t0, z3);
-  F::add(y3, y3, t0);
-  F::mul(t0, p.y, p.z);
-  F::add(t0, t0, t0);
-  F::mul(z3, t0, z3);
-  F::sub(x3, x3, z3);
-  F::mul(z3, t0, t1);
-  F::add(z3, z3, z3);
-  F::add(z3, z3, z3);
-  copy_n<8>(r.x, x3);
-  copy_n<8>(r.y, y3);
-  copy_n<8>(r.z, z3);
+ZK_HD void tom_set_generator(TomPt& p) {
+  WarAff g;
+  war_set_generator(g);
+  war_from_affine(p, g);
 }
-
-// Jacobian doubling for a = -3 ("dbl-2001-b", 3M + 5S = 8 multiplications instead of 13): used only
-// in the long DOUBLING CHAINS (16^j R for the per-proof table, the one-shot ladder u2*pk), which
-// are latency-bound with one thread per proof.  Doubling has no exceptional case on a prime-order
-// curve (no points of order 2) and maps the identity (Z = 0) to itself.
-struct P256Jac {
-  uint32_t x[8], y[8], z[8];   // x = X/Z^2, y = Y/Z^3
-};
-ZK_HD void p256_jac_dbl(P256Jac& r, const P256Jac& p) {
-  using F = P256p;
-  uint32_t delta[8], gamma[8], beta[8], alpha[8], t0[8], t1[8];
-  F::sqr(delta, p.z);
-  F::sqr(gamma, p.y);
-  F::mul(beta, p.x, gamma);
-  F::sub(t0, p.x, delta);
-  F::add(t1, p.x, delta);
-  F::mul(alpha, t0, t1);
-  F::add(t0, alpha, alpha);
-  F::add(alpha, t0, alpha);            // 3 (X - delta)(X + delta)
-  F::add(t0, p.y, p.z);
-  F::sqr(t0, t0);
-  F::sub(t0, t0, gamma);
-  F::sub(r.z, t0, delta);              // Z3 = (Y + Z)^2 - gamma - delta
-  F::add(t0, beta, beta);
-  F::add(t0, t0, t0);                  // 4 beta
-  F::add(t1, t0, t0);                  // 8 beta
-  F::sqr(r.x, alpha);
-  F::sub(r.x, r.x, t1);                // X3 = alpha^2 - 8 beta
-  F::sub(t0, t0, r.x);
-  F::mul(t0, alpha, t0);
-  F::sqr(t1, gamma);
-  F::add(t1, t1, t1);
-  F::add(t1, t1, t1);
-  F::add(t1, t1, t1);                  // 8 gamma^2
-  F::sub(r.y, t0, t1);                 // Y3 = alpha (4 beta - X3) - 8 gamma^2
-}
-// Jacobian (X:Y:Z) -> homogeneous (X Z : Y : Z^3);  homogeneous (X:Y:Z) -> Jacobian (X Z : Y Z^2 : Z)
-ZK_HD void p256_jac_to_hom(P256Pt& r, const P256Jac& p) {
-  using F = P256p;
-  uint32_t z2[8];
-  F::sqr(z2, p.z);
-  F::mul(r.x, p.x, p.z);
-  copy_n<8>(r.y, p.y);
-  F::mul(r.z, z2, p.z);
-}
-ZK_HD void p256_hom_to_jac(P256Jac& r, const P256Pt& p) {
-  using F = P256p;
-  uint32_t z2[8];
-  F::sqr(z2, p.z);
-  F::mul(r.x, p.x, p.z);
-  F::mul(r.y, p.y, z2);
+ZK_HD bool tom_on_curve(const uint32_t* x, const uint32_t* y) { return war_on_curve(x, y); }
+ZK_HD void tom_add(TomPt& r, const TomPt& p, const TomPt& q) { war_add(r, p, q); }
+template <bool kNeedT, class F = Warp>
+ZK_HD void tom_madd(TomPt& r, const TomPt& p, const TomPre& q) { war_madd(r, p, q); }
+ZK_HD void tom_dbl(TomPt& r, const TomPt& p) { war_dbl(r, p); }
+ZK_HD void tom_neg(TomPt& r, const TomPt& p) {
+  copy_n<8>(r.x, p.x);
+  Warp::neg(r.y, p.y);
   copy_n<8>(r.z, p.z);
-  if (is_zero_n<8>(p.z)) {   // identity (0:Y:0) -> (1:1:0); (0:0:0) would not survive the way back
-    F::set_one(r.x);
-    F::set_one(r.y);
-  }
 }
-
-// shared tail of RCB15 Alg. 4 / Alg. 5 after t0,t1,t2,t3,t4,y3 are formed:
-//   t0 = X1X2, t1 = Y1Y2, t2 = Z1Z2, t3 = X1Y2+X2Y1, t4 = Y1Z2+Y2Z1, y3 = X1Z2+X2Z1
-ZK_HD void p256_add_tail(P256Pt& r, uint32_t* t0, uint32_t* t1, uint32_t* t2, uint32_t* t3, uint32_t* t4,
-                         uint32_t* y3) {
-  using F = P256p;
-  uint32_t x3[8], z3[8], b[8];
-  p256_const_b(b);
-  F::mul(z3, b, t2);
-  F::sub(x3, y3, z3);
-  F::add(z3, x3, x3);
-  F::add(x3, x3, z3);
-  F::sub(z3, t1, x3);
-  F::add(x3, t1, x3);
-  F::mul(y3, b, y3);
-  F::add(t1, t2, t2);
-  F::add(t2, t1, t2);
-  F::sub(y3, y3, t2);
-  F::sub(y3, y3, t0);
-  F::add(t1, y3, y3);
-  F::add(y3, t1, y3);
-  F::add(t1, t0, t0);
-  F::add(t0, t1, t0);
-  F::sub(t0, t0, t2);
-  F::mul(t1, t4, y3);
-  F::mul(t2, t0, y3);
-  F::mul(y3, x3, z3);
-  F::add(y3, y3, t2);
-  F::mul(x3, t3, x3);
-  F::sub(x3, x3, t1);
-  F::mul(z3, t4, z3);
-  F::mul(t1, t3, t0);
-  F::add(z3, z3, t1);
-  copy_n<8>(r.x, x3);
-  copy_n<8>(r.y, y3);
-  copy_n<8>(r.z, z3);
-}
-
-// RCB15 Algorithm 4 (a = -3): 12M + 2m_b  (weier.ts:176-230)
-ZK_HD void p256_add(P256Pt& r, const P256Pt& p, const P256Pt& q) {
-  using F = P256p;
-  uint32_t t0[8], t1[8], t2[8], t3[8], t4[8], x3[8], y3[8];
-  F::mul(t0, p.x, q.x);
-  F::mul(t1, p.y, q.y);
-  F::mul(t2, p.z, q.z);
-  F::add(t3, p.x, p.y);
-  F::add(t4, q.x, q.y);
-  F::mul(t3, t3, t4);
-  F::add(t4, t0, t1);
-  F::sub(t3, t3, t4);
-  F::add(t4, p.y, p.z);
-  F::add(x3, q.y, q.z);
-  F::mul(t4, t4, x3);
-  F::add(x3, t1, t2);
-  F::sub(t4, t4, x3);
-  F::add(x3, p.x, p.z);
-  F::add(y3, q.x, q.z);
-  F::mul(x3, x3, y3);
-  F::add(y3, t0, t2);
-  F::sub(y3, x3, y3);
-  p256_add_tail(r, t0, t1, t2, t3, t4, y3);
-}
-
-// RCB15 Algorithm 5 (mixed, Z2 = 1, a = -3): 11M + 2m_b.  q must not be the identity.
-ZK_HD void p256_madd(P256Pt& r, const P256Pt& p, const P256Aff& q) {
-  using F = P256p;
-  uint32_t t0[8], t1[8], t2[8], t3[8], t4[8], y3[8];
-  F::mul(t0, p.x, q.x);
-  F::mul(t1, p.y, q.y);
-  F::add(t3, p.x, p.y);
-  F::add(t4, q.x, q.y);
-  F::mul(t3, t3, t4);
-  F::add(t4, t0, t1);
-  F::sub(t3, t3, t4);
-  F::mul(t4, q.y, p.z);
-  F::add(t4, t4, p.y);
-  F::mul(y3, q.x, p.z);
-  F::add(y3, y3, p.x);
-  copy_n<8>(t2, p.z);
-  p256_add_tail(r, t0, t1, t2, t3, t4, y3);
-}
-
+ZK_HD void pg_pre_neg(TomPre& q) { Warp::neg(q.y, q.y); }                       // -(x, y) = (x, -y)
+ZK_HD bool pg_is_identity(const TomPt& p) { return war_is_identity(p); }
+ZK_HD void pg_fixed_to_msm(TomPt&) {}   // commitments are already (X : Y : Z) of the curve itself
+#else
 // ----------------------------------------------------------------------------- tomEdwards256
 // Extended coordinates on the a'=1 image curve, lazy Montgomery residues mod tom.p.
 struct TomPt {
@@ -432,5 +278,30 @@ ZK_HD void tom_neg(TomPt& r, const TomPt& p) {
   Tomp::neg(r.t, p.t);
   copy_n<9>(r.z, p.z);
 }
+
+
+enum : int { PGL = 9 };        // limbs of a proof-group coordinate
+using PGp = Tomp;              // coordinate field of the proof group
+using FpPG = FpTom;
+ZK_HD void pg_pre_neg(TomPre& q) {   // -(x, y) = (-x, y); k = d x y changes sign too
+  Tomp::neg(q.x, q.x);
+  Tomp::neg(q.k, q.k);
+}
+// identity <=> X == 0 and Y == Z (edwards.ts:117-125 in projective form)
+ZK_HD bool pg_is_identity(const TomPt& p) { return Tomp::is_zero(p.x) && Tomp::eq(p.y, p.z); }
+// A fixed-base commitment comes out of the commitment kernels on the a = -1 image curve E2 as (W : V : Z) with
+// x' = W / (Z sqrt(-d1)), y = Z / V.  Same point in E1 extended coordinates with Z' = Z V:
+//   X = c W V,  Y = Z^2,  T = X Y / Z' = c W Z,   c = 1/sqrt(-d1).
+ZK_HD void pg_fixed_to_msm(TomPt& f) {
+  uint32_t cw[9], X[9], Y[9], Tt[9], Zp[9], c1[9];
+  tom_const(c1, TOM_INVSQRTND1);
+  Tomp::mul(cw, f.x, c1);
+  Tomp::mul(X, cw, f.y);
+  Tomp::sqr(Y, f.z);
+  Tomp::mul(Tt, cw, f.z);
+  Tomp::mul(Zp, f.z, f.y);
+  copy_n<9>(f.x, X); copy_n<9>(f.y, Y); copy_n<9>(f.t, Tt); copy_n<9>(f.z, Zp);
+}
+#endif   // ZKA_PG_WAR256
 
 }  // namespace zk

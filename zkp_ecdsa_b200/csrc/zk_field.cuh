@@ -51,6 +51,7 @@ namespace zk {
 ZK_FIELD_DESC(FpP256, ZK_P256P, 8, false)
 ZK_FIELD_DESC(FnP256, ZK_P256N, 8, false)
 ZK_FIELD_DESC(FpTom, ZK_TOMP, 9, true)
+ZK_FIELD_DESC(FpWar, ZK_WARP, 8, false)   // war256 coordinates (instances.ts:34-41), strict [0,p), generic CIOS
 #undef ZK_FIELD_DESC
 
 template <int N>
@@ -398,7 +399,8 @@ struct Field {
 using P256p = Field<FpP256>;
 using P256n = Field<FnP256>;
 using Tomp = Field<FpTom>;
-using Tomq = Field<FpP256>;  // tomEdwards256 scalar field == P-256 base field
+using Tomq = Field<FpP256>;  // tomEdwards256 scalar field == P-256 base field (war256.order is the same prime)
+using Warp = Field<FpWar>;
 
 // ------------------------------------------------------------------------------------
 // Big-endian byte <-> limb conversion (reference toBytes/fromBytes, big.ts:121-168)

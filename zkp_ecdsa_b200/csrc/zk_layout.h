@@ -20,10 +20,18 @@ namespace zk {
 
 enum : int {
   NP = 65,   // P-256 point bytes
-  WP = 67,   // tomEdwards256 point bytes
   NS = 32,   // P-256 scalar bytes
+#if defined(ZKA_PG_WAR256)
+  // ProofGroup = war256 (instances.ts:34-41): SEC1 points like P-256, scalars sized by its 256-bit field
+  WP = 65,
+  WS = 32,
+  WCB = 32,  // bytes of one coordinate
+#else
+  WP = 67,   // tomEdwards256 point bytes
   WS = 33,   // tomEdwards256 scalar bytes (sized by the 258-bit FIELD, group.ts:49-52)
-  EQ_LEN = 2 * WP + 3 * WS,                       // 233  EqualityProof (equality.ts:28-32)
+  WCB = 33,
+#endif
+  EQ_LEN = 2 * WP + 3 * WS,                       // 233 (tomEdwards256 sizes)  EqualityProof (equality.ts:28-32)
   MULT_LEN = 6 * WP + 7 * WS,                     // 633  MultProof     (mult.ts:27-39)
   PA_LEN = 4 * WP + 4 * MULT_LEN + 2 * EQ_LEN,    // 3266 PointAddProof (pointAdd.ts:29-38)
   REP_HEAD = 1 + NP + 2 * WP,                     // tag A Tx Ty

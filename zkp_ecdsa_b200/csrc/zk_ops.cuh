@@ -54,21 +54,29 @@ ZK_HD void st(uint32_t* p, const uint32_t* r) {
 enum : int {
   P256_PROJ_WORDS = 24,
   P256_AFF_WORDS = 16,
+#if defined(ZKA_PG_WAR256)
+  TOM_PROJ_WORDS = 24,   // war256 build: homogeneous (X, Y, Z), 8 limbs each
+  TOM_AFF_WORDS = 16,    // affine (x, y), Montgomery
+  TOM_PRE_WORDS = 16,    // table entry / parsed point = affine (x, y): one 64-byte half line
+#else
   TOM_PROJ_WORDS = 28,   // X, Y, Z (T is not needed after the last addition) + 1 pad word: 7 x 16 bytes
   TOM_AFF_WORDS = 18,    // x', y on the a'=1 image curve, Montgomery
   TOM_PRE_WORDS = 32,    // x', y, k = d' x' y + 5 pad words: one 128-byte line per entry
+#endif
   NORM_CHUNK_MAX = 64,   // max points per Montgomery-trick chunk (one Fermat inversion each)
 };
 
-ZK_HD void p256_ld_proj(P256Pt& p, const uint32_t* m) {
-  ld<8>(p.x, m); ld<8>(p.y, m + 8); ld<8>(p.z, m + 16);
-}
-ZK_HD void p256_st_proj(uint32_t* m, const P256Pt& p) {
-  st<8>(m, p.x); st<8>(m + 8, p.y); st<8>(m + 16, p.z);
-}
-ZK_HD void p256_ld_aff(P256Aff& a, const uint32_t* m) { ld<8>(a.x, m); ld<8>(a.y, m + 8); }
-ZK_HD void p256_st_aff(uint32_t* m, const P256Aff& a) { st<8>(m, a.x); st<8>(m + 8, a.y); }
 
+#if defined(ZKA_PG_WAR256)
+// staged war256 points: X, Y, Z at words 0, 8, 16 of a 96-byte slot; table entries are affine pairs
+ZK_HD void tom_st_xyz(uint32_t* m, const uint32_t* x, const uint32_t* y, const uint32_t* z) {
+  st<8>(m, x); st<8>(m + 8, y); st<8>(m + 16, z);
+}
+ZK_HD void tom_ld_xyz(uint32_t* x, uint32_t* y, uint32_t* z, const uint32_t* m) {
+  ld<8>(x, m); ld<8>(y, m + 8); ld<8>(z, m + 16);
+}
+ZK_HD void tom_ld_pre(TomPre& q, const uint32_t* m) { ld<8>(q.x, m); ld<8>(q.y, m + 8); }
+#else
 // staged tomEdwards256 points (X, Y, Z at words 0, 9, 18 of a 112-byte, 16-byte aligned slot):
 // seven 16-byte transactions instead of 27 four-byte ones (the slots are strided per thread)
 ZK_HD void tom_st_xyz(uint32_t* m, const uint32_t* x, const uint32_t* y, const uint32_t* z) {
@@ -128,6 +136,8 @@ ZK_HD void tom_ld_pre(TomPre& q, const uint32_t* m) {
   ld<9>(q.x, m); ld<9>(q.y, m + 9); ld<9>(q.k, m + 18);
 #endif
 }
+
+#endif
 
 // Encoded point (tag || x || y, big-endian coordinates of CB bytes) written as 32-bit words into a
 // 4-byte aligned BSTRIDE slot: 17 word stores instead of 65/67 byte stores (the byte index of
@@ -190,58 +200,20 @@ ZK_HD void tape_draw(uint32_t* r, const uint8_t* tape, int draw) {
 }
 
 // ============================================================================ P-256 tables
-// pows[j] = 2^(w j) * base  for j < nwin  (one thread per base; sequential doublings)
-struct P256PowsTask {
-  const uint32_t* base_aff;  // [nbase][16]
-  const uint8_t* base_inf;   // [nbase] or null
-  uint32_t* pows;            // [nbase][nwin][24]
-  int nbase, nwin, w;
-  const uint32_t* index = nullptr;      // optional: base t is base_aff[index[t]]
-  const uint32_t* count_dev = nullptr;  // optional: number of bases actually present (<= nbase)
-  const uint32_t* w_dev = nullptr;      // optional: window bits chosen on the device (key_window_bits); nwin follows
-  ZK_HD void operator()(int t) const {
-    if (count_dev && (uint32_t)t >= *count_dev) return;
-    const int w = w_dev ? (int)*w_dev : this->w;
-    const int nwin = w_dev ? fb_windows(w) : this->nwin;
-    const size_t src = index ? index[t] : (size_t)t;
-    P256Aff a;
-    p256_ld_aff(a, base_aff + src * P256_AFF_WORDS);
-    P256Pt p;
-    p256_from_affine(p, a);
-    if (base_inf && base_inf[src]) p256_set_identity(p);
-    // the doubling chain runs in Jacobian coordinates (8 instead of 13 multiplications per step)
-    P256Jac q;
-    p256_hom_to_jac(q, p);
-    for (int j = 0; j < nwin; j++) {
-      p256_jac_to_hom(p, q);
-      p256_st_proj(pows + ((size_t)t * nwin + j) * P256_PROJ_WORDS, p);
-      for (int k = 0; k < w; k++) p256_jac_dbl(q, q);
-    }
-  }
-};
-// rows[(b*nwin + j)*E + d] = d * pows[b][j], d = 1..2^(w-1), E = fb_entries(w)  (entry 0 is never read)
-struct P256RowsTask {
-  const uint32_t* pows;  // [nbase*nwin][24]
-  uint32_t* rows;        // [nbase*nwin][E][24]
-  int w;
-  const uint32_t* count_dev = nullptr;   // optional: number of bases actually present
-  const uint32_t* w_dev = nullptr;       // optional: window bits chosen on the device (key_window_bits)
-  ZK_HD void operator()(int t) const {
-    const int w = w_dev ? (int)*w_dev : this->w;
-    if (count_dev && (uint32_t)(t / fb_windows(w)) >= *count_dev) return;
-    P256Pt p, acc;
-    p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
-    acc = p;
-    const int ne = fb_entries(w);
-    uint32_t* out = rows + (size_t)t * ne * P256_PROJ_WORDS;
-    // entry 0: store the base itself so the normaliser never sees garbage (it is never read)
-    p256_st_proj(out, p);
-    for (int d = 1; d < ne; d++) {
-      p256_st_proj(out + (size_t)d * P256_PROJ_WORDS, acc);
-      p256_add(acc, acc, p);
-    }
-  }
-};
+#define WEI_PT P256Pt
+#define WEI_AFF P256Aff
+#define WEI_JAC P256Jac
+#define WEI_F P256p
+#define WEI_FN(n) p256_##n
+#define WEI_T(n) P256##n
+#include "zk_weier_ops.inc"
+#undef WEI_PT
+#undef WEI_AFF
+#undef WEI_JAC
+#undef WEI_F
+#undef WEI_FN
+#undef WEI_T
+
 // ---- per-KEY tables of the prover: the generic signed-digit format [fb_windows(w)][fb_entries(w)][16] with the window
 // bits chosen ON THE DEVICE from the number of distinct keys of the chunk (KeyRankTask).  Grids and buffers are sized
 // for the worst case (every proof its own key, w = 5: KEY_CAP entries per proof); fewer keys get wider windows inside
@@ -282,123 +254,6 @@ struct P256RowsSignedTask {
     }
   }
 };
-// Two-level rows for a wide fixed-base table (w > 8), same idea as TomRowsHi/LoTask
-struct P256RowsHiTask {
-  const uint32_t* pows;   // [nwin][24]
-  uint32_t* hi;           // [nwin][2^(w-9)][24]
-  uint32_t* rows;         // the top entry 2^(w-1) * pows of every window is written here directly
-  int w;
-  ZK_HD void operator()(int t) const {
-    P256Pt p, acc;
-    p256_ld_proj(p, pows + (size_t)t * P256_PROJ_WORDS);
-    for (int k = 0; k < 8; k++) p256_dbl(p, p);
-    p256_set_identity(acc);
-    const int nh = 1 << (w - 9);
-    for (int m = 0; m < nh; m++) {
-      p256_st_proj(hi + ((size_t)t * nh + m) * P256_PROJ_WORDS, acc);
-      p256_add(acc, acc, p);
-    }
-    p256_st_proj(rows + ((size_t)t * fb_entries(w) + ((size_t)1 << (w - 1))) * P256_PROJ_WORDS, acc);
-  }
-};
-struct P256RowsLoTask {
-  const uint32_t* pows;
-  const uint32_t* hi;
-  uint32_t* rows;         // [nwin][E][24]  (entry 0 of each window is the identity: never read)
-  int w;
-  ZK_HD void operator()(int t) const {
-    const int nh = 1 << (w - 9);
-    const int j = t / nh, m = t % nh;
-    P256Pt p, acc;
-    p256_ld_proj(p, pows + (size_t)j * P256_PROJ_WORDS);
-    p256_ld_proj(acc, hi + (size_t)t * P256_PROJ_WORDS);
-    uint32_t* out = rows + ((size_t)j * fb_entries(w) + ((size_t)m << 8)) * P256_PROJ_WORDS;
-    for (int d = 0; d < 256; d++) {
-      p256_st_proj(out + (size_t)d * P256_PROJ_WORDS, acc);
-      p256_add(acc, acc, p);
-    }
-  }
-};
-
-// Batched normalisation: proj[count] -> affine Montgomery (+ optional 65-byte encodings)
-struct P256NormTask {
-  const uint32_t* proj;  // [count][24]
-  uint32_t* aff;         // [count][16]
-  uint8_t* bytes;        // [count][BSTRIDE] or null
-  uint8_t* inf;          // [count] or null
-  int count;
-  int chunk;             // points per thread (<= NORM_CHUNK_MAX)
-  const uint32_t* groups_dev = nullptr;  // optional: only the first *groups_dev * group_size points exist
-  int group_size = 0;
-  const uint32_t* w_dev = nullptr;       // optional: group_size = entries of a key table with *w_dev window bits
-  ZK_HD void operator()(int t) const {
-    using F = P256p;
-    const int lo = t * chunk;
-    int total = count;
-    const int group_size = w_dev ? fb_windows((int)*w_dev) * fb_entries((int)*w_dev) : this->group_size;
-    if (groups_dev) {
-      const long long present = (long long)*groups_dev * group_size;
-      if (present < total) total = (int)present;
-    }
-    int n = total - lo;
-    if (n > chunk) n = chunk;
-    if (n <= 0) return;
-    uint32_t pre[NORM_CHUNK_MAX][8];
-    uint32_t acc[8], z[8], one[8];
-    F::set_one(one);
-    copy_n<8>(acc, one);
-    for (int k = 0; k < n; k++) {
-      ld<8>(z, proj + (size_t)(lo + k) * P256_PROJ_WORDS + 16);
-      if (is_zero_n<8>(z)) copy_n<8>(z, one);
-      F::mul(acc, acc, z);
-      copy_n<8>(pre[k], acc);
-    }
-    uint32_t inv[8];
-    F::inv(inv, acc);
-    for (int k = n - 1; k >= 0; k--) {
-      const uint32_t* src = proj + (size_t)(lo + k) * P256_PROJ_WORDS;
-      ld<8>(z, src + 16);
-      const bool isinf = is_zero_n<8>(z);
-      if (isinf) copy_n<8>(z, one);
-      uint32_t zi[8];
-      if (k > 0) F::mul(zi, inv, pre[k - 1]); else copy_n<8>(zi, inv);
-      F::mul(inv, inv, z);
-      P256Aff a;
-      uint32_t X[8], Y[8];
-      ld<8>(X, src);
-      ld<8>(Y, src + 8);
-      F::mul(a.x, X, zi);
-      F::mul(a.y, Y, zi);
-      p256_st_aff(aff + (size_t)(lo + k) * P256_AFF_WORDS, a);
-      if (inf) inf[lo + k] = isinf ? 1 : 0;
-      if (bytes) {
-        uint8_t* o = bytes + (size_t)(lo + k) * BSTRIDE;
-        uint32_t cx[8], cy[8];
-        F::from_mont(cx, a.x);
-        F::from_mont(cy, a.y);
-        if (isinf) { zero_n<8>(cx); zero_n<8>(cy); }
-        store_point_words<8, 32>(o, isinf ? 0x00u : 0x04u, cx, cy);
-      }
-    }
-  }
-};
-
-// acc += k * base on a fixed table [fb_windows(w)][fb_entries(w)] of affine entries (signed digits)
-ZK_HD void p256_accum_fixed(P256Pt& acc, const uint32_t* tab, const uint32_t* k, int w) {
-  const int nwin = fb_windows(w);
-  const size_t E = (size_t)fb_entries(w);
-  uint32_t carry = 0;
-  for (int j = 0; j < nwin; j++) {
-    bool neg;
-    const uint32_t d = signed_digit(k, j, w, carry, neg);
-    if (d) {
-      P256Aff q;
-      p256_ld_aff(q, tab + ((size_t)j * E + d) * P256_AFF_WORDS);
-      if (neg) P256p::neg(q.y, q.y);
-      p256_madd(acc, acc, q);
-    }
-  }
-}
 // acc += k * base on the signed 5-bit per-base table [RT_NWIN][RT_ROW] (P256RowsSignedTask)
 ZK_HD void p256_accum_rtab(P256Pt& acc, const uint32_t* tab, const uint32_t* k) {
   uint32_t carry = 0;
@@ -416,6 +271,37 @@ ZK_HD void p256_accum_rtab(P256Pt& acc, const uint32_t* tab, const uint32_t* k) 
     }
   }
 }
+// Split commitments for the 34 jobs of a 0-bit repetition.  Several of them commit to the SAME value
+// with different blinders (proveMult: A_z and A_4_1 both commit k_z, mult.ts:112-113; proveEquality:
+// A_1 and A_2 both commit k, equality.ts:67-68), so the g-parts v*g are computed once per distinct
+// value (28 per item) and every job continues from its g-part with the 16 lookups of r*h:
+//   34 x 32 = 1088 lookups  ->  28 x 16 + 34 x 16 = 992.
+#if defined(ZKA_PG_WAR256)
+enum : int { GJOBS_PER_ITEM = 28, TOM_EXT_WORDS = 24 };
+#else
+enum : int { GJOBS_PER_ITEM = 28, TOM_EXT_WORDS = 36 };
+#endif
+// job index (0..33) -> index of its g-part (0..27)
+ZK_HD int item_gpart_of_job(int j) {
+  if (j < 6) return j;                       // T1x T1y C8 C10 C11 C13
+  if (j < 30) {                              // MultProof m: C4 Ax Ay Az A4_1 A4_2 -> 0 1 2 3 3 4
+    const int m = (j - 6) / 6, u = (j - 6) % 6;
+    return 6 + 5 * m + (u < 4 ? u : u - 1);
+  }
+  return 26 + ((j - 30) >> 1);               // EqualityProof e: A1, A2 share k
+}
+// g-part index (0..27) -> a job that carries its value scalar
+ZK_HD int item_job_of_gpart(int g) {
+  if (g < 6) return g;
+  if (g < 26) {
+    const int m = (g - 6) / 5, u = (g - 6) % 5;
+    return 6 + 6 * m + (u < 4 ? u : 5);
+  }
+  return 30 + 2 * (g - 26);
+}
+#if defined(ZKA_PG_WAR256)
+#include "zk_ops_war.cuh"
+#else
 // ===================================================================== tomEdwards256 tables
 struct TomPowsTask {
   const uint32_t* base_aff;  // [nbase][18] image-curve affine (x', y), Montgomery
@@ -675,30 +561,6 @@ struct TomCommitTask {
   }
 };
 
-// Split commitments for the 34 jobs of a 0-bit repetition.  Several of them commit to the SAME value
-// with different blinders (proveMult: A_z and A_4_1 both commit k_z, mult.ts:112-113; proveEquality:
-// A_1 and A_2 both commit k, equality.ts:67-68), so the g-parts v*g are computed once per distinct
-// value (28 per item) and every job continues from its g-part with the 16 lookups of r*h:
-//   34 x 32 = 1088 lookups  ->  28 x 16 + 34 x 16 = 992.
-enum : int { GJOBS_PER_ITEM = 28, TOM_EXT_WORDS = 36 };
-// job index (0..33) -> index of its g-part (0..27)
-ZK_HD int item_gpart_of_job(int j) {
-  if (j < 6) return j;                       // T1x T1y C8 C10 C11 C13
-  if (j < 30) {                              // MultProof m: C4 Ax Ay Az A4_1 A4_2 -> 0 1 2 3 3 4
-    const int m = (j - 6) / 6, u = (j - 6) % 6;
-    return 6 + 5 * m + (u < 4 ? u : u - 1);
-  }
-  return 26 + ((j - 30) >> 1);               // EqualityProof e: A1, A2 share k
-}
-// g-part index (0..27) -> a job that carries its value scalar
-ZK_HD int item_job_of_gpart(int g) {
-  if (g < 6) return g;
-  if (g < 26) {
-    const int m = (g - 6) / 5, u = (g - 6) % 5;
-    return 6 + 6 * m + (u < 4 ? u : 5);
-  }
-  return 30 + 2 * (g - 26);
-}
 struct TomCommitGTask {   // one thread per (item, g-part): K = v*g as an extended E2 point
   const uint32_t* jv;     // [items*34][8]
   const uint32_t* gtab;
@@ -758,6 +620,8 @@ template <> struct TaskMinBlocks<TomCommitHTask> { static constexpr int value = 
 template <> struct TaskMinBlocks<TomCommitGTask> { static constexpr int value = ZKA_COMMIT_MINBLOCKS; };
 template <> struct TaskMinBlocks<TomCommitTask> { static constexpr int value = ZKA_COMMIT_MINBLOCKS; };
 #endif
+
+#endif   // ZKA_PG_WAR256
 
 // ============================================================================ Groth-Kohlweiss sums
 // sum over the 2^k ring entries i of block `blk` of coef_i * prod_j (bit_j(i) ? fo[j] : fz[j]),

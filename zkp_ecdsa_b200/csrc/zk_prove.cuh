@@ -708,9 +708,9 @@ struct ItemScalarsTask {
 struct DerivedTask {
   ProveCtx c;
   ZK_HD void ldaff(TomPt& p, const uint32_t* aff, size_t idx) const {
-    uint32_t x[9], y[9];
-    ld<9>(x, aff + idx * TOM_AFF_WORDS);
-    ld<9>(y, aff + idx * TOM_AFF_WORDS + 9);
+    uint32_t x[PGL], y[PGL];
+    ld<PGL>(x, aff + idx * TOM_AFF_WORDS);
+    ld<PGL>(y, aff + idx * TOM_AFF_WORDS + PGL);
     tom_from_affine(p, x, y);
   }
   ZK_HD void stp(size_t idx, const TomPt& p) const {

@@ -135,6 +135,21 @@ struct VerifyCtx {
 };
 
 // ---- small helpers ------------------------------------------------------------------------
+#if defined(ZKA_PG_WAR256)
+// parse a war256 point encoding (SEC1 uncompressed, weier.ts:74-89: 0x04 tag, coordinates < p, on curve) -> affine
+// Montgomery; returns validity.  (The identity has no 65-byte encoding in a proof slot: tag 0x00 is malformed here.)
+ZK_HD bool tom_parse(uint32_t* xm, uint32_t* ym, const uint8_t* b) {
+  uint32_t x[8], y[8];
+  limbs_from_be<8>(x, b + 1, 32);
+  limbs_from_be<8>(y, b + 33, 32);
+  const bool ok = (b[0] == 0x04) && lt_p<FpWar>(x) && lt_p<FpWar>(y);
+  reduce_once<FpWar>(x);
+  reduce_once<FpWar>(y);
+  Warp::to_mont(xm, x);
+  Warp::to_mont(ym, y);
+  return ok && war_on_curve(xm, ym);
+}
+#else
 // parse a tomEdwards256 point encoding -> image-curve affine Montgomery; returns validity
 // (edwards.ts:70-86: 0x04 tag, coordinates < p, on curve)
 ZK_HD bool tom_parse(uint32_t* xm, uint32_t* ym, const uint8_t* b) {
@@ -148,6 +163,7 @@ ZK_HD bool tom_parse(uint32_t* xm, uint32_t* ym, const uint8_t* b) {
   Tomp::mul(xm, xm, sa);
   return ok && tom_on_curve(xm, ym);
 }
+#endif
 // P-256 point encoding -> affine Montgomery. identity (65 zero bytes) -> inf.
 ZK_HD bool p256_parse(P256Aff& a, bool& inf, const uint8_t* b) {
   uint32_t x[8], y[8];
@@ -166,9 +182,9 @@ ZK_HD bool nscalar_parse(uint32_t* r, const uint8_t* b) {   // 32 bytes, mod p25
   limbs_from_be<8>(r, b, 32);
   return lt_p<FnP256>(r);
 }
-ZK_HD bool wscalar_parse(uint32_t* r, const uint8_t* b) {   // 33 bytes, mod tom.order
-  limbs_from_be<8>(r, b + 1, 32);
-  return b[0] == 0 && lt_p<FpP256>(r);
+ZK_HD bool wscalar_parse(uint32_t* r, const uint8_t* b) {   // WS bytes (33 tomEdwards256 / 32 war256), mod the group order
+  limbs_from_be<8>(r, b + (WS - 32), 32);
+  return (WS == 32 || b[0] == 0) && lt_p<FpP256>(r);
 }
 ZK_HD bool vdraw(uint32_t* r, const uint8_t* p, bool nist) {
   limbs_from_be<8>(r, p, 32);
@@ -276,7 +292,7 @@ struct VValidateTask {
   VerifyCtx c;
   ZK_HD bool wpts(const uint8_t* p, int k) const {
     bool ok = true;
-    uint32_t x[9], y[9];
+    uint32_t x[PGL], y[PGL];
     for (int i = 0; i < k; i++) ok = tom_parse(x, y, p + (size_t)i * WP) && ok;
     return ok;
   }
@@ -426,7 +442,7 @@ struct VSampleJobsTask {
 struct VDerivedTask {
   VerifyCtx c;
   ZK_HD void frombytes(TomPt& p, const uint8_t* b) const {
-    uint32_t x[9], y[9];
+    uint32_t x[PGL], y[PGL];
     tom_parse(x, y, b);
     tom_from_affine(p, x, y);
   }
@@ -444,10 +460,10 @@ struct VDerivedTask {
     frombytes(pkY, pr + 2 * NP + WP);
     frombytes(Tx, rep + 1 + NP);
     frombytes(Ty, rep + 1 + NP + WP);
-    uint32_t x[9], y[9];
-    ld<9>(x, c.ta_aff + c.ta_pt(t, 0) * TOM_AFF_WORDS); ld<9>(y, c.ta_aff + c.ta_pt(t, 0) * TOM_AFF_WORDS + 9);
+    uint32_t x[PGL], y[PGL];
+    ld<PGL>(x, c.ta_aff + c.ta_pt(t, 0) * TOM_AFF_WORDS); ld<PGL>(y, c.ta_aff + c.ta_pt(t, 0) * TOM_AFF_WORDS + PGL);
     tom_from_affine(T1x, x, y);
-    ld<9>(x, c.ta_aff + c.ta_pt(t, 1) * TOM_AFF_WORDS); ld<9>(y, c.ta_aff + c.ta_pt(t, 1) * TOM_AFF_WORDS + 9);
+    ld<PGL>(x, c.ta_aff + c.ta_pt(t, 1) * TOM_AFF_WORDS); ld<PGL>(y, c.ta_aff + c.ta_pt(t, 1) * TOM_AFF_WORDS + PGL);
     tom_from_affine(T1y, x, y);
     tom_neg(n, T1x); tom_add(r, pkX, n); stp(c.td_pt(t, DER_C7), r);
     tom_neg(n, T1y); tom_add(r, pkY, n); stp(c.td_pt(t, DER_C9), r);
@@ -741,8 +757,14 @@ struct VParseEntriesTask {
   uint32_t* pre;         // [count][32]
   int per_proof;
   ZK_HD void operator()(int t) const {
-    using F = Tomp;
     const int b = t / per_proof;
+#if defined(ZKA_PG_WAR256)
+    uint32_t x[8], y[8];
+    tom_parse(x, y, proofs + (size_t)b * proof_stride + off[t]);
+    uint32_t* o = pre + (size_t)t * TOM_PRE_WORDS;
+    st<8>(o, x); st<8>(o + 8, y);
+#else
+    using F = Tomp;
     uint32_t x[9], y[9], k[9], d1[9];
     tom_parse(x, y, proofs + (size_t)b * proof_stride + off[t]);
     tom_const(d1, TOM_D1);
@@ -751,6 +773,7 @@ struct VParseEntriesTask {
     F::reduce(x); F::reduce(y); F::reduce(k);
     uint32_t* o = pre + (size_t)t * TOM_PRE_WORDS;
     st<9>(o, x); st<9>(o + 9, y); st<9>(o + 18, k);
+#endif
   }
 };
 
@@ -892,6 +915,24 @@ struct VGkOffsetsTask {   // byte offsets of cl, ca, cb, cd, com for VParseEntri
 // buckets, then the running-sum reduction.  Instances: GK (4n+1 entries) and multiW.
 // ---------------------------------------------------------------------------------------------
 struct alignas(16) U4 { uint32_t x, y, z, w; };
+#if defined(ZKA_PG_WAR256)
+enum : int { PG_EXT_WORDS = 24, PG_EXT_U4 = 6 };   // a parked projective point: X, Y, Z
+ZK_HD void bk_load(TomPt& p, const U4* b) {
+  uint32_t w[24];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { const U4 u = b[i]; w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) { p.x[i] = w[i]; p.y[i] = w[8 + i]; p.z[i] = w[16 + i]; }
+}
+ZK_HD void bk_store(U4* b, const TomPt& p) {
+  uint32_t w[24];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { w[i] = p.x[i]; w[8 + i] = p.y[i]; w[16 + i] = p.z[i]; }
+#pragma unroll
+  for (int i = 0; i < 6; i++) { U4 u; u.x = w[4 * i]; u.y = w[4 * i + 1]; u.z = w[4 * i + 2]; u.w = w[4 * i + 3]; b[i] = u; }
+}
+#else
+enum : int { PG_EXT_WORDS = 36, PG_EXT_U4 = 9 };   // a parked extended point: X, Y, T, Z
 ZK_HD void bk_load(TomPt& p, const U4* b) {
   uint32_t w[36];
 #pragma unroll
@@ -906,6 +947,7 @@ ZK_HD void bk_store(U4* b, const TomPt& p) {
 #pragma unroll
   for (int i = 0; i < 9; i++) { U4 u; u.x = w[4 * i]; u.y = w[4 * i + 1]; u.z = w[4 * i + 2]; u.w = w[4 * i + 3]; b[i] = u; }
 }
+#endif
 // Signed window digits without a carry chain: with OFFS = sum_j 32 * 64^j the unsigned 6-bit windows of
 // k' = k + OFFS, minus 32, are digits d_j in [-32, 31] with sum_j d_j 64^j = k.  Returns |d_j| (the
 // bucket, 0..32) and its sign.  Half the buckets of an unsigned 6-bit window, one window fewer per
@@ -946,7 +988,7 @@ struct MsmTomWindowTask {
   int stride, groups, group_len, tail;   // entries of an instance = groups*group_len, then `tail` always-used ones
   int seg_groups, segs;     // the groups are walked in `segs` segments of <= seg_groups groups (one thread per segment
                             // and window: <= V_ENT_SEG entries each); the tail rides with segment 0
-  uint32_t* win;            // [inst][segs][MSM_NWIN][36]
+  uint32_t* win;            // [inst][segs][MSM_NWIN][PG_EXT_WORDS]
   ZK_HD void operator()(int t) const {
     const int is = t / MSM_NWIN, w = t % MSM_NWIN;
     const int inst = is / segs, seg = is % segs;
@@ -992,7 +1034,7 @@ struct MsmTomWindowTask {
     // pass 3: ONE flat loop over the entries with a non-zero digit (the trip count is the same for
     // every window of an instance up to a few entries, so the warp does not diverge); a finished
     // bucket sum is parked in local memory exactly once
-    U4 S[NB][9];
+    U4 S[NB][PG_EXT_U4];
     uint64_t present = 0;
     TomPt acc;
     tom_set_identity(acc);
@@ -1010,10 +1052,7 @@ struct MsmTomWindowTask {
       TomPre pt;
       const int loc = (int)(oe & 1023u);
       tom_ld_pre(pt, pp + (size_t)(loc < nloc ? gbase + loc : tbase + (loc - nloc)) * TOM_PRE_WORDS);
-      if (oe & 0x8000u) {            // negative digit: -(x, y) = (-x, y), k = d x y changes sign too
-        Tomp::neg(pt.x, pt.x);
-        Tomp::neg(pt.k, pt.k);
-      }
+      if (oe & 0x8000u) pg_pre_neg(pt);   // negative digit
       tom_madd<true, TompMsm>(acc, acc, pt);
     }
     bk_store(S[curd], acc);
@@ -1029,8 +1068,7 @@ struct MsmTomWindowTask {
       }
       tom_add(tot, tot, run);
     }
-    uint32_t* o = win + (size_t)t * 36;
-    st<9>(o, tot.x); st<9>(o + 9, tot.y); st<9>(o + 18, tot.t); st<9>(o + 27, tot.z);
+    bk_store(reinterpret_cast<U4*>(win + (size_t)t * PG_EXT_WORDS), tot);
   }
 };
 // Horner over the windows + the fixed-base part; verdict = identity?  One thread per instance.
@@ -1046,28 +1084,21 @@ struct MsmTomCombineTask {
     for (int w = MSM_NWIN - 1; w >= 0; w--) {
       for (int k = 0; k < MSM_C; k++) tom_dbl(acc, acc);
       for (int sg = 0; sg < segs; sg++) {
-        const uint32_t* s = win + (((size_t)inst * segs + sg) * MSM_NWIN + w) * 36;
-        ld<9>(wsum.x, s); ld<9>(wsum.y, s + 9); ld<9>(wsum.t, s + 18); ld<9>(wsum.z, s + 27);
+        bk_load(wsum, reinterpret_cast<const U4*>(win + (((size_t)inst * segs + sg) * MSM_NWIN + w) * PG_EXT_WORDS));
         tom_add(acc, acc, wsum);
       }
     }
     TomPt f;
     const uint32_t* fp = fixed + ((size_t)inst * fix_stride + fix_off) * TOM_PROJ_WORDS;
     tom_ld_xyz(f.x, f.y, f.z, fp);
+#if !defined(ZKA_PG_WAR256)
     // The commitment kernel works on the a = -1 image curve E2 and stores (W : V : Z) with
     // x' = W / (Z sqrt(-d1)), y = Z / V.  Same point in E1 extended coordinates with Z' = Z V:
     //   X = c W V,  Y = Z^2,  T = X Y / Z' = c W Z,   c = 1/sqrt(-d1).
-    uint32_t cw[9], X[9], Y[9], Tt[9], Zp[9], c1[9];
-    tom_const(c1, TOM_INVSQRTND1);
-    Tomp::mul(cw, f.x, c1);
-    Tomp::mul(X, cw, f.y);
-    Tomp::sqr(Y, f.z);
-    Tomp::mul(Tt, cw, f.z);
-    Tomp::mul(Zp, f.z, f.y);
-    copy_n<9>(f.x, X); copy_n<9>(f.y, Y); copy_n<9>(f.t, Tt); copy_n<9>(f.z, Zp);
+    pg_fixed_to_msm(f);
+#endif
     tom_add(acc, acc, f);
-    // identity <=> X == 0 and Y == Z (edwards.ts:117-125 in projective form)
-    const bool id = Tomp::is_zero(acc.x) && Tomp::eq(acc.y, acc.z);
+    const bool id = pg_is_identity(acc);
     flag[(size_t)inst * 3 + flag_off] = id ? 1 : 0;
   }
 };
@@ -1233,7 +1264,7 @@ struct VGkOnlyLayoutTask {
     c.gk_off[b] = bad ? 0 : HEAD_LEN;
     bool okp = true;
     if (!bad) {
-      uint32_t x[9], y[9], r[8];
+      uint32_t x[PGL], y[PGL], r[8];
       okp = tom_parse(x, y, pr + 2 * NP);
       const uint8_t* g = pr + HEAD_LEN;
       for (int i = 0; i < 4 * ngk; i++) okp = tom_parse(x, y, g + 1 + (size_t)i * WP) && okp;
@@ -1265,6 +1296,14 @@ ZK_LAYOUT_FN int sub_draws(int kind) { return kind == SUB_EQ ? 2 : kind == SUB_M
 ZK_LAYOUT_FN int sub_entries(int kind) { return kind == SUB_EQ ? 4 : kind == SUB_MULT ? 9 : SUB_ENT_MAX; }
 
 // encoding (67 bytes in a 68-byte slot) of an E1 affine point given as Montgomery (x', y)
+#if defined(ZKA_PG_WAR256)
+ZK_HD void tom_encode_affine(uint8_t* out, const uint32_t* xm, const uint32_t* ym) {
+  uint32_t cx[8], cy[8];
+  Warp::from_mont(cx, xm);
+  Warp::from_mont(cy, ym);
+  store_point_words<8, 32>(out, 0x04u, cx, cy);
+}
+#else
 ZK_HD void tom_encode_affine(uint8_t* out, const uint32_t* x1m, const uint32_t* ym) {
   uint32_t isa[9], cx[9], cy[9];
   tom_const(isa, TOM_INVSQRTA);
@@ -1273,14 +1312,14 @@ ZK_HD void tom_encode_affine(uint8_t* out, const uint32_t* x1m, const uint32_t* 
   Tomp::from_mont(cy, ym);
   store_point_words<9, 33>(out, 0x04u, cx, cy);
 }
+#endif
 ZK_HD void tom_encode_proj(uint8_t* out, const TomPt& p) {   // one inversion: low-volume paths only
-  uint32_t zi[9], x[9], y[9];
-  Tomp::inv(zi, p.z);
-  Tomp::mul(x, p.x, zi);
-  Tomp::mul(y, p.y, zi);
+  uint32_t zi[PGL], x[PGL], y[PGL];
+  PGp::inv(zi, p.z);
+  PGp::mul(x, p.x, zi);
+  PGp::mul(y, p.y, zi);
   tom_encode_affine(out, x, y);
 }
-
 struct VSubProofTask {
   int kind;
   const uint8_t* rows;     // [B][stride]
@@ -1386,7 +1425,7 @@ struct VSubProofTask {
     // deserialisation checks of every point and scalar (deserializePoint / deserializeScalar would throw)
     bool good = true;
     {
-      uint32_t x[9], y[9], r[8];
+      uint32_t x[PGL], y[PGL], r[8];
       for (int i = 0; i < np; i++) good = tom_parse(x, y, row + (size_t)i * WP) && good;
       if (kind == SUB_EQ) {
         for (int i = 0; i < 2; i++) good = tom_parse(x, y, proof + (size_t)i * WP) && good;
@@ -1431,7 +1470,7 @@ struct VSubProofTask {
       // aggregatePointAdd (pointAdd.ts:199-259): C1..C6 = PX QX RX PY QY RY
       const uint8_t *PX = row, *PY = row + WP, *QX = row + 2 * WP, *QY = row + 3 * WP, *RX = row + 4 * WP, *RY = row + 5 * WP;
       TomPt p1, p2, p3, p4, p5, p6, n, r;
-      uint32_t x[9], y[9];
+      uint32_t x[PGL], y[PGL];
       tom_parse(x, y, PX); tom_from_affine(p1, x, y);
       tom_parse(x, y, QX); tom_from_affine(p2, x, y);
       tom_parse(x, y, RX); tom_from_affine(p3, x, y);

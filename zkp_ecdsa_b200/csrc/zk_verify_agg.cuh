@@ -74,7 +74,7 @@ struct AggTomSrc {
   const uint32_t *ent_scalar, *ent_pre, *ent_cnt, *gk_scalar, *gk_pre;
   int B, ET, K, ngk;   // slots [0, B*ET): multiW entries (K samples x 34 + keyXcom, keyYcom); then B*ngk GK entries
   using Pt = TomPt;
-  enum { PTW = 36 };
+  enum { PTW = PG_EXT_WORDS };
   ZK_HD int slots() const { return B * (ET + ngk); }
   ZK_HD bool used(int s) const {
     if (s >= B * ET) return true;
@@ -88,10 +88,7 @@ struct AggTomSrc {
   ZK_HD void accumulate(Pt& acc, int s, bool neg) const {
     TomPre pt;
     tom_ld_pre(pt, s < B * ET ? ent_pre + (size_t)s * TOM_PRE_WORDS : gk_pre + (size_t)(s - B * ET) * TOM_PRE_WORDS);
-    if (neg) {   // -(x, y) = (-x, y); k = d x y changes sign too
-      Tomp::neg(pt.x, pt.x);
-      Tomp::neg(pt.k, pt.k);
-    }
+    if (neg) pg_pre_neg(pt);
     tom_madd<true, TompMsm>(acc, acc, pt);
   }
   ZK_HD static void identity(Pt& p) { tom_set_identity(p); }
@@ -374,17 +371,9 @@ struct AggFinalTask {
       TomPt acc, f;
       agg_horner<AggTomSrc>(acc, tomA, tomB, t_nwin, t_c);
       tom_ld_xyz(f.x, f.y, f.z, fx_proj);
-      // (W : V : Z) of the a = -1 image curve -> extended E1 coordinates (see MsmTomCombineTask)
-      uint32_t cw[9], X[9], Y[9], Tt[9], Zp[9], c1[9];
-      tom_const(c1, TOM_INVSQRTND1);
-      Tomp::mul(cw, f.x, c1);
-      Tomp::mul(X, cw, f.y);
-      Tomp::sqr(Y, f.z);
-      Tomp::mul(Tt, cw, f.z);
-      Tomp::mul(Zp, f.z, f.y);
-      copy_n<9>(f.x, X); copy_n<9>(f.y, Y); copy_n<9>(f.t, Tt); copy_n<9>(f.z, Zp);
+      pg_fixed_to_msm(f);
       tom_add(acc, acc, f);
-      ctl[AGG_TOM_PASS] = (Tomp::is_zero(acc.x) && Tomp::eq(acc.y, acc.z)) ? 1u : 0u;
+      ctl[AGG_TOM_PASS] = pg_is_identity(acc) ? 1u : 0u;
     } else if (t == 32) {
       P256Pt acc, p;
       agg_horner<AggNistSrc>(acc, nisA, nisB, n_nwin, n_c);

@@ -50,20 +50,17 @@ struct ParsePointsTask {   // host bytes -> affine Montgomery (+ validity), used
       if (inf) inf[t] = allz ? 1 : 0;
     }
     if (tom) {
-      const uint8_t* b = tom + (size_t)t * 67;
-      uint32_t x[9], y[9], sa[9];
-      limbs_from_be<9>(x, b + 1, 33);
-      limbs_from_be<9>(y, b + 34, 33);
-      bool ok = (b[0] == 0x04) && lt_p<FpTom>(x) && lt_p<FpTom>(y);   // edwards.ts:75-76 verifyPosRange
-      uint32_t xm[9], ym[9];
-      Tomp::to_mont(xm, x);
-      Tomp::to_mont(ym, y);
-      tom_const(sa, TOM_SQRTA);
-      Tomp::mul(xm, xm, sa);   // to the a'=1 image curve
-      ok = ok && tom_on_curve(xm, ym);
-      if (!ok) { tom_const(xm, TOM_GX1); tom_const(ym, TOM_GY); }
-      st<9>(tom_aff + (size_t)t * 18, xm);
-      st<9>(tom_aff + (size_t)t * 18 + 9, ym);
+      const uint8_t* b = tom + (size_t)t * WP;
+      uint32_t xm[PGL], ym[PGL];
+      bool ok = tom_parse(xm, ym, b);   // tag, coordinate range and curve equation (edwards.ts:70-86 / weier.ts:74-89)
+      if (!ok) {
+        TomPt g;
+        tom_set_generator(g);
+        copy_n<PGL>(xm, g.x);
+        copy_n<PGL>(ym, g.y);
+      }
+      st<PGL>(tom_aff + (size_t)t * TOM_AFF_WORDS, xm);
+      st<PGL>(tom_aff + (size_t)t * TOM_AFF_WORDS + PGL, ym);
       if (bad) bad[t] = ok ? 0 : 1;
     }
   }
@@ -76,11 +73,10 @@ struct GenAffTask {   // generator constants -> device
     P256Aff g;
     p256_set_generator(g);
     p256_st_aff(p256_g, g);
-    uint32_t x[9], y[9];
-    tom_const(x, TOM_GX1);
-    tom_const(y, TOM_GY);
-    st<9>(tom_g, x);
-    st<9>(tom_g + 9, y);
+    TomPt tg;
+    tom_set_generator(tg);     // affine generator of the proof group (z = 1)
+    st<PGL>(tom_g, tg.x);
+    st<PGL>(tom_g + PGL, tg.y);
   }
 };
 
@@ -110,11 +106,11 @@ struct GProjTask {
   const uint32_t* g;
   uint32_t* proj;
   ZK_HD void operator()(int) const {
-    uint32_t one[9];
-    Tomp::set_one(one);
-    st<9>(proj, g);
-    st<9>(proj + 9, g + 9);
-    st<9>(proj + 18, one);
+    uint32_t one[PGL];
+    PGp::set_one(one);
+    st<PGL>(proj, g);
+    st<PGL>(proj + PGL, g + PGL);
+    st<PGL>(proj + 2 * PGL, one);
   }
 };
 
@@ -331,7 +327,7 @@ struct zka_params {
   int h_w = 20;
   FixedTable th;          // ProofGroup.h table
   uint8_t h_nist[65];
-  uint8_t h_proof[67];
+  uint8_t h_proof[WP];
 };
 
 namespace {
@@ -482,6 +478,37 @@ void build_p256_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out,
   pows.release();
   rows.release();
 }
+#if defined(ZKA_PG_WAR256)
+// war256 positional table [fb_windows(w)][fb_entries(w)] of affine points from one affine base (16 words, device)
+void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) {
+  Stream& st = ctx->st;
+  const int w = ctx->tom_w, nwin = fb_windows(w);
+  const size_t E = (size_t)fb_entries(w), count = (size_t)nwin * E;
+  DevBuf pows, rows;
+  uint32_t* d_pows = pows.get<uint32_t>((size_t)nwin * P256_PROJ_WORDS);
+  uint32_t* d_rows = rows.get<uint32_t>(count * P256_PROJ_WORDS);
+  out.tab = out.buf.get<uint32_t>(count * TOM_PRE_WORDS);
+  launch(st, 1, WarPowsTask{base_aff_dev, nullptr, d_pows, 1, nwin, w});
+  if (w > 9) {
+    DevBuf hi;
+    const int nh = 1 << (w - 9);
+    uint32_t* d_hi = hi.get<uint32_t>((size_t)nwin * nh * P256_PROJ_WORDS);
+    launch(st, nwin, WarRowsHiTask{d_pows, d_hi, d_rows, w});
+    launch(st, (long long)nwin * nh, WarRowsLoTask{d_pows, d_hi, d_rows, w});
+    sync(st);
+    hi.release();
+  } else {
+    launch(st, nwin, WarRowsTask{d_pows, d_rows, w});
+  }
+  {
+    const int ch = norm_chunk_for((long long)count, 5);
+    launch(st, ((long long)count + ch - 1) / ch, WarNormTask{d_rows, out.tab, nullptr, nullptr, (int)count, ch});
+  }
+  sync(st);
+  pows.release();
+  rows.release();
+}
+#else
 // tomEdwards256 positional table [nwin][fb_entries(w)] from one image-curve affine base (18 words, device)
 void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) {
   Stream& st = ctx->st;
@@ -509,6 +536,8 @@ void build_tom_tab(zka_ctx* ctx, const uint32_t* base_aff_dev, FixedTable& out) 
   pows.release();
   rows.release();
 }
+
+#endif
 
 // stage a caller buffer on the device if it is a host pointer
 template <class T>
@@ -691,6 +720,20 @@ size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap) {
   }
   return j.size() + 1;
 }
+int zka_proof_group(char* name, size_t cap, int* point_bytes, int* scalar_bytes) {
+#if defined(ZKA_PG_WAR256)
+  const char* n = "war256";
+#else
+  const char* n = "tomEdwards256";
+#endif
+  if (name && cap) {
+    strncpy(name, n, cap - 1);
+    name[cap - 1] = 0;
+  }
+  if (point_bytes) *point_bytes = WP;
+  if (scalar_bytes) *scalar_bytes = WS;
+  return 0;
+}
 int zka_lanes(const zka_ctx* ctx) { return ctx ? ctx->nlanes : 0; }
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk) {
   if (!ctx) return ZKA_E_ARG;
@@ -760,7 +803,7 @@ int zka_init(int device, zka_ctx** out) {
       if (w >= 8 && w <= 24) ctx->p256_hw = w;
     }
     DevBuf gen;
-    uint32_t* d_gen = gen.get<uint32_t>(16 + 18);
+    uint32_t* d_gen = gen.get<uint32_t>(16 + TOM_AFF_WORDS);
     launch(ctx->st, 1, GenAffTask{d_gen, d_gen + 16});
     build_p256_tab(ctx, d_gen, ctx->g8, 8);
     build_p256_tab(ctx, d_gen, ctx->gw, ctx->p256_hw);
@@ -827,16 +870,16 @@ int zka_params_create(zka_ctx* ctx, const uint8_t h_nist[65], const uint8_t h_pr
     P->sec_level = sec_level;
     P->h_w = ctx->p256_hw;
     memcpy(P->h_nist, h_nist, 65);
-    memcpy(P->h_proof, h_proof, 67);
+    memcpy(P->h_proof, h_proof, WP);
     DevBuf bn, bt, an, at, bad, inf;
     uint8_t* d_bn = bn.get<uint8_t>(65);
-    uint8_t* d_bt = bt.get<uint8_t>(67);
+    uint8_t* d_bt = bt.get<uint8_t>(WP);
     uint32_t* d_an = an.get<uint32_t>(16);
-    uint32_t* d_at = at.get<uint32_t>(18);
+    uint32_t* d_at = at.get<uint32_t>(TOM_AFF_WORDS);
     uint8_t* d_bad = bad.get<uint8_t>(2);
     uint8_t* d_inf = inf.get<uint8_t>(1);
     copy_h2d(ctx->st, d_bn, h_nist, 65);
-    copy_h2d(ctx->st, d_bt, h_proof, 67);
+    copy_h2d(ctx->st, d_bt, h_proof, WP);
     launch(ctx->st, 1, ParsePointsTask{d_bn, nullptr, d_an, nullptr, d_bad, d_inf});
     launch(ctx->st, 1, ParsePointsTask{nullptr, d_bt, nullptr, d_at, d_bad + 1, nullptr});
     uint8_t hb[3];
@@ -955,13 +998,13 @@ int zka_field_op_batch(zka_ctx* ctx, int field, int op, uint32_t count, const ui
   if (count == 0) return 0;
   try {
     Stream& st = ctx->st;
-    const int nb = field == 2 ? 33 : 32;
+    const int nb = field == 2 ? WCB : 32;
     const uint8_t* da = stage_in(ctx, ctx->in[0], a, (size_t)count * nb);
     const uint8_t* db = b ? stage_in(ctx, ctx->in[1], b, (size_t)count * nb) : nullptr;
     uint8_t* dout = is_device_ptr(out) ? out : ctx->out[0].get<uint8_t>((size_t)count * nb);
     if (field == 0) launch(st, count, FieldOpTask<P256p, 32>{da, db, dout, op});
     else if (field == 1) launch(st, count, FieldOpTask<P256n, 32>{da, db, dout, op});
-    else launch(st, count, FieldOpTask<Tomp, 33>{da, db, dout, op});
+    else launch(st, count, FieldOpTask<PGp, WCB>{da, db, dout, op});
     if (dout != out) copy_d2h(st, out, dout, (size_t)count * nb);
     sync(st);
     return 0;
@@ -1006,7 +1049,7 @@ int zka_params_generate(zka_ctx* ctx, const uint8_t rnd[64], uint8_t h_nist[65],
     // v*g + 0*g: use the g table for both bases
     launch(st, 1, TomCommitTask{jv, jr, ctx->tg.tab, ctx->tg.tab, proj, ctx->tom_w, ctx->tom_nwin});
     launch_tom_norm(st, proj, aff, bytes, (long long)(1), 1);
-    copy_d2h(st, h_proof, bytes, 67);
+    copy_d2h(st, h_proof, bytes, WP);
     sync(st);
     return 0;
   } catch (const std::exception& e) {
