@@ -209,6 +209,8 @@ Napi::Value KeyToInt(const Napi::CallbackInfo& info) {
 Napi::Value ParamsGenerate(const Napi::CallbackInfo& info) {
   auto rnd = info[0].As<Napi::Uint8Array>();
   uint8_t hn[65], hp[67];
+  int wp = 67;   // ProofGroup point bytes of the linked library: 67 (libzkattest.so) or 65 (libzkattest_war256.so)
+  zka_proof_group(nullptr, 0, &wp, nullptr);
   int rc;
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -221,7 +223,7 @@ Napi::Value ParamsGenerate(const Napi::CallbackInfo& info) {
   }
   Napi::Object o = Napi::Object::New(info.Env());
   o.Set("hNist", Napi::Buffer<uint8_t>::Copy(info.Env(), hn, 65));
-  o.Set("hProof", Napi::Buffer<uint8_t>::Copy(info.Env(), hp, 67));
+  o.Set("hProof", Napi::Buffer<uint8_t>::Copy(info.Env(), hp, (size_t)wp));
   return o;
 }
 // SystemParametersList -> device tables (zka_params_create): synchronous, ~0.2 s, once per parameter set
@@ -229,7 +231,9 @@ Napi::Value ParamsCreate(const Napi::CallbackInfo& info) {
   auto hn = info[0].As<Napi::Uint8Array>();
   auto hp = info[1].As<Napi::Uint8Array>();
   const uint32_t sec = info[2].As<Napi::Number>().Uint32Value();
-  if (hn.ElementLength() != 65 || hp.ElementLength() != 67) {
+  int wp = 67;
+  zka_proof_group(nullptr, 0, &wp, nullptr);
+  if (hn.ElementLength() != 65 || hp.ElementLength() != (size_t)wp) {
     Napi::Error::New(info.Env(), "error deserializing Point").ThrowAsJavaScriptException();
     return info.Env().Undefined();
   }
@@ -270,4 +274,7 @@ Napi::Object InitAll(Napi::Env env, Napi::Object exports) {
 
 }  // namespace
 
-NODE_API_MODULE(zkattest, InitAll)
+#ifndef ZKA_NAPI_MODULE
+#define ZKA_NAPI_MODULE zkattest   // binding.gyp builds the same source a second time as zkattest_war256
+#endif
+NODE_API_MODULE(ZKA_NAPI_MODULE, InitAll)

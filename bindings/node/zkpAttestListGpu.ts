@@ -16,13 +16,24 @@ import { Group } from './curves/group.js'
 import { SignatureProofList, SystemParametersList } from './zkpAttestList.js'
 import { p256, tomEdwards256 } from './curves/instances.js'
 import { posMod, rnd, toBytes } from './bignum/big.js'
+// One native addon per ProofGroup: zkattest.node links libzkattest.so (tomEdwards256, what generateParamsList builds),
+// zkattest_war256.node links libzkattest_war256.so (war256, the other group the JSON initialiser of
+// curves/instances.ts:58-69 accepts for SystemParametersList.ProofGroup).  Same shim source, same exports; the
+// war256 addon is loaded on first use.
 // eslint-disable-next-line @typescript-eslint/no-require-imports
 const native = require('../build/Release/zkattest.node')
+let nativeWar: typeof native | undefined
+function nativeFor(params: SystemParametersList): typeof native {
+    const name = params.ProofGroup.g.group.name
+    if (name === 'tomEdwards256') return native
+    if (name !== 'war256') throw new Error(`invalid group name: ${name}`) // instances.ts:66
+    // eslint-disable-next-line @typescript-eslint/no-require-imports
+    if (nativeWar === undefined) nativeWar = require('../build/Release/zkattest_war256.node')
+    return nativeWar
+}
 
 const NP = 65,
-    WP = 67,
     NS = 32,
-    WS = 33,
     V_SAMPLES = 20, // verifySignatureList's literal secparam (zkpAttestList.ts:177)
     IDX_PAD = 96
 
@@ -31,20 +42,21 @@ const NP = 65,
 // parameter set.  At most MAX_HANDLES sets stay resident; the least recently used one is destroyed
 // (zka_params_destroy) when a new one is needed.
 const MAX_HANDLES = 4
-const handles = new Map<string, { h: unknown; used: number }>()
+const handles = new Map<string, { h: unknown; used: number; nat: typeof native }>()
 let tick = 0
 function paramsHandle(params: SystemParametersList): unknown {
     const hn = params.NistGroup.h.toBytes(),
         hp = params.ProofGroup.h.toBytes()
+    const nat = nativeFor(params)
     const key = Buffer.from(hn).toString('hex') + Buffer.from(hp).toString('hex') + ':' + params.SecLevel
     let e = handles.get(key)
     if (e === undefined) {
         if (handles.size >= MAX_HANDLES) {
             let oldest: string | undefined, age = Infinity
             for (const [k, v] of handles) if (v.used < age) { age = v.used; oldest = k }
-            if (oldest !== undefined) { native.paramsDestroy(handles.get(oldest)!.h); handles.delete(oldest) }
+            if (oldest !== undefined) { const o = handles.get(oldest)!; o.nat.paramsDestroy(o.h); handles.delete(oldest) }
         }
-        e = { h: native.paramsCreate(hn, hp, params.SecLevel), used: 0 }
+        e = { h: nat.paramsCreate(hn, hp, params.SecLevel), used: 0, nat }
         handles.set(key, e)
     }
     e.used = ++tick
@@ -78,7 +90,7 @@ function verifyTape(secLevel: number, n: number): Uint8Array {
 // ---- flat proof layout (include/zkattest.h): reader ------------------------------------------------------------
 class Reader {
     o = 0
-    constructor(private b: Uint8Array) {}
+    constructor(private b: Uint8Array, private pg: Group = tomEdwards256) {}
     take(n: number) {
         if (this.o + n > this.b.length) throw new Error('error deserializing Point')
         const v = this.b.subarray(this.o, this.o + n)
@@ -89,9 +101,9 @@ class Reader {
         const v = this.take(NP)
         return v.every((x) => x === 0) ? p256.identity() : p256.deserializePoint(v)
     }
-    wp() { return tomEdwards256.deserializePoint(this.take(WP)) }
+    wp() { return this.pg.deserializePoint(this.take(1 + 2 * this.pg.sizeFieldBytes())) } // 67 B tomEdwards256 / 65 B war256
     ns() { return p256.deserializeScalar(this.take(NS)) }
-    ws() { return tomEdwards256.deserializeScalar(this.take(WS)) }
+    ws() { return this.pg.deserializeScalar(this.take(this.pg.sizeFieldBytes())) } // 33 B / 32 B (group.ts:49-52)
 }
 function readMult(r: Reader) {
     const p = [r.wp(), r.wp(), r.wp(), r.wp(), r.wp(), r.wp()],
@@ -99,8 +111,8 @@ function readMult(r: Reader) {
     return new MultProof(p[0], p[1], p[2], p[3], p[4], p[5], s[0], s[1], s[2], s[3], s[4], s[5], s[6])
 }
 function readEq(r: Reader) { return new EqualityProof(r.wp(), r.wp(), r.ws(), r.ws(), r.ws()) }
-export function readProof(bytes: Uint8Array, secLevel: number): SignatureProofList {
-    const r = new Reader(bytes),
+export function readProof(bytes: Uint8Array, secLevel: number, pg: Group = tomEdwards256): SignatureProofList {
+    const r = new Reader(bytes, pg),
         R = r.np(), comS1 = r.np(), kx = r.wp(), ky = r.wp(),
         exps: ExpProof[] = []
     for (let i = 0; i < secLevel; i++) {
@@ -199,16 +211,16 @@ export async function proveSignatureList(params: SystemParametersList, msgHash: 
     publicKey: CryptoKey, which: number, keys: bigint[]): Promise<SignatureProofList> {
     const pk = new Uint8Array(await crypto.subtle.exportKey('raw', publicKey)) // zkpAttestList.ts:113
     const n = Math.ceil(Math.log2(keys.length)),
-        res = await native.proveBatch(paramsHandle(params), msgHash, sigBytes, pk, Uint32Array.of(which), ringBytes(keys),
+        res = await nativeFor(params).proveBatch(paramsHandle(params), msgHash, sigBytes, pk, Uint32Array.of(which), ringBytes(keys),
             proveTape(params.SecLevel, n), params.SecLevel)
-    return readProof(res.proofs.subarray(0, res.lens[0]), params.SecLevel)
+    return readProof(res.proofs.subarray(0, res.lens[0]), params.SecLevel, params.ProofGroup.g.group)
 }
 
 export async function verifySignatureList(params: SystemParametersList, msgHash: Uint8Array, keys: bigint[],
     proof: SignatureProofList): Promise<boolean> {
     const n = Math.ceil(Math.log2(keys.length)),
         bytes = writeProof(proof),
-        res = await native.verifyBatch(paramsHandle(params), msgHash, ringBytes(keys), bytes, Uint32Array.of(bytes.length),
+        res = await nativeFor(params).verifyBatch(paramsHandle(params), msgHash, ringBytes(keys), bytes, Uint32Array.of(bytes.length),
             bytes.length, verifyTape(params.SecLevel, n), params.SecLevel)
     return res.ok[0] !== 0 // a status != 0 has already been rethrown as Error(<reference message>) by the shim
 }
@@ -222,7 +234,7 @@ export async function proveSignatureListBatch(params: SystemParametersList, msgH
         cat = (a: Uint8Array[], w: number) => { const o = new Uint8Array(w * a.length); a.forEach((x, i) => o.set(x, w * i)); return o },
         pks = await Promise.all(publicKey.map(async (k) => new Uint8Array(await crypto.subtle.exportKey('raw', k)))),
         tapes = Array.from({ length: B }, () => proveTape(params.SecLevel, n)),
-        res = await native.proveBatch(paramsHandle(params), cat(msgHash, 32), cat(sigBytes, 64), cat(pks, 65), Uint32Array.from(which),
+        res = await nativeFor(params).proveBatch(paramsHandle(params), cat(msgHash, 32), cat(sigBytes, 64), cat(pks, 65), Uint32Array.from(which),
             ringBytes(keys), cat(tapes, tapes[0].length), params.SecLevel)
-    return Array.from({ length: B }, (_, b) => readProof(res.proofs.subarray(b * res.stride, b * res.stride + res.lens[b]), params.SecLevel))
+    return Array.from({ length: B }, (_, b) => readProof(res.proofs.subarray(b * res.stride, b * res.stride + res.lens[b]), params.SecLevel, params.ProofGroup.g.group))
 }

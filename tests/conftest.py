@@ -59,3 +59,10 @@ def gpu_engine():
     """The product path: libzkattest.so on cuda:0.  Fails loudly without it."""
     from zkp_ecdsa_b200 import api
     return api.Engine(device=0)
+
+
+@pytest.fixture(scope='session')
+def gpu_engine_war():
+    """The war256 build of the product (libzkattest_war256.so) on cuda:0."""
+    from zkp_ecdsa_b200 import api
+    return api.Engine(device=0, proof_group='war256')

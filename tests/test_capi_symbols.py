@@ -28,6 +28,21 @@ def test_shared_library_exports_all_symbols():
     assert lib.zka_version() >= 1
 
 
+def test_war256_library_exports_the_same_abi():
+    """libzkattest_war256.so (ProofGroup = war256): same entry points, 65-byte points / 32-byte scalars."""
+    import __graft_entry__ as g
+    g.build_lib_war()
+    lib = ctypes.CDLL(g.LIB_WAR)
+    for s in _declared():
+        assert hasattr(lib, s), s
+    name, pb, sb = ctypes.create_string_buffer(32), ctypes.c_int(), ctypes.c_int()
+    lib.zka_proof_group(name, 32, ctypes.byref(pb), ctypes.byref(sb))
+    assert (name.value, pb.value, sb.value) == (b'war256', 65, 32)
+    tom = ctypes.CDLL(g.LIB)
+    tom.zka_proof_group(name, 32, ctypes.byref(pb), ctypes.byref(sb))
+    assert (name.value, pb.value, sb.value) == (b'tomEdwards256', 67, 33)
+
+
 def test_product_path_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

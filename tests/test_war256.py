@@ -34,3 +34,22 @@ def test_war_prove_few_keys_and_aggregate(hostsim_war):
     common.check_prove_few_keys(hostsim_war, B=8, N=5, signers=1, seed=54, sec_level=16, spots=(0, 7))
     import test_verify_aggregate as tva
     tva.check_aggregate(hostsim_war, B=4, N=6, seed=55, cs=(0, 7))
+
+
+@pytest.mark.gpu
+def test_war_on_gpu(gpu_engine_war):
+    """The sm_100a war256 library through the C ABI: field, commitments, whole proofs (SecLevel 80 and 16, a ragged
+    ring, ring 256), verdicts incl. tampered proofs, the aggregate check and a prove -> verify round trip of 256 proofs."""
+    L = gpu_engine_war.lib
+    assert (L.group, L.wp, L.ws) == ('war256', 65, 32)
+    common.check_field_ops(L, count=50)
+    P, po = common.make_params(L, seed=5)
+    common.check_tom_commit(L, P, po)
+    L.params_destroy(P)
+    common.check_prove_parity(L, B=2, N=6, seed=61)
+    common.check_prove_parity(L, B=3, N=17, seed=62, sec_level=16)
+    common.check_prove_parity(L, B=1, N=256, seed=63)
+    common.check_verify_parity(L, N=6, seed=64, tampers=24)
+    common.check_prove_few_keys(L, B=256, N=64, signers=2, seed=65, sec_level=16, spots=(0, 255))
+    import test_verify_aggregate as tva
+    tva.check_aggregate(L, B=40, N=17, seed=66, cs=(0, 9, 13))

@@ -11,6 +11,11 @@ run default ZKA_AGG=1
 for c in 12 13 14 15 16; do run aggc$c ZKA_AGG_C=$c; done
 env ZKA_AGG=1 timeout 600 python bench.py --workload config1 --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_c1_r2i_default.json 2>> gpurun_out/bench_r2i.err
 tail -5 gpurun_out/bench_r2i.err
+if [ -f zkp_ecdsa_b200/libzkattest_war256.so ]; then
+  timeout 900 python -m pytest tests/test_war256.py -m gpu -x -q 2>&1 | tail -5
+  timeout 600 python tools/bench_war256.py 8192 256 3 > gpurun_out/bench_war256_r2i.json 2>> gpurun_out/bench_r2i.err
+  cat gpurun_out/bench_war256_r2i.json
+fi
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/bench_c?_r2i_*.json')):

@@ -38,15 +38,17 @@ class ZkaProofError(Exception):
 
 @dataclass
 class SystemParametersList:
-    """zkpAttestList.ts:65-78: NistGroup = (p256, G, h_nist), ProofGroup = (tomEdwards256, g, h_proof)."""
+    """zkpAttestList.ts:65-78: NistGroup = (p256, G, h_nist), ProofGroup = (tomEdwards256 | war256, g, h_proof)."""
     h_nist: bytes     # 65 B
-    h_proof: bytes    # 67 B
+    h_proof: bytes    # 67 B (tomEdwards256) / 65 B (war256)
     sec_level: int
     handle: object = None   # device tables (zka_params*): 7.3 GB of HBM with the default window widths
     _lib: object = None     # the ZkaLib that owns `handle`
+    proof_group: str = 'tomEdwards256'   # ProofGroup.name (instances.ts): selects the library build
 
     def eq(self, o: 'SystemParametersList') -> bool:
-        return self.h_nist == o.h_nist and self.h_proof == o.h_proof and self.sec_level == o.sec_level
+        return (self.h_nist == o.h_nist and self.h_proof == o.h_proof and self.sec_level == o.sec_level
+                and self.proof_group == o.proof_group)
 
     def close(self) -> None:
         """Free the device tables of this parameter set (zka_params_destroy); idempotent."""
@@ -89,10 +91,22 @@ def _keys_to_ring(keys: Sequence[int]) -> np.ndarray:
 
 
 class Engine:
-    """One GPU context (zka_ctx).  Raises ZkaError when the CUDA library/device is missing."""
+    """One GPU context (zka_ctx).  Raises ZkaError when the CUDA library/device is missing.
 
-    def __init__(self, device: int = 0, lib_path: Optional[str] = None):
+    `proof_group`: 'tomEdwards256' (libzkattest.so, what generateParamsList builds) or 'war256' (libzkattest_war256.so:
+    the same sources built for the other ProofGroup a SystemParametersList may carry, instances.ts:34-41)."""
+
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None, proof_group: str = 'tomEdwards256'):
+        chosen = lib_path is None and 'ZKA_LIB' not in os.environ
+        if chosen and proof_group != 'tomEdwards256':
+            if proof_group != 'war256':
+                raise ValueError(f'invalid group name: {proof_group}')      # instances.ts:66
+            from .capi import DEFAULT_LIB
+            lib_path = os.path.join(os.path.dirname(DEFAULT_LIB), 'libzkattest_war256.so')
         self.lib = ZkaLib(lib_path, device)
+        if chosen:
+            assert self.lib.group == proof_group, (self.lib.group, proof_group)
+        self.proof_group = self.lib.group
 
     def close(self):
         self.lib.close()
@@ -107,7 +121,7 @@ class Engine:
 
     def load_params(self, h_nist: bytes, h_proof: bytes, sec_level: int = 80) -> SystemParametersList:
         h = self.lib.params_create(h_nist, h_proof, sec_level)
-        return SystemParametersList(bytes(h_nist), bytes(h_proof), sec_level, h, self.lib)
+        return SystemParametersList(bytes(h_nist), bytes(h_proof), sec_level, h, self.lib, self.lib.group)
 
     def key_to_int(self, public_key: bytes) -> int:
         """keyToInt (zkpAttestList.ts:94-102) on the raw 65-byte key (WebCrypto exportKey('raw'))."""

@@ -87,6 +87,7 @@ ZK_HD void tom_neg(TomPt& r, const TomPt& p) {
   Warp::neg(r.y, p.y);
   copy_n<8>(r.z, p.z);
 }
+ZK_HD void pg_dbl_n(TomPt& p, int c) { war_dbl_n(p, c); }
 ZK_HD void pg_pre_neg(TomPre& q) { Warp::neg(q.y, q.y); }                       // -(x, y) = (x, -y)
 ZK_HD bool pg_is_identity(const TomPt& p) { return war_is_identity(p); }
 ZK_HD void pg_fixed_to_msm(TomPt&) {}   // commitments are already (X : Y : Z) of the curve itself
@@ -283,6 +284,9 @@ ZK_HD void tom_neg(TomPt& r, const TomPt& p) {
 enum : int { PGL = 9 };        // limbs of a proof-group coordinate
 using PGp = Tomp;              // coordinate field of the proof group
 using FpPG = FpTom;
+ZK_HD void pg_dbl_n(TomPt& p, int c) {
+  for (int i = 0; i < c; i++) tom_dbl(p, p);
+}
 ZK_HD void pg_pre_neg(TomPre& q) {   // -(x, y) = (-x, y); k = d x y changes sign too
   Tomp::neg(q.x, q.x);
   Tomp::neg(q.k, q.k);

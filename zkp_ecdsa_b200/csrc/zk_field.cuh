@@ -140,6 +140,14 @@ ZK_HD void csel_n(uint32_t* r, bool c, const uint32_t* a, const uint32_t* b) {  
 #include "zk_field_ptx.cuh"   // sm_100a multiplier kernels (device only)
 namespace zk {
 
+#if defined(__CUDA_ARCH__) && !defined(ZKA_NO_PTX_MUL)
+// non-inlined generic 8-limb Montgomery product (defined below Field): the war256 coordinate field has no special
+// multiplier; inlining the generic CIOS at each of the 13 products of a point addition bloats the kernels the way the
+// first inlined tomEdwards256 multiplier did (profiles/ncu_tomcommit_r1c_inlined_mul_w8.md)
+namespace ptx {
+template <class F> static __device__ __noinline__ V8 cios8_mul_fn(V8 a, V8 b);
+}
+#endif
 template <class A, class B> struct same_t { static constexpr bool value = false; };
 template <class A> struct same_t<A, A> { static constexpr bool value = true; };
 
@@ -216,7 +224,20 @@ struct Field {
     // product-scanning PTX kernels for the two hot moduli (zk_field_ptx.cuh)
     if (same_t<F, FpTom>::value) { ptx::tom_mul(r, a, b); return; }
     if (same_t<F, FpP256>::value) { ptx::p256_mul(r, a, b); return; }
+    if (same_t<F, FpWar>::value) {
+      ptx::V8 x, y;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+      const ptx::V8 z = ptx::cios8_mul_fn<FpWar>(x, y);
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = z.v[i];
+      return;
+    }
 #endif
+    mul_generic(r, a, b);
+  }
+  // generic CIOS (any modulus of N limbs)
+  ZK_HD static void mul_generic(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     uint32_t t[N + 2];
 #pragma unroll
     for (int i = 0; i < N + 2; i++) t[i] = 0;
@@ -395,6 +416,17 @@ struct Field {
     copy_n<N>(out, rr);
   }
 };
+
+#if defined(__CUDA_ARCH__) && !defined(ZKA_NO_PTX_MUL)
+namespace ptx {
+template <class F>
+static __device__ __noinline__ V8 cios8_mul_fn(V8 a, V8 b) {
+  V8 r;
+  Field<F>::mul_generic(r.v, a.v, b.v);
+  return r;
+}
+}  // namespace ptx
+#endif
 
 using P256p = Field<FpP256>;
 using P256n = Field<FnP256>;

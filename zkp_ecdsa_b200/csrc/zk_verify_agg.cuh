@@ -94,6 +94,7 @@ struct AggTomSrc {
   ZK_HD static void identity(Pt& p) { tom_set_identity(p); }
   ZK_HD static void add(Pt& r, const Pt& p, const Pt& q) { tom_add(r, p, q); }
   ZK_HD static void dbl(Pt& r, const Pt& p) { tom_dbl(r, p); }
+  ZK_HD static void dbl_n(Pt& p, int c) { pg_dbl_n(p, c); }
   ZK_HD static void ld_pt(Pt& p, const uint32_t* m) { bk_load(p, reinterpret_cast<const U4*>(m)); }
   ZK_HD static void st_pt(uint32_t* m, const Pt& p) { bk_store(reinterpret_cast<U4*>(m), p); }
 };
@@ -115,6 +116,7 @@ struct AggNistSrc {
   ZK_HD static void identity(Pt& p) { p256_set_identity(p); }
   ZK_HD static void add(Pt& r, const Pt& p, const Pt& q) { p256_add(r, p, q); }
   ZK_HD static void dbl(Pt& r, const Pt& p) { p256_dbl(r, p); }
+  ZK_HD static void dbl_n(Pt& p, int c) { p256_dbl_n(p, c); }
   ZK_HD static void ld_pt(Pt& p, const uint32_t* m) { p256_ld_proj(p, m); }
   ZK_HD static void st_pt(uint32_t* m, const Pt& p) { p256_st_proj(m, p); }
 };
@@ -280,7 +282,7 @@ struct AggLevelTask {
         Src::add(sb, sb, a);
       }
     }
-    for (int i = 0; i < dbl; i++) Src::dbl(tot, tot);
+    if (dbl) Src::dbl_n(tot, dbl);
     Src::add(sb, sb, tot);
     Src::st_pt(outA + (size_t)t * Src::PTW, run);
     Src::st_pt(outB + (size_t)t * Src::PTW, sb);
@@ -293,7 +295,7 @@ ZK_HD void agg_horner(typename Src::Pt& acc, const uint32_t* rootA, const uint32
   typename Src::Pt t, u;
   Src::identity(acc);
   for (int w = nwin - 1; w >= 0; w--) {
-    for (int i = 0; i < c; i++) Src::dbl(acc, acc);
+    Src::dbl_n(acc, c);
     Src::ld_pt(u, rootB + (size_t)w * Src::PTW);
     if (w != nwin - 1) {
       Src::ld_pt(t, rootA + (size_t)w * Src::PTW);
@@ -341,17 +343,17 @@ struct AggFixSumTask {
     st<8>(jr, sr);
   }
 };
-// P-256: sum_b (sR_b R_b + shN_b h) — R differs per proof, so the POINTS are summed (two levels)
+// P-256: sum_b (sR_b R_b + shN_b h) — R differs per proof, so the POINTS are summed: a tree of 32-way partial sums
 struct AggNistFixPartTask {
-  const uint32_t *ctl, *nfix;   // [B][24]
-  uint32_t* part;               // [groups][24]
-  int B;
+  const uint32_t *ctl, *in;     // [count][24]
+  uint32_t* part;               // [ceil(count / 32)][24]
+  int count;
   ZK_HD void operator()(int g) const {
     if (ctl[AGG_SKIP]) return;
     P256Pt acc, p;
     p256_set_identity(acc);
-    for (int i = g * 32; i < (g + 1) * 32 && i < B; i++) {
-      p256_ld_proj(p, nfix + (size_t)i * P256_PROJ_WORDS);
+    for (int i = g * 32; i < (g + 1) * 32 && i < count; i++) {
+      p256_ld_proj(p, in + (size_t)i * P256_PROJ_WORDS);
       p256_add(acc, acc, p);
     }
     p256_st_proj(part + (size_t)g * P256_PROJ_WORDS, acc);

@@ -1809,7 +1809,15 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
         launch(st, 1, AggFixSumTask{ctl, fpart, fjv, fjr, fgroups});
         launch(st, 1, TomCommitTask{fjv, fjr, c.tg_tab, c.th_tab, fproj, c.tom_w, c.tom_nwin});
         launch(st, ngroups, AggNistFixPartTask{ctl, c.nfix, npart, Bc});
-        launch(st, 33, AggFinalTask{ctl, tA, tB, fproj, tp.D.nwin, tp.D.c, nA, nB, npart, np.D.nwin, np.D.c, ngroups});
+        int nleft = ngroups;            // second level: at most Bc / 1024 partial sums reach the final thread
+        const uint32_t* nsum = npart;
+        if (nleft > 32) {
+          uint32_t* npart2 = A[45].get<uint32_t>((size_t)((nleft + 31) / 32) * P256_PROJ_WORDS);
+          launch(st, (nleft + 31) / 32, AggNistFixPartTask{ctl, npart, npart2, nleft});
+          nsum = npart2;
+          nleft = (nleft + 31) / 32;
+        }
+        launch(st, 33, AggFinalTask{ctl, tA, tB, fproj, tp.D.nwin, tp.D.c, nA, nB, nsum, np.D.nwin, np.D.c, nleft});
         c.agg_ctl = ctl;
       }
       {
