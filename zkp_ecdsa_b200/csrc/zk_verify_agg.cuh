@@ -18,6 +18,8 @@
 //   fail (some proof is wrong, or some proof was already rejected by the parsers): the per-proof kernels run
 //          exactly as before, so every verdict and status is the one the per-proof path gives.
 // The verdict of a VALID batch is unchanged; for an invalid proof the per-proof path decides, under the same tape.
+// tomEdwards256 has cofactor 4: a chunk in which some proof's points carry a small-order component also goes to the
+// per-proof path (AggTorsionTask), because such components of two proofs could cancel in the sum.
 #pragma once
 #include "zk_verify.cuh"
 
@@ -129,6 +131,54 @@ struct AggGateTask {
     if (c.status[b] != ZKA_OK || (c.mode == 0 && !c.gk_ok_len[b])) ctl[AGG_SKIP] = 1;
   }
 };
+
+#if !defined(ZKA_PG_WAR256)
+// A0b — tomEdwards256 has cofactor 4, and deserializePoint (edwards.ts:70-86) only checks the curve equation.  Points
+// with a small-order component make the reference's own verdict depend on its randomizers (a component of order 2
+// survives a relation iff its scalar is odd); two such proofs in one chunk could cancel each other's components in the
+// SUM although neither per-proof combination is the identity.  The aggregate verdict is therefore used only when no
+// proof of the chunk carries such a component:  with tau the projection onto E[4],  tau(sum_e s_e P_e) =
+// sum_e (s_e mod 4) tau(P_e) = tau(W_b)  for  W_b = sum_e (s_e mod 4) P_e  (fixed-base parts are multiples of g, h:
+// prime order), and  q W_b = (q mod 4) tau(W_b) = -tau(W_b)  (q = p256.p = 3 mod 4).  One thread per proof: ~n_b
+// mixed additions and 256 doublings; q = 2^256 - 2^224 + 2^192 + 2^96 - 1 costs four more additions.
+struct AggTorsionTask {
+  AggTomSrc src;
+  uint32_t* ctl;
+  ZK_HD void operator()(int b) const {
+    if (ctl[AGG_SKIP]) return;
+    TomPt a1, a2;                 // sum of the points with bit 0 / bit 1 of (s mod 4) set
+    tom_set_identity(a1);
+    tom_set_identity(a2);
+    for (int part = 0; part < 2; part++) {
+      const int cnt = part == 0 ? src.ET : src.ngk;
+      const int s0 = part == 0 ? b * src.ET : src.B * src.ET + b * src.ngk;
+      for (int e = 0; e < cnt; e++) {
+        const int s = s0 + e;
+        if (!src.used(s)) continue;
+        const uint32_t d = src.scalar(s)[0] & 3u;
+        if (d & 1u) src.accumulate(a1, s, false);
+        if (d & 2u) src.accumulate(a2, s, false);
+      }
+    }
+    TomPt w, t, r;
+    tom_dbl(a2, a2);
+    tom_add(w, a1, a2);           // W_b
+    t = w;
+    for (int i = 0; i < 96; i++) tom_dbl(t, t);
+    tom_neg(r, w);
+    tom_add(r, r, t);             // 2^96 W - W
+    for (int i = 96; i < 192; i++) tom_dbl(t, t);
+    tom_add(r, r, t);             // + 2^192 W
+    for (int i = 192; i < 224; i++) tom_dbl(t, t);
+    TomPt n;
+    tom_neg(n, t);
+    tom_add(r, r, n);             // - 2^224 W
+    for (int i = 224; i < 256; i++) tom_dbl(t, t);
+    tom_add(r, r, t);             // + 2^256 W
+    if (!pg_is_identity(r)) ctl[AGG_SKIP] = 1;
+  }
+};
+#endif
 
 // A1 — histogram of |digit| per window.  One thread per slot.
 template <class Src>

@@ -343,15 +343,16 @@ struct AggPlan {
   int levels;
   int lm[AGG_MAX_LEVELS];   // log2 fan-in of every level of the bucket reduction (sum = c - 1)
 };
-// window bits from a cost model: ceil(258/c) windows x (entries / warp efficiency + 2.3 x 2^(c-1) bucket additions); the
-// warp efficiency accounts for the spread of the bucket sizes inside a warp (Poisson: mean + ~2.2 sigma)
+// window bits from a cost model fitted to profiles/agg_window_sweep_r2i.md: ceil(258/c) windows x (entries / warp
+// efficiency + 3 x 2^(c-1) bucket-tree additions); the warp efficiency accounts for the spread of the bucket sizes inside
+// a warp (Poisson: about mean + sigma)
 AggPlan agg_plan(double entries, int c_forced) {
   int best = 4;
   double best_cost = 1e300;
   for (int c = 4; c <= 16; c++) {
     const double nb = (double)(1u << (c - 1)), load = entries / nb;
-    const double eff = load / (load + 2.2 * std::sqrt(load > 1.0 ? load : 1.0));
-    const double cost = std::ceil(258.0 / c) * (entries / (eff > 0.05 ? eff : 0.05) + 2.3 * nb);
+    const double eff = load / (load + std::sqrt(load > 1.0 ? load : 1.0));
+    const double cost = std::ceil(258.0 / c) * (entries / (eff > 0.05 ? eff : 0.05) + 3.0 * nb);
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   const int c = c_forced ? c_forced : best;
@@ -1667,41 +1668,73 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
     const uint32_t nchunks = (uint32_t)off.size() - 1;
     const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
     std::atomic<uint32_t> next_chunk((uint32_t)used);
+    const bool trace = getenv("ZKA_TRACE") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
     // every lane starts with chunk `li` and then claims chunks from a shared counter: copy-in, kernels and copy-out of a chunk are sequential on the
     // lane's stream; the copies of one lane overlap the kernels of the others
     auto run_lane = [&](int li) {
       Lane& ln = ctx->lane(li);
       Stream& st = ln.st;
       DevBuf* W = ln.w;
-      for (uint32_t k = (uint32_t)li; k < nchunks; k = next_chunk.fetch_add(1)) {
+      // the inputs of a lane's NEXT chunk travel on its copy-in stream (second set of staging buffers) while the current
+      // chunk computes; a chunk's kernels wait for its event only
+      struct VIn { const uint8_t* msg; const uint8_t* proofs; const uint32_t* plen; const uint8_t* tape; };
+      auto stage_chunk = [&](int slot, uint32_t kk) {
+        Stream& ci = ln.cs_in;
+        DevBuf* in = ln.in + 8 * slot;
+        const uint32_t b0 = off[kk];
+        const size_t Bc = off[kk + 1] - b0;
+        VIn v;
+        v.msg = msg_hash ? stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32) : nullptr;
+        if (is_device_ptr(proofs) || is_device_ptr(proof_len)) {
+          v.proofs = stage_in(ci, in[1], proofs + (size_t)b0 * proof_stride, Bc * proof_stride);
+        } else {
+          // host rows: only the bytes up to the longest proof of the chunk cross PCIe (rows are stride-padded;
+          // a length above the stride is rejected by VLayoutTask without reading the row)
+          size_t w = 0;
+          for (size_t i = 0; i < Bc; i++) w = std::max<size_t>(w, proof_len[b0 + i]);
+          w = std::min(proof_stride, (w + 15) & ~(size_t)15);
+          uint8_t* dp = in[1].get<uint8_t>(Bc * proof_stride);
+          copy_d2h_2d(ci, dp, proof_stride, proofs + (size_t)b0 * proof_stride, proof_stride, w, Bc);
+          v.proofs = dp;
+        }
+        v.plen = stage_in(ci, in[2], proof_len + b0, Bc);
+        v.tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
+        ev_record(ln.ev_small[slot], ci);
+        return v;
+      };
+      uint32_t k = (uint32_t)li;
+      if (k >= nchunks) return;
+      int slot = 0;
+      VIn cur = stage_chunk(slot, k);
+      for (;;) {
+      // claim the next chunk now and send its inputs on their way (the other slot's buffers were last read by the chunk
+      // before this one, which ended with a stream synchronisation)
+      const uint32_t kn = next_chunk.fetch_add(1);
+      VIn nxt{};
+      if (kn < nchunks) nxt = stage_chunk(slot ^ 1, kn);
+      ev_wait(st, ln.ev_small[slot]);
       const uint32_t b0 = off[k];
       const int Bc = (int)(off[k + 1] - b0);
+      const double t_begin = trace ? ms_now() : 0.0;
       VerifyCtx c;
       memset(&c, 0, sizeof(c));
       c.B = Bc; c.S = S; c.N = (int)N; c.n = n; c.K = K; c.mode = mode;
       c.q_ext = q_ext ? q_ext + (size_t)b0 * NP : nullptr;
       c.tom_w = ctx->tom_w; c.tom_nwin = ctx->tom_nwin;
-      c.msg_hash = msg_hash ? stage_in(st, ln.in[0], msg_hash + (size_t)b0 * 32, (size_t)Bc * 32) : nullptr;
-      if (is_device_ptr(proofs) || is_device_ptr(proof_len)) {
-        c.proofs = stage_in(st, ln.in[1], proofs + (size_t)b0 * proof_stride, (size_t)Bc * proof_stride);
-      } else {
-        // host rows: only the bytes up to the longest proof of the chunk cross PCIe (rows are stride-padded;
-        // a length above the stride is rejected by VLayoutTask without reading the row)
-        size_t w = 0;
-        for (int i = 0; i < Bc; i++) w = std::max<size_t>(w, proof_len[b0 + i]);
-        w = std::min(proof_stride, (w + 15) & ~(size_t)15);
-        uint8_t* dp = ln.in[1].get<uint8_t>((size_t)Bc * proof_stride);
-        copy_d2h_2d(st, dp, proof_stride, proofs + (size_t)b0 * proof_stride, proof_stride, w, (size_t)Bc);
-        c.proofs = dp;
-      }
+      c.msg_hash = cur.msg;
+      c.proofs = cur.proofs;
       c.proof_stride = proof_stride;
-      c.proof_len = stage_in(st, ln.in[2], proof_len + b0, (size_t)Bc);
-      c.tape = stage_in(st, ln.in[4], tape + (size_t)b0 * tape_stride, (size_t)Bc * tape_stride);
+      c.proof_len = cur.plen;
+      c.tape = cur.tape;
       c.tape_stride = tape_stride;
       c.ring_m = ring_m;
       c.g_tab8 = ctx->g8.tab; c.h_tab8 = P->h8.tab; c.h_w = P->h_w;
       c.tg_tab = ctx->tg.tab; c.th_tab = P->th.tab;
       c.tg_bytes = (const uint8_t*)ctx->tg_bytes.p;
+      double t_in = 0.0;
+      if (trace) { sync(st); t_in = ms_now(); }
       const size_t ns = (size_t)Bc * K;
       const int ET = c.ent_tom(), EN = c.ent_nist(), SG = c.segs();
       const int ngk = 4 * n + 1;
@@ -1792,6 +1825,9 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
         launch(st, Bc, AggGateTask{c, ctl});
         const AggTomSrc tsrc{c.ent_scalar, c.ent_pre, c.ent_cnt, c.gk_scalar, c.gk_pre, Bc, ET, K, ngk};
         const AggNistSrc nsrc{c.nent_scalar, c.nent_aff, c.nent_skip, Bc, EN};
+#if !defined(ZKA_PG_WAR256)
+        launch(st, Bc, AggTorsionTask{tsrc, ctl});   // cofactor 4: no small-order components, or the per-proof path decides
+#endif
         const AggPlan tp = agg_plan((double)Bc * (0.5 * K * V_ENT_PER_SAMPLE + 2 + ngk), ctx->agg_c);
         const AggPlan np = agg_plan((double)Bc * EN, 0);
         ctx->agg_c_last = tp.D.c;
@@ -1838,13 +1874,22 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
       if (!is_device_ptr(status)) copy_d2h(st, status + b0, c.status, (size_t)Bc * 4);
       uint32_t hctl[AGG_CTL_WORDS] = {0, 0, 0, 0};
       if (ctl) copy_d2h(st, hctl, ctl, sizeof(hctl));
+      const double t_enq = trace ? ms_now() : 0.0;
       sync(st);
+      if (trace)
+        fprintf(stderr, "VTRACE lane %d chunk %u rows %d begin %.2f inputs_on_device %.2f enqueued %.2f done %.2f\n", li, k, Bc, t_begin, t_in,
+                t_enq, ms_now());
       if (ctl) {
         std::lock_guard<std::mutex> g(ctx->stat_mu);
         if (hctl[AGG_TOM_PASS] && hctl[AGG_NIST_PASS]) ctx->agg_pass++;
         else ctx->agg_fail++;
       }
+      if (kn >= nchunks) break;
+      k = kn;
+      cur = nxt;
+      slot ^= 1;
     }
+    sync(ln.cs_in);
     };
     run_lanes(ctx, used, run_lane);
     return 0;
