@@ -23,6 +23,7 @@ def _pad(rows, width=None):
 
 
 def check_verify_exp(L, sec=12, K=12, with_q=False, seed=7, tampers=3):
+    tom = common.pg(L)   # the library's ProofGroup (tomEdwards256 or war256)
     P, po = common.make_params(L, seed, sec)
     d = synth.Drbg(seed, 'subexp')
     n_ord = p256.order
@@ -84,6 +85,7 @@ def check_verify_exp(L, sec=12, K=12, with_q=False, seed=7, tampers=3):
 
 
 def check_verify_membership(L, ring_vals, index, seed=9, tampers=3):
+    tom = common.pg(L)   # the library's ProofGroup (tomEdwards256 or war256)
     P, po = common.make_params(L, seed, 8)
     params = po.ProofGroup
     ptape = Tape(synth.random_tape(1, 32 * 200, seed=seed + 1)[0].tobytes())
@@ -157,6 +159,7 @@ def test_subproof_verifiers_on_gpu(gpu_engine):
 
 def check_verify_small(L, kind, seed=31, tampers=3):
     """verifyEquality / verifyMult / verifyPointAdd alone against the oracle, valid + tampered, same randomizers."""
+    tom = common.pg(L)   # the library's ProofGroup (tomEdwards256 or war256)
     P, po = common.make_params(L, seed, 8)
     params = po.ProofGroup
     q = tom.order
@@ -199,7 +202,7 @@ def check_verify_small(L, kind, seed=31, tampers=3):
     points = np.repeat(np.frombuffer(pbytes, np.uint8)[None, :], T, axis=0).copy()
     # one more case: a wrong statement (first input replaced by another valid commitment) with the valid proof
     other = params.commit(d.below(q), ptape).p.to_bytes()
-    points = np.concatenate([points, np.frombuffer(other + pbytes[67:], np.uint8)[None, :]], axis=0)
+    points = np.concatenate([points, np.frombuffer(other + pbytes[getattr(L, 'wp', 67):], np.uint8)[None, :]], axis=0)
     proofs = np.concatenate([proofs, proofs[:1]], axis=0)
     T += 1
     tape = synth.random_tape(T, 32 * draws, seed=seed + 2)
@@ -231,6 +234,7 @@ def test_verify_small_subproofs_on_gpu(gpu_engine, kind):
 def check_prove_exp(L, sec=10, with_q=False, seed=51, B=2):
     """zka_prove_exp_batch == oracle proveExp byte for byte (arbitrary base, optional Q), its output verifies with
     zka_verify_exp_batch, and a false statement reports "Points don't add up!"."""
+    tom = common.pg(L)   # the library's ProofGroup (tomEdwards256 or war256)
     P, po = common.make_params(L, seed, sec)
     d = synth.Drbg(seed, 'provexp')
     n_ord, q = p256.order, tom.order
@@ -279,6 +283,7 @@ def check_prove_exp(L, sec=10, with_q=False, seed=51, B=2):
 
 
 def check_prove_membership(L, ring_vals, indices, seed=61):
+    tom = common.pg(L)   # the library's ProofGroup (tomEdwards256 or war256)
     P, po = common.make_params(L, seed, 8)
     params = po.ProofGroup
     N = len(ring_vals)
@@ -328,6 +333,7 @@ def test_subproof_provers_on_gpu(gpu_engine):
 
 def check_prove_small(L, kind, seed=81, B=3):
     """zka_prove_{equality,mult,pointadd}_batch == the oracle's proof bytes; outputs verify with the stand-alone verifier."""
+    tom = common.pg(L)   # the library's ProofGroup (tomEdwards256 or war256)
     P, po = common.make_params(L, seed, 8)
     params = po.ProofGroup
     q = tom.order

@@ -53,3 +53,25 @@ def test_war_on_gpu(gpu_engine_war):
     common.check_prove_few_keys(L, B=256, N=64, signers=2, seed=65, sec_level=16, spots=(0, 255))
     import test_verify_aggregate as tva
     tva.check_aggregate(L, B=40, N=17, seed=66, cs=(0, 9, 13))
+    import test_subproofs as ts
+    ts.check_verify_exp(L, sec=16, K=7, with_q=True, seed=67)
+    ts.check_verify_membership(L, list(range(100, 100 + 37)), 20, seed=68)
+    for kind in ('equality', 'mult', 'pointadd'):
+        ts.check_verify_small(L, kind, seed=69, tampers=4)
+        ts.check_prove_small(L, kind, seed=70)
+    ts.check_prove_exp(L, sec=12, with_q=False, seed=77, B=3)
+
+
+def test_war_subproofs(hostsim_war):
+    """The stand-alone sub-proof entry points of the war256 build: verifyExp (with / without Q), verifyMembership,
+    verify / prove Equality, Mult, PointAdd, proveExp, proveMembership — against the oracle run on war256."""
+    import test_subproofs as ts
+    L = hostsim_war
+    ts.check_verify_exp(L, sec=12, K=12, with_q=False, seed=71, tampers=2)
+    ts.check_verify_exp(L, sec=10, K=6, with_q=True, seed=72, tampers=2)
+    ts.check_verify_membership(L, [3, 5, 7, 11, 13], 3, seed=73)
+    for kind in ('equality', 'mult', 'pointadd'):
+        ts.check_verify_small(L, kind, seed=74, tampers=2)
+        ts.check_prove_small(L, kind)
+    ts.check_prove_exp(L, sec=10, with_q=True, seed=75, B=2)
+    ts.check_prove_membership(L, [3, 5, 7, 11, 13, 17], [0, 5], seed=76)

@@ -139,26 +139,55 @@ struct AggGateTask {
 // SUM although neither per-proof combination is the identity.  The aggregate verdict is therefore used only when no
 // proof of the chunk carries such a component:  with tau the projection onto E[4],  tau(sum_e s_e P_e) =
 // sum_e (s_e mod 4) tau(P_e) = tau(W_b)  for  W_b = sum_e (s_e mod 4) P_e  (fixed-base parts are multiples of g, h:
-// prime order), and  q W_b = (q mod 4) tau(W_b) = -tau(W_b)  (q = p256.p = 3 mod 4).  One thread per proof: ~n_b
-// mixed additions and 256 doublings; q = 2^256 - 2^224 + 2^192 + 2^96 - 1 costs four more additions.
-struct AggTorsionTask {
+// prime order), and  q W_b = (q mod 4) tau(W_b) = -tau(W_b)  (q = p256.p = 3 mod 4).  ~n_b mixed additions and 256
+// doublings per proof; q = 2^256 - 2^224 + 2^192 + 2^96 - 1 costs four more additions.
+// Two steps: partial sums per (proof, sampled repetition) — the last part takes keyXcom, keyYcom and the GK points —
+// then one thread per proof for the 2 (K + 1) additions and the doubling chain.
+struct AggTorsionPartTask {
   AggTomSrc src;
-  uint32_t* ctl;
-  ZK_HD void operator()(int b) const {
+  const uint32_t* ctl;
+  uint32_t* part;    // [B][K + 1][2][PG_EXT_WORDS]: sums of the points with bit 0 / bit 1 of (s mod 4) set
+  ZK_HD void add_range(TomPt& a1, TomPt& a2, int s0, int cnt) const {
+    for (int e = 0; e < cnt; e++) {
+      const int s = s0 + e;
+      if (!src.used(s)) continue;
+      const uint32_t d = src.scalar(s)[0] & 3u;
+      if (d & 1u) src.accumulate(a1, s, false);
+      if (d & 2u) src.accumulate(a2, s, false);
+    }
+  }
+  ZK_HD void operator()(int t) const {
     if (ctl[AGG_SKIP]) return;
-    TomPt a1, a2;                 // sum of the points with bit 0 / bit 1 of (s mod 4) set
+    const int b = t / (src.K + 1), j = t % (src.K + 1);
+    TomPt a1, a2;
     tom_set_identity(a1);
     tom_set_identity(a2);
-    for (int part = 0; part < 2; part++) {
-      const int cnt = part == 0 ? src.ET : src.ngk;
-      const int s0 = part == 0 ? b * src.ET : src.B * src.ET + b * src.ngk;
-      for (int e = 0; e < cnt; e++) {
-        const int s = s0 + e;
-        if (!src.used(s)) continue;
-        const uint32_t d = src.scalar(s)[0] & 3u;
-        if (d & 1u) src.accumulate(a1, s, false);
-        if (d & 2u) src.accumulate(a2, s, false);
-      }
+    if (j < src.K) {
+      add_range(a1, a2, b * src.ET + j * V_ENT_PER_SAMPLE, V_ENT_PER_SAMPLE);
+    } else {
+      add_range(a1, a2, b * src.ET + src.K * V_ENT_PER_SAMPLE, src.ET - src.K * V_ENT_PER_SAMPLE);
+      add_range(a1, a2, src.B * src.ET + b * src.ngk, src.ngk);
+    }
+    uint32_t* o = part + (size_t)t * 2 * PG_EXT_WORDS;
+    bk_store(reinterpret_cast<U4*>(o), a1);
+    bk_store(reinterpret_cast<U4*>(o + PG_EXT_WORDS), a2);
+  }
+};
+struct AggTorsionTask {
+  const uint32_t* part;
+  uint32_t* ctl;
+  int K;
+  ZK_HD void operator()(int b) const {
+    if (ctl[AGG_SKIP]) return;
+    TomPt a1, a2, p;
+    tom_set_identity(a1);
+    tom_set_identity(a2);
+    for (int j = 0; j <= K; j++) {
+      const uint32_t* o = part + ((size_t)b * (K + 1) + j) * 2 * PG_EXT_WORDS;
+      bk_load(p, reinterpret_cast<const U4*>(o));
+      tom_add(a1, a1, p);
+      bk_load(p, reinterpret_cast<const U4*>(o + PG_EXT_WORDS));
+      tom_add(a2, a2, p);
     }
     TomPt w, t, r;
     tom_dbl(a2, a2);

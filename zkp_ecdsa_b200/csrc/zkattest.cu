@@ -1826,7 +1826,11 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
         const AggTomSrc tsrc{c.ent_scalar, c.ent_pre, c.ent_cnt, c.gk_scalar, c.gk_pre, Bc, ET, K, ngk};
         const AggNistSrc nsrc{c.nent_scalar, c.nent_aff, c.nent_skip, Bc, EN};
 #if !defined(ZKA_PG_WAR256)
-        launch(st, Bc, AggTorsionTask{tsrc, ctl});   // cofactor 4: no small-order components, or the per-proof path decides
+        {   // cofactor 4: no small-order components, or the per-proof path decides
+          uint32_t* tpart = A[46].get<uint32_t>((size_t)Bc * (K + 1) * 2 * PG_EXT_WORDS);
+          launch(st, (long long)Bc * (K + 1), AggTorsionPartTask{tsrc, ctl, tpart});
+          launch(st, Bc, AggTorsionTask{tpart, ctl, K});
+        }
 #endif
         const AggPlan tp = agg_plan((double)Bc * (0.5 * K * V_ENT_PER_SAMPLE + 2 + ngk), ctx->agg_c);
         const AggPlan np = agg_plan((double)Bc * EN, 0);
