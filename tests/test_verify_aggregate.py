@@ -60,3 +60,70 @@ def test_aggregate_check_hostsim(hostsim):
 @pytest.mark.gpu
 def test_aggregate_check_on_gpu(gpu_engine):
     check_aggregate(gpu_engine.lib, B=40, N=17, seed=33, cs=(0, 9, 13))
+
+
+def check_small_order_components(L, B=6, N=5, seed=91, sec_level=20, trials=8):
+    """tomEdwards256 has cofactor 4 and deserializePoint only checks the curve equation.  Proofs whose A_1 points of pi_x
+    carry the point of order 2 (added BEFORE the Fiat-Shamir hash, so everything else is consistent) are accepted by the
+    reference exactly when an even number of the affected relations got an odd randomizer.  Two rejected proofs of one
+    chunk would cancel in the chunk-wide sum — the torsion guard must send such a chunk to the per-proof path, whose
+    verdicts are the oracle's under the same tape."""
+    from oracle import commit as OC
+    from oracle import exp as OE
+    from oracle.curves import hash_points, tomEdwards256 as tom
+    from oracle.big import rnd
+    assert L.group == 'tomEdwards256'
+    P, po = common.make_params(L, seed, sec_level)
+    T2 = tom.deserialize_point(b'\x04' + (0).to_bytes(33, 'big') + (tom.p - 1).to_bytes(33, 'big'))     # (0, -1): order 2
+    assert T2.add(T2).is_identity() and not T2.is_identity()
+
+    def prove_equality_t2(params, x, C1, C2, tape):      # equality.ts:60-78 with A_1 + T2
+        k = rnd(params.c.order, tape)
+        A1 = params.commit(k, tape)
+        A2 = params.commit(k, tape)
+        A1p = A1.p.add(T2)
+        c = hash_points([C1.p, C2.p, A1p, A2.p])
+        cc, xx, kk = params.c.new_scalar(c), params.c.new_scalar(x), params.c.new_scalar(k)
+        return OC.EqualityProof(A1p, A2.p, kk.sub(cc.mul(xx)), A1.r.sub(cc.mul(C1.r)), A2.r.sub(cc.mul(C2.r)))
+    wl = synth.Workload(B=B, N=N, seed=seed)
+    tape = synth.random_tape(B, L.prove_tape_len(N, sec_level), seed=seed + 100)
+    orig = OE.prove_equality
+    OE.prove_equality = prove_equality_t2
+    try:
+        rows = [common.flat.ser_proof(common.oracle_proof(po, wl, tape, b)[0]) for b in range(B)]
+    finally:
+        OE.prove_equality = orig
+    ps = L.proof_max_len(N, sec_level)
+    proofs = np.zeros((B, ps), np.uint8)
+    plen = np.zeros(B, np.uint32)
+    for b, r in enumerate(rows):
+        proofs[b, :len(r)] = np.frombuffer(r, np.uint8)
+        plen[b] = len(r)
+    vts = L.verify_tape_len(N, sec_level)
+    ring_ints = wl.ring_ints()
+    dangerous = 0
+    try:
+        for t in range(trials):
+            vt = VT.random_verify_tape(B, vts, N, sec_level, seed=seed + 7 + t)
+            exp = [common.oracle_verdict(po, wl.msg_hash[b].tobytes(), ring_ints, rows[b], vt[b].tobytes(), N, sec_level) for b in range(B)]
+            assert all(e in (True, False) for e in exp), exp
+            p0 = L.stat('agg_pass')
+            ok, st = common.run_verify(L, P, wl.msg_hash, wl.ring, proofs, plen, vt)
+            assert not st.any() and [bool(v) for v in ok] == exp, (t, list(ok), exp)
+            rejected = exp.count(False)
+            if rejected:
+                assert L.stat('agg_pass') == p0          # never decided by the aggregate
+            if rejected >= 2 and rejected % 2 == 0:
+                dangerous += 1                           # the components would have cancelled in the sum
+        assert dangerous >= 1, 'no trial had an even number (>= 2) of rejected proofs: pick other seeds'
+    finally:
+        L.params_destroy(P)
+
+
+def test_small_order_components_hostsim(hostsim):
+    check_small_order_components(hostsim)
+
+
+@pytest.mark.gpu
+def test_small_order_components_on_gpu(gpu_engine):
+    check_small_order_components(gpu_engine.lib)      # same inputs as on the host simulator (3 of the 8 trials cancel)
