@@ -18,7 +18,7 @@ def _batch(L, B, N, seed, sec_level=80):
     return P, wl, proofs, plen, vt
 
 
-def check_aggregate(L, B=5, N=6, seed=31, cs=(0, 4, 7, 11)):
+def check_aggregate(L, B=5, N=6, seed=31, cs=(0, 4, 7, 11), ks=(33,)):
     P, wl, proofs, plen, vt = _batch(L, B, N, seed)
     try:
         for c in cs:
@@ -28,6 +28,15 @@ def check_aggregate(L, B=5, N=6, seed=31, cs=(0, 4, 7, 11)):
             ok, st = common.run_verify(L, P, wl.msg_hash, wl.ring, proofs, plen, vt)
             assert list(ok) == [1] * B and not st.any(), (c, ok, st)
             assert L.stat('agg_pass') > p0 and L.stat('agg_fail') == f0, c      # decided by the aggregate
+        # other sample counts (verifyExp's secparam): 33 and all 80 repetitions = 2 / 4 MSM segments per proof
+        for K in ks:
+            vtk = VT.random_verify_tape(B, L.verify_tape_len_ex(N, 80, K), N, 80, seed=seed + K)
+            okk = np.zeros(B, np.uint8)
+            stk = np.zeros(B, np.int32)
+            p0, f0 = L.stat('agg_pass'), L.stat('agg_fail')
+            L.verify_batch_ex(P, B, wl.msg_hash, wl.ring, N, proofs, proofs.shape[1], plen, vtk, vtk.shape[1], okk, stk, K)
+            assert list(okk) == [1] * B and not stk.any(), (K, okk, stk)
+            assert L.stat('agg_pass') > p0 and L.stat('agg_fail') == f0, K
         # one wrong proof (a flipped bit in the last GK response scalar, which every verification reads): the chunk
         # goes to the per-proof path
         bad = proofs.copy()
@@ -59,7 +68,7 @@ def test_aggregate_check_hostsim(hostsim):
 
 @pytest.mark.gpu
 def test_aggregate_check_on_gpu(gpu_engine):
-    check_aggregate(gpu_engine.lib, B=40, N=17, seed=33, cs=(0, 9, 13))
+    check_aggregate(gpu_engine.lib, B=40, N=17, seed=33, cs=(0, 9, 13), ks=(33, 80))
 
 
 def check_small_order_components(L, B=6, N=5, seed=91, sec_level=20, trials=8):
