@@ -15,7 +15,8 @@ def main(path):
     for r in csv.reader(l for l in open(path) if l.startswith('"')):
         if r[0] == 'ID':
             continue
-        rows[int(r[0])]['name'] = re.sub(r'void zk_task_kernel<(?:zk::)?(\w+)>.*', r'\1', r[4])
+        m = re.match(r'(?:void )?zk_task_kernel<(.*)>\(int', r[4])
+        rows[int(r[0])]['name'] = (m.group(1) if m else r[4]).replace('zk::', '')
         rows[int(r[0])][r[12]] = float(r[14].replace(',', ''))
     agg = defaultdict(lambda: defaultdict(float))
     for r in rows.values():

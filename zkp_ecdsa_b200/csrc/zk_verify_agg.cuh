@@ -143,34 +143,31 @@ struct AggGateTask {
 // doublings per proof; q = 2^256 - 2^224 + 2^192 + 2^96 - 1 costs four more additions.
 // Two steps: partial sums per (proof, sampled repetition) — the last part takes keyXcom, keyYcom and the GK points —
 // then one thread per proof for the 2 (K + 1) additions and the doubling chain.
-struct AggTorsionPartTask {
+struct AggTorsionPartTask {   // one thread per (proof, part, bit of s mod 4): ONE accumulator per thread (two spilled)
   AggTomSrc src;
   const uint32_t* ctl;
   uint32_t* part;    // [B][K + 1][2][PG_EXT_WORDS]: sums of the points with bit 0 / bit 1 of (s mod 4) set
-  ZK_HD void add_range(TomPt& a1, TomPt& a2, int s0, int cnt) const {
+  ZK_HD void add_range(TomPt& a, uint32_t mask, int s0, int cnt) const {
     for (int e = 0; e < cnt; e++) {
       const int s = s0 + e;
       if (!src.used(s)) continue;
-      const uint32_t d = src.scalar(s)[0] & 3u;
-      if (d & 1u) src.accumulate(a1, s, false);
-      if (d & 2u) src.accumulate(a2, s, false);
+      if (src.scalar(s)[0] & mask) src.accumulate(a, s, false);
     }
   }
   ZK_HD void operator()(int t) const {
     if (ctl[AGG_SKIP]) return;
-    const int b = t / (src.K + 1), j = t % (src.K + 1);
-    TomPt a1, a2;
-    tom_set_identity(a1);
-    tom_set_identity(a2);
+    const int bit = t & 1, bj = t >> 1;
+    const int b = bj / (src.K + 1), j = bj % (src.K + 1);
+    const uint32_t mask = 1u << bit;
+    TomPt a;
+    tom_set_identity(a);
     if (j < src.K) {
-      add_range(a1, a2, b * src.ET + j * V_ENT_PER_SAMPLE, V_ENT_PER_SAMPLE);
+      add_range(a, mask, b * src.ET + j * V_ENT_PER_SAMPLE, V_ENT_PER_SAMPLE);
     } else {
-      add_range(a1, a2, b * src.ET + src.K * V_ENT_PER_SAMPLE, src.ET - src.K * V_ENT_PER_SAMPLE);
-      add_range(a1, a2, src.B * src.ET + b * src.ngk, src.ngk);
+      add_range(a, mask, b * src.ET + src.K * V_ENT_PER_SAMPLE, src.ET - src.K * V_ENT_PER_SAMPLE);
+      add_range(a, mask, src.B * src.ET + b * src.ngk, src.ngk);
     }
-    uint32_t* o = part + (size_t)t * 2 * PG_EXT_WORDS;
-    bk_store(reinterpret_cast<U4*>(o), a1);
-    bk_store(reinterpret_cast<U4*>(o + PG_EXT_WORDS), a2);
+    bk_store(reinterpret_cast<U4*>(part + (size_t)t * PG_EXT_WORDS), a);
   }
 };
 struct AggTorsionTask {

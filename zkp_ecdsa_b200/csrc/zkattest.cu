@@ -1664,7 +1664,13 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
     const uint32_t* ring_m = (const uint32_t*)ctx->ring_m.p;
     const int lanes = ctx->nlanes;
     const bool all_dev = is_device_ptr(proofs) && is_device_ptr(tape);
-    const std::vector<uint32_t> off = chunk_schedule(B, (uint32_t)std::min(ctx->chunk, all_dev ? 4096 : std::min(4096, ctx->host_chunk)), lanes, !all_dev);
+    // host buffers: two equal chunks per lane (the next chunk's inputs travel while the current one computes).  A verify
+    // chunk has ~15 ms of latency-bound stages whatever its size (doubling chains, hashes, the tails of the aggregate
+    // check), so the tapered schedule of the prover — small first and last chunks — only adds rounds here
+    // (gpurun_out/bench_r2l_trace.err: 7 chunks of 512..1728 proofs took 18..28 ms each).
+    uint32_t vchunk = (uint32_t)std::min(ctx->chunk, 4096);
+    if (!all_dev) vchunk = std::min<uint32_t>(vchunk, std::max<uint32_t>(256, (B / (2u * (uint32_t)lanes) + 31) & ~31u));
+    const std::vector<uint32_t> off = chunk_schedule(B, vchunk, lanes, false);
     const uint32_t nchunks = (uint32_t)off.size() - 1;
     const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
     std::atomic<uint32_t> next_chunk((uint32_t)used);
@@ -1828,7 +1834,7 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
 #if !defined(ZKA_PG_WAR256)
         {   // cofactor 4: no small-order components, or the per-proof path decides
           uint32_t* tpart = A[46].get<uint32_t>((size_t)Bc * (K + 1) * 2 * PG_EXT_WORDS);
-          launch(st, (long long)Bc * (K + 1), AggTorsionPartTask{tsrc, ctl, tpart});
+          launch(st, (long long)Bc * (K + 1) * 2, AggTorsionPartTask{tsrc, ctl, tpart});
           launch(st, Bc, AggTorsionTask{tpart, ctl, K});
         }
 #endif

@@ -145,6 +145,9 @@ class ProofGather:
         out = torch.zeros((self.rows, self.stride), dtype=torch.uint8, device=self.dev)
         offs = torch.zeros(self.rows + 1, dtype=torch.int64, device=self.dev)
         lens = self.lens_all[g][r * self.rows:(r + 1) * self.rows].contiguous()
+        if self.cuda:
+            # `out` / `offs` were zero-filled on torch's current stream; the library runs on its own non-blocking stream
+            torch.cuda.current_stream().synchronize()
         self.lib.proofs_unpack(self.rows, self.recv[g][r * self.cap:].data_ptr(), self.cap, lens.data_ptr(), out.data_ptr(),
                                self.stride, offs.data_ptr(), 0)
         return out, lens
