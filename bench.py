@@ -41,6 +41,9 @@ SEC_LEVEL = 80
 # DRAM bytes per table lookup of the commitment kernels, from `ncu --set full` captures (profiles/):
 # window bits -> (dram read + write bytes per launch - algorithmic bytes) / lookups
 NCU_DRAM_BYTES_PER_LOOKUP = {16: 78.0, 22: 118.0}
+# DRAM bytes per (entry, window) of the aggregate verify MSM (profiles/pipes_r2m_config2.md: 5.75 GB over two launches of
+# 4096 proofs x ~373 entries x 18 windows); the algorithmic figure is a 128-byte entry + a 4-byte index
+NCU_DRAM_BYTES_PER_AGG_ENTRY_WINDOW = 105.0
 MODMUL_PER_MADD = 7      # a = -1 image curve, mixed addition with (v-w, v+w, 2 d2 w v) entries (zk_curves.cuh)
 MAC_PER_TOM_MODMUL = 117   # EXECUTED IMAD.WIDE per 258-bit product: 9 rows x (9 + 4) (zk_field_ptx.cuh tom_row;
                            # profiles/sass_tom_mul_r2.txt); the generic CIOS needs 171
@@ -366,7 +369,19 @@ def run_ours(args):
     stat_h = torch.zeros(B, dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     lib_stream = torch.cuda.ExternalStream(L.stream_ptr(), device=dev)
-    gather = sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, groups=args.gather_groups) if world > 1 else None
+    # N > 1: the all-gather of the proof bytes overlaps proving.  Default: ONE prove call per step; a second host thread
+    # queues the gather of every chunk the library reports complete (zka_set_progress), in chunk order.  --gather-groups G
+    # > 0 instead proves G sub-batches by separate calls (each call ends with a full synchronisation of its lanes: two
+    # groups cost 6 %, four 20 % of the 2-GPU throughput, profiles/README.md)
+    gather = None
+    if world > 1:
+        if args.gather_groups > 0:
+            gather = sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, groups=args.gather_groups)
+        else:
+            if args.gather_chunk > 0:
+                L.set_option('chunk', args.gather_chunk)     # more chunks than lanes: the early ones overlap the later ones
+            off = L.chunk_schedule(B, host_buffers=False)
+            gather = sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, ranges=list(zip(off[:-1], off[1:])))
 
     def prove_dev(b0, b1):
         L.prove_batch(params.handle, b1 - b0, d['msg'][b0:].data_ptr(), d['sig'][b0:].data_ptr(), d['pk'][b0:].data_ptr(),
@@ -379,6 +394,9 @@ def run_ours(args):
             return
         # N > 1: the rank's batch is proved group by group; the NCCL all-gather of a finished group's packed
         # proof bytes runs on the communication stream while the next group is being proved
+        if args.gather_groups <= 0:
+            gather.prove_overlapped(lambda: prove_dev(0, B), proofs_d, plen_d)
+            return
         gather.begin()
         for (b0, b1) in gather.ranges:
             prove_dev(b0, b1)
@@ -611,6 +629,11 @@ def run_ours(args):
         vroof = kernel_roofline(vprof, 'MsmTomWindowBothTask', 2, msm_macs / 2, (ent_w + ent_g) / 2 * (128 + 32) / 43 + 144,
                                 f'sorted-bucket Pippenger, signed 6-bit windows: ~{ent_w:.0f} + {ent_g} points per proof, '
                                 '8 modmul per bucket addition + 2 x 32 x 9 for the running sums, x 117 MAC')
+    if vroof and agg_on:
+        vroof['traffic'] = entries * nwin * NCU_DRAM_BYTES_PER_AGG_ENTRY_WINDOW / vroof['launches_per_step']
+        vroof['traffic_unit'] = 'bytes/launch'
+        vroof['traffic_note'] = ('scaled from the ncu capture in profiles/pipes_r2m_config2.md; algorithmic: 132 B per (entry, window) — '
+                                 'L2 serves a fifth of the entry reads')
     if vroof:
         vroof['share_of_step'] = next(e['ms'] for k, e in vprof.items() if short(k) == (agg_name if agg_on else 'MsmTomWindowBothTask')) / (ms_vprof_step * 2)
         if agg_on:
@@ -693,7 +716,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
                     help='default: config2 on one GPU, config3 (8192 per GPU x ring 1024) under torchrun')
-    ap.add_argument('--gather-groups', type=int, default=4, help='N>1: groups per rank whose all-gather overlaps the next group')
+    ap.add_argument('--gather-groups', type=int, default=0,
+                    help='N>1: 0 = one prove call per step, finished chunks are gathered while later ones are proved; '
+                         'G > 0 = G sub-batches proved by separate calls')
+    ap.add_argument('--gather-chunk', type=int, default=1408,
+                    help='N>1 with --gather-groups 0: largest chunk of the prove call (two chunks per lane at 8192 proofs, 3 lanes)')
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--ring', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')

@@ -245,6 +245,14 @@ int zka_set_option(zka_ctx* ctx, const char* key, long value);
  * ZKA_AGG=0 disables the aggregate check, ZKA_AGG_C=4..16 fixes its window bits. */
 long long zka_stat(zka_ctx* ctx, const char* key);
 
+/* Progress of a running zka_prove_batch (another host thread may watch it): the call cuts its batch into the chunks of
+ * zka_chunk_schedule (off[0..n], deterministic for a given B, kind of buffers and knobs — the same on every rank); flags[k]
+ * becomes 1 (written by a CUDA host callback) when the proofs of rows [off[k], off[k+1]) are complete in the caller's
+ * DEVICE buffers.  bench.py uses it to queue the all-gather of finished chunks, in chunk order, while later chunks are
+ * still being proved.  zka_set_progress(ctx, NULL, 0) switches it off. */
+int zka_set_progress(zka_ctx* ctx, volatile uint32_t* flags, uint32_t cap);
+int zka_chunk_schedule(zka_ctx* ctx, uint32_t B, int host_buffers, uint32_t* off /* cap entries */, uint32_t cap);
+
 /* ---- multi-GPU helpers: a rank's proofs as ONE contiguous block for the NCCL all-gather.
  * Proof b starts at offsets[b] = sum_{i<b} align16(proof_len[i]); offsets[B] is the block length (the caller
  * checks offsets[B] <= cap; pieces that would cross `cap` are not written).  Device pointers only.  With a

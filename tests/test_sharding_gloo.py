@@ -83,6 +83,33 @@ def _worker(rank, world, port, q):
             for k in range(b1 - b0):
                 j = r * per + b0 + k
                 assert int(lens[k]) == int(alll[j]) and torch.equal(rows[k, :int(lens[k])], allp[j, :int(lens[k])])
+    # one prove call per rank, finished chunks gathered while later ones are proved (zka_set_progress; bench.py's default
+    # N > 1 path): one-proof chunks here, so that there is more than one
+    import common
+    from zkp_ecdsa_b200 import synth
+    lib.set_option('chunk', 1)
+    lib.set_option('host_chunk', 1)
+    off = lib.chunk_schedule(hi - lo, host_buffers=True)
+    assert off[0] == 0 and off[-1] == hi - lo and len(off) == hi - lo + 1
+    P, _ = common.make_params(lib, seed=9, sec_level=SEC)
+    wl = synth.Workload(B=B, N=N, seed=9)
+    tape = np.ascontiguousarray(synth.random_tape(B, lib.prove_tape_len(N, SEC), seed=10)[lo:hi])
+    out = np.zeros((hi - lo, stride16), np.uint8)
+    olen = np.zeros(hi - lo, np.uint32)
+    ost = np.zeros(hi - lo, np.int32)
+    tp, tl = torch.from_numpy(out), torch.from_numpy(olen.view(np.int32))
+
+    def prove_again():
+        lib.prove_batch(P, hi - lo, np.ascontiguousarray(wl.msg_hash[lo:hi]), np.ascontiguousarray(wl.sig[lo:hi]),
+                        np.ascontiguousarray(wl.pk[lo:hi]), np.ascontiguousarray(wl.which[lo:hi]), wl.ring, N, tape, tape.shape[1],
+                        out, stride16, olen, ost)
+    pg2 = sharding.ProofGather(lib, world, rank, hi - lo, stride16, N, SEC, torch.device('cpu'), ranges=list(zip(off[:-1], off[1:])))
+    pg2.prove_overlapped(prove_again, tp, tl)
+    assert not ost.any()
+    info2 = pg2.check(tp, tl)
+    assert info2['checksums_match_all_ranks'] and info2['own_rows_roundtrip']
+    for k in range(hi - lo):
+        assert int(olen[k]) == int(plen[k]) and bytes(out[k, :olen[k]]) == bytes(proofs[k, :plen[k]])
     if rank == 0:
         q.put((allp.numpy(), alll.numpy()))
     dist.barrier()

@@ -28,7 +28,7 @@ SYMBOLS = [
     'zka_lanes', 'zka_set_option', 'zka_proofs_pack', 'zka_proofs_unpack', 'zka_verify_batch_ex', 'zka_verify_tape_len_ex',
     'zka_verify_exp_batch', 'zka_verify_membership_batch', 'zka_verify_equality_batch', 'zka_verify_mult_batch',
     'zka_verify_pointadd_batch', 'zka_prove_exp_batch', 'zka_prove_membership_batch',
-    'zka_prove_equality_batch', 'zka_prove_mult_batch', 'zka_prove_pointadd_batch', 'zka_stat', 'zka_proof_group',
+    'zka_prove_equality_batch', 'zka_prove_mult_batch', 'zka_prove_pointadd_batch', 'zka_stat', 'zka_proof_group', 'zka_set_progress', 'zka_chunk_schedule',
 ]
 
 STATUS_MESSAGES = {
@@ -196,6 +196,24 @@ class ZkaLib:
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.zka_set_option(self.ctx, key.encode(), int(value)), f'zka_set_option({key})')
+
+    def chunk_schedule(self, B: int, host_buffers: bool = False):
+        """Chunk offsets [0, ..., B] a prove call over B proofs will use (deterministic; the same on every rank)."""
+        off = np.zeros(4096, np.uint32)
+        self.lib.zka_chunk_schedule.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32]
+        n = self.lib.zka_chunk_schedule(self.ctx, B, 1 if host_buffers else 0, _ptr(off), off.size)
+        if n < 0:
+            raise ZkaError('zka_chunk_schedule')
+        return [int(v) for v in off[:n + 1]]
+
+    def set_progress(self, flags: Optional[np.ndarray]):
+        """flags[k] (uint32, kept alive by the caller) becomes 1 when chunk k of the running prove call is complete."""
+        self.lib.zka_set_progress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        if flags is None:
+            self._check(self.lib.zka_set_progress(self.ctx, None, 0), 'zka_set_progress')
+        else:
+            assert flags.dtype == np.uint32 and flags.flags['C_CONTIGUOUS']
+            self._check(self.lib.zka_set_progress(self.ctx, _ptr(flags), flags.size), 'zka_set_progress')
 
     def stat(self, key: str) -> int:
         """Counters since zka_init ('agg_pass', 'agg_fail': verifier chunks decided by the chunk-wide aggregate check /

@@ -303,6 +303,8 @@ struct zka_ctx : Lane {
                                    // (profiles/window_sweep_r1.txt: w=13 39.9k, w=16 58.8k proofs/s)
   int chunk = 4096;       // largest chunk of a call whose buffers are all device memory (ZKA_CHUNK)
   int host_chunk = 2048;  // chunk size when proofs return to host memory: copies of one chunk overlap the next
+  volatile uint32_t* progress = nullptr;   // zka_set_progress: flags[k] = 1 when chunk k of the running prove call is complete
+  uint32_t progress_cap = 0;
   int agg = 1;            // verifier: chunk-wide aggregate check before the per-proof MSMs (ZKA_AGG=0 disables it)
   int agg_c = 0;          // window bits of the aggregate MSM (0: chosen from the chunk size; ZKA_AGG_C)
   uint64_t agg_pass = 0, agg_fail = 0;   // chunks decided by the aggregate / sent to the per-proof path (zka_stat)
@@ -588,6 +590,14 @@ std::vector<uint32_t> chunk_schedule(uint32_t B, uint32_t cmax, int lanes, bool 
   return off;
 }
 
+// flags[k] = 1 once everything enqueued on `st` so far has run (a CUDA host callback: no thread of ours waits)
+#if !defined(ZKA_HOSTSIM)
+void CUDART_CB progress_cb(void* p) { *reinterpret_cast<volatile uint32_t*>(p) = 1u; }
+void notify_progress(Stream& st, volatile uint32_t* flag) { ZK_CUDA_CHECK(cudaLaunchHostFunc(st.s, progress_cb, (void*)flag)); }
+#else
+void notify_progress(Stream&, volatile uint32_t* flag) { *flag = 1u; }
+#endif
+
 // Run fn(lane index) for lanes 0..used-1: lane 0 on the calling thread, the others on their own host threads
 // (each binds the context's device).  The first exception of any lane is rethrown on the caller.
 template <class Fn>
@@ -734,6 +744,20 @@ int zka_proof_group(char* name, size_t cap, int* point_bytes, int* scalar_bytes)
   if (point_bytes) *point_bytes = WP;
   if (scalar_bytes) *scalar_bytes = WS;
   return 0;
+}
+int zka_set_progress(zka_ctx* ctx, volatile uint32_t* flags, uint32_t cap) {
+  if (!ctx) return ZKA_E_ARG;
+  ctx->progress = flags;
+  ctx->progress_cap = flags ? cap : 0;
+  return 0;
+}
+int zka_chunk_schedule(zka_ctx* ctx, uint32_t B, int host_buffers, uint32_t* off, uint32_t cap) {
+  if (!ctx || !off || cap == 0) return ZKA_E_ARG;
+  const std::vector<uint32_t> v = chunk_schedule(B, (uint32_t)(host_buffers ? std::min(ctx->chunk, ctx->host_chunk) : ctx->chunk), ctx->nlanes,
+                                                 host_buffers != 0);
+  if (v.size() > cap) return ZKA_E_ARG;
+  for (size_t i = 0; i < v.size(); i++) off[i] = v[i];
+  return (int)v.size() - 1;
 }
 int zka_lanes(const zka_ctx* ctx) { return ctx ? ctx->nlanes : 0; }
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk) {
@@ -1352,6 +1376,7 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         launch(st, (long long)Bc * FIN_PARTS, FinalizeTask{c});
         // --- results: on the output stream, behind this chunk's last kernel
         ev_record(ln.ev_done[slot], st);
+        if (ctx->progress && k_this < ctx->progress_cap) notify_progress(st, ctx->progress + k_this);
         if (!out_dev || !len_dev || !st_dev) {
           Stream& co = ln.cs_out;
           ev_wait(co, ln.ev_done[slot]);
@@ -1664,13 +1689,9 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
     const uint32_t* ring_m = (const uint32_t*)ctx->ring_m.p;
     const int lanes = ctx->nlanes;
     const bool all_dev = is_device_ptr(proofs) && is_device_ptr(tape);
-    // host buffers: two equal chunks per lane (the next chunk's inputs travel while the current one computes).  A verify
-    // chunk has ~15 ms of latency-bound stages whatever its size (doubling chains, hashes, the tails of the aggregate
-    // check), so the tapered schedule of the prover — small first and last chunks — only adds rounds here
-    // (gpurun_out/bench_r2l_trace.err: 7 chunks of 512..1728 proofs took 18..28 ms each).
-    uint32_t vchunk = (uint32_t)std::min(ctx->chunk, 4096);
-    if (!all_dev) vchunk = std::min<uint32_t>(vchunk, std::max<uint32_t>(256, (B / (2u * (uint32_t)lanes) + 31) & ~31u));
-    const std::vector<uint32_t> off = chunk_schedule(B, vchunk, lanes, false);
+    // (two equal chunks per lane instead of the tapered host schedule were measured: config2 e2e unchanged at ~105 k
+    // verifies/s, config1 57 k -> 36 k; gpurun_out/bench_c{1,2}_r2m.json)
+    const std::vector<uint32_t> off = chunk_schedule(B, (uint32_t)std::min(ctx->chunk, all_dev ? 4096 : std::min(4096, ctx->host_chunk)), lanes, !all_dev);
     const uint32_t nchunks = (uint32_t)off.size() - 1;
     const int used = (int)std::min<uint32_t>((uint32_t)lanes, nchunks);
     std::atomic<uint32_t> next_chunk((uint32_t)used);

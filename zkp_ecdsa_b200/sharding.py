@@ -71,22 +71,42 @@ def group_capacity(rows: int, ring_size: int, sec_level: int) -> int:
     return (min(worst, int(mean + Z_BOUND_SIGMAS * sigma) + 4096) + 255) & ~255
 
 
+def group_ranges(B: int, groups: int):
+    """Row ranges of the sub-batches: every group about half the size of the one before (2/3 + 1/3, 4/7 + 2/7 + 1/7,
+    ...), multiples of 32 rows.  Only the LAST group's all-gather is exposed after the last kernel, so it should be
+    small; few large groups keep the prover's chunks large (every zka_prove_batch call ends with a full
+    synchronisation of its lanes: four equal groups cost 25 % of the 2-GPU throughput, profiles/README.md)."""
+    groups = max(1, min(groups, B))
+    weights = [2 ** (groups - 1 - i) for i in range(groups)]
+    tot = sum(weights)
+    unit = 32 if B >= 64 * groups else 1
+    out, b0 = [], 0
+    for i, w in enumerate(weights):
+        n = B - b0 if i == groups - 1 else min(B - b0 - (groups - 1 - i), max(unit, (B * w // tot + unit - 1) // unit * unit))
+        if n <= 0:
+            break
+        out.append((b0, b0 + n))
+        b0 += n
+    return out
+
+
 class ProofGather:
-    def __init__(self, lib, world: int, rank: int, B: int, stride: int, ring_size: int, sec_level: int, device, groups: int = 4):
+    def __init__(self, lib, world: int, rank: int, B: int, stride: int, ring_size: int, sec_level: int, device, groups: int = 2,
+                 ranges=None):
         import torch
         self.lib, self.world, self.rank, self.B, self.stride = lib, world, rank, B, stride
-        groups = max(1, min(groups, B))
-        per = -(-B // groups)
-        self.ranges = [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
-        self.rows = per
-        self.cap = group_capacity(per, ring_size, sec_level)
+        # `ranges`: the chunk schedule of ONE prove call (lib.chunk_schedule) for prove_overlapped(); else sub-batches
+        # proved by separate calls (submit() after each)
+        self.ranges = [tuple(r) for r in ranges] if ranges is not None else group_ranges(B, groups)
         G = len(self.ranges)
+        self.nrows = [b1 - b0 for (b0, b1) in self.ranges]
+        self.caps = [group_capacity(n, ring_size, sec_level) for n in self.nrows]
         self.dev = device
-        self.send = [torch.zeros(self.cap, dtype=torch.uint8, device=device) for _ in range(G)]
-        self.recv = [torch.zeros(world * self.cap, dtype=torch.uint8, device=device) for _ in range(G)]
-        self.lens = [torch.zeros(per, dtype=torch.int32, device=device) for _ in range(G)]
-        self.lens_all = [torch.zeros(world * per, dtype=torch.int32, device=device) for _ in range(G)]
-        self.offs = [torch.zeros(per + 1, dtype=torch.int64, device=device) for _ in range(G)]
+        self.send = [torch.zeros(self.caps[g], dtype=torch.uint8, device=device) for g in range(G)]
+        self.recv = [torch.zeros(world * self.caps[g], dtype=torch.uint8, device=device) for g in range(G)]
+        self.lens = [torch.zeros(self.nrows[g], dtype=torch.int32, device=device) for g in range(G)]
+        self.lens_all = [torch.zeros(world * self.nrows[g], dtype=torch.int32, device=device) for g in range(G)]
+        self.offs = [torch.zeros(self.nrows[g] + 1, dtype=torch.int64, device=device) for g in range(G)]
         self.cuda = device.type == 'cuda'
         self.comm = torch.cuda.Stream(device=device) if self.cuda else None
         self.works = []
@@ -94,9 +114,9 @@ class ProofGather:
         self.exposed_ms = []
 
     def describe(self) -> str:
-        return (f'{len(self.ranges)} groups per rank; per group one NCCL all-gather of the proofs packed to their true lengths '
-                f'(capacity {self.cap} B per rank per group) + one of their lengths, queued on a communication stream while the '
-                'next group is proved; no host synchronisation sizes the transfer')
+        return (f'{len(self.ranges)} groups per rank of {self.nrows} proofs; per group one NCCL all-gather of the proofs packed to '
+                f'their true lengths (capacities {self.caps} B per rank) + one of their lengths, queued on a communication stream '
+                'while the next group is proved; no host synchronisation sizes the transfer')
 
     def begin(self):
         self.works = []
@@ -109,18 +129,54 @@ class ProofGather:
         g = self.g
         self.g += 1
         rows = b1 - b0
+        assert (b0, b1) == self.ranges[g] and rows == self.nrows[g]
         ctx = torch.cuda.stream(self.comm) if self.cuda else _Null()
         with ctx:
-            self.lens[g].zero_()
-            self.lens[g][:rows].copy_(plen[b0:b1])
-            self.lib.proofs_pack(self.rows, proofs[b0:].data_ptr(), self.stride, self.lens[g].data_ptr(), self.send[g].data_ptr(),
-                                 self.cap, self.offs[g].data_ptr(), self.comm.cuda_stream if self.cuda else 0)
+            self.lens[g].copy_(plen[b0:b1])
+            self.lib.proofs_pack(rows, proofs[b0:].data_ptr(), self.stride, self.lens[g].data_ptr(), self.send[g].data_ptr(),
+                                 self.caps[g], self.offs[g].data_ptr(), self.comm.cuda_stream if self.cuda else 0)
             if self.world > 1:
                 self.works.append(dist.all_gather_into_tensor(self.lens_all[g], self.lens[g], async_op=True))
                 self.works.append(dist.all_gather_into_tensor(self.recv[g], self.send[g], async_op=True))
             else:
                 self.lens_all[g].copy_(self.lens[g])
                 self.recv[g].copy_(self.send[g])
+
+    def prove_overlapped(self, prove_fn, proofs, plen, poll_s: float = 20e-6):
+        """ONE prove call over the whole batch (prove_fn blocks; it runs on a helper thread, ctypes releases the GIL) while
+        this thread watches the library's progress flags and queues the all-gather of every finished chunk — in chunk
+        order, which is the same on all ranks, so the collectives match.  Only the chunks that finish last are exposed."""
+        import threading
+        import time
+        import numpy as np
+        flags = np.zeros(len(self.ranges), np.uint32)
+        self.lib.set_progress(flags)
+        err = []
+
+        def work():
+            try:
+                prove_fn()
+            except Exception as e:      # noqa: BLE001
+                err.append(e)
+        th = threading.Thread(target=work)
+        self.begin()
+        th.start()
+        try:
+            for k, (b0, b1) in enumerate(self.ranges):
+                while flags[k] == 0:
+                    if err or not th.is_alive() and flags[k] == 0:
+                        break
+                    time.sleep(poll_s)
+                if err or flags[k] == 0:
+                    break
+                self.submit(proofs, plen, b0, b1)
+        finally:
+            th.join()
+            self.lib.set_progress(None)
+        if err:
+            raise err[0]
+        assert self.g == len(self.ranges), 'the prove call ended before every chunk reported completion'
+        self.finish()
 
     def finish(self):
         import time
@@ -136,19 +192,20 @@ class ProofGather:
     def totals(self, g: int):
         """Packed block length of every rank for group g (from the gathered lengths)."""
         import torch
-        l = self.lens_all[g].view(self.world, self.rows).to(torch.int64)
+        l = self.lens_all[g].view(self.world, self.nrows[g]).to(torch.int64)
         return ((l + 15) & ~15).sum(dim=1)
 
     def unpack(self, g: int, r: int):
         """Rows [rows, stride] of rank r's group g from the gathered block (zka_proofs_unpack)."""
         import torch
-        out = torch.zeros((self.rows, self.stride), dtype=torch.uint8, device=self.dev)
-        offs = torch.zeros(self.rows + 1, dtype=torch.int64, device=self.dev)
-        lens = self.lens_all[g][r * self.rows:(r + 1) * self.rows].contiguous()
+        n, cap = self.nrows[g], self.caps[g]
+        out = torch.zeros((n, self.stride), dtype=torch.uint8, device=self.dev)
+        offs = torch.zeros(n + 1, dtype=torch.int64, device=self.dev)
+        lens = self.lens_all[g][r * n:(r + 1) * n].contiguous()
         if self.cuda:
             # `out` / `offs` were zero-filled on torch's current stream; the library runs on its own non-blocking stream
             torch.cuda.current_stream().synchronize()
-        self.lib.proofs_unpack(self.rows, self.recv[g][r * self.cap:].data_ptr(), self.cap, lens.data_ptr(), out.data_ptr(),
+        self.lib.proofs_unpack(n, self.recv[g][r * cap:].data_ptr(), cap, lens.data_ptr(), out.data_ptr(),
                                self.stride, offs.data_ptr(), 0)
         return out, lens
 
@@ -158,17 +215,19 @@ class ProofGather:
         import torch
         import torch.distributed as dist
         G = len(self.ranges)
-        info = {'groups': G, 'capacity_bytes': self.cap, 'exposed_ms_per_step': sum(self.exposed_ms) / max(1, len(self.exposed_ms))}
+        info = {'groups': G, 'group_rows': self.nrows, 'capacity_bytes': self.caps,
+                'exposed_ms_per_step': sum(self.exposed_ms) / max(1, len(self.exposed_ms))}
         local = torch.zeros(G, dtype=torch.int64, device=self.dev)
         seen = torch.zeros((G, self.world), dtype=torch.int64, device=self.dev)
         maxfill = 0.0
         for g in range(G):
             tot = self.totals(g)
-            assert int(tot.max().item()) <= self.cap, 'packed block exceeded its capacity'
-            maxfill = max(maxfill, float(tot.max().item()) / self.cap)
+            cap = self.caps[g]
+            assert int(tot.max().item()) <= cap, 'packed block exceeded its capacity'
+            maxfill = max(maxfill, float(tot.max().item()) / cap)
             for r in range(self.world):
                 n = int(tot[r].item())
-                blk = self.recv[g][r * self.cap:r * self.cap + n]
+                blk = self.recv[g][r * cap:r * cap + n]
                 seen[g, r] = torch.sum(blk.view(torch.int32), dtype=torch.int64) if n else 0
             n = int(tot[self.rank].item())
             local[g] = torch.sum(self.send[g][:n].view(torch.int32), dtype=torch.int64) if n else 0
