@@ -369,39 +369,68 @@ def run_ours(args):
     stat_h = torch.zeros(B, dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     lib_stream = torch.cuda.ExternalStream(L.stream_ptr(), device=dev)
-    # N > 1: the all-gather of the proof bytes overlaps proving.  Default: ONE prove call per step; a second host thread
-    # queues the gather of every chunk the library reports complete (zka_set_progress), in chunk order.  --gather-groups G
-    # > 0 instead proves G sub-batches by separate calls (each call ends with a full synchronisation of its lanes: two
-    # groups cost 6 %, four 20 % of the 2-GPU throughput, profiles/README.md)
+    # N > 1: the all-gather of the proof bytes (packed to their true lengths) overlaps proving.  --gather-mode
+    #   pipeline (default): ONE prove call per step into one of two output buffer sets; the gather of step k is queued on a
+    #             communication stream and runs while step k + 1 is proved; the timed region ends when the last gather has
+    #             landed.  Whole-job throughput is what `value` reports; `gather.exposed_ms_per_step` is the part not hidden.
+    #   serial:   the gather follows its step and is fully exposed (3.3 ms at 2 GPUs, ~7x that at 8).
+    #   chunks:   one prove call; a second host thread queues the gather of every chunk the library reports complete
+    #             (zka_set_progress), in chunk order — needs more chunks than lanes, and chunks of 1376 instead of 2752
+    #             proofs cost 11 % of the 2-GPU throughput (profiles/README.md).
+    #   groups:   --gather-groups G sub-batches proved by separate calls (each call ends with a full synchronisation of
+    #             its lanes: two groups cost 6 %, four 20 %).
     gather = None
+    gathers, outbufs = [], [(proofs_d, plen_d)]
+    mode = args.gather_mode if world > 1 else 'none'
     if world > 1:
-        if args.gather_groups > 0:
-            gather = sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, groups=args.gather_groups)
-        else:
+        if mode == 'groups':
+            gather = sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, groups=max(1, args.gather_groups))
+        elif mode == 'chunks':
             if args.gather_chunk > 0:
                 L.set_option('chunk', args.gather_chunk)     # more chunks than lanes: the early ones overlap the later ones
             off = L.chunk_schedule(B, host_buffers=False)
             gather = sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, ranges=list(zip(off[:-1], off[1:])))
+        else:
+            nb = 2 if mode == 'pipeline' else 1
+            gathers = [sharding.ProofGather(L, world, rank, B, ps, N, SEC_LEVEL, dev, ranges=[(0, B)]) for _ in range(nb)]
+            gather = gathers[0]
+            if nb == 2:
+                outbufs.append((torch.zeros((B, ps), dtype=torch.uint8, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)))
+    step_no = [0]
 
-    def prove_dev(b0, b1):
+    def prove_dev(b0, b1, out=None):
+        pd, pl = out if out is not None else (proofs_d, plen_d)
         L.prove_batch(params.handle, b1 - b0, d['msg'][b0:].data_ptr(), d['sig'][b0:].data_ptr(), d['pk'][b0:].data_ptr(),
                       d['which'][4 * b0:].data_ptr(), d['ring'].data_ptr(), N, tape_d[b0:].data_ptr(), ts,
-                      proofs_d[b0:].data_ptr(), ps, plen_d[b0:].data_ptr(), stat_d[b0:].data_ptr())
+                      pd[b0:].data_ptr(), ps, pl[b0:].data_ptr(), stat_d[b0:].data_ptr())
 
     def step_device():
         if world == 1:
             prove_dev(0, B)
             return
-        # N > 1: the rank's batch is proved group by group; the NCCL all-gather of a finished group's packed
-        # proof bytes runs on the communication stream while the next group is being proved
-        if args.gather_groups <= 0:
+        if mode == 'chunks':
             gather.prove_overlapped(lambda: prove_dev(0, B), proofs_d, plen_d)
             return
-        gather.begin()
-        for (b0, b1) in gather.ranges:
-            prove_dev(b0, b1)
-            gather.submit(proofs_d, plen_d, b0, b1)
-        gather.finish()
+        if mode == 'groups':
+            gather.begin()
+            for (b0, b1) in gather.ranges:
+                prove_dev(b0, b1)
+                gather.submit(proofs_d, plen_d, b0, b1)
+            gather.finish()
+            return
+        i = step_no[0] % len(gathers)
+        step_no[0] += 1
+        g = gathers[i]
+        g.finish()                        # the gather that used this buffer set (two steps ago) has landed
+        prove_dev(0, B, outbufs[i])
+        g.begin()
+        g.submit(outbufs[i][0], outbufs[i][1], 0, B)
+        if mode == 'serial':
+            g.finish()
+
+    def drain():
+        for g in gathers:
+            g.finish()
 
     def step_host():
         L.prove_batch(params.handle, B, h['msg'].data_ptr(), h['sig'].data_ptr(), h['pk'].data_ptr(),
@@ -413,7 +442,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, end=None):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -423,6 +452,8 @@ def run_ours(args):
             flush.zero_()            # evict L2 between steps (torch stream; tiny vs a step)
             torch.cuda.current_stream().synchronize()
             fn()
+        if end:
+            end()
         torch.cuda.synchronize()
         e1.record(lib_stream)
         e1.synchronize()
@@ -437,6 +468,7 @@ def run_ours(args):
     # warm-up (>= 3 steps: allocator growth, table pages, clocks)
     for _ in range(max(args.warmup, 3)):
         step_device()
+    drain()
     torch.cuda.synchronize()
     assert int((stat_d != 0).sum().item()) == 0, 'prover reported per-proof errors'
 
@@ -444,12 +476,27 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = L.launch_count()
-    ms_total = timed(step_device, args.steps)
+    for g in gathers:
+        g.exposed_ms = []
+    ms_total = timed(step_device, args.steps, drain)
     launches = L.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
-    gather_info = gather.check(proofs_d, plen_d) if gather else None
+    gather_info = None
+    if gathers:
+        last = (step_no[0] - 1) % len(gathers)
+        for i in range(len(gathers)):
+            info = gathers[i].check(outbufs[i][0], outbufs[i][1])
+            if i == last:
+                gather_info = info
+        gather_info['mode'] = mode
+        gather_info['exposed_ms_per_step'] = sum(sum(g.exposed_ms) for g in gathers) / args.steps   # host time spent waiting for gathers
+        if len(gathers) == 2:      # both output sets hold the same proofs (same inputs, same tape)
+            assert torch.equal(outbufs[0][1], outbufs[1][1])
+    elif gather:
+        gather_info = gather.check(proofs_d, plen_d)
+        gather_info['mode'] = mode
 
     # per-kernel CUDA-event pairs on the launching streams: a separate, un-timed pass (the event pairs
     # serialise the lanes of a call, so they are kept out of the timed region)
@@ -530,6 +577,7 @@ def run_ours(args):
     L.set_profiling(False)
     L.set_option('lanes', lanes_cfg)
     vprof = L.profile()
+    agg_c_prof = L.stat('agg_c') if hasattr(L, 'stat') else 0     # window bits of the aggregate MSM in the profiled pass
     ms_vprof_step = sum(e['ms'] for e in vprof.values()) / 2
     verify_host()
     ve2e_ms = timed(verify_host, vsteps) / vsteps
@@ -609,7 +657,7 @@ def run_ours(args):
     vextra = {'MsmTomWindowBothTask': msm_macs / 2,       # items counts both instances' threads
               'MsmCombineAllTask': ((258 * 8 + 43 * 9) * 2 * MAC_PER_TOM_MODMUL + (256 * 13 + 64 * 14) * MAC_PER_P256_MODMUL) / 3,
               'VValidateTask': (2 + 32 * zero_bits / 80.0) * 7 * MAC_PER_TOM_MODMUL}
-    agg_c = L.stat('agg_c') if hasattr(L, 'stat') else 0
+    agg_c = agg_c_prof
     agg_name = 'AggBucketTask<AggTomSrc>'
     agg_e = next((v for k, v in vprof.items() if short(k) == agg_name), None)
     agg_on = bool(agg_e and agg_e['ms'] > 0 and agg_c > 0)
@@ -658,7 +706,13 @@ def run_ours(args):
                                + ('; verify leg = configs[4])' if wname == 'config3' else ')'),
                    'l2': 'working set per step > L2 (tape + proofs ~2.6 GB at 8192 proofs) and a 256 MiB buffer is rewritten between steps',
                    'tom_window_bits': cfg['tom_w'], 'chunk': cfg['chunk'], 'lanes': cfg.get('lanes'),
-                   'collective': 'none' if world == 1 else gather.describe()},
+                   'collective': 'none' if world == 1 else {
+                       'pipeline': "the NCCL all-gather of step k's proof bytes overlaps the proving of step k + 1 (two output "
+                                   'buffer sets); the timed K steps end when the last gather has landed; ',
+                       'serial': "the NCCL all-gather of a step's proof bytes follows the step (exposed); ",
+                       'chunks': 'one prove call per step, finished chunks are gathered while later ones are proved; ',
+                       'groups': 'sub-batches proved by separate calls, a finished one is gathered while the next is proved; ',
+                   }[mode] + gather.describe()},
         'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'proofs/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms, 'bit_identical_to_device_arm': same,
                 'tape_generation': {'s_per_proof': tape_gen_s_per_proof, 'bytes_per_proof': ts,
@@ -716,11 +770,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
                     help='default: config2 on one GPU, config3 (8192 per GPU x ring 1024) under torchrun')
-    ap.add_argument('--gather-groups', type=int, default=0,
-                    help='N>1: 0 = one prove call per step, finished chunks are gathered while later ones are proved; '
-                         'G > 0 = G sub-batches proved by separate calls')
+    ap.add_argument('--gather-mode', default='pipeline', choices=['pipeline', 'serial', 'chunks', 'groups'],
+                    help='N>1: how the all-gather of the proof bytes overlaps proving (see run_ours)')
+    ap.add_argument('--gather-groups', type=int, default=2, help='N>1, --gather-mode groups: sub-batches per step')
     ap.add_argument('--gather-chunk', type=int, default=1408,
-                    help='N>1 with --gather-groups 0: largest chunk of the prove call (two chunks per lane at 8192 proofs, 3 lanes)')
+                    help='N>1, --gather-mode chunks: largest chunk of the prove call (two chunks per lane at 8192 proofs, 3 lanes)')
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--ring', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
