@@ -1277,7 +1277,9 @@ static int prove_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint8
         }
         // the window bits of these tables are chosen on the device from the number of distinct keys (tab_count[1]);
         // grids are sized for the worst case, surplus threads return
-        launch(st, (long long)Bc * RT_NWIN, P256RowsTask{c.rpows, c.rrows, KEY_W_MIN, c.tab_count, c.tab_count + 1});
+        // (one thread per (key, window, block of 16 entries): keys x windows x blocks <= Bc x KEY_CAP / 16 by the memory
+        // rule of key_window_bits, e.g. 0.2 Bc keys x 33 x 8 at w = 8 or Bc x 52 x 1 at w = 5)
+        launch(st, (long long)Bc * ((KEY_CAP + 15) / 16), P256RowsBlockTask{c.rpows, c.rrows, KEY_W_MIN, c.tab_count, c.tab_count + 1});
         {
           const long long np = (long long)Bc * KEY_CAP;
           // points per thread from the EXPECTED table volume (at most min(N, Bc) distinct keys when every key is a ring
