@@ -80,6 +80,8 @@ struct VerifyCtx {
   uint32_t* tagbits;    // [B][3] tag of each repetition (bit i)
   uint32_t* chal;       // [B][3]
   uint8_t* gk_ok_len;   // [B] 1 if the GK length check passes (gk.ts:208-218)
+  uint8_t* gk_tape_bad; // [B] or null: a GK draw was out of range — recorded here and folded into status[] by VReduceTask when
+                        //     the GK chain runs beside the exp chain (same precedence as running it after), else written at once
   uint32_t* r_aff;      // [B][16]
   uint32_t* q_aff;      // [B][16]
   uint8_t* q_inf;       // [B]
@@ -709,6 +711,7 @@ struct VReduceTask {
   ZK_HD void operator()(int b) const {
     using F = Tomq;
     using Fn = P256n;
+    if (c.gk_tape_bad && c.gk_tape_bad[b]) ZK_SET_STATUS(c.status + b, ZKA_ERR_TAPE_RANGE);   // after every exp-side status
     uint32_t gW[8], hW[8], pX[8], pY[8], sR[8], sH[8], sC[8];
     zero_n<8>(gW); zero_n<8>(hW); zero_n<8>(pX); zero_n<8>(pY); zero_n<8>(sR); zero_n<8>(sH); zero_n<8>(sC);
     for (int j = 0; j < c.K; j++) {
@@ -821,6 +824,7 @@ struct VGkTask {
   ZK_HD void operator()(int b) const {
     using F = Tomq;
     const int n = c.n;
+    if (c.gk_tape_bad) c.gk_tape_bad[b] = 0;
     if (!c.gk_ok_len[b]) {   // length check fails -> verifyMembership returns false before any draw
       for (int k = 0; k < 4 * n + 1; k++) { uint32_t z[8]; zero_n<8>(z); st<8>(c.gk_scalar + ((size_t)b * (4 * n + 1) + k) * 8, z); }
       uint32_t z[8]; zero_n<8>(z);
@@ -896,7 +900,10 @@ struct VGkTask {
     F::mul(t0, rf, zd); F::sub(hS, hS, t0);
     F::from_mont(t1, gS); st<8>(c.fx_jv + (size_t)b * 2 * 8, t1);
     F::from_mont(t1, hS); st<8>(c.fx_jr + (size_t)b * 2 * 8, t1);
-    if (!tape_ok) ZK_SET_STATUS(c.status + b, ZKA_ERR_TAPE_RANGE);
+    if (!tape_ok) {
+      if (c.gk_tape_bad) c.gk_tape_bad[b] = 1;
+      else ZK_SET_STATUS(c.status + b, ZKA_ERR_TAPE_RANGE);
+    }
   }
 };
 struct VGkOffsetsTask {   // byte offsets of cl, ca, cb, cd, com for VParseEntriesTask

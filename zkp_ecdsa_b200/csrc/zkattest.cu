@@ -286,6 +286,8 @@ struct Lane {
   // copy streams + events of the host-buffer pipeline; slot = (lane-local chunk index) & 1
   Stream cs_in, cs_out;
   Event ev_small[2], ev_tape[2], ev_done[2], ev_out[2];
+  Stream aux[2];            // verifier: the torsion guard and the P-256 part of the aggregate check run beside the tomEdwards256 MSM
+  Event ev_fork, ev_join[2];
   // workspace (grow-only)
   DevBuf w[64];
   DevBuf in[16], out[8];
@@ -633,8 +635,8 @@ const char* zka_last_error(const zka_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 uint64_t zka_launch_count(const zka_ctx* ctx) {
   if (!ctx) return 0;
-  uint64_t n = ctx->st.launches;
-  for (const Lane* l : ctx->extra) n += l->st.launches;
+  uint64_t n = ctx->st.launches + ctx->aux[0].launches + ctx->aux[1].launches;
+  for (const Lane* l : ctx->extra) n += l->st.launches + l->aux[0].launches + l->aux[1].launches;
   return n;
 }
 
@@ -671,6 +673,8 @@ int zka_set_option(zka_ctx* ctx, const char* key, long value) {
         stream_create(l->st);
         stream_create(l->cs_in);
         stream_create(l->cs_out);
+        stream_create(l->aux[0]);
+        stream_create(l->aux[1]);
         l->st.profiling = ctx->st.profiling;
         ctx->extra.push_back(l);
       }
@@ -807,6 +811,8 @@ int zka_init(int device, zka_ctx** out) {
     }
     stream_create(ctx->cs_in);
     stream_create(ctx->cs_out);
+    stream_create(ctx->aux[0]);
+    stream_create(ctx->aux[1]);
     {
       int lanes = 3;
 #if defined(ZKA_HOSTSIM)
@@ -879,6 +885,9 @@ void zka_shutdown(zka_ctx* ctx) {
     }
     stream_destroy(l.cs_in);
     stream_destroy(l.cs_out);
+    stream_destroy(l.aux[0]);
+    stream_destroy(l.aux[1]);
+    ev_destroy(l.ev_fork); ev_destroy(l.ev_join[0]); ev_destroy(l.ev_join[1]);
     stream_destroy(l.st);
   }
   for (Lane* l : ctx->extra) delete l;
@@ -1815,13 +1824,36 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
 
       launch(st, Bc, VLayoutTask{c});
       launch(st, (long long)Bc * (S + 1), VValidateTask{c});
-      launch(st, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
-      launch(st, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows});
       {
-        const long long np = (long long)Bc * RT_ENTRIES;
-        launch_p256_norm(st, c.rrows, c.rtab, nullptr, nullptr, (long long)(np));
+        // the per-proof tables of R (a 255-doubling chain per proof, rows, normalisation: no status writes) run beside the
+        // Fiat-Shamir hash of the repetitions (one thread per proof, 16 KB) unless per-kernel profiling is on
+        const bool fork = !st.profiling;
+        Stream& sr = fork ? ln.aux[0] : st;
+        if (fork) { ev_record(ln.ev_fork, st); ev_wait(sr, ln.ev_fork); }
+        launch(sr, Bc, P256PowsTask{c.r_aff, nullptr, c.rpows, Bc, RT_NWIN, RT_W});
+        launch(sr, (long long)Bc * RT_NWIN, P256RowsSignedTask{c.rpows, c.rrows});
+        launch_p256_norm(sr, c.rrows, c.rtab, nullptr, nullptr, (long long)Bc * RT_ENTRIES);
+        launch(st, Bc, VChallengeTask{c});
+        if (fork) { ev_record(ln.ev_join[0], sr); ev_wait(st, ln.ev_join[0]); }
       }
-      launch(st, Bc, VChallengeTask{c});
+      // the Groth-Kohlweiss chain (ring polynomial, relations, offsets) only needs the layout: it runs on a side stream
+      // beside the sampled-repetition chain; its tape-range status is folded in by VReduceTask (same precedence)
+      const bool gk_fork = mode == 0 && !st.profiling;
+      Stream& sg = gk_fork ? ln.aux[1] : st;
+      auto gk_chain = [&] {
+        const int nblk = 1 << (n - gk_block_bits(n));
+        c.gk_part = nblk > 1 ? W[51].get<uint32_t>((size_t)Bc * nblk * 8) : nullptr;
+        if (nblk > 1) launch(sg, (long long)Bc * nblk, VGkSumTask{c});
+        launch(sg, Bc, VGkTask{c});
+        launch(sg, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
+      };
+      if (mode == 0) c.gk_tape_bad = W[54].get<uint8_t>(Bc);
+      if (gk_fork) {
+        ev_record(ln.ev_fork, st);
+        ev_wait(sg, ln.ev_fork);
+        gk_chain();
+        ev_record(ln.ev_join[1], sg);
+      }
       launch(st, (long long)ns, VSampleP256Task{c});
       launch_p256_norm(st, c.sp_T, c.sp_T_aff, nullptr, c.sp_T_inf, (long long)(ns));
       launch(st, (long long)ns, VSampleJobsTask{c});
@@ -1833,11 +1865,8 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
       dev_memset(st, c.ent_off, 0, (size_t)Bc * ET * 4);
       launch(st, (long long)ns, VRelationsTask{c});
       if (mode == 0) {
-        const int nblk = 1 << (n - gk_block_bits(n));
-        c.gk_part = nblk > 1 ? W[51].get<uint32_t>((size_t)Bc * nblk * 8) : nullptr;
-        if (nblk > 1) launch(st, (long long)Bc * nblk, VGkSumTask{c});
-        launch(st, Bc, VGkTask{c});
-        launch(st, (long long)Bc * ngk, VGkOffsetsTask{c, gk_offs});
+        if (gk_fork) ev_wait(st, ln.ev_join[1]);
+        else gk_chain();
       }
       launch(st, Bc, VReduceTask{c});
       launch(st, (long long)Bc * ET, VParseEntriesTask{c.proofs, proof_stride, c.ent_off, c.ent_pre, ET});
@@ -1854,11 +1883,23 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
         launch(st, Bc, AggGateTask{c, ctl});
         const AggTomSrc tsrc{c.ent_scalar, c.ent_pre, c.ent_cnt, c.gk_scalar, c.gk_pre, Bc, ET, K, ngk};
         const AggNistSrc nsrc{c.nent_scalar, c.nent_aff, c.nent_skip, Bc, EN};
+        // three independent chains from here to AggFinalTask: the tomEdwards256 MSM (this stream), the torsion guard and the
+        // P-256 MSM with its fixed parts (two side streams; with per-kernel profiling on, everything stays on one stream
+        // so that the event pairs time one kernel at a time).  A skip flag raised by the torsion guard may reach the MSM
+        // kernels late — they then only do work AggFinalTask discards.
+        const bool fork = !st.profiling;
+        Stream& sa = fork ? ln.aux[0] : st;
+        Stream& sb = fork ? ln.aux[1] : st;
+        if (fork) {
+          ev_record(ln.ev_fork, st);
+          ev_wait(sa, ln.ev_fork);
+          ev_wait(sb, ln.ev_fork);
+        }
 #if !defined(ZKA_PG_WAR256)
         {   // cofactor 4: no small-order components, or the per-proof path decides
           uint32_t* tpart = A[46].get<uint32_t>((size_t)Bc * (K + 1) * 2 * PG_EXT_WORDS);
-          launch(st, (long long)Bc * (K + 1) * 2, AggTorsionPartTask{tsrc, ctl, tpart});
-          launch(st, Bc, AggTorsionTask{tpart, ctl, K});
+          launch(sa, (long long)Bc * (K + 1) * 2, AggTorsionPartTask{tsrc, ctl, tpart});
+          launch(sa, Bc, AggTorsionTask{tpart, ctl, K});
         }
 #endif
         const AggPlan tp = agg_plan((double)Bc * (0.5 * K * V_ENT_PER_SAMPLE + 2 + ngk), ctx->agg_c);
@@ -1866,7 +1907,7 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
         ctx->agg_c_last = tp.D.c;
         const uint32_t *tA, *tB, *nA, *nB;
         agg_msm(st, A + 1, tsrc, tp, ctl, &tA, &tB);
-        agg_msm(st, A + 20, nsrc, np, ctl, &nA, &nB);
+        agg_msm(sb, A + 20, nsrc, np, ctl, &nA, &nB);
         // fixed-base parts: one commitment for the summed tomEdwards256 scalars, a two-level sum of the P-256 points
         const int fgroups = (Bc * 2 + 63) / 64, ngroups = (Bc + 31) / 32;
         uint32_t* fpart = A[40].get<uint32_t>((size_t)fgroups * 16);
@@ -1877,14 +1918,20 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
         launch(st, fgroups, AggFixPartTask{ctl, c.fx_jv, c.fx_jr, fpart, Bc});
         launch(st, 1, AggFixSumTask{ctl, fpart, fjv, fjr, fgroups});
         launch(st, 1, TomCommitTask{fjv, fjr, c.tg_tab, c.th_tab, fproj, c.tom_w, c.tom_nwin});
-        launch(st, ngroups, AggNistFixPartTask{ctl, c.nfix, npart, Bc});
+        launch(sb, ngroups, AggNistFixPartTask{ctl, c.nfix, npart, Bc});
         int nleft = ngroups;            // second level: at most Bc / 1024 partial sums reach the final thread
         const uint32_t* nsum = npart;
         if (nleft > 32) {
           uint32_t* npart2 = A[45].get<uint32_t>((size_t)((nleft + 31) / 32) * P256_PROJ_WORDS);
-          launch(st, (nleft + 31) / 32, AggNistFixPartTask{ctl, npart, npart2, nleft});
+          launch(sb, (nleft + 31) / 32, AggNistFixPartTask{ctl, npart, npart2, nleft});
           nsum = npart2;
           nleft = (nleft + 31) / 32;
+        }
+        if (fork) {
+          ev_record(ln.ev_join[0], sa);
+          ev_record(ln.ev_join[1], sb);
+          ev_wait(st, ln.ev_join[0]);
+          ev_wait(st, ln.ev_join[1]);
         }
         launch(st, 33, AggFinalTask{ctl, tA, tB, fproj, tp.D.nwin, tp.D.c, nA, nB, nsum, np.D.nwin, np.D.c, nleft});
         c.agg_ctl = ctl;
