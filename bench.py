@@ -334,7 +334,8 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # NCCL's INFO log (rank/topology/NVLS lines the driver greps) goes to stderr: fd 1 is already routed
         # there by quiet_stdout(), so nothing has to be silenced to keep stdout to the one JSON line
-        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'INFO'      # (the image presets a quieter level: only the version line appeared)
         os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
