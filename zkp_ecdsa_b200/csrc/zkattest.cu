@@ -311,6 +311,7 @@ struct zka_ctx : Lane {
   int agg_c = 0;          // window bits of the aggregate MSM (0: chosen from the chunk size; ZKA_AGG_C)
   uint64_t agg_pass = 0, agg_fail = 0;   // chunks decided by the aggregate / sent to the per-proof path (zka_stat)
   std::mutex stat_mu;
+  std::mutex copy_mu;     // keeps the copies of one chunk together on the shared copy-in stream (verify)
   int agg_c_last = 0;
   bool tape_split = true; // host tapes travel in two strided copies: the 3 + 4S draws before the challenge, then only the
                           // item / GK draws up to the longest proof of the chunk (ZKA_TAPE_SPLIT=0: one full-stride copy)
@@ -1711,47 +1712,55 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
     auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
     // every lane starts with chunk `li` and then claims chunks from a shared counter: copy-in, kernels and copy-out of a chunk are sequential on the
     // lane's stream; the copies of one lane overlap the kernels of the others
+    // the inputs of a lane's NEXT chunk travel on the copy-in stream (second set of staging buffers) while the current
+    // chunk computes; a chunk's kernels wait for its event only
+    struct VIn { const uint8_t* msg; const uint8_t* proofs; const uint32_t* plen; const uint8_t* tape; };
+    auto stage_chunk = [&](Lane& ln, int slot, uint32_t kk) {
+      // ONE copy-in stream for all lanes of the call: the chunks' inputs cross PCIe in the order they were queued, each at
+      // full bandwidth (with a copy stream per lane the first chunks and the prefetched ones were all in flight at once).
+      std::lock_guard<std::mutex> copy_lock(ctx->copy_mu);
+      Stream& ci = ctx->cs_in;
+      DevBuf* in = ln.in + 8 * slot;
+      const uint32_t b0 = off[kk];
+      const size_t Bc = off[kk + 1] - b0;
+      VIn v;
+      v.msg = msg_hash ? stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32) : nullptr;
+      if (is_device_ptr(proofs) || is_device_ptr(proof_len)) {
+        v.proofs = stage_in(ci, in[1], proofs + (size_t)b0 * proof_stride, Bc * proof_stride);
+      } else {
+        // host rows: only the bytes up to the longest proof of the chunk cross PCIe (rows are stride-padded;
+        // a length above the stride is rejected by VLayoutTask without reading the row)
+        size_t w = 0;
+        for (size_t i = 0; i < Bc; i++) w = std::max<size_t>(w, proof_len[b0 + i]);
+        w = std::min(proof_stride, (w + 15) & ~(size_t)15);
+        uint8_t* dp = in[1].get<uint8_t>(Bc * proof_stride);
+        copy_d2h_2d(ci, dp, proof_stride, proofs + (size_t)b0 * proof_stride, proof_stride, w, Bc);
+        v.proofs = dp;
+      }
+      v.plen = stage_in(ci, in[2], proof_len + b0, Bc);
+      v.tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
+      ev_record(ln.ev_small[slot], ci);
+      return v;
+    };
+    // the first chunk of every lane is queued here, in chunk order, before any lane prefetches its second one (the trace of
+    // the first version: a lane queued its first chunk and its prefetch back to back, another lane's first inputs landed
+    // after 27 ms)
+    std::vector<VIn> first((size_t)used);
+    for (int li = 0; li < used; li++) first[(size_t)li] = stage_chunk(ctx->lane(li), 0, (uint32_t)li);
     auto run_lane = [&](int li) {
       Lane& ln = ctx->lane(li);
       Stream& st = ln.st;
       DevBuf* W = ln.w;
-      // the inputs of a lane's NEXT chunk travel on its copy-in stream (second set of staging buffers) while the current
-      // chunk computes; a chunk's kernels wait for its event only
-      struct VIn { const uint8_t* msg; const uint8_t* proofs; const uint32_t* plen; const uint8_t* tape; };
-      auto stage_chunk = [&](int slot, uint32_t kk) {
-        Stream& ci = ln.cs_in;
-        DevBuf* in = ln.in + 8 * slot;
-        const uint32_t b0 = off[kk];
-        const size_t Bc = off[kk + 1] - b0;
-        VIn v;
-        v.msg = msg_hash ? stage_in(ci, in[0], msg_hash + (size_t)b0 * 32, Bc * 32) : nullptr;
-        if (is_device_ptr(proofs) || is_device_ptr(proof_len)) {
-          v.proofs = stage_in(ci, in[1], proofs + (size_t)b0 * proof_stride, Bc * proof_stride);
-        } else {
-          // host rows: only the bytes up to the longest proof of the chunk cross PCIe (rows are stride-padded;
-          // a length above the stride is rejected by VLayoutTask without reading the row)
-          size_t w = 0;
-          for (size_t i = 0; i < Bc; i++) w = std::max<size_t>(w, proof_len[b0 + i]);
-          w = std::min(proof_stride, (w + 15) & ~(size_t)15);
-          uint8_t* dp = in[1].get<uint8_t>(Bc * proof_stride);
-          copy_d2h_2d(ci, dp, proof_stride, proofs + (size_t)b0 * proof_stride, proof_stride, w, Bc);
-          v.proofs = dp;
-        }
-        v.plen = stage_in(ci, in[2], proof_len + b0, Bc);
-        v.tape = stage_in(ci, in[4], tape + (size_t)b0 * tape_stride, Bc * tape_stride);
-        ev_record(ln.ev_small[slot], ci);
-        return v;
-      };
       uint32_t k = (uint32_t)li;
       if (k >= nchunks) return;
       int slot = 0;
-      VIn cur = stage_chunk(slot, k);
+      VIn cur = first[(size_t)li];
       for (;;) {
       // claim the next chunk now and send its inputs on their way (the other slot's buffers were last read by the chunk
       // before this one, which ended with a stream synchronisation)
       const uint32_t kn = next_chunk.fetch_add(1);
       VIn nxt{};
-      if (kn < nchunks) nxt = stage_chunk(slot ^ 1, kn);
+      if (kn < nchunks) nxt = stage_chunk(ln, slot ^ 1, kn);
       ev_wait(st, ln.ev_small[slot]);
       const uint32_t b0 = off[k];
       const int Bc = (int)(off[k + 1] - b0);
@@ -1969,9 +1978,9 @@ static int verify_impl(zka_ctx* ctx, const zka_params* P, uint32_t B, const uint
       cur = nxt;
       slot ^= 1;
     }
-    sync(ln.cs_in);
     };
     run_lanes(ctx, used, run_lane);
+    sync(ctx->cs_in);
     return 0;
   } catch (const std::exception& e) {
     return fail(ctx, ZKA_E_CUDA, e.what());
