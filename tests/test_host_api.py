@@ -93,3 +93,22 @@ def test_wild_index_and_error_rows(hostsim):
     from oracle import flat
     assert proofs[0, :plen[0]].tobytes() == flat.ser_proof(pr)
     L.params_destroy(P)
+
+
+def test_engine_proof_group_selection(hostsim_war):
+    """api.Engine picks the library by ProofGroup name (instances.ts:58-69: only the groups the reference ships are
+    valid); the war256 engine runs the reference-shaped host functions end to end."""
+    with pytest.raises(ValueError):
+        api.Engine(proof_group='curve25519')
+    eng = api.Engine.__new__(api.Engine)
+    eng.lib = hostsim_war
+    eng.proof_group = hostsim_war.group
+    params = eng.generate_params_list(20, rnd=synth.params_rnd(6))     # verifySignatureList samples 20 repetitions
+    assert params.proof_group == 'war256' and len(params.h_proof) == 65
+    wl, (msg, sig, pk, which, keys) = _one(63)
+    proof = eng.prove_signature_list(params, msg, sig, pk, which, keys)
+    assert eng.verify_signature_list(params, msg, keys, proof) is True
+    bad = bytearray(proof.data)
+    bad[-1] ^= 1
+    assert eng.verify_signature_list(params, msg, keys, api.SignatureProofList(bytes(bad))) is False
+    params.close()
