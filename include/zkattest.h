@@ -232,7 +232,11 @@ size_t zka_profile_json(zka_ctx* ctx, char* buf, size_t cap);
  *                   into chunks dealt round-robin to the lanes; every lane has its own streams and workspace
  *                   and (beyond the first) its own host thread for the duration of the call, so the
  *                   latency-bound stages and the host<->device copies of one chunk overlap the
- *                   multiplier-bound kernels of another */
+ *                   multiplier-bound kernels of another
+ *   ZKA_TAPE_SPLIT  1 (default): a host tape travels in two strided copies — the 3 + 4 S draws before the challenge, then
+ *                   the item / GK draws up to the longest proof of the chunk; 0: one full-stride copy up front
+ *   ZKA_AGG, ZKA_AGG_C   the verifier's chunk-wide aggregate check (see zka_stat): 0 disables it / window bits 4..16
+ *   ZKA_TRACE       per-chunk timeline of the host-buffer pipelines on stderr (adds synchronisations) */
 int zka_config(const zka_ctx* ctx, int* tom_w, int* tom_nwin, int* chunk);
 int zka_lanes(const zka_ctx* ctx);
 /* change a knob between calls: key in {"lanes", "chunk", "host_chunk", "agg" (1 = off, 2 = on), "agg_c" (4..16)}, value >= 1 */
