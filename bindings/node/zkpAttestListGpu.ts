@@ -24,7 +24,7 @@ import { posMod, rnd, toBytes } from './bignum/big.js'
 const native = require('../build/Release/zkattest.node')
 let nativeWar: typeof native | undefined
 function nativeFor(params: SystemParametersList): typeof native {
-    const name = params.ProofGroup.g.group.name
+    const name = params.ProofGroup.c.name
     if (name === 'tomEdwards256') return native
     if (name !== 'war256') throw new Error(`invalid group name: ${name}`) // instances.ts:66
     // eslint-disable-next-line @typescript-eslint/no-require-imports
@@ -213,7 +213,7 @@ export async function proveSignatureList(params: SystemParametersList, msgHash: 
     const n = Math.ceil(Math.log2(keys.length)),
         res = await nativeFor(params).proveBatch(paramsHandle(params), msgHash, sigBytes, pk, Uint32Array.of(which), ringBytes(keys),
             proveTape(params.SecLevel, n), params.SecLevel)
-    return readProof(res.proofs.subarray(0, res.lens[0]), params.SecLevel, params.ProofGroup.g.group)
+    return readProof(res.proofs.subarray(0, res.lens[0]), params.SecLevel, params.ProofGroup.c)
 }
 
 export async function verifySignatureList(params: SystemParametersList, msgHash: Uint8Array, keys: bigint[],
@@ -236,5 +236,5 @@ export async function proveSignatureListBatch(params: SystemParametersList, msgH
         tapes = Array.from({ length: B }, () => proveTape(params.SecLevel, n)),
         res = await nativeFor(params).proveBatch(paramsHandle(params), cat(msgHash, 32), cat(sigBytes, 64), cat(pks, 65), Uint32Array.from(which),
             ringBytes(keys), cat(tapes, tapes[0].length), params.SecLevel)
-    return Array.from({ length: B }, (_, b) => readProof(res.proofs.subarray(b * res.stride, b * res.stride + res.lens[b]), params.SecLevel, params.ProofGroup.g.group))
+    return Array.from({ length: B }, (_, b) => readProof(res.proofs.subarray(b * res.stride, b * res.stride + res.lens[b]), params.SecLevel, params.ProofGroup.c))
 }
